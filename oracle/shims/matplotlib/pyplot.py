@@ -1,0 +1,1 @@
+"""stand-in, see matplotlib/__init__.py"""

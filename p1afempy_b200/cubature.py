@@ -1,0 +1,115 @@
+"""Cubature rules on the reference triangle (0,0),(1,0),(0,1) -- rule as DATA.
+
+The reference looks its rules up in the third-party ``triangle-cubature``
+package (``get_rule(rule).weights_and_integration_points`` with ``.weights``
+(n_qp,) and ``.integration_points`` (n_qp, 2) as (eta, xi); weights sum to
+1/2; call sites /root/reference/p1afempy/solvers.py:88-89, 316-317, 568-569).
+That package is not vendored by the reference, not pinned, and not available
+offline, so this module
+
+* accepts ANY of: a member of the real ``triangle_cubature`` enum (resolved
+  through that package when it is importable), a member of the enum below,
+  an object exposing ``weights``/``integration_points`` (optionally behind a
+  ``weights_and_integration_points`` attribute), or a ``(weights, points)``
+  pair;
+* ships MIDPOINT (one point (1/3,1/3), weight 1/2 -- the only table the
+  reference's tests pin numerically, test_solver.py:88-129), the vertex rule
+  and the edge-midpoint rule, and a degree-6 STAND-IN under the name DAYTAYLOR:
+  the 4x4 Gauss-Legendre rule on the unit square collapsed onto the triangle
+  by (s, t) -> (s, t(1-s)) with weight factor (1-s) (16 points, positive
+  weights, sum 1/2).  Its numeric values are NOT those of Day & Taylor's
+  11-point rule ("parity unpinned"); every test feeds
+  the oracle and the CUDA path the same arrays, so parity is unaffected.
+"""
+from __future__ import annotations
+
+import enum
+from dataclasses import dataclass
+
+import numpy as np
+
+
+class CubatureRuleEnum(enum.Enum):
+    MIDPOINT = 1
+    LAUFFER_LINEAR = 2
+    SMPLX1 = 3
+    DAYTAYLOR = 4
+
+
+@dataclass(frozen=True)
+class WeightsAndIntegrationPoints:
+    weights: np.ndarray
+    integration_points: np.ndarray
+
+
+@dataclass(frozen=True)
+class CubatureRule:
+    weights_and_integration_points: WeightsAndIntegrationPoints
+    degree_of_exactness: int
+    name: str
+
+
+def _conical_gauss(n: int) -> WeightsAndIntegrationPoints:
+    x, w = np.polynomial.legendre.leggauss(n)
+    s = 0.5 * (x + 1.0)
+    ws = 0.5 * w
+    pts = []
+    wts = []
+    for i in range(n):
+        for j in range(n):
+            pts.append((s[i], s[j] * (1.0 - s[i])))
+            wts.append(ws[i] * ws[j] * (1.0 - s[i]))
+    return WeightsAndIntegrationPoints(
+        weights=np.asarray(wts, dtype=np.float64),
+        integration_points=np.asarray(pts, dtype=np.float64))
+
+
+_TABLES = {
+    CubatureRuleEnum.MIDPOINT: CubatureRule(
+        WeightsAndIntegrationPoints(
+            weights=np.array([0.5]),
+            integration_points=np.array([[1. / 3., 1. / 3.]])),
+        degree_of_exactness=1, name='midpoint'),
+    CubatureRuleEnum.LAUFFER_LINEAR: CubatureRule(
+        WeightsAndIntegrationPoints(
+            weights=np.array([1. / 6., 1. / 6., 1. / 6.]),
+            integration_points=np.array([[0., 0.], [1., 0.], [0., 1.]])),
+        degree_of_exactness=1, name='lauffer-linear (vertices)'),
+    CubatureRuleEnum.SMPLX1: CubatureRule(
+        WeightsAndIntegrationPoints(
+            weights=np.array([1. / 6., 1. / 6., 1. / 6.]),
+            integration_points=np.array([[.5, 0.], [.5, .5], [0., .5]])),
+        degree_of_exactness=2, name='edge midpoints (stand-in for smplx1)'),
+    CubatureRuleEnum.DAYTAYLOR: CubatureRule(
+        _conical_gauss(4), degree_of_exactness=6,
+        name='4x4 conical Gauss (degree-6 stand-in for Day-Taylor)'),
+}
+
+
+def get_rule(rule: CubatureRuleEnum) -> CubatureRule:
+    """Same call shape as ``triangle_cubature.rule_factory.get_rule``."""
+    return _TABLES[CubatureRuleEnum(rule)]
+
+
+def resolve_rule(rule) -> tuple[np.ndarray, np.ndarray]:
+    """Turn whatever the caller passed as ``cubature_rule`` into
+    ``(weights (n_qp,), points (n_qp, 2))`` float64 C-contiguous arrays."""
+    if isinstance(rule, CubatureRuleEnum):
+        wip = get_rule(rule).weights_and_integration_points
+    elif isinstance(rule, enum.Enum):
+        # a member of the real triangle_cubature enum
+        from triangle_cubature.rule_factory import get_rule as real_get_rule
+        wip = real_get_rule(rule=rule).weights_and_integration_points
+    elif hasattr(rule, 'weights_and_integration_points'):
+        wip = rule.weights_and_integration_points
+    elif hasattr(rule, 'weights') and hasattr(rule, 'integration_points'):
+        wip = rule
+    else:
+        w, p = rule
+        wip = WeightsAndIntegrationPoints(np.asarray(w), np.asarray(p))
+    w = np.ascontiguousarray(wip.weights, dtype=np.float64).reshape(-1)
+    p = np.ascontiguousarray(wip.integration_points,
+                             dtype=np.float64).reshape(-1, 2)
+    if w.shape[0] != p.shape[0]:
+        raise ValueError('cubature rule: weights/points length mismatch')
+    return w, p
