@@ -104,6 +104,16 @@ def laplace_case():
                eta_matlab=np.loadtxt(d / 'indicators.dat'))
     out.update(csr_parts('stiff', ref.solvers.get_stiffness_matrix(c, e)))
     out['rhs_legacy'] = ref.solvers.get_right_hand_side(c, e, L.f)
+    # x.dat / energy.dat belong to THREE refinements (test_solver.py:38-57)
+    c3, e3, b3, _ = ref.refinement.refineNVB(
+        coordinates=c, elements=e, marked_elements=np.arange(e.shape[0]),
+        boundary_conditions=bcs)
+    x3, energy3 = ref.solvers.solve_laplace(
+        coordinates=c3, elements=e3, dirichlet=b3[0], neumann=b3[1],
+        f=L.f, g=L.g, uD=L.uD)
+    out.update(coordinates3=c3, elements3=e3, dirichlet3=b3[0],
+               neumann3=b3[1], x3_reference=x3,
+               energy3_reference=np.array(energy3))
     np.savez_compressed(os.path.join(HERE, 'laplace_example.npz'), **out)
     print('laplace_example', e.shape, eta.shape)
 

@@ -72,9 +72,11 @@ def test_laplace_example_matlab_indicators():
     same_csr(orc.stiffness_coo(g['coordinates'], g['elements']).tocsr(),
              csr_of(g, 'stiff'))
     # test_solver.py:53-57: energy = x.A.x against MATLAB
-    a = orc.stiffness_coo(g['coordinates'], g['elements']).tocsr()
+    a = orc.stiffness_coo(g['coordinates3'], g['elements3']).tocsr()
     xm = g['x_matlab']
-    assert np.allclose(xm.dot(a.dot(xm)), g['energy_matlab'])
+    assert np.allclose(g['x3_reference'], xm)
+    assert np.isclose(xm.dot(a.dot(xm)), g['energy_matlab'])
+    assert np.isclose(float(g['energy3_reference']), g['energy_matlab'])
     assert np.array_equal(
         orc.load_vector_midpoint(g['coordinates'], g['elements'], L.f),
         g['rhs_legacy'])
