@@ -1,0 +1,193 @@
+/* p1b200.h -- C ABI of libp1b200.so: the P1 assembly hot path on NVIDIA B200.
+ *
+ * The reference (leuraph/p1afempy v0.2.16) has no FFI layer: its boundary is a
+ * set of module-level Python functions over numpy arrays.  This header is what
+ * a binding for that path binds instead; every entry point names the reference
+ * code it replaces (file:line under /root/reference).  INTEGRATION.md shows the
+ * ctypes stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *  - all array arguments are DEVICE pointers unless the name ends in _host;
+ *  - row-major, C-contiguous; float64 values; int32 node/element indices on
+ *    the device (p1_narrow_i64 converts what numpy hands over);
+ *  - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *    calls are stream-ordered and asynchronous unless stated otherwise;
+ *  - every function returns 0 on success or a negative P1_E* code; the text
+ *    for the calling thread's last failure is p1_last_error();
+ *  - inputs are never modified; outputs are caller-allocated; scratch memory
+ *    comes from the context's stream-ordered pool and is released before the
+ *    call returns (stream-ordered), except what a p1_plan keeps.
+ */
+#ifndef P1B200_H
+#define P1B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define P1_OK 0
+#define P1_EINVAL (-1)      /* bad argument                                   */
+#define P1_EINDEX (-2)      /* element/boundary index outside [0, n_nodes)    */
+#define P1_ECUDA (-3)       /* CUDA runtime error, see p1_last_error()        */
+#define P1_ETOPOLOGY (-4)   /* mesh is not an edge-manifold / boundary edges  */
+                            /* not covered (the reference raises ValueError,  */
+                            /* mesh.py:150)                                   */
+#define P1_ERANGE (-5)      /* size exceeds what int32 device indices hold    */
+#define P1_ECOMM (-6)       /* NCCL / multi-GPU error                         */
+
+typedef struct p1_ctx p1_ctx;
+typedef struct p1_plan p1_plan;
+
+int p1_version(void);
+const char *p1_last_error(void);
+
+/* One context per (process, device).  Owns the error flags and the pool. */
+int p1_ctx_create(int device, p1_ctx **out);
+int p1_ctx_destroy(p1_ctx *ctx);
+
+/* numpy hands elements over as int64 (refinement.py:641) or uint32
+ * (io_helpers.py:91); the device works on int32.  Values outside
+ * [0, 2^31) are clamped to -1 so that the range check of p1_plan_create
+ * reports them.  src_kind: 0 = int64, 1 = uint32, 2 = int32 (plain copy). */
+int p1_narrow_indices(p1_ctx *ctx, const void *src, int src_kind,
+                      int64_t count, int32_t *dst, void *stream);
+/* int32 -> int64 widening of an index array (scipy switches the CSR index
+ * dtype to int64 when max(9M, N) >= 2^31, scipy/sparse/_coo.py:419). */
+int p1_widen_indices(p1_ctx *ctx, const int32_t *src, int64_t count,
+                     int64_t *dst, void *stream);
+
+/* ------------------------------------------------------------------------
+ * Plan = everything that depends on `elements` only: the node -> incident
+ * (element, local vertex) lists in the fixed order (element, vertex), the
+ * neighbour pairs, and the CSR row pointer.  Replaces what scipy's
+ * coo_tocsr + csr_sort_indices + csr_sum_duplicates derive on every call
+ * (scipy/sparse/_coo.py:368-439, _compressed.py:1072-1130).
+ *
+ * row_begin/row_end restrict the plan to the rows [row_begin,row_end) of the
+ * matrix (multi-GPU row ownership); pass 0, n_nodes for the whole matrix.
+ * SYNCHRONISES the stream once (the caller needs nnz to allocate outputs).
+ * ---------------------------------------------------------------------- */
+int p1_plan_create(p1_ctx *ctx, const int32_t *elements, int64_t n_elements,
+                   int64_t n_nodes, int64_t row_begin, int64_t row_end,
+                   void *stream, p1_plan **out);
+int p1_plan_destroy(p1_plan *plan);
+/* nnz: stored entries in the owned rows; max_index: largest node index that
+ * occurs in `elements` (the reference infers the shape of the stiffness and
+ * mass matrices as max_index+1, solvers.py:46-47,153). */
+int p1_plan_info(const p1_plan *plan, int64_t *nnz, int64_t *max_index,
+                 int64_t *n_elements, int64_t *n_nodes);
+
+/* What to assemble.  The value of local entry (r, c) of element T goes to
+ * (row, col) = (elements[T][r], elements[T][c]). */
+#define P1_OP_STIFFNESS 1 /* solvers.py:15-47   get_stiffness_matrix          */
+#define P1_OP_MASS 2      /* solvers.py:145-182 get_mass_matrix               */
+#define P1_OP_LOCAL 3     /* any 3x3 local matrix given per element, row-major
+                             local[T*9 + 3*r + c] (general stiffness, weighted
+                             mass after p1_local_* below)                     */
+
+/* Assemble to CSR over the owned rows.
+ *   indptr  : (row_end-row_begin+1) int32, local offsets starting at 0
+ *   indices : nnz int32, sorted and unique per row, explicit zeros kept
+ *   data    : nnz float64; duplicates summed in increasing (element, vertex)
+ * indptr and/or indices may be NULL (re-assembly on an unchanged mesh writes
+ * values only).  `coords` (n_nodes x 2) is used by P1_OP_STIFFNESS/MASS,
+ * `local` (n_elements x 9) by P1_OP_LOCAL. */
+int p1_assemble_csr(const p1_plan *plan, int op, const double *coords,
+                    const double *local, int32_t *indptr, int32_t *indices,
+                    double *data, void *stream);
+
+/* solvers.py:156-182 get_mass_matrix_elements: the 9M triplets in the
+ * reference's order (element-major, entry k: row = vertex k%3, col = k/3). */
+int p1_mass_triplets(p1_ctx *ctx, const double *coords,
+                     const int32_t *elements, int64_t n_elements,
+                     int64_t *rows, int64_t *cols, double *vals, void *stream);
+/* same stream of triplets for the stiffness matrix (solvers.py:34-47). */
+int p1_stiffness_triplets(p1_ctx *ctx, const double *coords,
+                          const int32_t *elements, int64_t n_elements,
+                          int64_t *rows, int64_t *cols, double *vals,
+                          void *stream);
+
+/* mesh.py:10-51 get_area / get_directional_vectors (any output may be NULL):
+ * area (M), d21 (M x 2), d31 (M x 2). */
+int p1_geometry(p1_ctx *ctx, const double *coords, const int32_t *elements,
+                int64_t n_elements, double *area, double *d21, double *d31,
+                void *stream);
+
+/* Points at which user coefficient callbacks are evaluated.
+ *  xq[q][T][0..1] = z0 + eta_q*dz1 + xi_q*dz2           (solvers.py:326,582)
+ *  uq[q][T]       = u1*(1-eta-xi) + u2*eta + u3*xi      (solvers.py:113-117)
+ *  centroids[T]   = c0 + (d21+d31)/3                    (solvers.py:421,
+ *                                                        indicators.py:84)
+ * points_host: n_qp x 2 (eta, xi) in HOST memory. */
+int p1_quadrature_points(p1_ctx *ctx, const double *coords,
+                         const int32_t *elements, int64_t n_elements,
+                         const double *points_host, int n_qp, double *xq,
+                         void *stream);
+int p1_nodal_at_quadrature(p1_ctx *ctx, const double *u,
+                           const int32_t *elements, int64_t n_elements,
+                           const double *points_host, int n_qp, double *uq,
+                           void *stream);
+int p1_centroids(p1_ctx *ctx, const double *coords, const int32_t *elements,
+                 int64_t n_elements, double *centroids, void *stream);
+
+/* solvers.py:278-377 get_general_stiffness_matrix: local 3x3 matrices from
+ * the coefficient values at the quadrature points, a_ij_q[q*M + T]. */
+int p1_local_general_stiffness(p1_ctx *ctx, const double *coords,
+                               const int32_t *elements, int64_t n_elements,
+                               const double *a11q, const double *a12q,
+                               const double *a21q, const double *a22q,
+                               const double *weights_host, int n_qp,
+                               double *local, void *stream);
+/* solvers.py:50-142 get_weighted_mass_matrix: phiq[q*M + T] = phi(u_q). */
+int p1_local_weighted_mass(p1_ctx *ctx, const double *coords,
+                           const int32_t *elements, int64_t n_elements,
+                           const double *phiq, const double *weights_host,
+                           const double *points_host, int n_qp, double *local,
+                           void *stream);
+
+/* solvers.py:540-598 get_right_hand_side_using_quadrature_rule; fq[q*M + T].
+ * b has n_nodes entries; summation order per node = the reference's
+ * sequential bincount order (element, vertex), i.e. bit-identical. */
+int p1_load_vector(const p1_plan *plan, const double *coords,
+                   const double *fq, const double *weights_host,
+                   const double *points_host, int n_qp, double *b,
+                   void *stream);
+/* solvers.py:414-426 legacy centroid rule; f_centroid[T]; summation order
+ * per node = (vertex, element), as bincount over elements.flatten('F'). */
+int p1_load_vector_midpoint(const p1_plan *plan, const double *coords,
+                            const double *f_centroid, double *b, void *stream);
+
+/* mesh.py:87-161 provide_geometric_data.  boundary_nodes: concatenated
+ * (K x 2) int32 rows of all boundaries; boundary_offsets_host: n_boundaries+1
+ * row offsets (host).  Outputs: element2edges (M x 3), edge2nodes (E x 2,
+ * capacity 3M+K rows... exactly (3M+K)/2 are written), boundary2edges (K);
+ * *n_edges_host receives E.  SYNCHRONISES the stream. */
+int p1_geometric_data(const p1_plan *plan, const int32_t *boundary_nodes,
+                      const int64_t *boundary_offsets_host, int n_boundaries,
+                      int64_t *element2edges, int64_t *edge2nodes,
+                      int64_t *boundary2edges, int64_t *n_edges_host,
+                      void *stream);
+/* number of undirected edges the call above will report: (3M+K)/2; returns
+ * P1_ETOPOLOGY when forward and backward half-edge counts differ. */
+
+/* indicators.py:7-86 compute_eta_r.  dirichlet / neumann: (K x 2) int32;
+ * neumann_term[j] = |E_j| * g(midpoint_j) (indicators.py:70-76, evaluated by
+ * the caller because g is a user callback); f_centroid[T] = f(centroid_T).
+ * eta has n_elements entries. */
+int p1_eta_r(const p1_plan *plan, const double *coords, const double *x,
+             const int32_t *dirichlet, int64_t n_dirichlet,
+             const int32_t *neumann, int64_t n_neumann,
+             const double *neumann_term, const double *f_centroid,
+             double *eta, void *stream);
+/* |E_j| and midpoints of boundary edges (indicators.py:70-76): length (K),
+ * midpoint (K x 2). */
+int p1_boundary_edges(p1_ctx *ctx, const double *coords,
+                      const int32_t *edges, int64_t n_edges, double *length,
+                      double *midpoint, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* P1B200_H */

@@ -1,0 +1,110 @@
+"""ctypes binding of libp1b200.so (include/p1b200.h).
+
+There is NO CPU fallback: if the shared library is missing or cannot be loaded
+every entry point of the package raises.  ``python __graft_entry__.py`` (or
+``make -C p1afempy_b200/csrc``) builds it in-tree.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libp1b200.so')
+
+P1_OK = 0
+P1_EINVAL = -1
+P1_EINDEX = -2
+P1_ECUDA = -3
+P1_ETOPOLOGY = -4
+P1_ERANGE = -5
+P1_ECOMM = -6
+
+OP_STIFFNESS = 1
+OP_MASS = 2
+OP_LOCAL = 3
+
+_vp = C.c_void_p
+_i64 = C.c_int64
+_int = C.c_int
+
+# name -> argtypes; every function returns int unless listed in _RESTYPES
+PROTOTYPES = {
+    'p1_version': [],
+    'p1_last_error': [],
+    'p1_ctx_create': [_int, C.POINTER(_vp)],
+    'p1_ctx_destroy': [_vp],
+    'p1_narrow_indices': [_vp, _vp, _int, _i64, _vp, _vp],
+    'p1_widen_indices': [_vp, _vp, _i64, _vp, _vp],
+    'p1_plan_create': [_vp, _vp, _i64, _i64, _i64, _i64, _vp, C.POINTER(_vp)],
+    'p1_plan_destroy': [_vp],
+    'p1_plan_info': [_vp, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64),
+                     C.POINTER(_i64)],
+    'p1_assemble_csr': [_vp, _int, _vp, _vp, _vp, _vp, _vp, _vp],
+    'p1_mass_triplets': [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp],
+    'p1_stiffness_triplets': [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp],
+    'p1_geometry': [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp],
+    'p1_quadrature_points': [_vp, _vp, _vp, _i64, _vp, _int, _vp, _vp],
+    'p1_nodal_at_quadrature': [_vp, _vp, _vp, _i64, _vp, _int, _vp, _vp],
+    'p1_centroids': [_vp, _vp, _vp, _i64, _vp, _vp],
+    'p1_local_general_stiffness': [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp,
+                                   _vp, _int, _vp, _vp],
+    'p1_local_weighted_mass': [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _int, _vp,
+                               _vp],
+    'p1_load_vector': [_vp, _vp, _vp, _vp, _vp, _int, _vp, _vp],
+    'p1_load_vector_midpoint': [_vp, _vp, _vp, _vp, _vp],
+    'p1_geometric_data': [_vp, _vp, _vp, _int, _vp, _vp, _vp, C.POINTER(_i64),
+                          _vp],
+    'p1_eta_r': [_vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp],
+    'p1_boundary_edges': [_vp, _vp, _vp, _i64, _vp, _vp, _vp],
+}
+_RESTYPES = {'p1_last_error': C.c_char_p}
+
+_lib = None
+_lock = threading.Lock()
+
+
+class P1Error(RuntimeError):
+    pass
+
+
+def load():
+    """Loads the shared library once; raises if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise P1Error(
+                'libp1b200.so is not built (%s missing). Build it with '
+                '`make -C p1afempy_b200/csrc` or `python -c "import '
+                '__graft_entry__ as g; g.build()"`. There is no CPU fallback.'
+                % LIB_PATH)
+        lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+        for name, argtypes in PROTOTYPES.items():
+            fn = getattr(lib, name)      # AttributeError if a symbol is missing
+            fn.argtypes = argtypes
+            fn.restype = _RESTYPES.get(name, _int)
+        _lib = lib
+    return _lib
+
+
+def last_error() -> str:
+    msg = load().p1_last_error()
+    return msg.decode('utf-8', 'replace') if msg else ''
+
+
+def check(rc: int):
+    """Maps a status code to the exception the reference would raise
+    (SURVEY.md section 8(b), row 'Errors')."""
+    if rc == P1_OK:
+        return
+    msg = last_error()
+    if rc == P1_EINDEX:
+        raise IndexError(msg)
+    if rc in (P1_EINVAL, P1_ETOPOLOGY, P1_ERANGE):
+        raise ValueError(msg)
+    raise P1Error('libp1b200 error %d: %s' % (rc, msg))

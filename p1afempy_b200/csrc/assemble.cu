@@ -1,0 +1,204 @@
+// assemble.cu -- numeric phase: one owner per CSR row gathers the local-matrix
+// rows of its incident elements (fixed order: element, vertex), sums duplicates
+// and writes the finished row (sorted unique columns, explicit zeros kept).
+//
+// Arithmetic mirrors the reference expression by expression (compile with
+// -fmad=false): /root/reference/p1afempy/solvers.py:31-45 (stiffness),
+// :176-181 (mass).  Local matrices of the generalised stiffness / weighted
+// mass come precomputed per element (local_ops.cu).
+#include "plan.cuh"
+
+namespace p1 {
+
+constexpr int THREADS = 128;
+
+struct Tri {  // vertex coordinates in ELEMENT order (v0, v1, v2)
+  double x0, y0, x1, y1, x2, y2;
+};
+
+// (self, next, prev) -> element order, given the local index k of `self`
+__device__ __forceinline__ Tri element_order(int k, double2 s, double2 n, double2 p) {
+  Tri t;
+  if (k == 0) { t.x0 = s.x; t.y0 = s.y; t.x1 = n.x; t.y1 = n.y; t.x2 = p.x; t.y2 = p.y; }
+  else if (k == 1) { t.x0 = p.x; t.y0 = p.y; t.x1 = s.x; t.y1 = s.y; t.x2 = n.x; t.y2 = n.y; }
+  else { t.x0 = n.x; t.y0 = n.y; t.x1 = p.x; t.y1 = p.y; t.x2 = s.x; t.y2 = s.y; }
+  return t;
+}
+
+struct StiffnessOp {
+  static constexpr bool needs_coords = true;
+  // row k of the local stiffness matrix: (k,k), (k,k+1), (k,k+2)
+  __device__ __forceinline__ void row(int64_t, int k, const Tri &t, double &vd,
+                                      double &vn, double &vp) const {
+    const double d21x = t.x1 - t.x0, d21y = t.y1 - t.y0;
+    const double d31x = t.x2 - t.x0, d31y = t.y2 - t.y0;
+    const double area4 = 4. * (0.5 * (d21x * d31y - d21y * d31x));
+    const double a = (d21x * d31x + d21y * d31y) / area4;
+    const double b = (d31x * d31x + d31y * d31y) / area4;
+    const double c = (d21x * d21x + d21y * d21y) / area4;
+    if (k == 0) { vd = -2. * a + b + c; vn = a - b; vp = a - c; }
+    else if (k == 1) { vd = b; vn = -a; vp = a - b; }
+    else { vd = c; vn = a - c; vp = -a; }
+  }
+};
+
+struct MassOp {
+  static constexpr bool needs_coords = true;
+  __device__ __forceinline__ void row(int64_t, int, const Tri &t, double &vd,
+                                      double &vn, double &vp) const {
+    const double d21x = t.x1 - t.x0, d21y = t.y1 - t.y0;
+    const double d31x = t.x2 - t.x0, d31y = t.y2 - t.y0;
+    const double area = 0.5 * (d21x * d31y - d21y * d31x);
+    vd = area / 6.;
+    vn = area / 12.;
+    vp = vn;
+  }
+};
+
+struct LocalOp {
+  static constexpr bool needs_coords = false;
+  const double *__restrict__ local;  // M x 9 row-major
+  __device__ __forceinline__ void row(int64_t T, int k, const Tri &, double &vd,
+                                      double &vn, double &vp) const {
+    const double *m = local + 9 * T + 3 * k;
+    vd = __ldg(m + k);
+    vn = __ldg(m + next_local(k));
+    vp = __ldg(m + prev_local(k));
+  }
+};
+
+template <class Op>
+__global__ void __launch_bounds__(THREADS)
+fill_rows_kernel(int n_own, int rb, const int *__restrict__ rec_off,
+                 const uint32_t *__restrict__ rec, const int2 *__restrict__ nbr,
+                 const int *__restrict__ indptr, const double2 *__restrict__ coords,
+                 Op op, int *__restrict__ indices, double *__restrict__ data) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= n_own) return;
+  const int beg = rec_off[a], deg = rec_off[a + 1] - beg;
+  if (deg == 0 || deg > DEG_MAX) return;
+  int2 nb[DEG_MAX];
+  for (int i = 0; i < deg; ++i) nb[i] = nbr[beg + i];
+  int cols[COL_MAX];
+  const int self = a + rb;
+  const int n = unique_columns(self, nb, deg, cols);
+  double vals[COL_MAX];
+  double2 pos[COL_MAX];
+  for (int j = 0; j < n; ++j) {
+    vals[j] = 0.;
+    if (Op::needs_coords) pos[j] = coords[cols[j]];
+  }
+  const int js = find_column(cols, n, self);
+  for (int i = 0; i < deg; ++i) {
+    const uint32_t r = rec[beg + i];
+    const int k = r & 3;
+    const int jn = find_column(cols, n, nb[i].x);
+    const int jp = find_column(cols, n, nb[i].y);
+    Tri t;
+    if (Op::needs_coords) t = element_order(k, pos[js], pos[jn], pos[jp]);
+    double vd, vn, vp;
+    op.row((int64_t)(r >> 2), k, t, vd, vn, vp);
+    vals[js] += vd;
+    vals[jn] += vn;
+    vals[jp] += vp;
+  }
+  const int64_t base = indptr[a];
+  for (int j = 0; j < n; ++j) {
+    if (indices) indices[base + j] = cols[j];
+    data[base + j] = vals[j];
+  }
+}
+
+__device__ __forceinline__ int big_candidate2(int self, const int2 *nb, int j) {
+  if (j == 0) return self;
+  const int2 p = nb[(j - 1) >> 1];
+  return ((j - 1) & 1) ? p.y : p.x;
+}
+
+// one block per row with more than DEG_MAX records (see plan.cu)
+template <class Op>
+__global__ void __launch_bounds__(THREADS)
+fill_big_kernel(const int *__restrict__ big_rows, int rb,
+                const int *__restrict__ rec_off, const uint32_t *__restrict__ rec,
+                const int2 *__restrict__ nbr, const unsigned char *__restrict__ first,
+                const int *__restrict__ indptr, const double2 *__restrict__ coords,
+                Op op, int *__restrict__ indices, double *__restrict__ data) {
+  const int a = big_rows[blockIdx.x];
+  const int beg = rec_off[a], deg = rec_off[a + 1] - beg;
+  const int2 *nb = nbr + beg;
+  const unsigned char *fl = first + 2 * (int64_t)beg + a;
+  const int self = a + rb;
+  const int ncand = 2 * deg + 1;
+  const int64_t base = indptr[a];
+  for (int j = threadIdx.x; j < ncand; j += blockDim.x) {
+    if (!fl[j]) continue;
+    const int c = big_candidate2(self, nb, j);
+    int rank = 0;
+    for (int i = 0; i < ncand; ++i)
+      rank += fl[i] && big_candidate2(self, nb, i) < c;
+    double sum = 0.;
+    for (int i = 0; i < deg; ++i) {
+      const int2 p = nb[i];
+      if (c != self && p.x != c && p.y != c) continue;
+      const uint32_t r = rec[beg + i];
+      const int k = r & 3;
+      Tri t;
+      if (Op::needs_coords)
+        t = element_order(k, coords[self], coords[p.x], coords[p.y]);
+      double vd, vn, vp;
+      op.row((int64_t)(r >> 2), k, t, vd, vn, vp);
+      if (c == self) sum += vd;
+      if (p.x == c) sum += vn;
+      if (p.y == c) sum += vp;
+    }
+    if (indices) indices[base + rank] = c;
+    data[base + rank] = sum;
+  }
+}
+
+template <class Op>
+int launch_fill(const p1_plan *p, Op op, const double *coords, int32_t *indices,
+                double *data, cudaStream_t s) {
+  const int n_own = (int)(p->row_end - p->row_begin);
+  if (n_own > 0)
+    fill_rows_kernel<Op><<<grid_for(n_own, THREADS), THREADS, 0, s>>>(
+        n_own, (int)p->row_begin, p->rec_off, p->rec, p->nbr, p->indptr,
+        (const double2 *)coords, op, indices, data);
+  if (p->n_big > 0)
+    fill_big_kernel<Op><<<p->n_big, THREADS, 0, s>>>(
+        p->big_rows, (int)p->row_begin, p->rec_off, p->rec, p->nbr, p->big_first,
+        p->indptr, (const double2 *)coords, op, indices, data);
+  P1_CUDA(cudaGetLastError());
+  return P1_OK;
+}
+
+}  // namespace p1
+
+using namespace p1;
+
+extern "C" int p1_assemble_csr(const p1_plan *plan, int op, const double *coords,
+                               const double *local, int32_t *indptr,
+                               int32_t *indices, double *data, void *stream) {
+  P1_REQUIRE(plan, "null plan");
+  P1_REQUIRE(data || plan->nnz == 0, "null data");
+  DeviceGuard guard(plan->ctx->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t n_own = plan->row_end - plan->row_begin;
+  if (indptr)
+    P1_CUDA(cudaMemcpyAsync(indptr, plan->indptr, (n_own + 1) * sizeof(int),
+                            cudaMemcpyDeviceToDevice, s));
+  switch (op) {
+    case P1_OP_STIFFNESS:
+      P1_REQUIRE(coords, "stiffness needs coords");
+      return launch_fill(plan, StiffnessOp{}, coords, indices, data, s);
+    case P1_OP_MASS:
+      P1_REQUIRE(coords, "mass needs coords");
+      return launch_fill(plan, MassOp{}, coords, indices, data, s);
+    case P1_OP_LOCAL:
+      P1_REQUIRE(local, "P1_OP_LOCAL needs the local matrices");
+      return launch_fill(plan, LocalOp{local}, coords, indices, data, s);
+    default:
+      set_error("p1_assemble_csr: unknown op %d", op);
+      return P1_EINVAL;
+  }
+}

@@ -1,0 +1,92 @@
+// common.cuh -- context, error plumbing, pool allocation, launch helpers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include "../../include/p1b200.h"
+
+namespace p1 {
+
+void set_error(const char *fmt, ...);
+
+#define P1_CUDA(expr)                                                         \
+  do {                                                                        \
+    cudaError_t e__ = (expr);                                                 \
+    if (e__ != cudaSuccess) {                                                 \
+      p1::set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #expr,        \
+                    cudaGetErrorString(e__));                                 \
+      return P1_ECUDA;                                                        \
+    }                                                                         \
+  } while (0)
+
+#define P1_TRY(expr)                                                          \
+  do {                                                                        \
+    int r__ = (expr);                                                         \
+    if (r__ != P1_OK) return r__;                                             \
+  } while (0)
+
+#define P1_REQUIRE(cond, msg)                                                 \
+  do {                                                                        \
+    if (!(cond)) {                                                            \
+      p1::set_error("%s: %s", __func__, msg);                                 \
+      return P1_EINVAL;                                                       \
+    }                                                                         \
+  } while (0)
+
+// device-side status word (one per context, zeroed by the calls that read it)
+enum : int {
+  FLAG_INDEX_RANGE = 1,    // element index outside [0, n_nodes)
+  FLAG_NONMANIFOLD = 2,    // directed edge appears twice
+  FLAG_BOUNDARY_MISS = 4,  // boundary edge not found among element edges
+  FLAG_UNCOVERED = 8,      // boundary half-edge not listed in any boundary
+};
+
+}  // namespace p1
+
+struct p1_ctx {
+  int device;
+  int sm_count;
+  int *d_flags;        // 4 ints: [0] status bits, [1] max node index, [2..3] spare
+  int *h_flags;        // pinned mirror
+};
+
+namespace p1 {
+
+// Stream-ordered scratch allocation from the device's default pool (the pool
+// keeps freed blocks: release threshold is set to "never" in p1_ctx_create).
+template <typename T>
+inline int pool_alloc(T **ptr, size_t count, cudaStream_t s) {
+  *ptr = nullptr;
+  if (count == 0) count = 1;
+  P1_CUDA(cudaMallocAsync((void **)ptr, count * sizeof(T), s));
+  return P1_OK;
+}
+inline void pool_free(void *ptr, cudaStream_t s) {
+  if (ptr) cudaFreeAsync(ptr, s);
+}
+
+struct DeviceGuard {
+  int prev;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+  }
+  ~DeviceGuard() { cudaSetDevice(prev); }
+};
+
+inline unsigned grid_for(int64_t n, int block, int per_thread = 1) {
+  int64_t per_block = (int64_t)block * per_thread;
+  int64_t g = (n + per_block - 1) / per_block;
+  if (g < 1) g = 1;
+  return (unsigned)g;
+}
+
+// exclusive prefix sum of n int32 values; out may alias in; out[n] = total
+// when write_total is true (out then has n+1 entries).
+int exclusive_scan_i32(const int *in, int *out, int64_t n, bool write_total,
+                       cudaStream_t s);
+
+}  // namespace p1

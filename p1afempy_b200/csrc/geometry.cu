@@ -1,0 +1,390 @@
+// geometry.cu -- half-edge twins, the reference's edge numbering
+// (/root/reference/p1afempy/mesh.py:87-161 provide_geometric_data) and the
+// residual estimator (/root/reference/p1afempy/indicators.py:7-86).
+//
+// The reference matches the two directions of an edge through two scipy
+// COO -> find() lexsorts.  Here the match comes from the plan's per-node fans:
+// the twin of half-edge (a -> x) of element T is the half-edge (x -> a) of the
+// element at node a whose PREVIOUS vertex is x.  Integer outputs are
+// bit-identical to the reference; jumps are sums of at most two terms, hence
+// order-free, hence bit-identical as well.
+#include "plan.cuh"
+
+namespace p1 {
+
+constexpr int THREADS = 256;
+
+// flags layout in ctx->d_flags: [0] status bits, [1] #half-edges without twin,
+// [2] #forward entries, [3] #backward entries
+
+__global__ void __launch_bounds__(THREADS)
+twin_kernel(int n_nodes, const int *__restrict__ rec_off,
+            const uint32_t *__restrict__ rec, const int2 *__restrict__ nbr,
+            int *__restrict__ twin, int *__restrict__ flags) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= n_nodes) return;
+  const int beg = rec_off[a], end = rec_off[a + 1];
+  for (int i = beg; i < end; ++i) {
+    const int target = nbr[i].x;  // half-edge a -> target
+    int found = -1, hits = 0;
+    for (int s = beg; s < end; ++s)
+      if (nbr[s].y == target) { found = s; ++hits; }
+    const uint32_t r = rec[i];
+    const int64_t he = 3 * (int64_t)(r >> 2) + (r & 3);
+    if (hits == 0) {
+      twin[he] = -1;
+      atomicAdd(flags + 1, 1);
+    } else {
+      const uint32_t q = rec[found];
+      twin[he] = (int)(3 * (q >> 2) + prev_local((int)(q & 3)));
+      if (hits > 1) atomicOr(flags, FLAG_NONMANIFOLD);
+    }
+    // the same directed edge twice is non-manifold as well
+    for (int s = i + 1; s < end; ++s)
+      if (nbr[s].x == target) atomicOr(flags, FLAG_NONMANIFOLD);
+  }
+}
+
+// position p of the reference's concatenated half-edge list:
+//   p = k*M + m            for element m, local edge k   (I = e[m][k], J = e[m][k+1])
+//   p = 3M + r             for boundary row r            (I = b[r][1], J = b[r][0])
+__global__ void __launch_bounds__(THREADS)
+forward_flags_kernel(const int *__restrict__ elements, int64_t M,
+                     const int *__restrict__ bnd, int64_t K, int *__restrict__ fwd,
+                     int *__restrict__ flags) {
+  const int64_t total = 3 * M + K;
+  int nf = 0, nb = 0;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < total;
+       p += (int64_t)gridDim.x * blockDim.x) {
+    int I, J;
+    if (p < 3 * M) {
+      const int k = (int)(p / M);
+      const int64_t m = p - (int64_t)k * M;
+      I = __ldg(elements + 3 * m + k);
+      J = __ldg(elements + 3 * m + next_local(k));
+    } else {
+      const int64_t r = p - 3 * M;
+      I = bnd[2 * r + 1];
+      J = bnd[2 * r];
+    }
+    fwd[p] = I < J;
+    nf += I < J;
+    nb += J < I;
+  }
+  nf = __reduce_add_sync(0xffffffffu, nf);
+  nb = __reduce_add_sync(0xffffffffu, nb);
+  if ((threadIdx.x & 31) == 0) {
+    if (nf) atomicAdd(flags + 2, nf);
+    if (nb) atomicAdd(flags + 3, nb);
+  }
+}
+
+// num[] = exclusive scan of fwd[]: the edge id of every forward entry
+__global__ void __launch_bounds__(THREADS)
+element_edges_kernel(const int *__restrict__ elements, int64_t M,
+                     const int *__restrict__ num, const int *__restrict__ twin,
+                     long long *__restrict__ element2edges,
+                     long long *__restrict__ edge2nodes) {
+  for (int64_t h = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; h < 3 * M;
+       h += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = h / 3;
+    const int k = (int)(h - 3 * m);
+    const int I = __ldg(elements + 3 * m + k);
+    const int J = __ldg(elements + 3 * m + next_local(k));
+    const int64_t p = (int64_t)k * M + m;
+    if (I < J) {
+      const int id = num[p];
+      element2edges[h] = id;
+      edge2nodes[2 * (int64_t)id] = I;
+      edge2nodes[2 * (int64_t)id + 1] = J;
+    } else {
+      const int t = twin[h];
+      if (t >= 0) {
+        const int64_t tm = t / 3;
+        const int tk = t - 3 * (int)tm;
+        element2edges[h] = num[(int64_t)tk * M + tm];
+      } else {
+        element2edges[h] = -1;  // set by boundary_edges_kernel, else uncovered
+      }
+    }
+  }
+}
+
+// finds the element half-edge b0 -> b1 through the fan of b0
+__device__ __forceinline__ int64_t locate_halfedge(int b0, int b1,
+                                                   const int *__restrict__ rec_off,
+                                                   const uint32_t *__restrict__ rec,
+                                                   const int2 *__restrict__ nbr) {
+  const int beg = rec_off[b0], end = rec_off[b0 + 1];
+  for (int i = beg; i < end; ++i)
+    if (nbr[i].x == b1) {
+      const uint32_t r = rec[i];
+      return 3 * (int64_t)(r >> 2) + (r & 3);
+    }
+  return -1;
+}
+
+__global__ void __launch_bounds__(THREADS)
+boundary_numbers_kernel(const int *__restrict__ bnd, int64_t K, int64_t M, int n_nodes,
+                        const int *__restrict__ rec_off, const uint32_t *__restrict__ rec,
+                        const int2 *__restrict__ nbr, const int *__restrict__ num,
+                        long long *__restrict__ element2edges,
+                        long long *__restrict__ edge2nodes,
+                        long long *__restrict__ boundary2edges, int *__restrict__ flags) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= K) return;
+  const int b0 = bnd[2 * r], b1 = bnd[2 * r + 1];
+  if ((unsigned)b0 >= (unsigned)n_nodes || (unsigned)b1 >= (unsigned)n_nodes) {
+    atomicOr(flags, FLAG_INDEX_RANGE);
+    return;
+  }
+  const int64_t h = locate_halfedge(b0, b1, rec_off, rec, nbr);
+  if (h < 0) {
+    atomicOr(flags, FLAG_BOUNDARY_MISS);
+    boundary2edges[r] = -1;
+    return;
+  }
+  const int64_t m = h / 3;
+  const int k = (int)(h - 3 * m);
+  if (b0 < b1) {
+    // the element half-edge is the forward one; the appended entry inherits
+    boundary2edges[r] = num[(int64_t)k * M + m];
+  } else {
+    // the appended (reversed) entry is forward and owns the number
+    const int id = num[3 * M + r];
+    boundary2edges[r] = id;
+    edge2nodes[2 * (int64_t)id] = b1;
+    edge2nodes[2 * (int64_t)id + 1] = b0;
+    element2edges[h] = id;
+  }
+}
+
+// ------------------------------------------------------------ estimator
+// indicators.py:47-62: dudn[3t+0] = dudn21, [3t+1] = dudn32, [3t+2] = dudn13
+__global__ void __launch_bounds__(THREADS)
+eta_local_kernel(const double2 *__restrict__ coords, const double *__restrict__ x,
+                 const int *__restrict__ elements, int64_t M, double *__restrict__ dudn) {
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < M;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int e0 = __ldg(elements + 3 * t), e1 = __ldg(elements + 3 * t + 1),
+              e2 = __ldg(elements + 3 * t + 2);
+    const double2 z0 = __ldg(coords + e0), z1 = __ldg(coords + e1), z2 = __ldg(coords + e2);
+    const double px = z1.x - z0.x, py = z1.y - z0.y;
+    const double qx = z2.x - z0.x, qy = z2.y - z0.y;
+    const double area2 = 2. * (0.5 * (px * qy - py * qx));
+    const double x0 = __ldg(x + e0);
+    const double u21 = __ldg(x + e1) - x0, u31 = __ldg(x + e2) - x0;
+    const double cx = (qx * u21 - px * u31) / area2;
+    const double cy = (qy * u21 - py * u31) / area2;
+    const double dn21 = px * cx + py * cy;
+    const double dn13 = -(qx * cx + qy * cy);
+    const double dn32 = -(dn13 + dn21);
+    dudn[3 * t] = dn21;
+    dudn[3 * t + 1] = dn32;
+    dudn[3 * t + 2] = dn13;
+  }
+}
+
+// mode 0: Neumann  (indicators.py:69-76)  jump -= |E| g(mid)
+// mode 1: Dirichlet (indicators.py:79-80) jump  = 0
+__global__ void __launch_bounds__(THREADS)
+eta_boundary_kernel(int mode, const int *__restrict__ bnd, int64_t K, int n_nodes,
+                    const int *__restrict__ rec_off, const uint32_t *__restrict__ rec,
+                    const int2 *__restrict__ nbr, const int *__restrict__ twin,
+                    const double *__restrict__ term, double *__restrict__ dudn,
+                    int *__restrict__ flags) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= K) return;
+  const int b0 = bnd[2 * r], b1 = bnd[2 * r + 1];
+  if ((unsigned)b0 >= (unsigned)n_nodes || (unsigned)b1 >= (unsigned)n_nodes) {
+    atomicOr(flags, FLAG_INDEX_RANGE);
+    return;
+  }
+  const int64_t h = locate_halfedge(b0, b1, rec_off, rec, nbr);
+  if (h < 0) { atomicOr(flags, FLAG_BOUNDARY_MISS); return; }
+  if (mode == 0) {
+    dudn[h] = dudn[h] - term[r];
+  } else {
+    dudn[h] = 0.;
+    if (twin[h] >= 0) dudn[twin[h]] = 0.;
+  }
+}
+
+// indicators.py:82-85
+__global__ void __launch_bounds__(THREADS)
+eta_final_kernel(const double2 *__restrict__ coords, const int *__restrict__ elements,
+                 int64_t M, const int *__restrict__ twin, const double *__restrict__ dudn,
+                 const double *__restrict__ f_centroid, double *__restrict__ eta) {
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < M;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    double sq[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int64_t h = 3 * t + k;
+      const int tw = twin[h];
+      double j = dudn[h];
+      if (tw >= 0) j = j + __ldg(dudn + tw);
+      sq[k] = j * j;
+    }
+    const int e0 = __ldg(elements + 3 * t), e1 = __ldg(elements + 3 * t + 1),
+              e2 = __ldg(elements + 3 * t + 2);
+    const double2 z0 = __ldg(coords + e0), z1 = __ldg(coords + e1), z2 = __ldg(coords + e2);
+    const double px = z1.x - z0.x, py = z1.y - z0.y;
+    const double qx = z2.x - z0.x, qy = z2.y - z0.y;
+    const double area2 = 2. * (0.5 * (px * qy - py * qx));
+    const double vol = 0.5 * area2 * f_centroid[t];
+    eta[t] = (sq[0] + sq[1] + sq[2]) + vol * vol;
+  }
+}
+
+static inline unsigned egrid(const p1_ctx *ctx, int64_t n) {
+  unsigned g = grid_for(n, THREADS);
+  unsigned cap = (unsigned)ctx->sm_count * 32u;
+  return g < cap ? g : cap;
+}
+
+static int read_flags(p1_ctx *ctx, cudaStream_t s) {
+  P1_CUDA(cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, 4 * sizeof(int),
+                          cudaMemcpyDeviceToHost, s));
+  P1_CUDA(cudaStreamSynchronize(s));
+  return P1_OK;
+}
+
+static int full_plan_required(const p1_plan *p, const char *who) {
+  if (p->row_begin != 0 || p->row_end != p->N) {
+    set_error("%s needs a plan over all rows", who);
+    return P1_EINVAL;
+  }
+  return P1_OK;
+}
+
+int ensure_twins(p1_plan *p, cudaStream_t s) {
+  if (p->twin) return P1_OK;
+  P1_TRY(full_plan_required(p, "half-edge twins"));
+  P1_TRY(pool_alloc(&p->twin, (size_t)(3 * p->M), s));
+  P1_CUDA(cudaMemsetAsync(p->ctx->d_flags, 0, 4 * sizeof(int), s));
+  if (p->N > 0)
+    twin_kernel<<<grid_for(p->N, THREADS), THREADS, 0, s>>>(
+        (int)p->N, p->rec_off, p->rec, p->nbr, p->twin, p->ctx->d_flags);
+  P1_CUDA(cudaGetLastError());
+  P1_TRY(read_flags(p->ctx, s));
+  if (p->ctx->h_flags[0] & FLAG_NONMANIFOLD) {
+    pool_free(p->twin, s);
+    p->twin = nullptr;
+    set_error("mesh is not an edge-manifold: a directed edge occurs in two elements");
+    return P1_ETOPOLOGY;
+  }
+  p->n_open = p->ctx->h_flags[1];
+  return P1_OK;
+}
+
+}  // namespace p1
+
+using namespace p1;
+
+extern "C" int p1_geometric_data(const p1_plan *cplan, const int32_t *boundary_nodes,
+                                 const int64_t *boundary_offsets_host, int n_boundaries,
+                                 int64_t *element2edges, int64_t *edge2nodes,
+                                 int64_t *boundary2edges, int64_t *n_edges_host,
+                                 void *stream) {
+  P1_REQUIRE(cplan && n_edges_host, "null plan/n_edges_host");
+  P1_REQUIRE(n_boundaries >= 0 && (n_boundaries == 0 || boundary_offsets_host),
+             "bad boundary list");
+  p1_plan *p = const_cast<p1_plan *>(cplan);
+  p1_ctx *ctx = p->ctx;
+  DeviceGuard guard(ctx->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t M = p->M;
+  const int64_t K = n_boundaries ? boundary_offsets_host[n_boundaries] : 0;
+  P1_REQUIRE(K == 0 || boundary_nodes, "null boundary_nodes");
+  P1_REQUIRE(M == 0 || (element2edges && edge2nodes), "null output");
+  if (3 * M + K > 0x7fffffffLL) { set_error("too many half-edges"); return P1_ERANGE; }
+  P1_TRY(ensure_twins(p, s));
+  const int64_t total = 3 * M + K;
+  int *num = nullptr;
+  P1_TRY(pool_alloc(&num, (size_t)total + 1, s));
+  P1_CUDA(cudaMemsetAsync(ctx->d_flags, 0, 4 * sizeof(int), s));
+  if (total > 0)
+    forward_flags_kernel<<<egrid(ctx, total), THREADS, 0, s>>>(
+        p->elements, M, boundary_nodes, K, num, ctx->d_flags);
+  int rc = exclusive_scan_i32(num, num, total, true, s);
+  if (rc) { pool_free(num, s); return rc; }
+  if (M > 0)
+    element_edges_kernel<<<egrid(ctx, 3 * M), THREADS, 0, s>>>(
+        p->elements, M, num, p->twin, (long long *)element2edges, (long long *)edge2nodes);
+  if (K > 0)
+    boundary_numbers_kernel<<<grid_for(K, THREADS), THREADS, 0, s>>>(
+        boundary_nodes, K, M, (int)p->N, p->rec_off, p->rec, p->nbr, num,
+        (long long *)element2edges, (long long *)edge2nodes, (long long *)boundary2edges,
+        ctx->d_flags);
+  pool_free(num, s);
+  P1_CUDA(cudaGetLastError());
+  P1_TRY(read_flags(ctx, s));
+  const int st = ctx->h_flags[0];
+  if (st & FLAG_INDEX_RANGE) {
+    set_error("p1_geometric_data: boundary node index out of range");
+    return P1_EINDEX;
+  }
+  if (ctx->h_flags[2] != ctx->h_flags[3] || (st & FLAG_BOUNDARY_MISS)) {
+    set_error("p1_geometric_data: shape mismatch: %d forward vs %d backward half-edges%s "
+              "(every boundary edge must be listed once, oriented like its element)",
+              ctx->h_flags[2], ctx->h_flags[3],
+              (st & FLAG_BOUNDARY_MISS) ? "; a boundary edge is not an element edge" : "");
+    return P1_ETOPOLOGY;
+  }
+  *n_edges_host = ctx->h_flags[2];
+  return P1_OK;
+}
+
+extern "C" int p1_eta_r(const p1_plan *cplan, const double *coords, const double *x,
+                        const int32_t *dirichlet, int64_t n_dirichlet,
+                        const int32_t *neumann, int64_t n_neumann,
+                        const double *neumann_term, const double *f_centroid,
+                        double *eta, void *stream) {
+  P1_REQUIRE(cplan, "null plan");
+  p1_plan *p = const_cast<p1_plan *>(cplan);
+  p1_ctx *ctx = p->ctx;
+  const int64_t M = p->M;
+  P1_REQUIRE(M == 0 || (coords && x && f_centroid && eta), "null argument");
+  P1_REQUIRE(n_dirichlet >= 0 && n_neumann >= 0, "negative boundary size");
+  P1_REQUIRE(n_dirichlet == 0 || dirichlet, "null dirichlet");
+  P1_REQUIRE(n_neumann == 0 || (neumann && neumann_term), "null neumann");
+  DeviceGuard guard(ctx->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  P1_TRY(ensure_twins(p, s));
+  if (p->n_open != n_dirichlet + n_neumann) {
+    set_error("p1_eta_r: shape mismatch: the mesh has %lld boundary edges but "
+              "dirichlet+neumann list %lld", (long long)p->n_open,
+              (long long)(n_dirichlet + n_neumann));
+    return P1_ETOPOLOGY;
+  }
+  if (M == 0) return P1_OK;
+  double *dudn = nullptr;
+  P1_TRY(pool_alloc(&dudn, (size_t)(3 * M), s));
+  P1_CUDA(cudaMemsetAsync(ctx->d_flags, 0, 4 * sizeof(int), s));
+  eta_local_kernel<<<egrid(ctx, M), THREADS, 0, s>>>((const double2 *)coords, x,
+                                                     p->elements, M, dudn);
+  if (n_neumann > 0)
+    eta_boundary_kernel<<<grid_for(n_neumann, THREADS), THREADS, 0, s>>>(
+        0, neumann, n_neumann, (int)p->N, p->rec_off, p->rec, p->nbr, p->twin,
+        neumann_term, dudn, ctx->d_flags);
+  if (n_dirichlet > 0)
+    eta_boundary_kernel<<<grid_for(n_dirichlet, THREADS), THREADS, 0, s>>>(
+        1, dirichlet, n_dirichlet, (int)p->N, p->rec_off, p->rec, p->nbr, p->twin,
+        nullptr, dudn, ctx->d_flags);
+  eta_final_kernel<<<egrid(ctx, M), THREADS, 0, s>>>((const double2 *)coords, p->elements,
+                                                     M, p->twin, dudn, f_centroid, eta);
+  pool_free(dudn, s);
+  P1_CUDA(cudaGetLastError());
+  P1_TRY(read_flags(ctx, s));
+  if (ctx->h_flags[0] & FLAG_INDEX_RANGE) {
+    set_error("p1_eta_r: boundary node index out of range");
+    return P1_EINDEX;
+  }
+  if (ctx->h_flags[0] & FLAG_BOUNDARY_MISS) {
+    set_error("p1_eta_r: a dirichlet/neumann edge is not an element edge "
+              "(boundary edges must be oriented like their element)");
+    return P1_ETOPOLOGY;
+  }
+  return P1_OK;
+}

@@ -1,0 +1,376 @@
+"""Device-resident side of the drop-in: buffers (torch), the plan, and one
+method per C-ABI entry point.  PyTorch is used for device memory and streams
+only; all arithmetic happens in libp1b200.so.
+
+``DeviceMesh`` is also the public device-resident API: torch CUDA tensors in,
+CSR triple of torch CUDA tensors out (no PCIe traffic), for callers that keep
+the mesh on the GPU across an adaptive loop.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+
+import numpy as np
+import torch
+
+from . import _lib
+
+_contexts = {}
+_ctx_lock = threading.Lock()
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise _lib.P1Error(
+            'p1afempy_b200 needs a CUDA device (B200, sm_100a); there is no '
+            'CPU fallback.')
+
+
+def context(device: int | None = None):
+    """Returns (ctx handle, device index); one context per device."""
+    _require_cuda()
+    if device is None:
+        device = torch.cuda.current_device()
+    device = int(device)
+    with _ctx_lock:
+        if device not in _contexts:
+            torch.cuda.init()
+            with torch.cuda.device(device):
+                torch.zeros(1, device='cuda')   # make sure a primary context exists
+            handle = C.c_void_p()
+            _lib.check(_lib.load().p1_ctx_create(device, C.byref(handle)))
+            _contexts[device] = handle
+        return _contexts[device], device
+
+
+def _stream(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    return C.c_void_p(t.data_ptr())
+
+
+def _host_f64(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+
+
+def to_device_f64(a, device, shape=None):
+    """numpy / torch (any device) -> contiguous float64 CUDA tensor."""
+    if isinstance(a, torch.Tensor):
+        t = a.to(device=torch.device('cuda', device), dtype=torch.float64)
+    else:
+        t = torch.from_numpy(_host_f64(a)).to(torch.device('cuda', device))
+    t = t.contiguous()
+    if shape is not None:
+        t = t.reshape(shape)
+    return t
+
+
+def to_device_indices(a, device, ctx):
+    """Integer index array (numpy of any integer dtype, or torch) -> int32
+    CUDA tensor of the same shape.  The narrowing runs on the device
+    (p1_narrow_indices); values outside int32 become -1 and are reported by
+    the range check of the consumer."""
+    dev = torch.device('cuda', device)
+    lib = _lib.load()
+    if isinstance(a, torch.Tensor):
+        if a.dtype == torch.int32:
+            return a.to(dev).contiguous()
+        src = a.to(device=dev, dtype=torch.int64).contiguous()
+        kind = 0
+        shape = tuple(src.shape)
+    else:
+        a = np.asarray(a)
+        if a.dtype.kind not in 'iu':
+            if a.size and not np.all(np.mod(a, 1) == 0):
+                raise IndexError('arrays used as indices must be of integer type')
+            a = a.astype(np.int64)
+        shape = a.shape
+        if a.dtype == np.int32:
+            return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        if a.dtype == np.uint32:
+            src = torch.from_numpy(np.ascontiguousarray(a).view(np.int32)).to(dev)
+            kind = 1
+        else:
+            if a.dtype != np.int64:
+                a = a.astype(np.int64)
+            src = torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+            kind = 0
+    dst = torch.empty(shape, dtype=torch.int32, device=dev)
+    _lib.check(lib.p1_narrow_indices(ctx, _ptr(src), kind, src.numel(), _ptr(dst),
+                                     _stream(device)))
+    return dst
+
+
+def to_host(t: torch.Tensor) -> np.ndarray:
+    """Device tensor -> numpy through a pinned staging buffer (torch caches
+    pinned blocks, so repeated calls do not re-register memory)."""
+    if t.numel() == 0:
+        return np.empty(tuple(t.shape), dtype=torch.empty(0, dtype=t.dtype).numpy().dtype)
+    host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    host.copy_(t, non_blocking=False)
+    return host.numpy()
+
+
+def scipy_index_dtype(n_elements, n_rows, n_cols):
+    """Index dtype scipy gives ``coo_matrix(...).tocsr()`` for 9M triplets
+    (scipy/sparse/_coo.py:419: maxval = max(nnz, N))."""
+    big = max(9 * n_elements, n_rows, n_cols)
+    return np.int64 if big > np.iinfo(np.int32).max else np.int32
+
+
+class DeviceMesh:
+    """Coordinates + elements on one GPU, plus the plan derived from
+    ``elements`` (node -> incident elements, CSR row pointer).
+
+    rows=(begin, end) restricts the plan to a contiguous row range (one rank of
+    a multi-GPU assembly); everything else is identical.
+    """
+
+    def __init__(self, coordinates, elements, device=None, rows=None,
+                 n_nodes=None):
+        self.ctx, self.device = context(device)
+        self._lib = _lib.load()
+        self.elements = to_device_indices(elements, self.device, self.ctx)
+        if self.elements.numel() == 0:
+            self.elements = self.elements.reshape(0, 3)
+        if self.elements.ndim != 2 or self.elements.shape[1] != 3:
+            raise ValueError('elements must have shape (M, 3)')
+        self.coords = None
+        if coordinates is not None:
+            self.coords = to_device_f64(coordinates, self.device)
+            if self.coords.ndim != 2 or self.coords.shape[1] != 2:
+                raise ValueError('coordinates must have shape (N, 2)')
+            n_nodes = self.coords.shape[0]
+        if n_nodes is None:
+            n_nodes = int(self.elements.max().item()) + 1 if self.elements.numel() else 0
+        self.n_nodes = int(n_nodes)
+        self.n_elements = int(self.elements.shape[0])
+        self.rows = (0, self.n_nodes) if rows is None else (int(rows[0]), int(rows[1]))
+        self._plan = None
+        self.nnz = None
+        self.max_index = None
+
+    # ------------------------------------------------------------------ plan
+    @property
+    def plan(self):
+        if self._plan is None:
+            handle = C.c_void_p()
+            _lib.check(self._lib.p1_plan_create(
+                self.ctx, _ptr(self.elements), self.n_elements, self.n_nodes,
+                self.rows[0], self.rows[1], _stream(self.device), C.byref(handle)))
+            self._plan = handle
+            nnz, mx = C.c_int64(), C.c_int64()
+            _lib.check(self._lib.p1_plan_info(handle, C.byref(nnz), C.byref(mx),
+                                              None, None))
+            self.nnz, self.max_index = nnz.value, mx.value
+        return self._plan
+
+    def close(self):
+        if self._plan is not None:
+            self._lib.p1_plan_destroy(self._plan)
+            self._plan = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _empty(self, shape, dtype=torch.float64):
+        return torch.empty(shape, dtype=dtype, device=torch.device('cuda', self.device))
+
+    # -------------------------------------------------------------- assembly
+    def assemble(self, op, local=None, pattern=True):
+        """-> (indptr, indices, data) CUDA tensors over the owned rows.
+        pattern=False skips the index arrays (re-assembly on the same mesh)."""
+        plan = self.plan
+        n_own = self.rows[1] - self.rows[0]
+        data = self._empty(self.nnz)
+        indptr = self._empty(n_own + 1, torch.int32) if pattern else None
+        indices = self._empty(self.nnz, torch.int32) if pattern else None
+        _lib.check(self._lib.p1_assemble_csr(
+            plan, op, _ptr(self.coords), _ptr(local), _ptr(indptr), _ptr(indices),
+            _ptr(data), _stream(self.device)))
+        return indptr, indices, data
+
+    def stiffness_csr(self, pattern=True):
+        return self.assemble(_lib.OP_STIFFNESS, pattern=pattern)
+
+    def mass_csr(self, pattern=True):
+        return self.assemble(_lib.OP_MASS, pattern=pattern)
+
+    def general_stiffness_csr(self, a11q, a12q, a21q, a22q, weights, pattern=True):
+        """a_ij_q: (n_qp, M) CUDA float64 values of the coefficients at the
+        quadrature points (see ``quadrature_points``)."""
+        w = _host_f64(weights)
+        local = self._empty((self.n_elements, 9))
+        qs = [to_device_f64(a, self.device, (w.shape[0], self.n_elements))
+              for a in (a11q, a12q, a21q, a22q)]
+        _lib.check(self._lib.p1_local_general_stiffness(
+            self.ctx, _ptr(self.coords), _ptr(self.elements), self.n_elements,
+            _ptr(qs[0]), _ptr(qs[1]), _ptr(qs[2]), _ptr(qs[3]),
+            w.ctypes.data_as(C.c_void_p), w.shape[0], _ptr(local),
+            _stream(self.device)))
+        return self.assemble(_lib.OP_LOCAL, local=local, pattern=pattern)
+
+    def weighted_mass_csr(self, phiq, weights, points, pattern=True):
+        w, p = _host_f64(weights), _host_f64(points)
+        local = self._empty((self.n_elements, 9))
+        phiq = to_device_f64(phiq, self.device, (w.shape[0], self.n_elements))
+        _lib.check(self._lib.p1_local_weighted_mass(
+            self.ctx, _ptr(self.coords), _ptr(self.elements), self.n_elements,
+            _ptr(phiq), w.ctypes.data_as(C.c_void_p), p.ctypes.data_as(C.c_void_p),
+            w.shape[0], _ptr(local), _stream(self.device)))
+        return self.assemble(_lib.OP_LOCAL, local=local, pattern=pattern)
+
+    def triplets(self, stiffness=False):
+        m = self.n_elements
+        rows = self._empty(9 * m, torch.int64)
+        cols = self._empty(9 * m, torch.int64)
+        vals = self._empty(9 * m)
+        fn = self._lib.p1_stiffness_triplets if stiffness else self._lib.p1_mass_triplets
+        _lib.check(fn(self.ctx, _ptr(self.coords), _ptr(self.elements), m, _ptr(rows),
+                      _ptr(cols), _ptr(vals), _stream(self.device)))
+        return rows, cols, vals
+
+    # ----------------------------------------------------- per-element data
+    def geometry(self, area=True, vectors=False):
+        m = self.n_elements
+        a = self._empty(m) if area else None
+        d21 = self._empty((m, 2)) if vectors else None
+        d31 = self._empty((m, 2)) if vectors else None
+        _lib.check(self._lib.p1_geometry(self.ctx, _ptr(self.coords), _ptr(self.elements),
+                                         m, _ptr(a), _ptr(d21), _ptr(d31),
+                                         _stream(self.device)))
+        return a, d21, d31
+
+    def quadrature_points(self, points):
+        p = _host_f64(points).reshape(-1, 2)
+        out = self._empty((p.shape[0], self.n_elements, 2))
+        _lib.check(self._lib.p1_quadrature_points(
+            self.ctx, _ptr(self.coords), _ptr(self.elements), self.n_elements,
+            p.ctypes.data_as(C.c_void_p), p.shape[0], _ptr(out), _stream(self.device)))
+        return out
+
+    def nodal_at_quadrature(self, u, points):
+        p = _host_f64(points).reshape(-1, 2)
+        u = to_device_f64(u, self.device, (self.n_nodes,))
+        out = self._empty((p.shape[0], self.n_elements))
+        _lib.check(self._lib.p1_nodal_at_quadrature(
+            self.ctx, _ptr(u), _ptr(self.elements), self.n_elements,
+            p.ctypes.data_as(C.c_void_p), p.shape[0], _ptr(out), _stream(self.device)))
+        return out
+
+    def centroids(self):
+        out = self._empty((self.n_elements, 2))
+        _lib.check(self._lib.p1_centroids(self.ctx, _ptr(self.coords), _ptr(self.elements),
+                                          self.n_elements, _ptr(out),
+                                          _stream(self.device)))
+        return out
+
+    def boundary_edges(self, edges_i32):
+        k = int(edges_i32.shape[0])
+        length = self._empty(k)
+        mid = self._empty((k, 2))
+        _lib.check(self._lib.p1_boundary_edges(self.ctx, _ptr(self.coords),
+                                               _ptr(edges_i32), k, _ptr(length),
+                                               _ptr(mid), _stream(self.device)))
+        return length, mid
+
+    # ---------------------------------------------------------- load vectors
+    def load_vector(self, fq, weights, points):
+        w, p = _host_f64(weights), _host_f64(points)
+        fq = to_device_f64(fq, self.device, (w.shape[0], self.n_elements))
+        b = self._empty(self.rows[1] - self.rows[0])
+        _lib.check(self._lib.p1_load_vector(
+            self.plan, _ptr(self.coords), _ptr(fq), w.ctypes.data_as(C.c_void_p),
+            p.ctypes.data_as(C.c_void_p), w.shape[0], _ptr(b), _stream(self.device)))
+        return b
+
+    def load_vector_midpoint(self, f_centroid):
+        fc = to_device_f64(f_centroid, self.device, (self.n_elements,))
+        b = self._empty(self.rows[1] - self.rows[0])
+        _lib.check(self._lib.p1_load_vector_midpoint(
+            self.plan, _ptr(self.coords), _ptr(fc), _ptr(b), _stream(self.device)))
+        return b
+
+    # ------------------------------------------------- edges and estimator
+    def geometric_data(self, boundaries):
+        """boundaries: list of (K_j, 2) integer arrays (host or device).
+        -> (element2edges (M,3), edge2nodes (E,2), [K_j] edge ids), int64 CUDA."""
+        dev = torch.device('cuda', self.device)
+        parts = [to_device_indices(np.asarray(b).reshape(-1, 2)
+                                   if not isinstance(b, torch.Tensor) else b,
+                                   self.device, self.ctx).reshape(-1, 2)
+                 for b in boundaries]
+        offsets = np.zeros(len(parts) + 1, dtype=np.int64)
+        for j, b in enumerate(parts):
+            offsets[j + 1] = offsets[j] + b.shape[0]
+        k = int(offsets[-1])
+        bnd = (torch.cat(parts).contiguous() if parts
+               else torch.empty((0, 2), dtype=torch.int32, device=dev))
+        m = self.n_elements
+        e2e = self._empty((m, 3), torch.int64)
+        cap = (3 * m + k + 1) // 2
+        e2n = self._empty((cap, 2), torch.int64)
+        b2e = self._empty(k, torch.int64)
+        n_edges = C.c_int64()
+        _lib.check(self._lib.p1_geometric_data(
+            self.plan, _ptr(bnd), offsets.ctypes.data_as(C.c_void_p), len(parts),
+            _ptr(e2e), _ptr(e2n), _ptr(b2e), C.byref(n_edges), _stream(self.device)))
+        pieces = [b2e[offsets[j]:offsets[j + 1]] for j in range(len(parts))]
+        return e2e, e2n[:n_edges.value], pieces
+
+    def eta_r(self, x, dirichlet, neumann, neumann_term, f_centroid):
+        x = to_device_f64(x, self.device, (self.n_nodes,))
+        fc = to_device_f64(f_centroid, self.device, (self.n_elements,))
+        nt = (to_device_f64(neumann_term, self.device, (neumann.shape[0],))
+              if neumann.shape[0] else None)
+        eta = self._empty(self.n_elements)
+        _lib.check(self._lib.p1_eta_r(
+            self.plan, _ptr(self.coords), _ptr(x),
+            _ptr(dirichlet) if dirichlet.shape[0] else None, int(dirichlet.shape[0]),
+            _ptr(neumann) if neumann.shape[0] else None, int(neumann.shape[0]),
+            _ptr(nt), _ptr(fc), _ptr(eta), _stream(self.device)))
+        return eta
+
+    # ------------------------------------------------------------ host side
+    def to_scipy(self, indptr, indices, data, inferred_shape):
+        """CSR triple (CUDA) -> scipy.sparse.csr_matrix equal to
+        ``reference(...).tocsr()``: shape max_index+1 when the reference lets
+        scipy infer it (solvers.py:46-47,153) or (N, N) when it passes it
+        (solvers.py:140-141,375-376); index dtype by scipy's rule."""
+        from scipy.sparse import csr_matrix
+        n = (self.max_index + 1) if inferred_shape else self.n_nodes
+        if self.rows != (0, self.n_nodes):
+            raise ValueError('to_scipy needs a plan over all rows')
+        idx_dtype = scipy_index_dtype(self.n_elements, n, n)
+        ip = indptr[:n + 1]
+        if idx_dtype == np.int64:
+            ip64 = self._empty(ip.shape, torch.int64)
+            ix64 = self._empty(indices.shape, torch.int64)
+            _lib.check(self._lib.p1_widen_indices(self.ctx, _ptr(ip.contiguous()),
+                                                  ip.numel(), _ptr(ip64),
+                                                  _stream(self.device)))
+            _lib.check(self._lib.p1_widen_indices(self.ctx, _ptr(indices),
+                                                  indices.numel(), _ptr(ix64),
+                                                  _stream(self.device)))
+            ip, indices = ip64, ix64
+        h_ip, h_ix, h_data = to_host(ip), to_host(indices), to_host(data)
+        if n == 0:
+            return csr_matrix((0, 0), dtype=np.float64)
+        a = csr_matrix((h_data, h_ix, h_ip), shape=(n, n), copy=False)
+        a.has_sorted_indices = True
+        a.has_canonical_format = True
+        return a

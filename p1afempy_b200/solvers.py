@@ -1,0 +1,139 @@
+"""Drop-in for the assembly builders of ``p1afempy.solvers`` -- same names,
+parameter names, order and defaults (/root/reference/p1afempy/solvers.py:15-598).
+
+numpy arrays in; ``scipy.sparse.csr_matrix`` (== ``reference(...).tocsr()``)
+or ``np.ndarray`` out.  Everything between is CUDA (libp1b200.so); user
+callbacks (``f``, ``a_ij``, ``phi``) are evaluated on the host on exactly the
+points the reference would pass them, everything else stays on the device.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _lib
+from .cubature import resolve_rule
+from .device import DeviceMesh, to_host
+
+__all__ = ['get_stiffness_matrix', 'get_mass_matrix', 'get_mass_matrix_elements',
+           'get_general_stiffness_matrix', 'get_weighted_mass_matrix',
+           'get_right_hand_side', 'get_right_hand_side_using_quadrature_rule']
+
+
+def _values_on_host(fn, points_host, n):
+    """Calls a user callback like the reference does (one (n, d) array in,
+    (n,) out) and normalises what it returns (scalar, list, (n,1) ...)."""
+    out = np.asarray(fn(points_host), dtype=np.float64)
+    if out.ndim == 0:
+        out = np.full(n, float(out))
+    out = out.reshape(-1)
+    if out.shape[0] != n:
+        raise ValueError('callback returned %d values for %d points'
+                         % (out.shape[0], n))
+    return out
+
+
+def _callback_at_points(fns, xq):
+    """fns evaluated at every quadrature point set; xq: CUDA (n_qp, M, 2).
+    -> list of host arrays (n_qp, M), one per callback."""
+    pts = to_host(xq)
+    n_qp, m = pts.shape[0], pts.shape[1]
+    outs = [np.empty((n_qp, m)) for _ in fns]
+    for q in range(n_qp):
+        for o, fn in zip(outs, fns):
+            o[q] = _values_on_host(fn, pts[q], m)
+    return outs
+
+
+def _need_inferable(mesh):
+    if mesh.n_elements == 0:
+        raise ValueError('cannot infer dimensions from zero sized index arrays')
+
+
+def get_stiffness_matrix(coordinates, elements):
+    """P1 stiffness matrix (solvers.py:15-47) as CSR."""
+    with DeviceMesh(coordinates, elements) as mesh:
+        _need_inferable(mesh)
+        return mesh.to_scipy(*mesh.stiffness_csr(), inferred_shape=True)
+
+
+def get_mass_matrix(coordinates, elements):
+    """P1 mass matrix (solvers.py:145-153) as CSR."""
+    with DeviceMesh(coordinates, elements) as mesh:
+        _need_inferable(mesh)
+        return mesh.to_scipy(*mesh.mass_csr(), inferred_shape=True)
+
+
+def get_mass_matrix_elements(coordinates, elements):
+    """(I, J, D) triplets in the reference's order (solvers.py:156-182)."""
+    with DeviceMesh(coordinates, elements) as mesh:
+        _check_range(mesh)
+        rows, cols, vals = mesh.triplets(stiffness=False)
+        kind = np.asarray(elements).dtype
+        i, j = to_host(rows), to_host(cols)
+        if kind.kind in 'iu' and kind != np.int64:
+            i, j = i.astype(kind), j.astype(kind)
+        return i, j, to_host(vals)
+
+
+def _check_range(mesh):
+    """Kernels that gather by element index without a plan rely on the range
+    check the plan performs."""
+    mesh.plan  # noqa: B018  (raises IndexError on out-of-range indices)
+
+
+def get_general_stiffness_matrix(coordinates, elements, a_11, a_12, a_21, a_22,
+                                 cubature_rule):
+    """Stiffness matrix of -div(A(x) grad u) (solvers.py:278-377) as CSR with
+    explicit shape (N, N)."""
+    weights, points = resolve_rule(cubature_rule)
+    with DeviceMesh(coordinates, elements) as mesh:
+        _check_range(mesh)
+        xq = mesh.quadrature_points(points)
+        q11, q12, q21, q22 = _callback_at_points((a_11, a_12, a_21, a_22), xq)
+        del xq
+        return mesh.to_scipy(*mesh.general_stiffness_csr(q11, q12, q21, q22, weights),
+                             inferred_shape=False)
+
+
+def get_weighted_mass_matrix(coordinates, elements, current_iterate, phi,
+                             cubature_rule):
+    """M_ij = int phi(u_h) phi_i phi_j (solvers.py:50-142) as CSR (N, N)."""
+    weights, points = resolve_rule(cubature_rule)
+    with DeviceMesh(coordinates, elements) as mesh:
+        _check_range(mesh)
+        u = np.asarray(current_iterate, dtype=np.float64).reshape(-1)
+        if u.shape[0] < mesh.max_index + 1:
+            raise IndexError('current_iterate has %d entries, elements reference '
+                             'node %d' % (u.shape[0], mesh.max_index))
+        if u.shape[0] != mesh.n_nodes:   # numpy would only read what it needs
+            u = np.concatenate([u, np.zeros(max(0, mesh.n_nodes - u.shape[0]))])[:mesh.n_nodes]
+        uq = to_host(mesh.nodal_at_quadrature(u, points))
+        phiq = np.empty_like(uq)
+        for q in range(uq.shape[0]):
+            phiq[q] = _values_on_host(phi, uq[q], uq.shape[1])
+        return mesh.to_scipy(*mesh.weighted_mass_csr(phiq, weights, points),
+                             inferred_shape=False)
+
+
+def get_right_hand_side(coordinates, elements, f, cubature_rule=None):
+    """Load vector (solvers.py:380-426); legacy centroid rule when
+    ``cubature_rule`` is None."""
+    if cubature_rule is not None:
+        return get_right_hand_side_using_quadrature_rule(
+            coordinates=coordinates, elements=elements, f=f,
+            cubature_rule=cubature_rule)
+    with DeviceMesh(coordinates, elements) as mesh:
+        _check_range(mesh)
+        cent = to_host(mesh.centroids())
+        fc = _values_on_host(f, cent, mesh.n_elements)
+        return to_host(mesh.load_vector_midpoint(fc))
+
+
+def get_right_hand_side_using_quadrature_rule(coordinates, elements, f,
+                                              cubature_rule):
+    """Load vector with a cubature rule (solvers.py:540-598)."""
+    weights, points = resolve_rule(cubature_rule)
+    with DeviceMesh(coordinates, elements) as mesh:
+        _check_range(mesh)
+        (fq,) = _callback_at_points((f,), mesh.quadrature_points(points))
+        return to_host(mesh.load_vector(fq, weights, points))

@@ -1,0 +1,317 @@
+"""Parity of the CUDA path (through the drop-in functions, i.e. through the
+C ABI) with the oracle and with the committed golden fixtures.
+
+Contract: CSR index arrays bit-exact (dtype and shape
+included); values within 1e-12 of the row maximum; load vectors, estimator,
+edge numbering and triplets bit-exact.
+"""
+import os
+
+import numpy as np
+import pytest
+from scipy.sparse import csr_matrix
+
+from oracle import p1_oracle as orc
+from p1afempy_b200 import cubature, meshgen
+import helpers as H
+import helpers_laplace as L
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-12
+
+
+@pytest.fixture(scope='module')
+def api():
+    from p1afempy_b200 import solvers, mesh, indicators
+    return solvers, mesh, indicators
+
+
+def load(name):
+    return np.load(os.path.join(H.GOLDEN, name + '.npz'))
+
+
+def csr_of(g, prefix):
+    return csr_matrix((g[prefix + '_data'], g[prefix + '_indices'],
+                       g[prefix + '_indptr']), shape=tuple(g[prefix + '_shape']))
+
+
+MESHES = {
+    'perturbed_s5': lambda: H.perturbed_square(5),
+    'graded': lambda: H.graded_square(),
+    'lshape_u4': lambda: meshgen.refine_uniform(*meshgen.l_shape(), times=4),
+    'two_triangles': lambda: meshgen.two_triangle_square(),
+    'uniform_s7': lambda: meshgen.unit_square(7),
+}
+
+
+@pytest.fixture(scope='module', params=list(MESHES))
+def mesh_case(request):
+    return MESHES[request.param]()
+
+
+def test_stiffness_vs_oracle(api, mesh_case):
+    c, e, _ = mesh_case
+    a = api[0].get_stiffness_matrix(c, e)
+    H.csr_values_close(a, orc.stiffness_coo(c, e).tocsr(), RTOL)
+    assert a.has_sorted_indices
+
+
+def test_mass_vs_oracle(api, mesh_case):
+    c, e, _ = mesh_case
+    H.csr_values_close(api[0].get_mass_matrix(c, e), orc.mass_coo(c, e).tocsr(), RTOL)
+    i, j, d = api[0].get_mass_matrix_elements(c, e)
+    oi, oj, od = orc.mass_triplets(c, e)
+    assert np.array_equal(i, oi) and np.array_equal(j, oj)
+    assert np.array_equal(d, od)                      # bit-exact
+
+
+@pytest.mark.parametrize('rule', ['MIDPOINT', 'DAYTAYLOR'])
+def test_general_stiffness_vs_oracle(api, mesh_case, rule):
+    c, e, _ = mesh_case
+    r = cubature.CubatureRuleEnum[rule]
+    w, p = cubature.resolve_rule(r)
+    a = api[0].get_general_stiffness_matrix(c, e, H.a11, H.a12, H.a21, H.a22, r)
+    ref = orc.general_stiffness_coo(c, e, H.a11, H.a12, H.a21, H.a22, w, p).tocsr()
+    H.csr_values_close(a, ref, RTOL)
+
+
+@pytest.mark.parametrize('rule', ['MIDPOINT', 'DAYTAYLOR'])
+def test_weighted_mass_vs_oracle(api, mesh_case, rule):
+    c, e, _ = mesh_case
+    r = cubature.CubatureRuleEnum[rule]
+    w, p = cubature.resolve_rule(r)
+    u = H.u_nodal(c)
+    a = api[0].get_weighted_mass_matrix(c, e, u, H.phi, r)
+    H.csr_values_close(a, orc.weighted_mass_coo(c, e, u, H.phi, w, p).tocsr(), RTOL)
+
+
+def test_load_vectors_bit_exact(api, mesh_case):
+    c, e, _ = mesh_case
+    assert np.array_equal(api[0].get_right_hand_side(c, e, H.f_load),
+                          orc.load_vector_midpoint(c, e, H.f_load))
+    for rule in ('MIDPOINT', 'SMPLX1', 'DAYTAYLOR'):
+        r = cubature.CubatureRuleEnum[rule]
+        w, p = cubature.resolve_rule(r)
+        mine = api[0].get_right_hand_side(c, e, H.f_load, cubature_rule=r)
+        assert np.array_equal(mine, orc.load_vector_cubature(c, e, H.f_load, w, p))
+        # the rule is data: a (weights, points) pair works as well
+        assert np.array_equal(
+            api[0].get_right_hand_side_using_quadrature_rule(c, e, H.f_load, (w, p)),
+            mine)
+
+
+def test_geometry_bit_exact(api, mesh_case):
+    c, e, _ = mesh_case
+    assert np.array_equal(api[1].get_area(c, e), orc.signed_area(c, e))
+    d21, d31 = api[1].get_directional_vectors(c, e)
+    o21, o31 = orc.edge_vectors(c, e)
+    assert np.array_equal(d21, o21) and np.array_equal(d31, o31)
+
+
+def _split(b):
+    allb = np.vstack(b)
+    cut = (3 * allb.shape[0]) // 5
+    return allb[:cut], allb[cut:]
+
+
+def test_geometric_data_bit_exact(api, mesh_case):
+    _, e, b = mesh_case
+    parts = list(_split(b))
+    e2e, e2n, b2e = api[1].provide_geometric_data(e, parts)
+    o2e, o2n, ob2e = orc.geometric_data(e, parts)
+    assert e2e.dtype == o2e.dtype == np.int64
+    assert np.array_equal(e2e, o2e) and np.array_equal(e2n, o2n)
+    assert len(b2e) == 2
+    for x, y in zip(b2e, ob2e):
+        assert np.array_equal(x, y)
+
+
+@pytest.mark.parametrize('with_neumann', [True, False])
+def test_eta_r_bit_exact(api, mesh_case, with_neumann):
+    c, e, b = mesh_case
+    if with_neumann:
+        dirichlet, neumann = _split(b)
+    else:
+        dirichlet, neumann = np.vstack(b), np.zeros((0, 2), dtype=int)
+    x = H.u_nodal(c) + 0.1 * c[:, 0]
+    mine = api[2].compute_eta_r(x, c, e, dirichlet, neumann, H.f_load, H.g_neu)
+    ref = orc.eta_r(x, c, e, dirichlet, neumann, H.f_load, H.g_neu)
+    assert np.array_equal(mine, ref)
+
+
+# ------------------------------------------------------------ golden fixtures
+@pytest.mark.parametrize('case', ['perturbed_s4', 'graded', 'lshape_u3'])
+def test_against_reference_fixtures(api, case):
+    """Outputs of the REAL reference, committed under tests/golden."""
+    solvers, mesh, indicators = api
+    g = load(case)
+    c, e, u, x = g['coordinates'], g['elements'], g['u'], g['x']
+    H.csr_values_close(solvers.get_stiffness_matrix(c, e), csr_of(g, 'stiff'), RTOL)
+    H.csr_values_close(solvers.get_mass_matrix(c, e), csr_of(g, 'mass'), RTOL)
+    i, j, d = solvers.get_mass_matrix_elements(c, e)
+    assert np.array_equal(i, g['mass_I']) and np.array_equal(j, g['mass_J'])
+    assert np.array_equal(d, g['mass_D'])
+    for r in ('MIDPOINT', 'DAYTAYLOR'):
+        rule = (g['rule_%s_w' % r], g['rule_%s_p' % r])
+        H.csr_values_close(
+            solvers.get_general_stiffness_matrix(c, e, H.a11, H.a12, H.a21, H.a22, rule),
+            csr_of(g, 'gen_' + r), RTOL)
+        H.csr_values_close(solvers.get_weighted_mass_matrix(c, e, u, H.phi, rule),
+                           csr_of(g, 'wmass_' + r), RTOL)
+        assert np.array_equal(solvers.get_right_hand_side(c, e, H.f_load, rule),
+                              g['rhs_' + r])
+    assert np.array_equal(solvers.get_right_hand_side(c, e, H.f_load), g['rhs_legacy'])
+    e2e, e2n, b2e = mesh.provide_geometric_data(e, [g['dirichlet'], g['neumann']])
+    assert np.array_equal(e2e, g['element2edges'])
+    assert np.array_equal(e2n, g['edge2nodes'])
+    assert np.array_equal(b2e[0], g['dir2edges'])
+    assert np.array_equal(b2e[1], g['neu2edges'])
+    assert np.array_equal(
+        indicators.compute_eta_r(x, c, e, g['dirichlet'], g['neumann'], H.f_load, H.g_neu),
+        g['eta'])
+    assert np.array_equal(mesh.get_area(c, e), g['area'])
+
+
+def test_laplace_example_matlab(api):
+    """test_indicators.py:12-55 / test_solver.py:20-57 of the reference."""
+    solvers, _, indicators = api
+    g = load('laplace_example')
+    eta = indicators.compute_eta_r(g['x_reference'], g['coordinates'], g['elements'],
+                                   g['dirichlet'], g['neumann'], L.f, L.g)
+    assert np.array_equal(eta, g['eta_reference'])
+    assert np.allclose(eta, g['eta_matlab'])
+    a = solvers.get_stiffness_matrix(g['coordinates3'], g['elements3'])
+    xm = g['x_matlab']
+    assert np.isclose(xm.dot(a.dot(xm)), g['energy_matlab'])
+
+
+def test_ahw_mass_triplets_matlab(api):
+    """test_solver.py:59-86: triplet order pinned by MATLAB data."""
+    g = load('ahw_example')
+    i, j, d = api[0].get_mass_matrix_elements(g['coordinates'], g['elements'])
+    assert np.array_equal(i, g['mass_I_matlab']) and np.array_equal(j, g['mass_J_matlab'])
+    assert np.allclose(d, g['mass_D_matlab'])
+    assert np.allclose(api[1].get_area(g['coordinates'], g['elements']), g['area_matlab'])
+
+
+def test_edge_numbering_known_answers(api):
+    """test_mesh.py:29-112 (uint32 inputs, as io_helpers returns them)."""
+    g = load('edge_numbering')
+    for pre, nb in (('sq', 2), ('l', 3)):
+        bnds = [g['%s_b%d' % (pre, k)] for k in range(nb)]
+        e2e, e2n, b2e = api[1].provide_geometric_data(g[pre + '_elements'], bnds)
+        assert np.array_equal(e2e, g[pre + '_element2edges'])
+        assert np.array_equal(e2n, g[pre + '_edge2nodes'])
+        for k in range(nb):
+            assert np.array_equal(b2e[k], g['%s_b2e%d' % (pre, k)])
+
+
+def test_sanity_energy_exactly_four(api):
+    """test_sanity_check.py:80-119: assertEqual(4.0, x.A.x)."""
+    g = load('sanity_check')
+    for level in range(4):
+        c, e = g['c%d' % level], g['e%d' % level]
+        x = L.sanity_u(c)
+        a = api[0].get_stiffness_matrix(c, e)
+        assert x.dot(a.dot(x)) == 4.0
+
+
+def test_general_minus_identity_equals_stiffness(api):
+    """test_general_stiffness_matrices.py:22-59; callbacks build their result
+    from .shape[0] on the host."""
+    c, e, _ = H.perturbed_square(4)
+    minus_one = lambda r: -np.ones(r.shape[0])   # noqa: E731
+    zero = lambda r: np.zeros(r.shape[0])        # noqa: E731
+    gen = api[0].get_general_stiffness_matrix(
+        c, e, minus_one, zero, zero, minus_one, cubature.CubatureRuleEnum.DAYTAYLOR)
+    assert np.allclose(gen.toarray(), api[0].get_stiffness_matrix(c, e).toarray())
+
+
+# ---------------------------------------------------------------- edge cases
+def test_index_dtypes_and_unused_nodes(api):
+    c, e, _ = H.perturbed_square(3)
+    ref = orc.stiffness_coo(c, e).tocsr()
+    for dt in (np.int32, np.int64, np.uint32, np.int16):
+        H.csr_values_close(api[0].get_stiffness_matrix(c, e.astype(dt)), ref, RTOL)
+    # trailing unused nodes: inferred shape shrinks, explicit shape does not
+    c2 = np.vstack([c, [[5., 5.], [6., 6.]]])
+    a = api[0].get_stiffness_matrix(c2, e)
+    assert a.shape == ref.shape
+    w, p = cubature.resolve_rule(cubature.CubatureRuleEnum.MIDPOINT)
+    gen = api[0].get_general_stiffness_matrix(c2, e, H.a11, H.a12, H.a21, H.a22, (w, p))
+    gref = orc.general_stiffness_coo(c2, e, H.a11, H.a12, H.a21, H.a22, w, p).tocsr()
+    H.csr_values_close(gen, gref, RTOL)
+    assert gen.shape == (c2.shape[0],) * 2
+    b = api[0].get_right_hand_side(c2, e, H.f_load)
+    assert np.array_equal(b, orc.load_vector_midpoint(c2, e, H.f_load))
+    # an unused node in the middle -> empty row
+    e3 = e.copy()
+    e3[e3 >= 7] += 1
+    c3 = np.insert(c, 7, [[9., 9.]], axis=0)
+    H.csr_values_close(api[0].get_stiffness_matrix(c3, e3),
+                       orc.stiffness_coo(c3, e3).tocsr(), RTOL)
+
+
+def test_out_of_range_index_raises(api):
+    c, e, _ = meshgen.unit_square(2)
+    bad = e.copy()
+    bad[3, 1] = c.shape[0]
+    with pytest.raises(IndexError):
+        api[0].get_stiffness_matrix(c, bad)
+    bad[3, 1] = -1
+    with pytest.raises(IndexError):
+        api[0].get_right_hand_side(c, bad, H.f_load)
+
+
+def test_incomplete_boundary_raises(api):
+    c, e, b = meshgen.unit_square(3)
+    partial = [np.vstack(b)[:-3]]
+    with pytest.raises(ValueError):
+        api[1].provide_geometric_data(e, partial)
+    with pytest.raises(ValueError):
+        api[2].compute_eta_r(H.u_nodal(c), c, e, partial[0],
+                             np.zeros((0, 2), dtype=int), H.f_load, H.g_neu)
+
+
+def test_high_valence_fan(api):
+    """One node shared by 40 triangles (more than the fast path's DEG_MAX):
+    exercises the block-per-row path."""
+    n = 40
+    ang = 2 * np.pi * np.arange(n) / n
+    c = np.vstack([[0., 0.], np.column_stack([np.cos(ang), np.sin(ang)])])
+    c[1:] *= (1 + 0.1 * np.sin(5 * ang))[:, None]
+    e = np.column_stack([np.zeros(n, dtype=int), 1 + np.arange(n),
+                         1 + (np.arange(n) + 1) % n])
+    H.csr_values_close(api[0].get_stiffness_matrix(c, e),
+                       orc.stiffness_coo(c, e).tocsr(), RTOL)
+    H.csr_values_close(api[0].get_mass_matrix(c, e), orc.mass_coo(c, e).tocsr(), RTOL)
+    assert np.array_equal(api[0].get_right_hand_side(c, e, H.f_load),
+                          orc.load_vector_midpoint(c, e, H.f_load))
+    rim = np.column_stack([1 + np.arange(n), 1 + (np.arange(n) + 1) % n])
+    e2e, e2n, b2e = api[1].provide_geometric_data(e, [rim])
+    o2e, o2n, ob2e = orc.geometric_data(e, [rim])
+    assert np.array_equal(e2e, o2e) and np.array_equal(e2n, o2n)
+    assert np.array_equal(b2e[0], ob2e[0])
+
+
+def test_non_manifold_still_assembles(api):
+    """Three triangles on one edge: not a mesh, but the reference just sums
+    triplets; so must the assembly."""
+    c = np.array([[0., 0.], [1., 0.], [0., 1.], [1., 1.], [.5, -1.]])
+    e = np.array([[0, 1, 2], [1, 0, 4], [0, 1, 3]])
+    H.csr_values_close(api[0].get_stiffness_matrix(c, e),
+                       orc.stiffness_coo(c, e).tocsr(), RTOL)
+
+
+def test_large_uniform_invariants(api):
+    """S(9) (1M triangles, config C1): full parity against the oracle plus
+    size-independent properties (row sums of the stiffness matrix vanish,
+    symmetry, total mass = area of the domain)."""
+    c, e, _ = meshgen.unit_square(9)
+    a = api[0].get_stiffness_matrix(c, e)
+    H.csr_values_close(a, orc.stiffness_coo(c, e).tocsr(), RTOL)
+    assert np.abs(a @ np.ones(a.shape[0])).max() < 1e-9
+    assert abs(a - a.T).max() == 0.0
+    m = api[0].get_mass_matrix(c, e)
+    assert abs(m.sum() - 1.0) < 1e-12
