@@ -53,6 +53,13 @@ int p1_ctx_destroy(p1_ctx *ctx);
  * reports them.  src_kind: 0 = int64, 1 = uint32, 2 = int32 (plain copy). */
 int p1_narrow_indices(p1_ctx *ctx, const void *src, int src_kind,
                       int64_t count, int32_t *dst, void *stream);
+/* Per-kernel device timing (CUDA events on the launching stream) for
+ * bench.py's roofline line.  Off by default; p1_profile_report writes one
+ * "name total_ms launches" line per kernel into buf and SYNCHRONISES. */
+int p1_profile_enable(p1_ctx *ctx, int on);
+int p1_profile_reset(p1_ctx *ctx);
+int p1_profile_report(p1_ctx *ctx, char *buf, int64_t cap);
+
 /* int32 -> int64 widening of an index array (scipy switches the CSR index
  * dtype to int64 when max(9M, N) >= 2^31, scipy/sparse/_coo.py:419). */
 int p1_widen_indices(p1_ctx *ctx, const int32_t *src, int64_t count,

@@ -35,6 +35,9 @@ PROTOTYPES = {
     'p1_last_error': [],
     'p1_ctx_create': [_int, C.POINTER(_vp)],
     'p1_ctx_destroy': [_vp],
+    'p1_profile_enable': [_vp, _int],
+    'p1_profile_reset': [_vp],
+    'p1_profile_report': [_vp, C.c_char_p, _i64],
     'p1_narrow_indices': [_vp, _vp, _int, _i64, _vp, _vp],
     'p1_widen_indices': [_vp, _vp, _i64, _vp, _vp],
     'p1_plan_create': [_vp, _vp, _i64, _i64, _i64, _i64, _vp, C.POINTER(_vp)],

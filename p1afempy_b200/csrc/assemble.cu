@@ -161,9 +161,10 @@ int launch_fill(const p1_plan *p, Op op, const double *coords, int32_t *indices,
                 double *data, cudaStream_t s) {
   const int n_own = (int)(p->row_end - p->row_begin);
   if (n_own > 0)
-    fill_rows_kernel<Op><<<grid_for(n_own, THREADS), THREADS, 0, s>>>(
-        n_own, (int)p->row_begin, p->rec_off, p->rec, p->nbr, p->indptr,
-        (const double2 *)coords, op, indices, data);
+    P1_TIMED(p->ctx, "fill_rows", s,
+             (fill_rows_kernel<Op><<<grid_for(n_own, THREADS), THREADS, 0, s>>>(
+                 n_own, (int)p->row_begin, p->rec_off, p->rec, p->nbr, p->indptr,
+                 (const double2 *)coords, op, indices, data)));
   if (p->n_big > 0)
     fill_big_kernel<Op><<<p->n_big, THREADS, 0, s>>>(
         p->big_rows, (int)p->row_begin, p->rec_off, p->rec, p->nbr, p->big_first,

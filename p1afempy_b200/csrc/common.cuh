@@ -46,11 +46,13 @@ enum : int {
 
 }  // namespace p1
 
+struct p1_prof;
 struct p1_ctx {
   int device;
   int sm_count;
   int *d_flags;        // 4 ints: [0] status bits, [1] max node index, [2..3] spare
   int *h_flags;        // pinned mirror
+  p1_prof *prof;       // per-kernel CUDA-event timing, off unless enabled
 };
 
 namespace p1 {
@@ -84,9 +86,20 @@ inline unsigned grid_for(int64_t n, int block, int per_thread = 1) {
   return (unsigned)g;
 }
 
+// Per-kernel timing with CUDA events on the launching stream (bench.py reads
+// it through p1_profile_report).  No-ops unless p1_profile_enable(ctx, 1).
+void prof_begin(p1_ctx *ctx, const char *name, cudaStream_t s);
+void prof_end(p1_ctx *ctx, cudaStream_t s);
+#define P1_TIMED(ctx, name, s, ...)                                           \
+  do {                                                                        \
+    p1::prof_begin((ctx), (name), (s));                                       \
+    __VA_ARGS__;                                                              \
+    p1::prof_end((ctx), (s));                                                 \
+  } while (0)
+
 // exclusive prefix sum of n int32 values; out may alias in; out[n] = total
 // when write_total is true (out then has n+1 entries).
-int exclusive_scan_i32(const int *in, int *out, int64_t n, bool write_total,
-                       cudaStream_t s);
+int exclusive_scan_i32(p1_ctx *ctx, const int *in, int *out, int64_t n,
+                       bool write_total, cudaStream_t s);
 
 }  // namespace p1

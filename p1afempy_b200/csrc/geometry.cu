@@ -307,7 +307,7 @@ extern "C" int p1_geometric_data(const p1_plan *cplan, const int32_t *boundary_n
   if (total > 0)
     forward_flags_kernel<<<egrid(ctx, total), THREADS, 0, s>>>(
         p->elements, M, boundary_nodes, K, num, ctx->d_flags);
-  int rc = exclusive_scan_i32(num, num, total, true, s);
+  int rc = exclusive_scan_i32(ctx, num, num, total, true, s);
   if (rc) { pool_free(num, s); return rc; }
   if (M > 0)
     element_edges_kernel<<<egrid(ctx, 3 * M), THREADS, 0, s>>>(

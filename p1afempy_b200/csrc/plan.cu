@@ -211,8 +211,9 @@ extern "C" int p1_plan_create(p1_ctx *ctx, const int32_t *elements,
   cudaMemsetAsync(cnt, 0, ((size_t)n_own + 1) * sizeof(int), s);
 
   const unsigned eg = min(grid_for(M, THREADS), (unsigned)(ctx->sm_count * 32));
-  count_kernel<<<eg, THREADS, 0, s>>>(elements, M, N, rb, re, cnt, ctx->d_flags);
-  if ((rc = exclusive_scan_i32(cnt, p->rec_off, n_own, true, s))) return fail(rc);
+  P1_TIMED(ctx, "count", s,
+           count_kernel<<<eg, THREADS, 0, s>>>(elements, M, N, rb, re, cnt, ctx->d_flags));
+  if ((rc = exclusive_scan_i32(ctx, cnt, p->rec_off, n_own, true, s))) return fail(rc);
   // n_rec is needed on the host to size rec/nbr; for the whole matrix it is
   // 3M, for a row range it is read back
   int64_t n_rec = 3 * M;
@@ -231,12 +232,14 @@ extern "C" int p1_plan_create(p1_ctx *ctx, const int32_t *elements,
   if ((rc = pool_alloc(&p->nbr, (size_t)n_rec, s))) return fail(rc);
   if ((rc = pool_alloc(&p->big_rows, (size_t)(n_rec / (DEG_MAX + 1)) + 1, s)))
     return fail(rc);
-  scatter_kernel<<<eg, THREADS, 0, s>>>(elements, M, N, rb, re, cnt, p->rec_off,
-                                        p->rec);
+  P1_TIMED(ctx, "scatter", s,
+           scatter_kernel<<<eg, THREADS, 0, s>>>(elements, M, N, rb, re, cnt, p->rec_off,
+                                                 p->rec));
   d_nbig = ctx->d_flags + 2;
   // cnt is all zero again: reuse it as rowlen
-  rowlen_kernel<<<grid_for(n_own, THREADS), THREADS, 0, s>>>(
-      elements, n_own, rb, p->rec_off, p->rec, p->nbr, cnt, p->big_rows, d_nbig);
+  P1_TIMED(ctx, "rowlen", s,
+           rowlen_kernel<<<grid_for(n_own, THREADS), THREADS, 0, s>>>(
+               elements, n_own, rb, p->rec_off, p->rec, p->nbr, cnt, p->big_rows, d_nbig));
   cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, 4 * sizeof(int),
                   cudaMemcpyDeviceToHost, s);
   if (cudaStreamSynchronize(s) != cudaSuccess) {
@@ -264,7 +267,7 @@ extern "C" int p1_plan_create(p1_ctx *ctx, const int32_t *elements,
                                                    p->nbr, p->big_first, cnt);
     pool_free(tmp, s);
   }
-  if ((rc = exclusive_scan_i32(cnt, p->indptr, n_own, true, s))) {
+  if ((rc = exclusive_scan_i32(ctx, cnt, p->indptr, n_own, true, s))) {
     pool_free(cnt, s);
     return fail(rc);
   }

@@ -99,16 +99,18 @@ scan_down_kernel(const int *__restrict__ in, int *__restrict__ out, int64_t n,
     out[n] = block_sums[gridDim.x];
 }
 
-int exclusive_scan_i32(const int *in, int *out, int64_t n, bool write_total,
-                       cudaStream_t s) {
+int exclusive_scan_i32(p1_ctx *ctx, const int *in, int *out, int64_t n,
+                       bool write_total, cudaStream_t s) {
   if (n < 0) return P1_EINVAL;
   const unsigned nb = grid_for(n, SCAN_TILE);
   int *sums = nullptr;
   P1_TRY(pool_alloc(&sums, (size_t)nb + 1, s));
-  scan_reduce_kernel<<<nb, SCAN_THREADS, 0, s>>>(in, n, sums);
-  scan_sums_kernel<<<1, 1024, 0, s>>>(sums, (int)nb);
-  scan_down_kernel<<<nb, SCAN_THREADS, 0, s>>>(in, out, n, sums,
-                                               write_total ? 1 : 0);
+  P1_TIMED(ctx, "scan", s, {
+    scan_reduce_kernel<<<nb, SCAN_THREADS, 0, s>>>(in, n, sums);
+    scan_sums_kernel<<<1, 1024, 0, s>>>(sums, (int)nb);
+    scan_down_kernel<<<nb, SCAN_THREADS, 0, s>>>(in, out, n, sums,
+                                                 write_total ? 1 : 0);
+  });
   P1_CUDA(cudaGetLastError());
   pool_free(sums, s);
   return P1_OK;
