@@ -67,55 +67,129 @@ struct LocalOp {
   }
 };
 
+// ------------------------------------------------------------ fill rows
+// One block = ROWS consecutive rows = one contiguous span of the CSR arrays.
+// Every thread builds its row (sorted unique columns by insertion, values
+// accumulated in place) inside a shared-memory image of that span; the block
+// then streams the image out with fully coalesced stores.  HBM traffic per
+// triangle: 24 B neighbour pairs (+12 B records for P1_OP_LOCAL) + gathered
+// coordinates (L1/L2 resident on locally ordered meshes) + 42 B CSR output.
+constexpr int ROWS = THREADS;        // rows per block
+constexpr int STAGE_CAP = ROWS * 20; // CSR entries staged per pass
+
+__device__ __forceinline__ int lower_bound(const int *cols, int n, int c) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (cols[mid] < c) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// sorted insert without duplicates; returns the new length
+__device__ __forceinline__ int insert_unique(int *cols, int n, int c) {
+  int j = n;
+  while (j > 0 && cols[j - 1] > c) --j;
+  if (j > 0 && cols[j - 1] == c) return n;
+  for (int m = n; m > j; --m) cols[m] = cols[m - 1];
+  cols[j] = c;
+  return n + 1;
+}
+
+template <class Op>
+__device__ __forceinline__ void build_row(int self, const int2 *__restrict__ nb,
+                                          const uint32_t *__restrict__ rec, int deg,
+                                          const double2 *__restrict__ coords, const Op &op,
+                                          int *cs, double *vs, int len) {
+  int n = insert_unique(cs, 0, self);
+  for (int i = 0; i < deg; ++i) {
+    const int2 p = nb[i];
+    n = insert_unique(cs, n, p.x);
+    n = insert_unique(cs, n, nbr_prev(p));
+  }
+  for (int j = 0; j < len; ++j) vs[j] = 0.;
+  const int js = lower_bound(cs, len, self);
+  double2 zs = make_double2(0., 0.);
+  if (Op::needs_coords) zs = __ldg(coords + self);
+  // canonical summation order: records by ascending `next` (the order of the
+  // columns), independent of the order the scatter happened to produce
+  for (int j = 0; j < len; ++j) {
+    const int c = cs[j];
+    for (int i = 0; i < deg; ++i) {
+      const int2 p = nb[i];
+      if (p.x != c) continue;
+      const int pv = nbr_prev(p), k = nbr_k(p);
+      Tri t;
+      if (Op::needs_coords)
+        t = element_order(k, zs, __ldg(coords + c), __ldg(coords + pv));
+      double vd, vn, vp;
+      op.row(Op::needs_coords ? 0 : (int64_t)(rec[i] >> 2), k, t, vd, vn, vp);
+      vs[js] += vd;
+      vs[j] += vn;
+      vs[lower_bound(cs, len, pv)] += vp;
+    }
+  }
+}
+
 template <class Op>
 __global__ void __launch_bounds__(THREADS)
 fill_rows_kernel(int n_own, int rb, const int *__restrict__ rec_off,
                  const uint32_t *__restrict__ rec, const int2 *__restrict__ nbr,
                  const int *__restrict__ indptr, const double2 *__restrict__ coords,
                  Op op, int *__restrict__ indices, double *__restrict__ data) {
-  const int a = blockIdx.x * blockDim.x + threadIdx.x;
-  if (a >= n_own) return;
-  const int beg = rec_off[a], deg = rec_off[a + 1] - beg;
-  if (deg == 0 || deg > DEG_MAX) return;
-  int2 nb[DEG_MAX];
-  for (int i = 0; i < deg; ++i) nb[i] = nbr[beg + i];
-  int cols[COL_MAX];
-  const int self = a + rb;
-  const int n = unique_columns(self, nb, deg, cols);
-  double vals[COL_MAX];
-  double2 pos[COL_MAX];
-  for (int j = 0; j < n; ++j) {
-    vals[j] = 0.;
-    if (Op::needs_coords) pos[j] = coords[cols[j]];
+  __shared__ int cols_s[STAGE_CAP];
+  __shared__ double vals_s[STAGE_CAP];
+  __shared__ int chunk_rows;
+  const int row0 = blockIdx.x * ROWS;
+  const int nrows = min(ROWS, n_own - row0);
+  const int tid = threadIdx.x;
+  const int a = row0 + tid;
+  int my_off = 0, my_len = 0, beg = 0, deg = 0;
+  if (tid < nrows) {
+    my_off = indptr[a];
+    my_len = indptr[a + 1] - my_off;
+    beg = rec_off[a];
+    deg = rec_off[a + 1] - beg;
   }
-  const int js = find_column(cols, n, self);
-  for (int i = 0; i < deg; ++i) {
-    const uint32_t r = rec[beg + i];
-    const int k = r & 3;
-    const int jn = find_column(cols, n, nb[i].x);
-    const int jp = find_column(cols, n, nb[i].y);
-    Tri t;
-    if (Op::needs_coords) t = element_order(k, pos[js], pos[jn], pos[jp]);
-    double vd, vn, vp;
-    op.row((int64_t)(r >> 2), k, t, vd, vn, vp);
-    vals[js] += vd;
-    vals[jn] += vn;
-    vals[jp] += vp;
-  }
-  const int64_t base = indptr[a];
-  for (int j = 0; j < n; ++j) {
-    if (indices) indices[base + j] = cols[j];
-    data[base + j] = vals[j];
+  int first = 0;  // first row of the current pass (block-uniform)
+  while (first < nrows) {
+    const int base = indptr[row0 + first];
+    int last = nrows;  // one pass in the common case
+    if (indptr[row0 + nrows] - base > STAGE_CAP) {
+      __syncthreads();
+      if (tid == 0) {
+        int r = first;
+        while (r < nrows && indptr[row0 + r + 1] - base <= STAGE_CAP) ++r;
+        chunk_rows = r == first ? first + 1 : r;  // an oversize row passes alone
+      }
+      __syncthreads();
+      last = chunk_rows;
+    }
+    const int span = indptr[row0 + last] - base;
+    const bool staged = span <= STAGE_CAP;  // false only for a lone big row
+    if (staged && tid >= first && tid < last && deg > 0 && deg <= DEG_BIG)
+      build_row(a + rb, nbr + beg, rec + beg, deg, coords, op,
+                cols_s + (my_off - base), vals_s + (my_off - base), my_len);
+    __syncthreads();
+    if (staged) {
+      for (int i = tid; i < span; i += THREADS) {
+        if (indices) indices[(int64_t)base + i] = cols_s[i];
+        data[(int64_t)base + i] = vals_s[i];
+      }
+    }
+    __syncthreads();
+    first = last;
   }
 }
 
 __device__ __forceinline__ int big_candidate2(int self, const int2 *nb, int j) {
   if (j == 0) return self;
   const int2 p = nb[(j - 1) >> 1];
-  return ((j - 1) & 1) ? p.y : p.x;
+  return ((j - 1) & 1) ? nbr_prev(p) : p.x;
 }
 
-// one block per row with more than DEG_MAX records (see plan.cu)
+// one block per row with more than DEG_BIG records (see plan.cu); runs AFTER
+// fill_rows_kernel and overwrites whatever that kernel staged for these rows
 template <class Op>
 __global__ void __launch_bounds__(THREADS)
 fill_big_kernel(const int *__restrict__ big_rows, int rb,
@@ -137,19 +211,19 @@ fill_big_kernel(const int *__restrict__ big_rows, int rb,
     for (int i = 0; i < ncand; ++i)
       rank += fl[i] && big_candidate2(self, nb, i) < c;
     double sum = 0.;
-    for (int i = 0; i < deg; ++i) {
+    for (int i = 0; i < deg; ++i) {  // records are in (element, vertex) order
       const int2 p = nb[i];
-      if (c != self && p.x != c && p.y != c) continue;
-      const uint32_t r = rec[beg + i];
-      const int k = r & 3;
+      const int px = p.x, py = nbr_prev(p);
+      if (c != self && px != c && py != c) continue;
+      const int k = nbr_k(p);
       Tri t;
       if (Op::needs_coords)
-        t = element_order(k, coords[self], coords[p.x], coords[p.y]);
+        t = element_order(k, coords[self], coords[px], coords[py]);
       double vd, vn, vp;
-      op.row((int64_t)(r >> 2), k, t, vd, vn, vp);
+      op.row((int64_t)(rec[beg + i] >> 2), k, t, vd, vn, vp);
       if (c == self) sum += vd;
-      if (p.x == c) sum += vn;
-      if (p.y == c) sum += vp;
+      if (px == c) sum += vn;
+      if (py == c) sum += vp;
     }
     if (indices) indices[base + rank] = c;
     data[base + rank] = sum;
@@ -162,7 +236,7 @@ int launch_fill(const p1_plan *p, Op op, const double *coords, int32_t *indices,
   const int n_own = (int)(p->row_end - p->row_begin);
   if (n_own > 0)
     P1_TIMED(p->ctx, "fill_rows", s,
-             (fill_rows_kernel<Op><<<grid_for(n_own, THREADS), THREADS, 0, s>>>(
+             (fill_rows_kernel<Op><<<grid_for(n_own, ROWS), THREADS, 0, s>>>(
                  n_own, (int)p->row_begin, p->rec_off, p->rec, p->nbr, p->indptr,
                  (const double2 *)coords, op, indices, data)));
   if (p->n_big > 0)

@@ -28,7 +28,7 @@ twin_kernel(int n_nodes, const int *__restrict__ rec_off,
     const int target = nbr[i].x;  // half-edge a -> target
     int found = -1, hits = 0;
     for (int s = beg; s < end; ++s)
-      if (nbr[s].y == target) { found = s; ++hits; }
+      if (nbr_prev(nbr[s]) == target) { found = s; ++hits; }
     const uint32_t r = rec[i];
     const int64_t he = 3 * (int64_t)(r >> 2) + (r & 3);
     if (hits == 0) {

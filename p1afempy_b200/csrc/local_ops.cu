@@ -521,6 +521,7 @@ extern "C" int p1_load_vector(const p1_plan *plan, const double *coords,
   P1_REQUIRE(M == 0 || (coords && fq), "null argument");
   DeviceGuard guard(plan->ctx->device);
   cudaStream_t s = (cudaStream_t)stream;
+  P1_TRY(ensure_sorted(const_cast<p1_plan *>(plan), s));
   double *w = nullptr, *pts = nullptr, *L = nullptr;
   P1_TRY(upload_small(&w, weights_host, (size_t)n_qp, s));
   P1_TRY(upload_small(&pts, points_host, (size_t)2 * n_qp, s));
@@ -548,6 +549,7 @@ extern "C" int p1_load_vector_midpoint(const p1_plan *plan, const double *coords
   P1_REQUIRE(M == 0 || (coords && f_centroid), "null argument");
   DeviceGuard guard(plan->ctx->device);
   cudaStream_t s = (cudaStream_t)stream;
+  P1_TRY(ensure_sorted(const_cast<p1_plan *>(plan), s));
   double *share = nullptr;
   P1_TRY(pool_alloc(&share, (size_t)M, s));
   if (M > 0)

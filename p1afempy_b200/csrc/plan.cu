@@ -1,5 +1,5 @@
-// plan.cu -- symbolic phase: node -> incident (element, vertex) lists in the
-// fixed order (element, vertex), neighbour pairs, CSR row pointer.
+// plan.cu -- symbolic phase: node -> incident (element, vertex) records with
+// their neighbour pair, and the CSR row pointer.
 //
 // Replaces, for the assembly hot path, what scipy derives on every
 // coo_matrix(...).tocsr() call: coo_tocsr (counting sort by row),
@@ -7,6 +7,9 @@
 // (scipy/sparse/_coo.py:368-439, _compressed.py:1072-1130), but on the 3M
 // (node, element) incidences instead of the 9M triplets: row i of any P1
 // matrix has the columns {i} U {next, prev vertex of every element at i}.
+//
+// HBM traffic per triangle (int32): count 12 B read (+ node counters, L2
+// atomics), scatter 12 B read + 36 B write, rowlen 24 B read + 2 B write.
 #include "plan.cuh"
 
 namespace p1 {
@@ -45,7 +48,7 @@ count_kernel(const int *__restrict__ elements, int64_t M, int N, int rb, int re,
 __global__ void __launch_bounds__(THREADS)
 scatter_kernel(const int *__restrict__ elements, int64_t M, int N, int rb, int re,
                int *__restrict__ cnt, const int *__restrict__ rec_off,
-               uint32_t *__restrict__ rec) {
+               uint32_t *__restrict__ rec, int2 *__restrict__ nbr) {
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < M;
        t += (int64_t)gridDim.x * blockDim.x) {
     int e[3];
@@ -59,73 +62,70 @@ scatter_kernel(const int *__restrict__ elements, int64_t M, int N, int rb, int r
     for (int k = 0; k < 3; ++k)
       if (e[k] >= rb && e[k] < re) {
         const int a = e[k] - rb;
-        const int slot = atomicSub(cnt + a, 1) - 1;
-        rec[rec_off[a] + slot] = ((uint32_t)t << 2) | (uint32_t)k;
+        const int pos = rec_off[a] + atomicSub(cnt + a, 1) - 1;
+        rec[pos] = ((uint32_t)t << 2) | (uint32_t)k;
+        nbr[pos] = make_int2(e[k == 2 ? 0 : k + 1],
+                             e[k == 0 ? 2 : k - 1] | (k << NODE_BITS));
       }
   }
 }
 
 // --------------------------------------------------------------- rowlen
-// One thread per owned row: put its records into the fixed order, look the
-// neighbours up once, count distinct columns.
+// One thread per owned row: number of distinct values in
+// {self} U {next_i} U {prev_i}.  No per-thread arrays: the records of a row
+// are a few contiguous bytes that stay in L1 while they are compared.
 __global__ void __launch_bounds__(THREADS)
-rowlen_kernel(const int *__restrict__ elements, int n_own, int rb,
-              const int *__restrict__ rec_off, uint32_t *__restrict__ rec,
-              int2 *__restrict__ nbr, int *__restrict__ rowlen,
+rowlen_kernel(int n_own, int rb, const int *__restrict__ rec_off,
+              const int2 *__restrict__ nbr, int *__restrict__ rowlen,
               int *__restrict__ big_rows, int *__restrict__ n_big) {
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= n_own) return;
   const int beg = rec_off[a], deg = rec_off[a + 1] - beg;
   if (deg == 0) { rowlen[a] = 0; return; }
-  if (deg > DEG_MAX) {
+  if (deg > DEG_BIG) {
     big_rows[atomicAdd(n_big, 1)] = a;
     rowlen[a] = 0;  // filled in by rowlen_big_kernel
     return;
   }
-  uint32_t r[DEG_MAX];
-  for (int i = 0; i < deg; ++i) {  // insertion sort while loading
-    const uint32_t v = rec[beg + i];
-    int j = i;
-    while (j > 0 && r[j - 1] > v) { r[j] = r[j - 1]; --j; }
-    r[j] = v;
-  }
-  int2 nb[DEG_MAX];
+  const int self = a + rb;
+  const int2 *nb = nbr + beg;
+  int n = 1;
   for (int i = 0; i < deg; ++i) {
-    rec[beg + i] = r[i];
-    const int64_t T = r[i] >> 2;
-    const int k = r[i] & 3;
-    const int nx = __ldg(elements + 3 * T + next_local(k));
-    const int pv = __ldg(elements + 3 * T + prev_local(k));
-    nb[i] = make_int2(nx, pv);
-    nbr[beg + i] = nb[i];
+    const int x = nb[i].x, y = nbr_prev(nb[i]);
+    bool fx = x != self, fy = y != self && y != x;
+    for (int j = 0; j < deg; ++j) {
+      const int2 q = nb[j];
+      const int qx = q.x, qy = nbr_prev(q);
+      // x is new unless an earlier next equals it
+      fx = fx && !(j < i && qx == x);
+      // y is new unless ANY next equals it or an earlier prev does
+      fy = fy && qx != y && !(j < i && qy == y);
+    }
+    n += fx + fy;
   }
-  int cols[COL_MAX];
-  rowlen[a] = unique_columns(a + rb, nb, deg, cols);
+  rowlen[a] = n;
 }
 
-// Rows with more than DEG_MAX records: one block per row, O(deg^2) without
+// Rows with more than DEG_BIG records: one block per row, O(deg^2) without
 // any capacity limit (pathological fans only; never on a shape-regular mesh).
 __global__ void __launch_bounds__(THREADS)
-sort_big_kernel(const int *__restrict__ elements, const int *__restrict__ big_rows,
-                const int *__restrict__ rec_off, uint32_t *__restrict__ rec,
-                uint32_t *__restrict__ tmp, int2 *__restrict__ nbr) {
+sort_big_kernel(const int *__restrict__ big_rows, const int *__restrict__ rec_off,
+                uint32_t *__restrict__ rec, int2 *__restrict__ nbr,
+                uint32_t *__restrict__ tmp_rec, int2 *__restrict__ tmp_nbr) {
   const int a = big_rows[blockIdx.x];
   const int beg = rec_off[a], deg = rec_off[a + 1] - beg;
-  // rank sort (records of one row are distinct)
+  // rank sort by (element, vertex); records of one row are distinct
   for (int i = threadIdx.x; i < deg; i += blockDim.x) {
     const uint32_t v = rec[beg + i];
     int rank = 0;
     for (int j = 0; j < deg; ++j) rank += rec[beg + j] < v;
-    tmp[beg + rank] = v;
+    tmp_rec[beg + rank] = v;
+    tmp_nbr[beg + rank] = nbr[beg + i];
   }
   __syncthreads();
   for (int i = threadIdx.x; i < deg; i += blockDim.x) {
-    const uint32_t v = tmp[beg + i];
-    rec[beg + i] = v;
-    const int64_t T = v >> 2;
-    const int k = v & 3;
-    nbr[beg + i] = make_int2(__ldg(elements + 3 * T + next_local(k)),
-                             __ldg(elements + 3 * T + prev_local(k)));
+    rec[beg + i] = tmp_rec[beg + i];
+    nbr[beg + i] = tmp_nbr[beg + i];
   }
 }
 
@@ -133,7 +133,7 @@ sort_big_kernel(const int *__restrict__ elements, const int *__restrict__ big_ro
 __device__ __forceinline__ int big_candidate(int self, const int2 *nb, int j) {
   if (j == 0) return self;
   const int2 p = nb[(j - 1) >> 1];
-  return ((j - 1) & 1) ? p.y : p.x;
+  return ((j - 1) & 1) ? nbr_prev(p) : p.x;
 }
 
 __global__ void __launch_bounds__(THREADS)
@@ -162,6 +162,43 @@ rowlen_big_kernel(const int *__restrict__ big_rows, int rb,
   if (threadIdx.x == 0) rowlen[a] = total;
 }
 
+// ------------------------------------------------------ (T,k) row order
+__global__ void __launch_bounds__(THREADS)
+sort_rows_kernel(int n_own, const int *__restrict__ rec_off,
+                 const uint32_t *__restrict__ rec, const int2 *__restrict__ nbr,
+                 uint32_t *__restrict__ out_rec, int2 *__restrict__ out_nbr) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= n_own) return;
+  const int beg = rec_off[a], end = rec_off[a + 1];
+  for (int i = beg; i < end; ++i) {
+    const uint32_t v = rec[i];
+    int rank = 0;
+    for (int j = beg; j < end; ++j) rank += rec[j] < v;
+    out_rec[beg + rank] = v;
+    out_nbr[beg + rank] = nbr[i];
+  }
+}
+
+int ensure_sorted(p1_plan *p, cudaStream_t s) {
+  if (p->sorted) return P1_OK;
+  const int n_own = (int)(p->row_end - p->row_begin);
+  uint32_t *r2 = nullptr;
+  int2 *n2 = nullptr;
+  P1_TRY(pool_alloc(&r2, (size_t)p->n_rec, s));
+  P1_TRY(pool_alloc(&n2, (size_t)p->n_rec, s));
+  if (n_own > 0)
+    P1_TIMED(p->ctx, "sort_rows", s,
+             sort_rows_kernel<<<grid_for(n_own, THREADS), THREADS, 0, s>>>(
+                 n_own, p->rec_off, p->rec, p->nbr, r2, n2));
+  P1_CUDA(cudaGetLastError());
+  pool_free(p->rec, s);
+  pool_free(p->nbr, s);
+  p->rec = r2;
+  p->nbr = n2;
+  p->sorted = true;
+  return P1_OK;
+}
+
 }  // namespace p1
 
 using namespace p1;
@@ -174,10 +211,11 @@ extern "C" int p1_plan_create(p1_ctx *ctx, const int32_t *elements,
   P1_REQUIRE(n_elements >= 0 && n_nodes >= 0, "negative size");
   P1_REQUIRE(row_begin >= 0 && row_begin <= row_end && row_end <= n_nodes,
              "row range outside [0, n_nodes]");
-  if (n_nodes > 0x7fffffffLL || n_elements >= (1LL << 30) ||
+  if (n_nodes > (int64_t)NODE_MASK || n_elements >= (1LL << 30) ||
       3 * n_elements + n_nodes > 0x7fffffffLL) {
     set_error("p1_plan_create: mesh too large for int32 device indices "
-              "(M=%lld N=%lld)", (long long)n_elements, (long long)n_nodes);
+              "(M=%lld N=%lld; limits: N < 2^29, 3M+N < 2^31)",
+              (long long)n_elements, (long long)n_nodes);
     return P1_ERANGE;
   }
   P1_REQUIRE(elements || n_elements == 0, "null elements");
@@ -196,8 +234,7 @@ extern "C" int p1_plan_create(p1_ctx *ctx, const int32_t *elements,
 
   int rc = P1_OK;
   int *cnt = nullptr, *d_nbig = nullptr;
-  uint32_t *tmp = nullptr;
-  auto fail = [&](int code) { p1_plan_destroy(p); return code; };
+  auto fail = [&](int code) { pool_free(cnt, s); p1_plan_destroy(p); return code; };
 
   // flags: [0] status, [1] max index, [2] n_big
   if (cudaMemsetAsync(ctx->d_flags, 0, 4 * sizeof(int), s) != cudaSuccess ||
@@ -230,50 +267,52 @@ extern "C" int p1_plan_create(p1_ctx *ctx, const int32_t *elements,
   p->n_rec = n_rec;
   if ((rc = pool_alloc(&p->rec, (size_t)n_rec, s))) return fail(rc);
   if ((rc = pool_alloc(&p->nbr, (size_t)n_rec, s))) return fail(rc);
-  if ((rc = pool_alloc(&p->big_rows, (size_t)(n_rec / (DEG_MAX + 1)) + 1, s)))
+  if ((rc = pool_alloc(&p->big_rows, (size_t)(n_rec / (DEG_BIG + 1)) + 1, s)))
     return fail(rc);
   P1_TIMED(ctx, "scatter", s,
            scatter_kernel<<<eg, THREADS, 0, s>>>(elements, M, N, rb, re, cnt, p->rec_off,
-                                                 p->rec));
+                                                 p->rec, p->nbr));
   d_nbig = ctx->d_flags + 2;
   // cnt is all zero again: reuse it as rowlen
-  P1_TIMED(ctx, "rowlen", s,
-           rowlen_kernel<<<grid_for(n_own, THREADS), THREADS, 0, s>>>(
-               elements, n_own, rb, p->rec_off, p->rec, p->nbr, cnt, p->big_rows, d_nbig));
+  if (n_own > 0)
+    P1_TIMED(ctx, "rowlen", s,
+             rowlen_kernel<<<grid_for(n_own, THREADS), THREADS, 0, s>>>(
+                 n_own, rb, p->rec_off, p->nbr, cnt, p->big_rows, d_nbig));
   cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, 4 * sizeof(int),
                   cudaMemcpyDeviceToHost, s);
   if (cudaStreamSynchronize(s) != cudaSuccess) {
     set_error("p1_plan_create: %s", cudaGetErrorString(cudaGetLastError()));
-    pool_free(cnt, s);
     return fail(P1_ECUDA);
   }
   if (ctx->h_flags[0] & FLAG_INDEX_RANGE) {
     set_error("p1_plan_create: element index out of range [0, %lld)",
               (long long)n_nodes);
-    pool_free(cnt, s);
     return fail(P1_EINDEX);
   }
   p->max_index = ctx->h_flags[1];
   p->n_big = ctx->h_flags[2];
   if (p->n_big > 0) {
-    if ((rc = pool_alloc(&tmp, (size_t)n_rec, s)) ||
+    uint32_t *tmp_rec = nullptr;
+    int2 *tmp_nbr = nullptr;
+    if ((rc = pool_alloc(&tmp_rec, (size_t)n_rec, s)) ||
+        (rc = pool_alloc(&tmp_nbr, (size_t)n_rec, s)) ||
         (rc = pool_alloc(&p->big_first, (size_t)(2 * n_rec + n_own + 1), s))) {
-      pool_free(cnt, s);
+      pool_free(tmp_rec, s);
+      pool_free(tmp_nbr, s);
       return fail(rc);
     }
-    sort_big_kernel<<<p->n_big, THREADS, 0, s>>>(elements, p->big_rows, p->rec_off,
-                                                 p->rec, tmp, p->nbr);
+    sort_big_kernel<<<p->n_big, THREADS, 0, s>>>(p->big_rows, p->rec_off, p->rec, p->nbr,
+                                                 tmp_rec, tmp_nbr);
     rowlen_big_kernel<<<p->n_big, THREADS, 0, s>>>(p->big_rows, rb, p->rec_off,
                                                    p->nbr, p->big_first, cnt);
-    pool_free(tmp, s);
+    pool_free(tmp_rec, s);
+    pool_free(tmp_nbr, s);
   }
-  if ((rc = exclusive_scan_i32(ctx, cnt, p->indptr, n_own, true, s))) {
-    pool_free(cnt, s);
-    return fail(rc);
-  }
+  if ((rc = exclusive_scan_i32(ctx, cnt, p->indptr, n_own, true, s))) return fail(rc);
   int h_nnz = 0;
   cudaMemcpyAsync(&h_nnz, p->indptr + n_own, sizeof(int), cudaMemcpyDeviceToHost, s);
   pool_free(cnt, s);
+  cnt = nullptr;
   cudaError_t e = cudaStreamSynchronize(s);
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) {

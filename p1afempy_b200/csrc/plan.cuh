@@ -12,10 +12,11 @@ struct p1_plan {
   int64_t nnz;
   int max_index;
   int *rec_off;        // n_own+1 : node -> first record
-  uint32_t *rec;       // n_rec   : (T<<2)|k ascending per node
-  int2 *nbr;           // n_rec   : (next, prev) node of the record
+  uint32_t *rec;       // n_rec   : (T<<2)|k, arrival order until `sorted`
+  int2 *nbr;           // n_rec   : x = next node, y = prev node | k<<29
+  bool sorted;         // records of every row ascending in (T,k)
   int *indptr;         // n_own+1
-  int *big_rows;       // local row ids with more than DEG_MAX records
+  int *big_rows;       // local row ids with more than DEG_BIG records
   int n_big;
   unsigned char *big_first;  // scratch flags for big rows (2*n_rec+n_own) or null
   int *twin;           // lazily built: 3M, twin half-edge id T'*3+k' or -1
@@ -24,44 +25,20 @@ struct p1_plan {
 
 namespace p1 {
 
-constexpr int DEG_MAX = 16;               // records per row on the fast path
-constexpr int COL_MAX = 2 * DEG_MAX + 1;  // distinct columns a fast row can have
+// rows with more records than this take the block-per-row path
+constexpr int DEG_BIG = 40;
+// node ids must leave the top 3 bits of an int free (k is packed into nbr.y)
+constexpr int NODE_BITS = 29;
+constexpr int NODE_MASK = (1 << NODE_BITS) - 1;
 
 __device__ __forceinline__ int next_local(int k) { return k == 2 ? 0 : k + 1; }
 __device__ __forceinline__ int prev_local(int k) { return k == 0 ? 2 : k - 1; }
-
-// Sorted, duplicate-free column list of one row: {self} U {next_i} U {prev_i}.
-// `cols` must hold 2*deg+1 ints.  Returns the number of distinct columns.
-__device__ __forceinline__ int unique_columns(int self, const int2 *nb, int deg,
-                                              int *cols) {
-  int n = 0;
-  cols[n++] = self;
-  for (int i = 0; i < deg; ++i) {
-    const int2 p = nb[i];
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int c = h == 0 ? p.x : p.y;
-      // sorted insert, skipping duplicates
-      int j = n;
-      while (j > 0 && cols[j - 1] > c) --j;
-      if (j > 0 && cols[j - 1] == c) continue;
-      for (int m = n; m > j; --m) cols[m] = cols[m - 1];
-      cols[j] = c;
-      ++n;
-    }
-  }
-  return n;
-}
-
-__device__ __forceinline__ int find_column(const int *cols, int n, int c) {
-  int lo = 0, hi = n - 1;
-  while (lo < hi) {
-    int mid = (lo + hi) >> 1;
-    if (cols[mid] < c) lo = mid + 1; else hi = mid;
-  }
-  return lo;
-}
+__device__ __forceinline__ int nbr_prev(int2 p) { return p.y & NODE_MASK; }
+__device__ __forceinline__ int nbr_k(int2 p) { return (int)((unsigned)p.y >> NODE_BITS); }
 
 int ensure_twins(p1_plan *plan, cudaStream_t s);
+// puts the records of every row into ascending (element, vertex) order: the
+// order of the reference's sequential np.bincount (load vectors)
+int ensure_sorted(p1_plan *plan, cudaStream_t s);
 
 }  // namespace p1
