@@ -1,16 +1,21 @@
-// assemble.cu -- numeric phase: one owner per CSR row gathers the local-matrix
-// rows of its incident elements (fixed order: element, vertex), sums duplicates
-// and writes the finished row (sorted unique columns, explicit zeros kept).
+// assemble.cu -- numeric phase: the owner of a CSR row gathers the local-matrix
+// rows of its incident elements, sums duplicates and writes the finished row
+// (sorted unique columns, explicit zeros kept).
 //
 // Arithmetic mirrors the reference expression by expression (compile with
 // -fmad=false): /root/reference/p1afempy/solvers.py:31-45 (stiffness),
 // :176-181 (mass).  Local matrices of the generalised stiffness / weighted
 // mass come precomputed per element (local_ops.cu).
+//
+// Fast path: 8 lanes per row, one record per lane, all-pairs comparison by
+// warp shuffles (plan.cuh: analyse_row) -- no per-thread arrays, no shared
+// memory, no serial sort.  HBM traffic per triangle: 48 B records + gathered
+// coordinates (L1/L2 resident on locally ordered meshes) + 42 B CSR output.
 #include "plan.cuh"
 
 namespace p1 {
 
-constexpr int THREADS = 128;
+constexpr int THREADS = 256;
 
 struct Tri {  // vertex coordinates in ELEMENT order (v0, v1, v2)
   double x0, y0, x1, y1, x2, y2;
@@ -67,15 +72,71 @@ struct LocalOp {
   }
 };
 
-// ------------------------------------------------------------ fill rows
-// One block = ROWS consecutive rows = one contiguous span of the CSR arrays.
-// Every thread builds its row (sorted unique columns by insertion, values
-// accumulated in place) inside a shared-memory image of that span; the block
-// then streams the image out with fully coalesced stores.  HBM traffic per
-// triangle: 24 B neighbour pairs (+12 B records for P1_OP_LOCAL) + gathered
-// coordinates (L1/L2 resident on locally ordered meshes) + 42 B CSR output.
-constexpr int ROWS = THREADS;        // rows per block
-constexpr int STAGE_CAP = ROWS * 20; // CSR entries staged per pass
+// ------------------------------------------------------ fast path: 8 lanes/row
+template <class Op>
+__global__ void __launch_bounds__(THREADS)
+fill_rows_kernel(int n_own, int rb, const int *__restrict__ rec_off,
+                 const int4 *__restrict__ rec, const int *__restrict__ indptr,
+                 const double2 *__restrict__ coords, Op op,
+                 int *__restrict__ indices, double *__restrict__ data) {
+  const int lane = threadIdx.x & 31, lane8 = lane & (GROUP - 1);
+  const int shift = lane & ~(GROUP - 1);
+  const unsigned gmask = 0xffu << shift;
+  const int a = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / GROUP);
+  if (a >= n_own) return;
+  const int beg = __ldg(rec_off + a), deg = __ldg(rec_off + a + 1) - beg;
+  if (deg == 0 || deg > GROUP) return;  // group-uniform
+  const int self = a + rb;
+  const RowLane r = analyse_row(self, beg, deg, rec, gmask, lane8, shift);
+  if (!r.simple) return;  // group-uniform; fill_slow_kernel takes the row
+
+  Tri t;
+  if (Op::needs_coords) {
+    const double2 zs = __ldg(coords + self);
+    double2 zn = make_double2(0., 0.);
+    if (r.valid) zn = __ldg(coords + r.nx);
+    // the previous vertex is the `next` of the element before me in the fan
+    const int from = r.src < 0 ? 0 : r.src;
+    double2 zp;
+    zp.x = __shfl_sync(gmask, zn.x, from, GROUP);
+    zp.y = __shfl_sync(gmask, zn.y, from, GROUP);
+    if (r.extra) zp = __ldg(coords + r.pv);  // open fan end
+    t = element_order(r.k, zs, zn, zp);
+  }
+  double vd = 0., vn = 0., vp = 0.;
+  if (r.valid) op.row((int64_t)r.elem, r.k, t, vd, vn, vp);
+
+  // column `next`: my (k,k+1) entry plus the (k,k+2) entry of the element
+  // after me in the fan (two terms: order-free)
+  const double vp_mate = __shfl_sync(gmask, vp, r.mate < 0 ? 0 : r.mate, GROUP);
+  const double off = r.mate < 0 ? vn : vn + vp_mate;
+  // diagonal: fixed order = ascending `next`
+  double diag = 0.;
+  for (int q = 0; q < deg; ++q) {
+    const unsigned who = (__ballot_sync(gmask, r.valid && r.rk == q) & gmask) >> shift;
+    diag += __shfl_sync(gmask, vd, __ffs(who) - 1, GROUP);
+  }
+  const int64_t base = __ldg(indptr + a);
+  if (r.valid) {
+    if (indices) indices[base + r.slot_nx] = r.nx;
+    data[base + r.slot_nx] = off;
+    if (r.extra) {
+      if (indices) indices[base + r.slot_pv] = r.pv;
+      data[base + r.slot_pv] = vp;
+    }
+  }
+  if (lane8 == 0) {
+    if (indices) indices[base + r.slot_self] = self;
+    data[base + r.slot_self] = diag;
+  }
+}
+
+// -------------------------------------------- slow path: one thread per row
+// more than 8 records, or repeated neighbours (non-manifold / degenerate
+// elements): sorted unique columns by insertion into a private shared-memory
+// slice, values accumulated in the output row itself.
+constexpr int SLOW_THREADS = 64;
+constexpr int SLOW_COLS = 2 * DEG_BIG + 1;
 
 __device__ __forceinline__ int lower_bound(const int *cols, int n, int c) {
   int lo = 0, hi = n;
@@ -86,7 +147,6 @@ __device__ __forceinline__ int lower_bound(const int *cols, int n, int c) {
   return lo;
 }
 
-// sorted insert without duplicates; returns the new length
 __device__ __forceinline__ int insert_unique(int *cols, int n, int c) {
   int j = n;
   while (j > 0 && cols[j - 1] > c) --j;
@@ -97,109 +157,68 @@ __device__ __forceinline__ int insert_unique(int *cols, int n, int c) {
 }
 
 template <class Op>
-__device__ __forceinline__ void build_row(int self, const int2 *__restrict__ nb,
-                                          const uint32_t *__restrict__ rec, int deg,
-                                          const double2 *__restrict__ coords, const Op &op,
-                                          int *cs, double *vs, int len) {
-  int n = insert_unique(cs, 0, self);
-  for (int i = 0; i < deg; ++i) {
-    const int2 p = nb[i];
-    n = insert_unique(cs, n, p.x);
-    n = insert_unique(cs, n, nbr_prev(p));
-  }
-  for (int j = 0; j < len; ++j) vs[j] = 0.;
-  const int js = lower_bound(cs, len, self);
-  double2 zs = make_double2(0., 0.);
-  if (Op::needs_coords) zs = __ldg(coords + self);
-  // canonical summation order: records by ascending `next` (the order of the
-  // columns), independent of the order the scatter happened to produce
-  for (int j = 0; j < len; ++j) {
-    const int c = cs[j];
-    for (int i = 0; i < deg; ++i) {
-      const int2 p = nb[i];
-      if (p.x != c) continue;
-      const int pv = nbr_prev(p), k = nbr_k(p);
-      Tri t;
-      if (Op::needs_coords)
-        t = element_order(k, zs, __ldg(coords + c), __ldg(coords + pv));
-      double vd, vn, vp;
-      op.row(Op::needs_coords ? 0 : (int64_t)(rec[i] >> 2), k, t, vd, vn, vp);
-      vs[js] += vd;
-      vs[j] += vn;
-      vs[lower_bound(cs, len, pv)] += vp;
-    }
-  }
-}
-
-template <class Op>
-__global__ void __launch_bounds__(THREADS)
-fill_rows_kernel(int n_own, int rb, const int *__restrict__ rec_off,
-                 const uint32_t *__restrict__ rec, const int2 *__restrict__ nbr,
+__global__ void __launch_bounds__(SLOW_THREADS)
+fill_slow_kernel(const int *__restrict__ slow_rows, int n_slow, int rb,
+                 const int *__restrict__ rec_off, const int4 *__restrict__ rec,
                  const int *__restrict__ indptr, const double2 *__restrict__ coords,
                  Op op, int *__restrict__ indices, double *__restrict__ data) {
-  __shared__ int cols_s[STAGE_CAP];
-  __shared__ double vals_s[STAGE_CAP];
-  __shared__ int chunk_rows;
-  const int row0 = blockIdx.x * ROWS;
-  const int nrows = min(ROWS, n_own - row0);
-  const int tid = threadIdx.x;
-  const int a = row0 + tid;
-  int my_off = 0, my_len = 0, beg = 0, deg = 0;
-  if (tid < nrows) {
-    my_off = indptr[a];
-    my_len = indptr[a + 1] - my_off;
-    beg = rec_off[a];
-    deg = rec_off[a + 1] - beg;
+  __shared__ int cols_s[SLOW_THREADS * SLOW_COLS];
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_slow) return;
+  const int a = slow_rows[idx];
+  const int beg = rec_off[a], deg = rec_off[a + 1] - beg;
+  const int self = a + rb;
+  const int4 *nb = rec + beg;
+  int *cs = cols_s + threadIdx.x * SLOW_COLS;
+  int n = insert_unique(cs, 0, self);
+  for (int i = 0; i < deg; ++i) {
+    n = insert_unique(cs, n, rec_next(nb[i]));
+    n = insert_unique(cs, n, rec_prev(nb[i]));
   }
-  int first = 0;  // first row of the current pass (block-uniform)
-  while (first < nrows) {
-    const int base = indptr[row0 + first];
-    int last = nrows;  // one pass in the common case
-    if (indptr[row0 + nrows] - base > STAGE_CAP) {
-      __syncthreads();
-      if (tid == 0) {
-        int r = first;
-        while (r < nrows && indptr[row0 + r + 1] - base <= STAGE_CAP) ++r;
-        chunk_rows = r == first ? first + 1 : r;  // an oversize row passes alone
-      }
-      __syncthreads();
-      last = chunk_rows;
+  const int64_t base = indptr[a];
+  double *vs = data + base;
+  for (int j = 0; j < n; ++j) {
+    if (indices) indices[base + j] = cs[j];
+    vs[j] = 0.;
+  }
+  const int js = lower_bound(cs, n, self);
+  double2 zs = make_double2(0., 0.);
+  if (Op::needs_coords) zs = coords[self];
+  // fixed summation order: ascending `next`, ties in stored order
+  for (int j = 0; j < n; ++j) {
+    const int c = cs[j];
+    for (int i = 0; i < deg; ++i) {
+      const int4 p = nb[i];
+      if (rec_next(p) != c) continue;
+      const int pv = rec_prev(p), k = rec_k(p);
+      Tri t;
+      if (Op::needs_coords) t = element_order(k, zs, coords[c], coords[pv]);
+      double vd, vn, vp;
+      op.row((int64_t)rec_elem(p), k, t, vd, vn, vp);
+      vs[js] += vd;
+      vs[j] += vn;
+      vs[lower_bound(cs, n, pv)] += vp;
     }
-    const int span = indptr[row0 + last] - base;
-    const bool staged = span <= STAGE_CAP;  // false only for a lone big row
-    if (staged && tid >= first && tid < last && deg > 0 && deg <= DEG_BIG)
-      build_row(a + rb, nbr + beg, rec + beg, deg, coords, op,
-                cols_s + (my_off - base), vals_s + (my_off - base), my_len);
-    __syncthreads();
-    if (staged) {
-      for (int i = tid; i < span; i += THREADS) {
-        if (indices) indices[(int64_t)base + i] = cols_s[i];
-        data[(int64_t)base + i] = vals_s[i];
-      }
-    }
-    __syncthreads();
-    first = last;
   }
 }
 
-__device__ __forceinline__ int big_candidate2(int self, const int2 *nb, int j) {
+// ------------------------------------------------ big path: one block per row
+__device__ __forceinline__ int big_candidate2(int self, const int4 *nb, int j) {
   if (j == 0) return self;
-  const int2 p = nb[(j - 1) >> 1];
-  return ((j - 1) & 1) ? nbr_prev(p) : p.x;
+  const int4 p = nb[(j - 1) >> 1];
+  return ((j - 1) & 1) ? rec_prev(p) : rec_next(p);
 }
 
-// one block per row with more than DEG_BIG records (see plan.cu); runs AFTER
-// fill_rows_kernel and overwrites whatever that kernel staged for these rows
 template <class Op>
 __global__ void __launch_bounds__(THREADS)
 fill_big_kernel(const int *__restrict__ big_rows, int rb,
-                const int *__restrict__ rec_off, const uint32_t *__restrict__ rec,
-                const int2 *__restrict__ nbr, const unsigned char *__restrict__ first,
+                const int *__restrict__ rec_off, const int4 *__restrict__ rec,
+                const unsigned char *__restrict__ first,
                 const int *__restrict__ indptr, const double2 *__restrict__ coords,
                 Op op, int *__restrict__ indices, double *__restrict__ data) {
   const int a = big_rows[blockIdx.x];
   const int beg = rec_off[a], deg = rec_off[a + 1] - beg;
-  const int2 *nb = nbr + beg;
+  const int4 *nb = rec + beg;
   const unsigned char *fl = first + 2 * (int64_t)beg + a;
   const int self = a + rb;
   const int ncand = 2 * deg + 1;
@@ -212,15 +231,15 @@ fill_big_kernel(const int *__restrict__ big_rows, int rb,
       rank += fl[i] && big_candidate2(self, nb, i) < c;
     double sum = 0.;
     for (int i = 0; i < deg; ++i) {  // records are in (element, vertex) order
-      const int2 p = nb[i];
-      const int px = p.x, py = nbr_prev(p);
+      const int4 p = nb[i];
+      const int px = rec_next(p), py = rec_prev(p);
       if (c != self && px != c && py != c) continue;
-      const int k = nbr_k(p);
+      const int k = rec_k(p);
       Tri t;
       if (Op::needs_coords)
         t = element_order(k, coords[self], coords[px], coords[py]);
       double vd, vn, vp;
-      op.row((int64_t)(rec[beg + i] >> 2), k, t, vd, vn, vp);
+      op.row((int64_t)rec_elem(p), k, t, vd, vn, vp);
       if (c == self) sum += vd;
       if (px == c) sum += vn;
       if (py == c) sum += vp;
@@ -234,15 +253,21 @@ template <class Op>
 int launch_fill(const p1_plan *p, Op op, const double *coords, int32_t *indices,
                 double *data, cudaStream_t s) {
   const int n_own = (int)(p->row_end - p->row_begin);
+  const int rb = (int)p->row_begin;
+  const double2 *xy = (const double2 *)coords;
   if (n_own > 0)
     P1_TIMED(p->ctx, "fill_rows", s,
-             (fill_rows_kernel<Op><<<grid_for(n_own, ROWS), THREADS, 0, s>>>(
-                 n_own, (int)p->row_begin, p->rec_off, p->rec, p->nbr, p->indptr,
-                 (const double2 *)coords, op, indices, data)));
+             (fill_rows_kernel<Op><<<grid_for((int64_t)n_own * GROUP, THREADS), THREADS, 0, s>>>(
+                 n_own, rb, p->rec_off, p->rec, p->indptr, xy, op, indices, data)));
+  if (p->n_slow > 0)
+    P1_TIMED(p->ctx, "fill_slow", s,
+             (fill_slow_kernel<Op><<<grid_for(p->n_slow, SLOW_THREADS), SLOW_THREADS, 0, s>>>(
+                 p->slow_rows, p->n_slow, rb, p->rec_off, p->rec, p->indptr, xy, op,
+                 indices, data)));
   if (p->n_big > 0)
     fill_big_kernel<Op><<<p->n_big, THREADS, 0, s>>>(
-        p->big_rows, (int)p->row_begin, p->rec_off, p->rec, p->nbr, p->big_first,
-        p->indptr, (const double2 *)coords, op, indices, data);
+        p->big_rows, rb, p->rec_off, p->rec, p->big_first, p->indptr, xy, op, indices,
+        data);
   P1_CUDA(cudaGetLastError());
   return P1_OK;
 }

@@ -270,15 +270,15 @@ local_load_midpoint_kernel(const double2 *__restrict__ coords,
 // sequential np.bincount over elements.flatten() (solvers.py:593-596).
 __global__ void __launch_bounds__(THREADS)
 gather_load_kernel(int n_own, const int *__restrict__ rec_off,
-                   const uint32_t *__restrict__ rec, const double *__restrict__ L,
+                   const int4 *__restrict__ rec, const double *__restrict__ L,
                    double *__restrict__ b) {
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= n_own) return;
   const int beg = rec_off[a], end = rec_off[a + 1];
   double sum = 0.;
   for (int i = beg; i < end; ++i) {
-    const uint32_t r = rec[i];
-    sum += __ldg(L + 3 * (int64_t)(r >> 2) + (r & 3));
+    const int4 r = rec[i];
+    sum += __ldg(L + 3 * (int64_t)rec_elem(r) + rec_k(r));
   }
   b[a] = sum;
 }
@@ -287,7 +287,7 @@ gather_load_kernel(int n_own, const int *__restrict__ rec_off,
 // (solvers.py:422-425)
 __global__ void __launch_bounds__(THREADS)
 gather_load_midpoint_kernel(int n_own, const int *__restrict__ rec_off,
-                            const uint32_t *__restrict__ rec,
+                            const int4 *__restrict__ rec,
                             const double *__restrict__ share, double *__restrict__ b) {
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= n_own) return;
@@ -295,8 +295,8 @@ gather_load_midpoint_kernel(int n_own, const int *__restrict__ rec_off,
   double sum = 0.;
   for (int kk = 0; kk < 3; ++kk)
     for (int i = beg; i < end; ++i) {
-      const uint32_t r = rec[i];
-      if ((int)(r & 3) == kk) sum += __ldg(share + (r >> 2));
+      const int4 r = rec[i];
+      if (rec_k(r) == kk) sum += __ldg(share + rec_elem(r));
     }
   b[a] = sum;
 }

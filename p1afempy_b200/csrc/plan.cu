@@ -8,8 +8,10 @@
 // (node, element) incidences instead of the 9M triplets: row i of any P1
 // matrix has the columns {i} U {next, prev vertex of every element at i}.
 //
-// HBM traffic per triangle (int32): count 12 B read (+ node counters, L2
-// atomics), scatter 12 B read + 36 B write, rowlen 24 B read + 2 B write.
+// The kernels here are bound by L2 transactions (one 32 B sector per random
+// access), not by HBM bytes, so the layout minimises accesses per incidence:
+// count = 1 atomic; scatter = 1 atomic (cursor preloaded with the row offset)
+// + 1 aligned 16 B store; rowlen = coalesced 16 B loads, shuffles only.
 #include "plan.cuh"
 
 namespace p1 {
@@ -44,11 +46,10 @@ count_kernel(const int *__restrict__ elements, int64_t M, int N, int rb, int re,
 }
 
 // -------------------------------------------------------------- scatter
-// cnt holds the per-node counts on entry and zeros on exit.
+// cursor[a] starts at rec_off[a] and ends at rec_off[a+1].
 __global__ void __launch_bounds__(THREADS)
 scatter_kernel(const int *__restrict__ elements, int64_t M, int N, int rb, int re,
-               int *__restrict__ cnt, const int *__restrict__ rec_off,
-               uint32_t *__restrict__ rec, int2 *__restrict__ nbr) {
+               int *__restrict__ cursor, int4 *__restrict__ rec) {
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < M;
        t += (int64_t)gridDim.x * blockDim.x) {
     int e[3];
@@ -61,45 +62,62 @@ scatter_kernel(const int *__restrict__ elements, int64_t M, int N, int rb, int r
 #pragma unroll
     for (int k = 0; k < 3; ++k)
       if (e[k] >= rb && e[k] < re) {
-        const int a = e[k] - rb;
-        const int pos = rec_off[a] + atomicSub(cnt + a, 1) - 1;
-        rec[pos] = ((uint32_t)t << 2) | (uint32_t)k;
-        nbr[pos] = make_int2(e[k == 2 ? 0 : k + 1],
-                             e[k == 0 ? 2 : k - 1] | (k << NODE_BITS));
+        const int pos = atomicAdd(cursor + (e[k] - rb), 1);
+        rec[pos] = make_int4(e[k == 2 ? 0 : k + 1],
+                             e[k == 0 ? 2 : k - 1] | (k << NODE_BITS), (int)t, 0);
       }
   }
 }
 
 // --------------------------------------------------------------- rowlen
-// One thread per owned row: number of distinct values in
-// {self} U {next_i} U {prev_i}.  No per-thread arrays: the records of a row
-// are a few contiguous bytes that stay in L1 while they are compared.
+// 8 lanes per owned row (see analyse_row); rows the fast path does not take
+// are appended to slow_rows / big_rows and counted by the kernels below.
 __global__ void __launch_bounds__(THREADS)
 rowlen_kernel(int n_own, int rb, const int *__restrict__ rec_off,
-              const int2 *__restrict__ nbr, int *__restrict__ rowlen,
-              int *__restrict__ big_rows, int *__restrict__ n_big) {
-  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+              const int4 *__restrict__ rec, int *__restrict__ rowlen,
+              int *__restrict__ slow_rows, int *__restrict__ big_rows,
+              int *__restrict__ counters /* [0] n_big, [1] n_slow */) {
+  const int lane = threadIdx.x & 31, lane8 = lane & (GROUP - 1);
+  const int shift = lane & ~(GROUP - 1);
+  const unsigned gmask = 0xffu << shift;
+  const int a = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / GROUP);
   if (a >= n_own) return;
-  const int beg = rec_off[a], deg = rec_off[a + 1] - beg;
-  if (deg == 0) { rowlen[a] = 0; return; }
-  if (deg > DEG_BIG) {
-    big_rows[atomicAdd(n_big, 1)] = a;
-    rowlen[a] = 0;  // filled in by rowlen_big_kernel
+  const int beg = __ldg(rec_off + a), deg = __ldg(rec_off + a + 1) - beg;
+  if (deg == 0) {
+    if (lane8 == 0) rowlen[a] = 0;
     return;
   }
+  const RowLane r = analyse_row(a + rb, beg, deg, rec, gmask, lane8, shift);
+  if (lane8 != 0) return;
+  if (r.simple) {
+    rowlen[a] = r.len;
+  } else if (deg > DEG_BIG) {
+    big_rows[atomicAdd(counters, 1)] = a;
+  } else {
+    slow_rows[atomicAdd(counters + 1, 1)] = a;
+  }
+}
+
+// distinct values of {self} U {next_i} U {prev_i}, any number of records;
+// the few contiguous records stay in L1 while they are compared
+__global__ void __launch_bounds__(THREADS)
+rowlen_slow_kernel(const int *__restrict__ slow_rows, int n_slow, int rb,
+                   const int *__restrict__ rec_off, const int4 *__restrict__ rec,
+                   int *__restrict__ rowlen) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_slow) return;
+  const int a = slow_rows[idx];
+  const int beg = rec_off[a], deg = rec_off[a + 1] - beg;
   const int self = a + rb;
-  const int2 *nb = nbr + beg;
+  const int4 *nb = rec + beg;
   int n = 1;
   for (int i = 0; i < deg; ++i) {
-    const int x = nb[i].x, y = nbr_prev(nb[i]);
+    const int x = rec_next(nb[i]), y = rec_prev(nb[i]);
     bool fx = x != self, fy = y != self && y != x;
     for (int j = 0; j < deg; ++j) {
-      const int2 q = nb[j];
-      const int qx = q.x, qy = nbr_prev(q);
-      // x is new unless an earlier next equals it
-      fx = fx && !(j < i && qx == x);
-      // y is new unless ANY next equals it or an earlier prev does
-      fy = fy && qx != y && !(j < i && qy == y);
+      const int qx = rec_next(nb[j]), qy = rec_prev(nb[j]);
+      fx = fx && !(j < i && qx == x);           // an earlier next equals it
+      fy = fy && qx != y && !(j < i && qy == y);  // any next / an earlier prev
     }
     n += fx + fy;
   }
@@ -110,39 +128,38 @@ rowlen_kernel(int n_own, int rb, const int *__restrict__ rec_off,
 // any capacity limit (pathological fans only; never on a shape-regular mesh).
 __global__ void __launch_bounds__(THREADS)
 sort_big_kernel(const int *__restrict__ big_rows, const int *__restrict__ rec_off,
-                uint32_t *__restrict__ rec, int2 *__restrict__ nbr,
-                uint32_t *__restrict__ tmp_rec, int2 *__restrict__ tmp_nbr) {
+                int4 *__restrict__ rec, int4 *__restrict__ tmp) {
   const int a = big_rows[blockIdx.x];
   const int beg = rec_off[a], deg = rec_off[a + 1] - beg;
   // rank sort by (element, vertex); records of one row are distinct
   for (int i = threadIdx.x; i < deg; i += blockDim.x) {
-    const uint32_t v = rec[beg + i];
+    const int4 v = rec[beg + i];
+    const unsigned key = ((unsigned)v.z << 2) | (unsigned)rec_k(v);
     int rank = 0;
-    for (int j = 0; j < deg; ++j) rank += rec[beg + j] < v;
-    tmp_rec[beg + rank] = v;
-    tmp_nbr[beg + rank] = nbr[beg + i];
+    for (int j = 0; j < deg; ++j) {
+      const int4 q = rec[beg + j];
+      rank += (((unsigned)q.z << 2) | (unsigned)rec_k(q)) < key;
+    }
+    tmp[beg + rank] = v;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < deg; i += blockDim.x) {
-    rec[beg + i] = tmp_rec[beg + i];
-    nbr[beg + i] = tmp_nbr[beg + i];
-  }
+  for (int i = threadIdx.x; i < deg; i += blockDim.x) rec[beg + i] = tmp[beg + i];
 }
 
 // candidate j of a big row: 0 = the row itself, 1+2i = next_i, 2+2i = prev_i
-__device__ __forceinline__ int big_candidate(int self, const int2 *nb, int j) {
+__device__ __forceinline__ int big_candidate(int self, const int4 *nb, int j) {
   if (j == 0) return self;
-  const int2 p = nb[(j - 1) >> 1];
-  return ((j - 1) & 1) ? nbr_prev(p) : p.x;
+  const int4 p = nb[(j - 1) >> 1];
+  return ((j - 1) & 1) ? rec_prev(p) : rec_next(p);
 }
 
 __global__ void __launch_bounds__(THREADS)
 rowlen_big_kernel(const int *__restrict__ big_rows, int rb,
-                  const int *__restrict__ rec_off, const int2 *__restrict__ nbr,
+                  const int *__restrict__ rec_off, const int4 *__restrict__ rec,
                   unsigned char *__restrict__ first, int *__restrict__ rowlen) {
   const int a = big_rows[blockIdx.x];
   const int beg = rec_off[a], deg = rec_off[a + 1] - beg;
-  const int2 *nb = nbr + beg;
+  const int4 *nb = rec + beg;
   unsigned char *fl = first + 2 * (int64_t)beg + a;
   const int ncand = 2 * deg + 1;
   int mine = 0;
@@ -165,36 +182,34 @@ rowlen_big_kernel(const int *__restrict__ big_rows, int rb,
 // ------------------------------------------------------ (T,k) row order
 __global__ void __launch_bounds__(THREADS)
 sort_rows_kernel(int n_own, const int *__restrict__ rec_off,
-                 const uint32_t *__restrict__ rec, const int2 *__restrict__ nbr,
-                 uint32_t *__restrict__ out_rec, int2 *__restrict__ out_nbr) {
+                 const int4 *__restrict__ rec, int4 *__restrict__ out) {
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= n_own) return;
   const int beg = rec_off[a], end = rec_off[a + 1];
   for (int i = beg; i < end; ++i) {
-    const uint32_t v = rec[i];
+    const int4 v = rec[i];
+    const unsigned key = ((unsigned)v.z << 2) | (unsigned)rec_k(v);
     int rank = 0;
-    for (int j = beg; j < end; ++j) rank += rec[j] < v;
-    out_rec[beg + rank] = v;
-    out_nbr[beg + rank] = nbr[i];
+    for (int j = beg; j < end; ++j) {
+      const int4 q = rec[j];
+      rank += (((unsigned)q.z << 2) | (unsigned)rec_k(q)) < key;
+    }
+    out[beg + rank] = v;
   }
 }
 
 int ensure_sorted(p1_plan *p, cudaStream_t s) {
   if (p->sorted) return P1_OK;
   const int n_own = (int)(p->row_end - p->row_begin);
-  uint32_t *r2 = nullptr;
-  int2 *n2 = nullptr;
+  int4 *r2 = nullptr;
   P1_TRY(pool_alloc(&r2, (size_t)p->n_rec, s));
-  P1_TRY(pool_alloc(&n2, (size_t)p->n_rec, s));
   if (n_own > 0)
     P1_TIMED(p->ctx, "sort_rows", s,
              sort_rows_kernel<<<grid_for(n_own, THREADS), THREADS, 0, s>>>(
-                 n_own, p->rec_off, p->rec, p->nbr, r2, n2));
+                 n_own, p->rec_off, p->rec, r2));
   P1_CUDA(cudaGetLastError());
   pool_free(p->rec, s);
-  pool_free(p->nbr, s);
   p->rec = r2;
-  p->nbr = n2;
   p->sorted = true;
   return P1_OK;
 }
@@ -233,10 +248,10 @@ extern "C" int p1_plan_create(p1_ctx *ctx, const int32_t *elements,
   *out = nullptr;
 
   int rc = P1_OK;
-  int *cnt = nullptr, *d_nbig = nullptr;
+  int *cnt = nullptr;
   auto fail = [&](int code) { pool_free(cnt, s); p1_plan_destroy(p); return code; };
 
-  // flags: [0] status, [1] max index, [2] n_big
+  // flags: [0] status, [1] max index, [2] n_big, [3] n_slow
   if (cudaMemsetAsync(ctx->d_flags, 0, 4 * sizeof(int), s) != cudaSuccess ||
       cudaMemsetAsync(ctx->d_flags + 1, 0xff, sizeof(int), s) != cudaSuccess) {
     set_error("p1_plan_create: memset failed");
@@ -251,8 +266,8 @@ extern "C" int p1_plan_create(p1_ctx *ctx, const int32_t *elements,
   P1_TIMED(ctx, "count", s,
            count_kernel<<<eg, THREADS, 0, s>>>(elements, M, N, rb, re, cnt, ctx->d_flags));
   if ((rc = exclusive_scan_i32(ctx, cnt, p->rec_off, n_own, true, s))) return fail(rc);
-  // n_rec is needed on the host to size rec/nbr; for the whole matrix it is
-  // 3M, for a row range it is read back
+  // n_rec is needed on the host to size rec; for the whole matrix it is 3M,
+  // for a row range it is read back
   int64_t n_rec = 3 * M;
   if (!(rb == 0 && re == N)) {
     int h = 0;
@@ -266,18 +281,19 @@ extern "C" int p1_plan_create(p1_ctx *ctx, const int32_t *elements,
   }
   p->n_rec = n_rec;
   if ((rc = pool_alloc(&p->rec, (size_t)n_rec, s))) return fail(rc);
-  if ((rc = pool_alloc(&p->nbr, (size_t)n_rec, s))) return fail(rc);
+  if ((rc = pool_alloc(&p->slow_rows, (size_t)(n_rec < n_own ? n_rec : n_own) + 1, s))) return fail(rc);
   if ((rc = pool_alloc(&p->big_rows, (size_t)(n_rec / (DEG_BIG + 1)) + 1, s)))
     return fail(rc);
+  // cursor := row offsets (cnt is free again)
+  cudaMemcpyAsync(cnt, p->rec_off, (size_t)n_own * sizeof(int), cudaMemcpyDeviceToDevice, s);
   P1_TIMED(ctx, "scatter", s,
-           scatter_kernel<<<eg, THREADS, 0, s>>>(elements, M, N, rb, re, cnt, p->rec_off,
-                                                 p->rec, p->nbr));
-  d_nbig = ctx->d_flags + 2;
-  // cnt is all zero again: reuse it as rowlen
+           scatter_kernel<<<eg, THREADS, 0, s>>>(elements, M, N, rb, re, cnt, p->rec));
+  // cnt becomes rowlen (every entry is rewritten)
   if (n_own > 0)
     P1_TIMED(ctx, "rowlen", s,
-             rowlen_kernel<<<grid_for(n_own, THREADS), THREADS, 0, s>>>(
-                 n_own, rb, p->rec_off, p->nbr, cnt, p->big_rows, d_nbig));
+             rowlen_kernel<<<grid_for((int64_t)n_own * GROUP, THREADS), THREADS, 0, s>>>(
+                 n_own, rb, p->rec_off, p->rec, cnt, p->slow_rows, p->big_rows,
+                 ctx->d_flags + 2));
   cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, 4 * sizeof(int),
                   cudaMemcpyDeviceToHost, s);
   if (cudaStreamSynchronize(s) != cudaSuccess) {
@@ -291,22 +307,21 @@ extern "C" int p1_plan_create(p1_ctx *ctx, const int32_t *elements,
   }
   p->max_index = ctx->h_flags[1];
   p->n_big = ctx->h_flags[2];
+  p->n_slow = ctx->h_flags[3];
+  if (p->n_slow > 0)
+    rowlen_slow_kernel<<<grid_for(p->n_slow, THREADS), THREADS, 0, s>>>(
+        p->slow_rows, p->n_slow, rb, p->rec_off, p->rec, cnt);
   if (p->n_big > 0) {
-    uint32_t *tmp_rec = nullptr;
-    int2 *tmp_nbr = nullptr;
-    if ((rc = pool_alloc(&tmp_rec, (size_t)n_rec, s)) ||
-        (rc = pool_alloc(&tmp_nbr, (size_t)n_rec, s)) ||
+    int4 *tmp = nullptr;
+    if ((rc = pool_alloc(&tmp, (size_t)n_rec, s)) ||
         (rc = pool_alloc(&p->big_first, (size_t)(2 * n_rec + n_own + 1), s))) {
-      pool_free(tmp_rec, s);
-      pool_free(tmp_nbr, s);
+      pool_free(tmp, s);
       return fail(rc);
     }
-    sort_big_kernel<<<p->n_big, THREADS, 0, s>>>(p->big_rows, p->rec_off, p->rec, p->nbr,
-                                                 tmp_rec, tmp_nbr);
+    sort_big_kernel<<<p->n_big, THREADS, 0, s>>>(p->big_rows, p->rec_off, p->rec, tmp);
     rowlen_big_kernel<<<p->n_big, THREADS, 0, s>>>(p->big_rows, rb, p->rec_off,
-                                                   p->nbr, p->big_first, cnt);
-    pool_free(tmp_rec, s);
-    pool_free(tmp_nbr, s);
+                                                   p->rec, p->big_first, cnt);
+    pool_free(tmp, s);
   }
   if ((rc = exclusive_scan_i32(ctx, cnt, p->indptr, n_own, true, s))) return fail(rc);
   int h_nnz = 0;
@@ -327,7 +342,7 @@ extern "C" int p1_plan_create(p1_ctx *ctx, const int32_t *elements,
 extern "C" int p1_plan_destroy(p1_plan *p) {
   if (!p) return P1_OK;
   DeviceGuard guard(p->ctx->device);
-  void *blocks[] = {p->rec_off, p->rec, p->nbr, p->indptr, p->big_rows,
+  void *blocks[] = {p->rec_off, p->rec, p->indptr, p->slow_rows, p->big_rows,
                     p->big_first, p->twin};
   for (void *b : blocks) pool_free(b, p->stream);
   delete p;

@@ -1,4 +1,5 @@
-// plan.cuh -- the p1_plan object and helpers shared by the row-owner kernels.
+// plan.cuh -- the p1_plan object and the 8-lane row analysis shared by the
+// symbolic (row length) and numeric (fill) kernels.
 #pragma once
 #include "common.cuh"
 
@@ -12,11 +13,14 @@ struct p1_plan {
   int64_t nnz;
   int max_index;
   int *rec_off;        // n_own+1 : node -> first record
-  uint32_t *rec;       // n_rec   : (T<<2)|k, arrival order until `sorted`
-  int2 *nbr;           // n_rec   : x = next node, y = prev node | k<<29
-  bool sorted;         // records of every row ascending in (T,k)
+  int4 *rec;           // n_rec   : x = next node, y = prev node | k<<29, z = element,
+                       //           w = 0; arrival order within a row until `sorted`
+  bool sorted;         // records of every row ascending in (element, vertex)
   int *indptr;         // n_own+1
-  int *big_rows;       // local row ids with more than DEG_BIG records
+  int *slow_rows;      // rows the 8-lane kernels do not take: more than 8 records
+                       // or repeated neighbours (non-manifold / degenerate)
+  int n_slow;
+  int *big_rows;       // rows with more than DEG_BIG records
   int n_big;
   unsigned char *big_first;  // scratch flags for big rows (2*n_rec+n_own) or null
   int *twin;           // lazily built: 3M, twin half-edge id T'*3+k' or -1
@@ -25,16 +29,85 @@ struct p1_plan {
 
 namespace p1 {
 
-// rows with more records than this take the block-per-row path
-constexpr int DEG_BIG = 40;
-// node ids must leave the top 3 bits of an int free (k is packed into nbr.y)
+constexpr int GROUP = 8;      // lanes per row in the fast kernels = max records
+constexpr int DEG_BIG = 40;   // rows with more records take the block-per-row path
+// node ids must leave the top 3 bits of an int free (k is packed into rec.y)
 constexpr int NODE_BITS = 29;
 constexpr int NODE_MASK = (1 << NODE_BITS) - 1;
 
 __device__ __forceinline__ int next_local(int k) { return k == 2 ? 0 : k + 1; }
 __device__ __forceinline__ int prev_local(int k) { return k == 0 ? 2 : k - 1; }
-__device__ __forceinline__ int nbr_prev(int2 p) { return p.y & NODE_MASK; }
-__device__ __forceinline__ int nbr_k(int2 p) { return (int)((unsigned)p.y >> NODE_BITS); }
+__device__ __forceinline__ int rec_next(const int4 &r) { return r.x; }
+__device__ __forceinline__ int rec_prev(const int4 &r) { return r.y & NODE_MASK; }
+__device__ __forceinline__ int rec_k(const int4 &r) { return (int)((unsigned)r.y >> NODE_BITS); }
+__device__ __forceinline__ int rec_elem(const int4 &r) { return r.z; }
+
+// What one lane of an 8-lane group knows about "its" record and its row after
+// the all-pairs comparison (shuffles only).  A row is `simple` when it has at
+// most 8 records, all `next` distinct, all `prev` distinct and none equal to
+// the row itself -- every row of an edge-manifold mesh of valence <= 8.
+struct RowLane {
+  bool valid;     // this lane holds a record
+  bool simple;    // group-uniform
+  int nx, pv, k, elem;
+  int rk;         // rank of nx among the row's nexts = canonical record order
+  int src;        // lane whose next == my prev (the element before me), or -1
+  int mate;       // lane whose prev == my next (the element after me), or -1
+  bool extra;     // my prev is a column no `next` provides (open fan end)
+  int slot_nx, slot_pv, slot_self;  // positions in the sorted row
+  int len;        // number of distinct columns
+};
+
+__device__ __forceinline__ RowLane analyse_row(int self, int beg, int deg,
+                                               const int4 *__restrict__ rec,
+                                               unsigned gmask, int lane8, int shift) {
+  RowLane o;
+  o.valid = lane8 < deg && deg <= GROUP;
+  int4 r = make_int4(-1, -2, 0, 0);
+  if (o.valid) r = __ldg(rec + beg + lane8);
+  o.nx = rec_next(r);
+  o.pv = o.valid ? rec_prev(r) : -2;
+  o.k = rec_k(r);
+  o.elem = rec_elem(r);
+  bool ok = deg <= GROUP;
+  int rk = 0, src = -1, mate = -1, below_pv = 0, below_self = 0;
+#pragma unroll
+  for (int j = 0; j < GROUP; ++j) {
+    const int qn = __shfl_sync(gmask, o.nx, j, GROUP);
+    const int qp = __shfl_sync(gmask, o.pv, j, GROUP);
+    if (j < deg) {
+      if (qn == self || qp == self) ok = false;
+      if (o.valid) {
+        if (j != lane8 && (qn == o.nx || qp == o.pv)) ok = false;
+        rk += qn < o.nx;
+        below_pv += qn < o.pv;
+        if (qn == o.pv) src = j;
+        if (qp == o.nx) mate = j;
+      }
+      below_self += qn < self;
+    }
+  }
+  o.simple = (__ballot_sync(gmask, !ok) & gmask) == 0;
+  o.rk = rk; o.src = src; o.mate = mate;
+  o.extra = o.valid && src < 0;
+  const unsigned emask = (__ballot_sync(gmask, o.extra) & gmask) >> shift;
+  o.slot_nx = (self < o.nx) + rk;
+  o.slot_pv = (self < o.pv) + below_pv;
+  o.slot_self = below_self;
+  if (emask) {  // open fan: the extra prev columns shift everything above them
+#pragma unroll
+    for (int j = 0; j < GROUP; ++j) {
+      const int qp = __shfl_sync(gmask, o.pv, j, GROUP);
+      if ((emask >> j) & 1) {
+        o.slot_nx += qp < o.nx;
+        o.slot_pv += qp < o.pv;
+        o.slot_self += qp < self;
+      }
+    }
+  }
+  o.len = 1 + deg + __popc(emask);
+  return o;
+}
 
 int ensure_twins(p1_plan *plan, cudaStream_t s);
 // puts the records of every row into ascending (element, vertex) order: the
