@@ -79,15 +79,20 @@ fill_rows_kernel(int n_own, int rb, const int *__restrict__ rec_off,
                  const int4 *__restrict__ rec, const int *__restrict__ indptr,
                  const double2 *__restrict__ coords, Op op,
                  int *__restrict__ indices, double *__restrict__ data) {
+  __shared__ int2 xch[THREADS];
+  __shared__ double2 s_zn[THREADS];
+  __shared__ double s_vp[THREADS];
+  __shared__ double s_vd[THREADS];
   const int lane = threadIdx.x & 31, lane8 = lane & (GROUP - 1);
   const int shift = lane & ~(GROUP - 1);
   const unsigned gmask = 0xffu << shift;
+  const int gbase = threadIdx.x & ~(GROUP - 1);
   const int a = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / GROUP);
   if (a >= n_own) return;
   const int beg = __ldg(rec_off + a), deg = __ldg(rec_off + a + 1) - beg;
   if (deg == 0 || deg > GROUP) return;  // group-uniform
   const int self = a + rb;
-  const RowLane r = analyse_row(self, beg, deg, rec, gmask, lane8, shift);
+  const RowLane r = analyse_row(self, beg, deg, rec, gmask, lane8, shift, xch);
   if (!r.simple) return;  // group-uniform; fill_slow_kernel takes the row
 
   Tri t;
@@ -95,29 +100,23 @@ fill_rows_kernel(int n_own, int rb, const int *__restrict__ rec_off,
     const double2 zs = __ldg(coords + self);
     double2 zn = make_double2(0., 0.);
     if (r.valid) zn = __ldg(coords + r.nx);
+    s_zn[threadIdx.x] = zn;
+    __syncwarp(gmask);
     // the previous vertex is the `next` of the element before me in the fan
-    const int from = r.src < 0 ? 0 : r.src;
-    double2 zp;
-    zp.x = __shfl_sync(gmask, zn.x, from, GROUP);
-    zp.y = __shfl_sync(gmask, zn.y, from, GROUP);
+    double2 zp = s_zn[gbase + (r.src < 0 ? 0 : r.src)];
     if (r.extra) zp = __ldg(coords + r.pv);  // open fan end
     t = element_order(r.k, zs, zn, zp);
   }
   double vd = 0., vn = 0., vp = 0.;
   if (r.valid) op.row((int64_t)r.elem, r.k, t, vd, vn, vp);
-
-  // column `next`: my (k,k+1) entry plus the (k,k+2) entry of the element
-  // after me in the fan (two terms: order-free)
-  const double vp_mate = __shfl_sync(gmask, vp, r.mate < 0 ? 0 : r.mate, GROUP);
-  const double off = r.mate < 0 ? vn : vn + vp_mate;
-  // diagonal: fixed order = ascending `next`
-  double diag = 0.;
-  for (int q = 0; q < deg; ++q) {
-    const unsigned who = (__ballot_sync(gmask, r.valid && r.rk == q) & gmask) >> shift;
-    diag += __shfl_sync(gmask, vd, __ffs(who) - 1, GROUP);
-  }
+  s_vp[threadIdx.x] = vp;
+  if (r.valid) s_vd[gbase + r.rk] = vd;  // canonical order: ascending `next`
+  __syncwarp(gmask);
   const int64_t base = __ldg(indptr + a);
   if (r.valid) {
+    // column `next`: my (k,k+1) entry plus the (k,k+2) entry of the element
+    // after me in the fan (two terms: order-free)
+    const double off = r.mate < 0 ? vn : vn + s_vp[gbase + r.mate];
     if (indices) indices[base + r.slot_nx] = r.nx;
     data[base + r.slot_nx] = off;
     if (r.extra) {
@@ -126,6 +125,8 @@ fill_rows_kernel(int n_own, int rb, const int *__restrict__ rec_off,
     }
   }
   if (lane8 == 0) {
+    double diag = 0.;
+    for (int q = 0; q < deg; ++q) diag += s_vd[gbase + q];
     if (indices) indices[base + r.slot_self] = self;
     data[base + r.slot_self] = diag;
   }

@@ -77,6 +77,7 @@ rowlen_kernel(int n_own, int rb, const int *__restrict__ rec_off,
               const int4 *__restrict__ rec, int *__restrict__ rowlen,
               int *__restrict__ slow_rows, int *__restrict__ big_rows,
               int *__restrict__ counters /* [0] n_big, [1] n_slow */) {
+  __shared__ int2 xch[THREADS];
   const int lane = threadIdx.x & 31, lane8 = lane & (GROUP - 1);
   const int shift = lane & ~(GROUP - 1);
   const unsigned gmask = 0xffu << shift;
@@ -87,7 +88,7 @@ rowlen_kernel(int n_own, int rb, const int *__restrict__ rec_off,
     if (lane8 == 0) rowlen[a] = 0;
     return;
   }
-  const RowLane r = analyse_row(a + rb, beg, deg, rec, gmask, lane8, shift);
+  const RowLane r = analyse_row(a + rb, beg, deg, rec, gmask, lane8, shift, xch);
   if (lane8 != 0) return;
   if (r.simple) {
     rowlen[a] = r.len;

@@ -58,9 +58,14 @@ struct RowLane {
   int len;        // number of distinct columns
 };
 
+// `xch` is one int2 slot per thread of the block (shared memory); lanes of a
+// group exchange (next, prev) through it.  (Shuffles would do, but 16 of them
+// per lane saturate the ADU pipe -- measured 93 % -- while broadcast LDS is
+// one wavefront per warp.)
 __device__ __forceinline__ RowLane analyse_row(int self, int beg, int deg,
                                                const int4 *__restrict__ rec,
-                                               unsigned gmask, int lane8, int shift) {
+                                               unsigned gmask, int lane8, int shift,
+                                               int2 *xch) {
   RowLane o;
   o.valid = lane8 < deg && deg <= GROUP;
   int4 r = make_int4(-1, -2, 0, 0);
@@ -69,22 +74,24 @@ __device__ __forceinline__ RowLane analyse_row(int self, int beg, int deg,
   o.pv = o.valid ? rec_prev(r) : -2;
   o.k = rec_k(r);
   o.elem = rec_elem(r);
+  int2 *grp = xch + (threadIdx.x & ~(GROUP - 1));
+  grp[lane8] = make_int2(o.nx, o.pv);
+  __syncwarp(gmask);
   bool ok = deg <= GROUP;
   int rk = 0, src = -1, mate = -1, below_pv = 0, below_self = 0;
 #pragma unroll
   for (int j = 0; j < GROUP; ++j) {
-    const int qn = __shfl_sync(gmask, o.nx, j, GROUP);
-    const int qp = __shfl_sync(gmask, o.pv, j, GROUP);
+    const int2 q = grp[j];
     if (j < deg) {
-      if (qn == self || qp == self) ok = false;
+      if (q.x == self || q.y == self) ok = false;
       if (o.valid) {
-        if (j != lane8 && (qn == o.nx || qp == o.pv)) ok = false;
-        rk += qn < o.nx;
-        below_pv += qn < o.pv;
-        if (qn == o.pv) src = j;
-        if (qp == o.nx) mate = j;
+        if (j != lane8 && (q.x == o.nx || q.y == o.pv)) ok = false;
+        rk += q.x < o.nx;
+        below_pv += q.x < o.pv;
+        if (q.x == o.pv) src = j;
+        if (q.y == o.nx) mate = j;
       }
-      below_self += qn < self;
+      below_self += q.x < self;
     }
   }
   o.simple = (__ballot_sync(gmask, !ok) & gmask) == 0;
@@ -97,7 +104,7 @@ __device__ __forceinline__ RowLane analyse_row(int self, int beg, int deg,
   if (emask) {  // open fan: the extra prev columns shift everything above them
 #pragma unroll
     for (int j = 0; j < GROUP; ++j) {
-      const int qp = __shfl_sync(gmask, o.pv, j, GROUP);
+      const int qp = grp[j].y;
       if ((emask >> j) & 1) {
         o.slot_nx += qp < o.nx;
         o.slot_pv += qp < o.pv;
