@@ -253,11 +253,11 @@ def run_b200(args):
 
     sampler = ClockSampler(local_rank)
     lib.p1_profile_reset(ctx)
-    lib.p1_profile_enable(ctx, 1)
+    lib.p1_profile_enable(ctx, 0 if os.environ.get('P1_NO_PROF') else 1)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    if rank == 0:
+    if rank == 0 and not os.environ.get('P1_NO_CLOCKS'):
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)

@@ -36,6 +36,10 @@ extern "C" {
                             /* mesh.py:150)                                   */
 #define P1_ERANGE (-5)      /* size exceeds what int32 device indices hold    */
 #define P1_ECOMM (-6)       /* NCCL / multi-GPU error                         */
+#define P1_ERETRY (-7)      /* the plan's closed-fan shortcut was contradicted */
+                            /* by the mesh (non-manifold vertex, degenerate   */
+                            /* element): rebuild the plan with P1_PLAN_EXACT  */
+                            /* and assemble again                             */
 
 typedef struct p1_ctx p1_ctx;
 typedef struct p1_plan p1_plan;
@@ -46,6 +50,9 @@ const char *p1_last_error(void);
 /* One context per (process, device).  Owns the error flags and the pool. */
 int p1_ctx_create(int device, p1_ctx **out);
 int p1_ctx_destroy(p1_ctx *ctx);
+/* Scratch memory is cached in the context between calls (same sizes recur on
+ * the same mesh); p1_ctx_trim returns the unused blocks to the driver. */
+int p1_ctx_trim(p1_ctx *ctx);
 
 /* numpy hands elements over as int64 (refinement.py:641) or uint32
  * (io_helpers.py:91); the device works on int32.  Values outside
@@ -76,9 +83,11 @@ int p1_widen_indices(p1_ctx *ctx, const int32_t *src, int64_t count,
  * matrix (multi-GPU row ownership); pass 0, n_nodes for the whole matrix.
  * SYNCHRONISES the stream once (the caller needs nnz to allocate outputs).
  * ---------------------------------------------------------------------- */
+#define P1_PLAN_DEFAULT 0
+#define P1_PLAN_EXACT 1     /* count the columns of every row by comparison   */
 int p1_plan_create(p1_ctx *ctx, const int32_t *elements, int64_t n_elements,
                    int64_t n_nodes, int64_t row_begin, int64_t row_end,
-                   void *stream, p1_plan **out);
+                   int flags, void *stream, p1_plan **out);
 int p1_plan_destroy(p1_plan *plan);
 /* nnz: stored entries in the owned rows; max_index: largest node index that
  * occurs in `elements` (the reference infers the shape of the stiffness and

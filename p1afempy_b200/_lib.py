@@ -20,6 +20,10 @@ P1_ECUDA = -3
 P1_ETOPOLOGY = -4
 P1_ERANGE = -5
 P1_ECOMM = -6
+P1_ERETRY = -7
+
+PLAN_DEFAULT = 0
+PLAN_EXACT = 1
 
 OP_STIFFNESS = 1
 OP_MASS = 2
@@ -35,12 +39,13 @@ PROTOTYPES = {
     'p1_last_error': [],
     'p1_ctx_create': [_int, C.POINTER(_vp)],
     'p1_ctx_destroy': [_vp],
+    'p1_ctx_trim': [_vp],
     'p1_profile_enable': [_vp, _int],
     'p1_profile_reset': [_vp],
     'p1_profile_report': [_vp, C.c_char_p, _i64],
     'p1_narrow_indices': [_vp, _vp, _int, _i64, _vp, _vp],
     'p1_widen_indices': [_vp, _vp, _i64, _vp, _vp],
-    'p1_plan_create': [_vp, _vp, _i64, _i64, _i64, _i64, _vp, C.POINTER(_vp)],
+    'p1_plan_create': [_vp, _vp, _i64, _i64, _i64, _i64, _int, _vp, C.POINTER(_vp)],
     'p1_plan_destroy': [_vp],
     'p1_plan_info': [_vp, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64),
                      C.POINTER(_i64)],

@@ -1,5 +1,6 @@
 // api.cu -- context lifetime and error text of the C ABI (include/p1b200.h).
 #include "common.cuh"
+#include <mutex>
 #include <vector>
 
 namespace p1 {
@@ -44,7 +45,67 @@ struct p1_prof {
   }
 };
 
+struct p1_arena {
+  struct Block { void *ptr; size_t bytes; bool used; cudaStream_t last; };
+  std::vector<Block> blocks;
+  std::mutex lock;
+};
+
 namespace p1 {
+
+int arena_alloc(p1_ctx *ctx, void **ptr, size_t bytes, cudaStream_t s) {
+  *ptr = nullptr;
+  bytes = (bytes + 511) & ~(size_t)511;
+  p1_arena *ar = ctx->arena;
+  {
+    std::lock_guard<std::mutex> g(ar->lock);
+    int best = -1;
+    for (int i = 0; i < (int)ar->blocks.size(); ++i) {
+      auto &b = ar->blocks[i];
+      if (b.used || b.bytes < bytes || b.bytes > bytes + bytes / 8 + 4096) continue;
+      if (best < 0 || b.bytes < ar->blocks[best].bytes) best = i;
+    }
+    if (best >= 0) {
+      auto &b = ar->blocks[best];
+      // work queued on another stream may still read the block
+      if (b.last != s) cudaStreamSynchronize(b.last);
+      b.used = true;
+      b.last = s;
+      *ptr = b.ptr;
+      return P1_OK;
+    }
+  }
+  void *p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) {
+    // give cached blocks back and try once more
+    {
+      std::lock_guard<std::mutex> g(ar->lock);
+      cudaDeviceSynchronize();
+      for (auto it = ar->blocks.begin(); it != ar->blocks.end();)
+        if (!it->used) { cudaFree(it->ptr); it = ar->blocks.erase(it); } else ++it;
+    }
+    cudaGetLastError();
+    e = cudaMalloc(&p, bytes);
+  }
+  if (e != cudaSuccess) {
+    set_error("out of device memory: %zu bytes: %s", bytes, cudaGetErrorString(e));
+    cudaGetLastError();
+    return P1_ECUDA;
+  }
+  std::lock_guard<std::mutex> g(ar->lock);
+  ar->blocks.push_back({p, bytes, true, s});
+  *ptr = p;
+  return P1_OK;
+}
+
+void arena_free(p1_ctx *ctx, void *ptr, cudaStream_t s) {
+  p1_arena *ar = ctx->arena;
+  std::lock_guard<std::mutex> g(ar->lock);
+  for (auto &b : ar->blocks)
+    if (b.ptr == ptr) { b.used = false; b.last = s; return; }
+}
+
 void prof_begin(p1_ctx *ctx, const char *name, cudaStream_t s) {
   if (!ctx || !ctx->prof || !ctx->prof->on) return;
   p1_prof::Span sp{name, ctx->prof->get(), ctx->prof->get()};
@@ -92,6 +153,18 @@ extern "C" int p1_profile_report(p1_ctx *ctx, char *buf, int64_t cap) {
   return P1_OK;
 }
 
+// returns every cached, unused scratch block to the driver
+extern "C" int p1_ctx_trim(p1_ctx *ctx) {
+  P1_REQUIRE(ctx, "null ctx");
+  DeviceGuard guard(ctx->device);
+  std::lock_guard<std::mutex> g(ctx->arena->lock);
+  cudaDeviceSynchronize();
+  auto &bl = ctx->arena->blocks;
+  for (auto it = bl.begin(); it != bl.end();)
+    if (!it->used) { cudaFree(it->ptr); it = bl.erase(it); } else ++it;
+  return P1_OK;
+}
+
 extern "C" int p1_version(void) { return 100; }  // 0.1.0
 
 extern "C" const char *p1_last_error(void) { return g_error; }
@@ -113,18 +186,13 @@ extern "C" int p1_ctx_create(int device, p1_ctx **out) {
               "sm_%d%d", device, prop.major, prop.minor);
     return P1_EINVAL;
   }
-  // scratch comes from the device's default stream-ordered pool; keep freed
-  // blocks cached instead of returning them to the OS at every sync
-  cudaMemPool_t pool;
-  P1_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
-  uint64_t keep = UINT64_MAX;
-  P1_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
   p1_ctx *ctx = new p1_ctx();
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
   ctx->d_flags = nullptr;
   ctx->h_flags = nullptr;
   ctx->prof = nullptr;
+  ctx->arena = new p1_arena();
   if (cudaMalloc((void **)&ctx->d_flags, 4 * sizeof(int)) != cudaSuccess ||
       cudaMallocHost((void **)&ctx->h_flags, 4 * sizeof(int)) != cudaSuccess) {
     set_error("p1_ctx_create: allocation failed: %s",
@@ -142,6 +210,11 @@ extern "C" int p1_ctx_destroy(p1_ctx *ctx) {
   if (ctx->d_flags) cudaFree(ctx->d_flags);
   if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
   if (ctx->prof) { ctx->prof->drain(); delete ctx->prof; }
+  if (ctx->arena) {
+    cudaDeviceSynchronize();
+    for (auto &b : ctx->arena->blocks) cudaFree(b.ptr);
+    delete ctx->arena;
+  }
   delete ctx;
   return P1_OK;
 }

@@ -1,46 +1,65 @@
-// assemble.cu -- numeric phase: the owner of a CSR row gathers the local-matrix
-// rows of its incident elements, sums duplicates and writes the finished row
-// (sorted unique columns, explicit zeros kept).
+// assemble.cu -- numeric phase.
 //
-// Arithmetic mirrors the reference expression by expression (compile with
-// -fmad=false): /root/reference/p1afempy/solvers.py:31-45 (stiffness),
-// :176-181 (mass).  Local matrices of the generalised stiffness / weighted
-// mass come precomputed per element (local_ops.cu).
+// Step 1 (one thread per triangle): the coefficients every entry of the local
+// 3x3 matrix derives from, computed ONCE per element with the reference's
+// arithmetic (compile with -fmad=false): /root/reference/p1afempy/
+// solvers.py:31-45 (stiffness: a, b, c), :176-181 (mass: area/6, area/12).
+// Local matrices of the generalised stiffness / weighted mass come as 9 values
+// per element (local_ops.cu).
+// Step 2: the owner of a CSR row gathers the entries (k,k), (k,k+1), (k,k+2)
+// of its incident elements, sums duplicates in a fixed order and writes the
+// finished row (sorted unique columns, explicit zeros kept).
 //
-// Fast path: 8 lanes per row, one record per lane, all-pairs comparison by
-// warp shuffles (plan.cuh: analyse_row) -- no per-thread arrays, no shared
-// memory, no serial sort.  HBM traffic per triangle: 48 B records + gathered
-// coordinates (L1/L2 resident on locally ordered meshes) + 42 B CSR output.
+// Fast path: 8 lanes per row, one record per lane, all-pairs comparison through
+// shared memory (plan.cuh: analyse_row).  HBM traffic per triangle: 12 B indices
+// + gathered coordinates + 24 B coefficients (step 1); 48 B records + 24 B
+// gathered coefficients + 42 B CSR output (step 2).
 #include "plan.cuh"
 
 namespace p1 {
 
 constexpr int THREADS = 256;
 
-struct Tri {  // vertex coordinates in ELEMENT order (v0, v1, v2)
-  double x0, y0, x1, y1, x2, y2;
-};
-
-// (self, next, prev) -> element order, given the local index k of `self`
-__device__ __forceinline__ Tri element_order(int k, double2 s, double2 n, double2 p) {
-  Tri t;
-  if (k == 0) { t.x0 = s.x; t.y0 = s.y; t.x1 = n.x; t.y1 = n.y; t.x2 = p.x; t.y2 = p.y; }
-  else if (k == 1) { t.x0 = p.x; t.y0 = p.y; t.x1 = s.x; t.y1 = s.y; t.x2 = n.x; t.y2 = n.y; }
-  else { t.x0 = n.x; t.y0 = n.y; t.x1 = p.x; t.y1 = p.y; t.x2 = s.x; t.y2 = s.y; }
-  return t;
+// ------------------------------------------------ per-element coefficients
+__global__ void __launch_bounds__(THREADS)
+elem_stiffness_kernel(const double2 *__restrict__ coords, const int *__restrict__ elements,
+                      int64_t M, double *__restrict__ abc) {
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < M;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const double2 z0 = __ldg(coords + __ldg(elements + 3 * t));
+    const double2 z1 = __ldg(coords + __ldg(elements + 3 * t + 1));
+    const double2 z2 = __ldg(coords + __ldg(elements + 3 * t + 2));
+    const double d21x = z1.x - z0.x, d21y = z1.y - z0.y;
+    const double d31x = z2.x - z0.x, d31y = z2.y - z0.y;
+    const double area4 = 4. * (0.5 * (d21x * d31y - d21y * d31x));
+    abc[3 * t] = (d21x * d31x + d21y * d31y) / area4;
+    abc[3 * t + 1] = (d31x * d31x + d31y * d31y) / area4;
+    abc[3 * t + 2] = (d21x * d21x + d21y * d21y) / area4;
+  }
 }
 
+__global__ void __launch_bounds__(THREADS)
+elem_mass_kernel(const double2 *__restrict__ coords, const int *__restrict__ elements,
+                 int64_t M, double2 *__restrict__ on_off) {
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < M;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const double2 z0 = __ldg(coords + __ldg(elements + 3 * t));
+    const double2 z1 = __ldg(coords + __ldg(elements + 3 * t + 1));
+    const double2 z2 = __ldg(coords + __ldg(elements + 3 * t + 2));
+    const double d21x = z1.x - z0.x, d21y = z1.y - z0.y;
+    const double d31x = z2.x - z0.x, d31y = z2.y - z0.y;
+    const double area = 0.5 * (d21x * d31y - d21y * d31x);
+    on_off[t] = make_double2(area / 6., area / 12.);
+  }
+}
+
+// row k of the local matrix of element T: entries (k,k), (k,k+1), (k,k+2)
 struct StiffnessOp {
-  static constexpr bool needs_coords = true;
-  // row k of the local stiffness matrix: (k,k), (k,k+1), (k,k+2)
-  __device__ __forceinline__ void row(int64_t, int k, const Tri &t, double &vd,
-                                      double &vn, double &vp) const {
-    const double d21x = t.x1 - t.x0, d21y = t.y1 - t.y0;
-    const double d31x = t.x2 - t.x0, d31y = t.y2 - t.y0;
-    const double area4 = 4. * (0.5 * (d21x * d31y - d21y * d31x));
-    const double a = (d21x * d31x + d21y * d31y) / area4;
-    const double b = (d31x * d31x + d31y * d31y) / area4;
-    const double c = (d21x * d21x + d21y * d21y) / area4;
+  const double *__restrict__ abc;  // M x 3
+  __device__ __forceinline__ void row(int64_t T, int k, double &vd, double &vn,
+                                      double &vp) const {
+    const double a = __ldg(abc + 3 * T), b = __ldg(abc + 3 * T + 1),
+                 c = __ldg(abc + 3 * T + 2);
     if (k == 0) { vd = -2. * a + b + c; vn = a - b; vp = a - c; }
     else if (k == 1) { vd = b; vn = -a; vp = a - b; }
     else { vd = c; vn = a - c; vp = -a; }
@@ -48,23 +67,18 @@ struct StiffnessOp {
 };
 
 struct MassOp {
-  static constexpr bool needs_coords = true;
-  __device__ __forceinline__ void row(int64_t, int, const Tri &t, double &vd,
-                                      double &vn, double &vp) const {
-    const double d21x = t.x1 - t.x0, d21y = t.y1 - t.y0;
-    const double d31x = t.x2 - t.x0, d31y = t.y2 - t.y0;
-    const double area = 0.5 * (d21x * d31y - d21y * d31x);
-    vd = area / 6.;
-    vn = area / 12.;
-    vp = vn;
+  const double2 *__restrict__ on_off;  // M: (area/6, area/12)
+  __device__ __forceinline__ void row(int64_t T, int, double &vd, double &vn,
+                                      double &vp) const {
+    const double2 m = __ldg(on_off + T);
+    vd = m.x; vn = m.y; vp = m.y;
   }
 };
 
 struct LocalOp {
-  static constexpr bool needs_coords = false;
   const double *__restrict__ local;  // M x 9 row-major
-  __device__ __forceinline__ void row(int64_t T, int k, const Tri &, double &vd,
-                                      double &vn, double &vp) const {
+  __device__ __forceinline__ void row(int64_t T, int k, double &vd, double &vn,
+                                      double &vp) const {
     const double *m = local + 9 * T + 3 * k;
     vd = __ldg(m + k);
     vn = __ldg(m + next_local(k));
@@ -75,12 +89,12 @@ struct LocalOp {
 // ------------------------------------------------------ fast path: 8 lanes/row
 template <class Op>
 __global__ void __launch_bounds__(THREADS)
-fill_rows_kernel(int n_own, int rb, const int *__restrict__ rec_off,
-                 const int4 *__restrict__ rec, const int *__restrict__ indptr,
-                 const double2 *__restrict__ coords, Op op,
-                 int *__restrict__ indices, double *__restrict__ data) {
+fill_rows_kernel(int n_own, int rb, int exact,
+                 const unsigned long long *__restrict__ acc,
+                 const int *__restrict__ rec_off, const int4 *__restrict__ rec,
+                 const int *__restrict__ indptr, Op op, int *__restrict__ indices,
+                 double *__restrict__ data, int *__restrict__ flags) {
   __shared__ int2 xch[THREADS];
-  __shared__ double2 s_zn[THREADS];
   __shared__ double s_vp[THREADS];
   __shared__ double s_vd[THREADS];
   const int lane = threadIdx.x & 31, lane8 = lane & (GROUP - 1);
@@ -89,26 +103,22 @@ fill_rows_kernel(int n_own, int rb, const int *__restrict__ rec_off,
   const int gbase = threadIdx.x & ~(GROUP - 1);
   const int a = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / GROUP);
   if (a >= n_own) return;
-  const int beg = __ldg(rec_off + a), deg = __ldg(rec_off + a + 1) - beg;
-  if (deg == 0 || deg > GROUP) return;  // group-uniform
+  const unsigned long long v = __ldg(acc + a);
+  const int deg = (int)(unsigned)v;
+  // group-uniform exits: empty rows; rows the slow / big kernels take
+  if (deg == 0 || deg > GROUP) return;
+  if (!exact && (unsigned)(v >> 32) != 0u) return;
+  const int beg = __ldg(rec_off + a);
   const int self = a + rb;
   const RowLane r = analyse_row(self, beg, deg, rec, gmask, lane8, shift, xch);
-  if (!r.simple) return;  // group-uniform; fill_slow_kernel takes the row
-
-  Tri t;
-  if (Op::needs_coords) {
-    const double2 zs = __ldg(coords + self);
-    double2 zn = make_double2(0., 0.);
-    if (r.valid) zn = __ldg(coords + r.nx);
-    s_zn[threadIdx.x] = zn;
-    __syncwarp(gmask);
-    // the previous vertex is the `next` of the element before me in the fan
-    double2 zp = s_zn[gbase + (r.src < 0 ? 0 : r.src)];
-    if (r.extra) zp = __ldg(coords + r.pv);  // open fan end
-    t = element_order(r.k, zs, zn, zp);
+  if (!r.simple || (!exact && r.len != 1 + deg)) {
+    // exact plan: the row is in slow_rows.  Hash plan: the shortcut
+    // "closed fan => 1 + #records columns" does not hold for this row.
+    if (!exact && lane8 == 0) atomicOr(flags, FLAG_RETRY);
+    return;
   }
   double vd = 0., vn = 0., vp = 0.;
-  if (r.valid) op.row((int64_t)r.elem, r.k, t, vd, vn, vp);
+  if (r.valid) op.row((int64_t)r.elem, r.k, vd, vn, vp);
   s_vp[threadIdx.x] = vp;
   if (r.valid) s_vd[gbase + r.rk] = vd;  // canonical order: ascending `next`
   __syncwarp(gmask);
@@ -133,9 +143,9 @@ fill_rows_kernel(int n_own, int rb, const int *__restrict__ rec_off,
 }
 
 // -------------------------------------------- slow path: one thread per row
-// more than 8 records, or repeated neighbours (non-manifold / degenerate
-// elements): sorted unique columns by insertion into a private shared-memory
-// slice, values accumulated in the output row itself.
+// open fans (boundary nodes), more than 8 records, repeated neighbours
+// (non-manifold / degenerate elements): sorted unique columns by insertion into
+// a private shared-memory slice, values accumulated in the output row itself.
 constexpr int SLOW_THREADS = 64;
 constexpr int SLOW_COLS = 2 * DEG_BIG + 1;
 
@@ -161,8 +171,8 @@ template <class Op>
 __global__ void __launch_bounds__(SLOW_THREADS)
 fill_slow_kernel(const int *__restrict__ slow_rows, int n_slow, int rb,
                  const int *__restrict__ rec_off, const int4 *__restrict__ rec,
-                 const int *__restrict__ indptr, const double2 *__restrict__ coords,
-                 Op op, int *__restrict__ indices, double *__restrict__ data) {
+                 const int *__restrict__ indptr, Op op, int *__restrict__ indices,
+                 double *__restrict__ data) {
   __shared__ int cols_s[SLOW_THREADS * SLOW_COLS];
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n_slow) return;
@@ -183,22 +193,17 @@ fill_slow_kernel(const int *__restrict__ slow_rows, int n_slow, int rb,
     vs[j] = 0.;
   }
   const int js = lower_bound(cs, n, self);
-  double2 zs = make_double2(0., 0.);
-  if (Op::needs_coords) zs = coords[self];
   // fixed summation order: ascending `next`, ties in stored order
   for (int j = 0; j < n; ++j) {
     const int c = cs[j];
     for (int i = 0; i < deg; ++i) {
       const int4 p = nb[i];
       if (rec_next(p) != c) continue;
-      const int pv = rec_prev(p), k = rec_k(p);
-      Tri t;
-      if (Op::needs_coords) t = element_order(k, zs, coords[c], coords[pv]);
       double vd, vn, vp;
-      op.row((int64_t)rec_elem(p), k, t, vd, vn, vp);
+      op.row((int64_t)rec_elem(p), rec_k(p), vd, vn, vp);
       vs[js] += vd;
       vs[j] += vn;
-      vs[lower_bound(cs, n, pv)] += vp;
+      vs[lower_bound(cs, n, rec_prev(p))] += vp;
     }
   }
 }
@@ -215,8 +220,8 @@ __global__ void __launch_bounds__(THREADS)
 fill_big_kernel(const int *__restrict__ big_rows, int rb,
                 const int *__restrict__ rec_off, const int4 *__restrict__ rec,
                 const unsigned char *__restrict__ first,
-                const int *__restrict__ indptr, const double2 *__restrict__ coords,
-                Op op, int *__restrict__ indices, double *__restrict__ data) {
+                const int *__restrict__ indptr, Op op, int *__restrict__ indices,
+                double *__restrict__ data) {
   const int a = big_rows[blockIdx.x];
   const int beg = rec_off[a], deg = rec_off[a + 1] - beg;
   const int4 *nb = rec + beg;
@@ -235,12 +240,8 @@ fill_big_kernel(const int *__restrict__ big_rows, int rb,
       const int4 p = nb[i];
       const int px = rec_next(p), py = rec_prev(p);
       if (c != self && px != c && py != c) continue;
-      const int k = rec_k(p);
-      Tri t;
-      if (Op::needs_coords)
-        t = element_order(k, coords[self], coords[px], coords[py]);
       double vd, vn, vp;
-      op.row((int64_t)rec_elem(p), k, t, vd, vn, vp);
+      op.row((int64_t)rec_elem(p), rec_k(p), vd, vn, vp);
       if (c == self) sum += vd;
       if (px == c) sum += vn;
       if (py == c) sum += vp;
@@ -251,24 +252,23 @@ fill_big_kernel(const int *__restrict__ big_rows, int rb,
 }
 
 template <class Op>
-int launch_fill(const p1_plan *p, Op op, const double *coords, int32_t *indices,
-                double *data, cudaStream_t s) {
+int launch_fill(const p1_plan *p, Op op, int32_t *indices, double *data,
+                cudaStream_t s) {
   const int n_own = (int)(p->row_end - p->row_begin);
   const int rb = (int)p->row_begin;
-  const double2 *xy = (const double2 *)coords;
   if (n_own > 0)
     P1_TIMED(p->ctx, "fill_rows", s,
              (fill_rows_kernel<Op><<<grid_for((int64_t)n_own * GROUP, THREADS), THREADS, 0, s>>>(
-                 n_own, rb, p->rec_off, p->rec, p->indptr, xy, op, indices, data)));
+                 n_own, rb, p->exact ? 1 : 0, p->acc, p->rec_off, p->rec, p->indptr, op,
+                 indices, data, p->ctx->d_flags)));
   if (p->n_slow > 0)
     P1_TIMED(p->ctx, "fill_slow", s,
              (fill_slow_kernel<Op><<<grid_for(p->n_slow, SLOW_THREADS), SLOW_THREADS, 0, s>>>(
-                 p->slow_rows, p->n_slow, rb, p->rec_off, p->rec, p->indptr, xy, op,
-                 indices, data)));
+                 p->slow_rows, p->n_slow, rb, p->rec_off, p->rec, p->indptr, op, indices,
+                 data)));
   if (p->n_big > 0)
     fill_big_kernel<Op><<<p->n_big, THREADS, 0, s>>>(
-        p->big_rows, rb, p->rec_off, p->rec, p->big_first, p->indptr, xy, op, indices,
-        data);
+        p->big_rows, rb, p->rec_off, p->rec, p->big_first, p->indptr, op, indices, data);
   P1_CUDA(cudaGetLastError());
   return P1_OK;
 }
@@ -282,24 +282,58 @@ extern "C" int p1_assemble_csr(const p1_plan *plan, int op, const double *coords
                                int32_t *indices, double *data, void *stream) {
   P1_REQUIRE(plan, "null plan");
   P1_REQUIRE(data || plan->nnz == 0, "null data");
-  DeviceGuard guard(plan->ctx->device);
+  p1_ctx *ctx = plan->ctx;
+  DeviceGuard guard(ctx->device);
   cudaStream_t s = (cudaStream_t)stream;
   const int64_t n_own = plan->row_end - plan->row_begin;
+  const int64_t M = plan->M;
   if (indptr)
     P1_CUDA(cudaMemcpyAsync(indptr, plan->indptr, (n_own + 1) * sizeof(int),
                             cudaMemcpyDeviceToDevice, s));
+  P1_CUDA(cudaMemsetAsync(ctx->d_flags, 0, sizeof(int), s));
+  const unsigned eg = min(grid_for(M, THREADS), (unsigned)(ctx->sm_count * 32));
+  int rc = P1_OK;
+  double *coef = nullptr;
   switch (op) {
     case P1_OP_STIFFNESS:
-      P1_REQUIRE(coords, "stiffness needs coords");
-      return launch_fill(plan, StiffnessOp{}, coords, indices, data, s);
+      P1_REQUIRE(coords || M == 0, "stiffness needs coords");
+      P1_TRY(pool_alloc(ctx, &coef, (size_t)3 * M, s));
+      if (M > 0)
+        P1_TIMED(ctx, "elem_coef", s,
+                 elem_stiffness_kernel<<<eg, THREADS, 0, s>>>(
+                     (const double2 *)coords, plan->elements, M, coef));
+      rc = launch_fill(plan, StiffnessOp{coef}, indices, data, s);
+      break;
     case P1_OP_MASS:
-      P1_REQUIRE(coords, "mass needs coords");
-      return launch_fill(plan, MassOp{}, coords, indices, data, s);
+      P1_REQUIRE(coords || M == 0, "mass needs coords");
+      P1_TRY(pool_alloc(ctx, &coef, (size_t)2 * M, s));
+      if (M > 0)
+        P1_TIMED(ctx, "elem_coef", s,
+                 elem_mass_kernel<<<eg, THREADS, 0, s>>>(
+                     (const double2 *)coords, plan->elements, M, (double2 *)coef));
+      rc = launch_fill(plan, MassOp{(const double2 *)coef}, indices, data, s);
+      break;
     case P1_OP_LOCAL:
-      P1_REQUIRE(local, "P1_OP_LOCAL needs the local matrices");
-      return launch_fill(plan, LocalOp{local}, coords, indices, data, s);
+      P1_REQUIRE(local || M == 0, "P1_OP_LOCAL needs the local matrices");
+      rc = launch_fill(plan, LocalOp{local}, indices, data, s);
+      break;
     default:
       set_error("p1_assemble_csr: unknown op %d", op);
       return P1_EINVAL;
   }
+  pool_free(ctx, coef, s);
+  P1_TRY(rc);
+  if (!plan->exact) {
+    // the closed-fan shortcut is verified while filling: read the verdict
+    P1_CUDA(cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, sizeof(int),
+                            cudaMemcpyDeviceToHost, s));
+    P1_CUDA(cudaStreamSynchronize(s));
+    if (ctx->h_flags[0] & FLAG_RETRY) {
+      set_error("p1_assemble_csr: the mesh contradicts the plan's closed-fan shortcut "
+                "(non-manifold vertex or degenerate element); rebuild the plan with "
+                "P1_PLAN_EXACT");
+      return P1_ERETRY;
+    }
+  }
+  return P1_OK;
 }

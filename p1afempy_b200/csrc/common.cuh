@@ -42,32 +42,40 @@ enum : int {
   FLAG_NONMANIFOLD = 2,    // directed edge appears twice
   FLAG_BOUNDARY_MISS = 4,  // boundary edge not found among element edges
   FLAG_UNCOVERED = 8,      // boundary half-edge not listed in any boundary
+  FLAG_RETRY = 16,         // a row contradicted the closed-fan shortcut: re-plan exactly
 };
 
 }  // namespace p1
 
 struct p1_prof;
+struct p1_arena;
 struct p1_ctx {
   int device;
   int sm_count;
   int *d_flags;        // 4 ints: [0] status bits, [1] max node index, [2..3] spare
   int *h_flags;        // pinned mirror
   p1_prof *prof;       // per-kernel CUDA-event timing, off unless enabled
+  p1_arena *arena;     // cached scratch blocks
 };
 
 namespace p1 {
 
-// Stream-ordered scratch allocation from the device's default pool (the pool
-// keeps freed blocks: release threshold is set to "never" in p1_ctx_create).
+// Scratch memory comes from a context-owned caching arena: freed blocks are
+// kept and handed out again to requests of (nearly) the same size.  The
+// assembly of one mesh repeats the same request sizes every call, so after the
+// first call no cudaMalloc happens on the hot path.  (cudaMallocAsync's pool
+// was tried first: it splits large free blocks for small requests and then
+// regrows, which showed up as 40 ms spikes every few calls.)
+int arena_alloc(p1_ctx *ctx, void **ptr, size_t bytes, cudaStream_t s);
+void arena_free(p1_ctx *ctx, void *ptr, cudaStream_t s);
+
 template <typename T>
-inline int pool_alloc(T **ptr, size_t count, cudaStream_t s) {
-  *ptr = nullptr;
+inline int pool_alloc(p1_ctx *ctx, T **ptr, size_t count, cudaStream_t s) {
   if (count == 0) count = 1;
-  P1_CUDA(cudaMallocAsync((void **)ptr, count * sizeof(T), s));
-  return P1_OK;
+  return arena_alloc(ctx, (void **)ptr, count * sizeof(T), s);
 }
-inline void pool_free(void *ptr, cudaStream_t s) {
-  if (ptr) cudaFreeAsync(ptr, s);
+inline void pool_free(p1_ctx *ctx, void *ptr, cudaStream_t s) {
+  if (ptr) arena_free(ctx, ptr, s);
 }
 
 struct DeviceGuard {

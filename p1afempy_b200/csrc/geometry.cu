@@ -257,8 +257,9 @@ static int full_plan_required(const p1_plan *p, const char *who) {
 
 int ensure_twins(p1_plan *p, cudaStream_t s) {
   if (p->twin) return P1_OK;
+  p1_ctx *ctx = p->ctx;
   P1_TRY(full_plan_required(p, "half-edge twins"));
-  P1_TRY(pool_alloc(&p->twin, (size_t)(3 * p->M), s));
+  P1_TRY(pool_alloc(ctx, &p->twin, (size_t)(3 * p->M), s));
   P1_CUDA(cudaMemsetAsync(p->ctx->d_flags, 0, 4 * sizeof(int), s));
   if (p->N > 0)
     twin_kernel<<<grid_for(p->N, THREADS), THREADS, 0, s>>>(
@@ -266,7 +267,7 @@ int ensure_twins(p1_plan *p, cudaStream_t s) {
   P1_CUDA(cudaGetLastError());
   P1_TRY(read_flags(p->ctx, s));
   if (p->ctx->h_flags[0] & FLAG_NONMANIFOLD) {
-    pool_free(p->twin, s);
+    pool_free(ctx, p->twin, s);
     p->twin = nullptr;
     set_error("mesh is not an edge-manifold: a directed edge occurs in two elements");
     return P1_ETOPOLOGY;
@@ -299,13 +300,13 @@ extern "C" int p1_geometric_data(const p1_plan *cplan, const int32_t *boundary_n
   P1_TRY(ensure_twins(p, s));
   const int64_t total = 3 * M + K;
   int *num = nullptr;
-  P1_TRY(pool_alloc(&num, (size_t)total + 1, s));
+  P1_TRY(pool_alloc(ctx, &num, (size_t)total + 1, s));
   P1_CUDA(cudaMemsetAsync(ctx->d_flags, 0, 4 * sizeof(int), s));
   if (total > 0)
     forward_flags_kernel<<<egrid(ctx, total), THREADS, 0, s>>>(
         p->elements, M, boundary_nodes, K, num, ctx->d_flags);
   int rc = exclusive_scan_i32(ctx, num, num, total, true, s);
-  if (rc) { pool_free(num, s); return rc; }
+  if (rc) { pool_free(ctx, num, s); return rc; }
   if (M > 0)
     element_edges_kernel<<<egrid(ctx, 3 * M), THREADS, 0, s>>>(
         p->elements, M, num, p->twin, (long long *)element2edges, (long long *)edge2nodes);
@@ -314,7 +315,7 @@ extern "C" int p1_geometric_data(const p1_plan *cplan, const int32_t *boundary_n
         boundary_nodes, K, M, (int)p->N, p->rec_off, p->rec, num,
         (long long *)element2edges, (long long *)edge2nodes, (long long *)boundary2edges,
         ctx->d_flags);
-  pool_free(num, s);
+  pool_free(ctx, num, s);
   P1_CUDA(cudaGetLastError());
   P1_TRY(read_flags(ctx, s));
   const int st = ctx->h_flags[0];
@@ -357,7 +358,7 @@ extern "C" int p1_eta_r(const p1_plan *cplan, const double *coords, const double
   }
   if (M == 0) return P1_OK;
   double *dudn = nullptr;
-  P1_TRY(pool_alloc(&dudn, (size_t)(3 * M), s));
+  P1_TRY(pool_alloc(ctx, &dudn, (size_t)(3 * M), s));
   P1_CUDA(cudaMemsetAsync(ctx->d_flags, 0, 4 * sizeof(int), s));
   eta_local_kernel<<<egrid(ctx, M), THREADS, 0, s>>>((const double2 *)coords, x,
                                                      p->elements, M, dudn);
@@ -371,7 +372,7 @@ extern "C" int p1_eta_r(const p1_plan *cplan, const double *coords, const double
         nullptr, dudn, ctx->d_flags);
   eta_final_kernel<<<egrid(ctx, M), THREADS, 0, s>>>((const double2 *)coords, p->elements,
                                                      M, p->twin, dudn, f_centroid, eta);
-  pool_free(dudn, s);
+  pool_free(ctx, dudn, s);
   P1_CUDA(cudaGetLastError());
   P1_TRY(read_flags(ctx, s));
   if (ctx->h_flags[0] & FLAG_INDEX_RANGE) {

@@ -329,8 +329,9 @@ static inline unsigned egrid(const p1_ctx *ctx, int64_t n) {
 
 // copies a small host array to pool memory (valid in stream order)
 template <typename T>
-static int upload_small(T **dst, const T *src_host, size_t count, cudaStream_t s) {
-  P1_TRY(pool_alloc(dst, count, s));
+static int upload_small(p1_ctx *ctx, T **dst, const T *src_host, size_t count,
+                        cudaStream_t s) {
+  P1_TRY(pool_alloc(ctx, dst, count, s));
   P1_CUDA(cudaMemcpyAsync(*dst, src_host, count * sizeof(T), cudaMemcpyHostToDevice, s));
   return P1_OK;
 }
@@ -419,10 +420,10 @@ extern "C" int p1_quadrature_points(p1_ctx *ctx, const double *coords,
   if (M == 0) return P1_OK;
   cudaStream_t s = (cudaStream_t)stream;
   double *pts = nullptr;
-  P1_TRY(upload_small(&pts, points_host, (size_t)2 * n_qp, s));
+  P1_TRY(upload_small(ctx, &pts, points_host, (size_t)2 * n_qp, s));
   quad_points_kernel<<<egrid(ctx, M), THREADS, 0, s>>>(
       (const double2 *)coords, elements, M, (const double2 *)pts, n_qp, (double2 *)xq);
-  pool_free(pts, s);
+  pool_free(ctx, pts, s);
   P1_CUDA(cudaGetLastError());
   return P1_OK;
 }
@@ -437,10 +438,10 @@ extern "C" int p1_nodal_at_quadrature(p1_ctx *ctx, const double *u,
   if (M == 0) return P1_OK;
   cudaStream_t s = (cudaStream_t)stream;
   double *pts = nullptr;
-  P1_TRY(upload_small(&pts, points_host, (size_t)2 * n_qp, s));
+  P1_TRY(upload_small(ctx, &pts, points_host, (size_t)2 * n_qp, s));
   nodal_at_quad_kernel<<<egrid(ctx, M), THREADS, 0, s>>>(
       u, elements, M, (const double2 *)pts, n_qp, uq);
-  pool_free(pts, s);
+  pool_free(ctx, pts, s);
   P1_CUDA(cudaGetLastError());
   return P1_OK;
 }
@@ -481,10 +482,10 @@ extern "C" int p1_local_general_stiffness(p1_ctx *ctx, const double *coords,
   if (M == 0) return P1_OK;
   cudaStream_t s = (cudaStream_t)stream;
   double *w = nullptr;
-  P1_TRY(upload_small(&w, weights_host, (size_t)n_qp, s));
+  P1_TRY(upload_small(ctx, &w, weights_host, (size_t)n_qp, s));
   local_general_kernel<<<egrid(ctx, M), THREADS, 0, s>>>(
       (const double2 *)coords, elements, M, a11q, a12q, a21q, a22q, w, n_qp, local);
-  pool_free(w, s);
+  pool_free(ctx, w, s);
   P1_CUDA(cudaGetLastError());
   return P1_OK;
 }
@@ -500,12 +501,12 @@ extern "C" int p1_local_weighted_mass(p1_ctx *ctx, const double *coords,
   if (M == 0) return P1_OK;
   cudaStream_t s = (cudaStream_t)stream;
   double *w = nullptr, *pts = nullptr;
-  P1_TRY(upload_small(&w, weights_host, (size_t)n_qp, s));
-  P1_TRY(upload_small(&pts, points_host, (size_t)2 * n_qp, s));
+  P1_TRY(upload_small(ctx, &w, weights_host, (size_t)n_qp, s));
+  P1_TRY(upload_small(ctx, &pts, points_host, (size_t)2 * n_qp, s));
   local_wmass_kernel<<<egrid(ctx, M), THREADS, 0, s>>>(
       (const double2 *)coords, elements, M, phiq, w, (const double2 *)pts, n_qp, local);
-  pool_free(w, s);
-  pool_free(pts, s);
+  pool_free(ctx, w, s);
+  pool_free(ctx, pts, s);
   P1_CUDA(cudaGetLastError());
   return P1_OK;
 }
@@ -519,22 +520,23 @@ extern "C" int p1_load_vector(const p1_plan *plan, const double *coords,
   const int n_own = (int)(plan->row_end - plan->row_begin);
   P1_REQUIRE(n_own == 0 || b, "null b");
   P1_REQUIRE(M == 0 || (coords && fq), "null argument");
-  DeviceGuard guard(plan->ctx->device);
+  p1_ctx *ctx = plan->ctx;
+  DeviceGuard guard(ctx->device);
   cudaStream_t s = (cudaStream_t)stream;
   P1_TRY(ensure_sorted(const_cast<p1_plan *>(plan), s));
   double *w = nullptr, *pts = nullptr, *L = nullptr;
-  P1_TRY(upload_small(&w, weights_host, (size_t)n_qp, s));
-  P1_TRY(upload_small(&pts, points_host, (size_t)2 * n_qp, s));
-  P1_TRY(pool_alloc(&L, (size_t)3 * M, s));
+  P1_TRY(upload_small(ctx, &w, weights_host, (size_t)n_qp, s));
+  P1_TRY(upload_small(ctx, &pts, points_host, (size_t)2 * n_qp, s));
+  P1_TRY(pool_alloc(ctx, &L, (size_t)3 * M, s));
   if (M > 0)
     local_load_kernel<<<egrid(plan->ctx, M), THREADS, 0, s>>>(
         (const double2 *)coords, plan->elements, M, fq, w, (const double2 *)pts, n_qp, L);
   if (n_own > 0)
     gather_load_kernel<<<grid_for(n_own, THREADS), THREADS, 0, s>>>(
         n_own, plan->rec_off, plan->rec, L, b);
-  pool_free(L, s);
-  pool_free(w, s);
-  pool_free(pts, s);
+  pool_free(ctx, L, s);
+  pool_free(ctx, w, s);
+  pool_free(ctx, pts, s);
   P1_CUDA(cudaGetLastError());
   return P1_OK;
 }
@@ -547,18 +549,19 @@ extern "C" int p1_load_vector_midpoint(const p1_plan *plan, const double *coords
   const int n_own = (int)(plan->row_end - plan->row_begin);
   P1_REQUIRE(n_own == 0 || b, "null b");
   P1_REQUIRE(M == 0 || (coords && f_centroid), "null argument");
-  DeviceGuard guard(plan->ctx->device);
+  p1_ctx *ctx = plan->ctx;
+  DeviceGuard guard(ctx->device);
   cudaStream_t s = (cudaStream_t)stream;
   P1_TRY(ensure_sorted(const_cast<p1_plan *>(plan), s));
   double *share = nullptr;
-  P1_TRY(pool_alloc(&share, (size_t)M, s));
+  P1_TRY(pool_alloc(ctx, &share, (size_t)M, s));
   if (M > 0)
     local_load_midpoint_kernel<<<egrid(plan->ctx, M), THREADS, 0, s>>>(
         (const double2 *)coords, plan->elements, M, f_centroid, share);
   if (n_own > 0)
     gather_load_midpoint_kernel<<<grid_for(n_own, THREADS), THREADS, 0, s>>>(
         n_own, plan->rec_off, plan->rec, share, b);
-  pool_free(share, s);
+  pool_free(ctx, share, s);
   P1_CUDA(cudaGetLastError());
   return P1_OK;
 }

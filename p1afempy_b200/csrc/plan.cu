@@ -19,9 +19,16 @@ namespace p1 {
 constexpr int THREADS = 256;
 
 // ---------------------------------------------------------------- count
+// One 64-bit atomic per incidence: low word counts the records of the node,
+// high word sums hash(next) - hash(prev).  The nexts and prevs of a closed fan
+// are the same set, so the high word of an interior node ends up 0; a non-zero
+// high word marks the rows whose length is not simply 1 + #records (open fans
+// = boundary nodes, O(sqrt(M)) of them).  The shortcut is verified row by row
+// when the matrix is filled (FLAG_RETRY), so a hash coincidence cannot go
+// unnoticed.
 __global__ void __launch_bounds__(THREADS)
 count_kernel(const int *__restrict__ elements, int64_t M, int N, int rb, int re,
-             int *__restrict__ cnt, int *__restrict__ flags) {
+             unsigned long long *__restrict__ acc, int *__restrict__ flags) {
   int mx = -1;
   bool bad = false;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < M;
@@ -36,13 +43,38 @@ count_kernel(const int *__restrict__ elements, int64_t M, int N, int rb, int re,
       continue;
     }
     mx = max(mx, max(e[0], max(e[1], e[2])));
+    const unsigned h[3] = {mix32((unsigned)e[0]), mix32((unsigned)e[1]),
+                           mix32((unsigned)e[2])};
 #pragma unroll
     for (int k = 0; k < 3; ++k)
-      if (e[k] >= rb && e[k] < re) atomicAdd(cnt + (e[k] - rb), 1);
+      if (e[k] >= rb && e[k] < re) {
+        const unsigned d = h[k == 2 ? 0 : k + 1] - h[k == 0 ? 2 : k - 1];
+        atomicAdd(acc + (e[k] - rb), ((unsigned long long)d << 32) + 1ull);
+      }
   }
   mx = __reduce_max_sync(0xffffffffu, mx);
   if ((threadIdx.x & 31) == 0 && mx >= 0) atomicMax(flags + 1, mx);
   if (bad) atomicOr(flags, FLAG_INDEX_RANGE);
+}
+
+// acc -> per-row record count (for the record offsets) and, unless `exact`,
+// the row length of every regular row; irregular rows are listed.
+__global__ void __launch_bounds__(THREADS)
+split_kernel(int n_own, const unsigned long long *__restrict__ acc, int exact,
+             int *__restrict__ cnt, int *__restrict__ rowlen,
+             int *__restrict__ slow_rows, int *__restrict__ big_rows,
+             int *__restrict__ counters /* [0] n_big, [1] n_slow */) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= n_own) return;
+  const unsigned long long v = acc[a];
+  const int deg = (int)(unsigned)v;
+  cnt[a] = deg;
+  if (exact) return;
+  if (deg == 0) { rowlen[a] = 0; return; }
+  if ((unsigned)(v >> 32) == 0u && deg <= GROUP) { rowlen[a] = 1 + deg; return; }
+  rowlen[a] = 0;  // written by rowlen_slow_kernel / rowlen_big_kernel
+  if (deg > DEG_BIG) big_rows[atomicAdd(counters, 1)] = a;
+  else slow_rows[atomicAdd(counters + 1, 1)] = a;
 }
 
 // -------------------------------------------------------------- scatter
@@ -201,15 +233,16 @@ sort_rows_kernel(int n_own, const int *__restrict__ rec_off,
 
 int ensure_sorted(p1_plan *p, cudaStream_t s) {
   if (p->sorted) return P1_OK;
+  p1_ctx *ctx = p->ctx;
   const int n_own = (int)(p->row_end - p->row_begin);
   int4 *r2 = nullptr;
-  P1_TRY(pool_alloc(&r2, (size_t)p->n_rec, s));
+  P1_TRY(pool_alloc(ctx, &r2, (size_t)p->n_rec, s));
   if (n_own > 0)
     P1_TIMED(p->ctx, "sort_rows", s,
              sort_rows_kernel<<<grid_for(n_own, THREADS), THREADS, 0, s>>>(
                  n_own, p->rec_off, p->rec, r2));
   P1_CUDA(cudaGetLastError());
-  pool_free(p->rec, s);
+  pool_free(ctx, p->rec, s);
   p->rec = r2;
   p->sorted = true;
   return P1_OK;
@@ -221,8 +254,8 @@ using namespace p1;
 
 extern "C" int p1_plan_create(p1_ctx *ctx, const int32_t *elements,
                               int64_t n_elements, int64_t n_nodes,
-                              int64_t row_begin, int64_t row_end, void *stream,
-                              p1_plan **out) {
+                              int64_t row_begin, int64_t row_end, int flags,
+                              void *stream, p1_plan **out) {
   P1_REQUIRE(ctx && out, "null ctx/out");
   P1_REQUIRE(n_elements >= 0 && n_nodes >= 0, "negative size");
   P1_REQUIRE(row_begin >= 0 && row_begin <= row_end && row_end <= n_nodes,
@@ -246,11 +279,17 @@ extern "C" int p1_plan_create(p1_ctx *ctx, const int32_t *elements,
   memset(p, 0, sizeof(*p));
   p->ctx = ctx; p->stream = s; p->elements = elements; p->M = M; p->N = n_nodes;
   p->row_begin = row_begin; p->row_end = row_end;
+  p->exact = (flags & P1_PLAN_EXACT) != 0;
   *out = nullptr;
 
   int rc = P1_OK;
-  int *cnt = nullptr;
-  auto fail = [&](int code) { pool_free(cnt, s); p1_plan_destroy(p); return code; };
+  int *cnt = nullptr, *rowlen = nullptr;
+  auto fail = [&](int code) {
+    pool_free(ctx, cnt, s);
+    pool_free(ctx, rowlen, s);
+    p1_plan_destroy(p);
+    return code;
+  };
 
   // flags: [0] status, [1] max index, [2] n_big, [3] n_slow
   if (cudaMemsetAsync(ctx->d_flags, 0, 4 * sizeof(int), s) != cudaSuccess ||
@@ -258,14 +297,25 @@ extern "C" int p1_plan_create(p1_ctx *ctx, const int32_t *elements,
     set_error("p1_plan_create: memset failed");
     return fail(P1_ECUDA);
   }
-  if ((rc = pool_alloc(&p->rec_off, (size_t)n_own + 1, s))) return fail(rc);
-  if ((rc = pool_alloc(&p->indptr, (size_t)n_own + 1, s))) return fail(rc);
-  if ((rc = pool_alloc(&cnt, (size_t)n_own + 1, s))) return fail(rc);
-  cudaMemsetAsync(cnt, 0, ((size_t)n_own + 1) * sizeof(int), s);
+  if ((rc = pool_alloc(ctx, &p->rec_off, (size_t)n_own + 1, s))) return fail(rc);
+  if ((rc = pool_alloc(ctx, &p->indptr, (size_t)n_own + 1, s))) return fail(rc);
+  if ((rc = pool_alloc(ctx, &cnt, (size_t)n_own + 1, s))) return fail(rc);
+  if ((rc = pool_alloc(ctx, &rowlen, (size_t)n_own + 1, s))) return fail(rc);
+  if ((rc = pool_alloc(ctx, &p->acc, (size_t)n_own + 1, s))) return fail(rc);
+  if ((rc = pool_alloc(ctx, &p->slow_rows, (size_t)n_own + 1, s))) return fail(rc);
+  if ((rc = pool_alloc(ctx, &p->big_rows, (size_t)((3 * M) / (DEG_BIG + 1) < n_own ? (3 * M) / (DEG_BIG + 1) : n_own) + 1, s)))
+    return fail(rc);
+  cudaMemsetAsync(p->acc, 0, ((size_t)n_own + 1) * sizeof(unsigned long long), s);
 
   const unsigned eg = min(grid_for(M, THREADS), (unsigned)(ctx->sm_count * 32));
   P1_TIMED(ctx, "count", s,
-           count_kernel<<<eg, THREADS, 0, s>>>(elements, M, N, rb, re, cnt, ctx->d_flags));
+           count_kernel<<<eg, THREADS, 0, s>>>(elements, M, N, rb, re, p->acc,
+                                               ctx->d_flags));
+  if (n_own > 0)
+    P1_TIMED(ctx, "split", s,
+             split_kernel<<<grid_for(n_own, THREADS), THREADS, 0, s>>>(
+                 n_own, p->acc, p->exact ? 1 : 0, cnt, rowlen, p->slow_rows,
+                 p->big_rows, ctx->d_flags + 2));
   if ((rc = exclusive_scan_i32(ctx, cnt, p->rec_off, n_own, true, s))) return fail(rc);
   // n_rec is needed on the host to size rec; for the whole matrix it is 3M,
   // for a row range it is read back
@@ -281,19 +331,15 @@ extern "C" int p1_plan_create(p1_ctx *ctx, const int32_t *elements,
     n_rec = h;
   }
   p->n_rec = n_rec;
-  if ((rc = pool_alloc(&p->rec, (size_t)n_rec, s))) return fail(rc);
-  if ((rc = pool_alloc(&p->slow_rows, (size_t)(n_rec < n_own ? n_rec : n_own) + 1, s))) return fail(rc);
-  if ((rc = pool_alloc(&p->big_rows, (size_t)(n_rec / (DEG_BIG + 1)) + 1, s)))
-    return fail(rc);
+  if ((rc = pool_alloc(ctx, &p->rec, (size_t)n_rec, s))) return fail(rc);
   // cursor := row offsets (cnt is free again)
   cudaMemcpyAsync(cnt, p->rec_off, (size_t)n_own * sizeof(int), cudaMemcpyDeviceToDevice, s);
   P1_TIMED(ctx, "scatter", s,
            scatter_kernel<<<eg, THREADS, 0, s>>>(elements, M, N, rb, re, cnt, p->rec));
-  // cnt becomes rowlen (every entry is rewritten)
-  if (n_own > 0)
+  if (p->exact && n_own > 0)
     P1_TIMED(ctx, "rowlen", s,
              rowlen_kernel<<<grid_for((int64_t)n_own * GROUP, THREADS), THREADS, 0, s>>>(
-                 n_own, rb, p->rec_off, p->rec, cnt, p->slow_rows, p->big_rows,
+                 n_own, rb, p->rec_off, p->rec, rowlen, p->slow_rows, p->big_rows,
                  ctx->d_flags + 2));
   cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, 4 * sizeof(int),
                   cudaMemcpyDeviceToHost, s);
@@ -311,24 +357,25 @@ extern "C" int p1_plan_create(p1_ctx *ctx, const int32_t *elements,
   p->n_slow = ctx->h_flags[3];
   if (p->n_slow > 0)
     rowlen_slow_kernel<<<grid_for(p->n_slow, THREADS), THREADS, 0, s>>>(
-        p->slow_rows, p->n_slow, rb, p->rec_off, p->rec, cnt);
+        p->slow_rows, p->n_slow, rb, p->rec_off, p->rec, rowlen);
   if (p->n_big > 0) {
     int4 *tmp = nullptr;
-    if ((rc = pool_alloc(&tmp, (size_t)n_rec, s)) ||
-        (rc = pool_alloc(&p->big_first, (size_t)(2 * n_rec + n_own + 1), s))) {
-      pool_free(tmp, s);
+    if ((rc = pool_alloc(ctx, &tmp, (size_t)n_rec, s)) ||
+        (rc = pool_alloc(ctx, &p->big_first, (size_t)(2 * n_rec + n_own + 1), s))) {
+      pool_free(ctx, tmp, s);
       return fail(rc);
     }
     sort_big_kernel<<<p->n_big, THREADS, 0, s>>>(p->big_rows, p->rec_off, p->rec, tmp);
     rowlen_big_kernel<<<p->n_big, THREADS, 0, s>>>(p->big_rows, rb, p->rec_off,
-                                                   p->rec, p->big_first, cnt);
-    pool_free(tmp, s);
+                                                   p->rec, p->big_first, rowlen);
+    pool_free(ctx, tmp, s);
   }
-  if ((rc = exclusive_scan_i32(ctx, cnt, p->indptr, n_own, true, s))) return fail(rc);
+  if ((rc = exclusive_scan_i32(ctx, rowlen, p->indptr, n_own, true, s))) return fail(rc);
   int h_nnz = 0;
   cudaMemcpyAsync(&h_nnz, p->indptr + n_own, sizeof(int), cudaMemcpyDeviceToHost, s);
-  pool_free(cnt, s);
-  cnt = nullptr;
+  pool_free(ctx, cnt, s);
+  pool_free(ctx, rowlen, s);
+  cnt = rowlen = nullptr;
   cudaError_t e = cudaStreamSynchronize(s);
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) {
@@ -343,9 +390,9 @@ extern "C" int p1_plan_create(p1_ctx *ctx, const int32_t *elements,
 extern "C" int p1_plan_destroy(p1_plan *p) {
   if (!p) return P1_OK;
   DeviceGuard guard(p->ctx->device);
-  void *blocks[] = {p->rec_off, p->rec, p->indptr, p->slow_rows, p->big_rows,
+  void *blocks[] = {p->rec_off, p->rec, p->acc, p->indptr, p->slow_rows, p->big_rows,
                     p->big_first, p->twin};
-  for (void *b : blocks) pool_free(b, p->stream);
+  for (void *b : blocks) pool_free(p->ctx, b, p->stream);
   delete p;
   return P1_OK;
 }

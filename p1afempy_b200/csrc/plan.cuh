@@ -16,6 +16,9 @@ struct p1_plan {
   int4 *rec;           // n_rec   : x = next node, y = prev node | k<<29, z = element,
                        //           w = 0; arrival order within a row until `sorted`
   bool sorted;         // records of every row ascending in (element, vertex)
+  bool exact;          // row lengths from the all-pairs kernel (no hash shortcut)
+  unsigned long long *acc;  // n_own: low 32 bits = #records, high 32 bits = sum over the
+                       // records of hash(next) - hash(prev): 0 for a closed fan
   int *indptr;         // n_own+1
   int *slow_rows;      // rows the 8-lane kernels do not take: more than 8 records
                        // or repeated neighbours (non-manifold / degenerate)
@@ -28,6 +31,12 @@ struct p1_plan {
 };
 
 namespace p1 {
+
+// 32-bit mixer (lowbias32) for the closed-fan test
+__host__ __device__ __forceinline__ unsigned mix32(unsigned x) {
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  return x;
+}
 
 constexpr int GROUP = 8;      // lanes per row in the fast kernels = max records
 constexpr int DEG_BIG = 40;   // rows with more records take the block-per-row path

@@ -104,7 +104,7 @@ int exclusive_scan_i32(p1_ctx *ctx, const int *in, int *out, int64_t n,
   if (n < 0) return P1_EINVAL;
   const unsigned nb = grid_for(n, SCAN_TILE);
   int *sums = nullptr;
-  P1_TRY(pool_alloc(&sums, (size_t)nb + 1, s));
+  P1_TRY(pool_alloc(ctx, &sums, (size_t)nb + 1, s));
   P1_TIMED(ctx, "scan", s, {
     scan_reduce_kernel<<<nb, SCAN_THREADS, 0, s>>>(in, n, sums);
     scan_sums_kernel<<<1, 1024, 0, s>>>(sums, (int)nb);
@@ -112,7 +112,7 @@ int exclusive_scan_i32(p1_ctx *ctx, const int *in, int *out, int64_t n,
                                                  write_total ? 1 : 0);
   });
   P1_CUDA(cudaGetLastError());
-  pool_free(sums, s);
+  pool_free(ctx, sums, s);
   return P1_OK;
 }
 

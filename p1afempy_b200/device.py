@@ -152,6 +152,7 @@ class DeviceMesh:
         self.n_elements = int(self.elements.shape[0])
         self.rows = (0, self.n_nodes) if rows is None else (int(rows[0]), int(rows[1]))
         self._plan = None
+        self._exact = False
         self.nnz = None
         self.max_index = None
 
@@ -162,7 +163,9 @@ class DeviceMesh:
             handle = C.c_void_p()
             _lib.check(self._lib.p1_plan_create(
                 self.ctx, _ptr(self.elements), self.n_elements, self.n_nodes,
-                self.rows[0], self.rows[1], _stream(self.device), C.byref(handle)))
+                self.rows[0], self.rows[1],
+                _lib.PLAN_EXACT if self._exact else _lib.PLAN_DEFAULT,
+                _stream(self.device), C.byref(handle)))
             self._plan = handle
             nnz, mx = C.c_int64(), C.c_int64()
             _lib.check(self._lib.p1_plan_info(handle, C.byref(nnz), C.byref(mx),
@@ -194,15 +197,23 @@ class DeviceMesh:
     def assemble(self, op, local=None, pattern=True):
         """-> (indptr, indices, data) CUDA tensors over the owned rows.
         pattern=False skips the index arrays (re-assembly on the same mesh)."""
-        plan = self.plan
-        n_own = self.rows[1] - self.rows[0]
-        data = self._empty(self.nnz)
-        indptr = self._empty(n_own + 1, torch.int32) if pattern else None
-        indices = self._empty(self.nnz, torch.int32) if pattern else None
-        _lib.check(self._lib.p1_assemble_csr(
-            plan, op, _ptr(self.coords), _ptr(local), _ptr(indptr), _ptr(indices),
-            _ptr(data), _stream(self.device)))
-        return indptr, indices, data
+        for attempt in (0, 1):
+            plan = self.plan
+            n_own = self.rows[1] - self.rows[0]
+            data = self._empty(self.nnz)
+            indptr = self._empty(n_own + 1, torch.int32) if pattern else None
+            indices = self._empty(self.nnz, torch.int32) if pattern else None
+            rc = self._lib.p1_assemble_csr(
+                plan, op, _ptr(self.coords), _ptr(local), _ptr(indptr), _ptr(indices),
+                _ptr(data), _stream(self.device))
+            if rc == _lib.P1_ERETRY and attempt == 0 and not self._exact:
+                # non-manifold vertex / degenerate element: the closed-fan
+                # shortcut of the default plan does not hold; count exactly
+                self.close()
+                self._exact = True
+                continue
+            _lib.check(rc)
+            return indptr, indices, data
 
     def stiffness_csr(self, pattern=True):
         return self.assemble(_lib.OP_STIFFNESS, pattern=pattern)

@@ -315,3 +315,28 @@ def test_large_uniform_invariants(api):
     assert abs(a - a.T).max() == 0.0
     m = api[0].get_mass_matrix(c, e)
     assert abs(m.sum() - 1.0) < 1e-12
+
+
+def test_pinched_vertex_falls_back_to_exact_plan(api):
+    """Two closed fans that share only one vertex: the default plan's
+    closed-fan shortcut is contradicted while filling (P1_ERETRY) and the
+    wrapper re-plans exactly.  A degenerate element (repeated vertex) too."""
+    def fan(center, first, n, c0):
+        ang = 2 * np.pi * np.arange(n) / n
+        pts = np.column_stack([c0[0] + np.cos(ang), c0[1] + np.sin(ang)])
+        ids = first + np.arange(n)
+        return pts, np.column_stack([np.full(n, center), ids, np.roll(ids, -1)])
+    p1, e1 = fan(0, 1, 6, (-1., 0.))
+    p2, e2 = fan(0, 7, 6, (1., 0.))
+    c = np.vstack([[0., 0.], p1 * 0.9, p2 * 0.9])
+    c[1:7] += [-0.2, 0.]
+    c[7:] += [0.2, 0.]
+    e = np.vstack([e1, e2])
+    H.csr_values_close(api[0].get_stiffness_matrix(c, e),
+                       orc.stiffness_coo(c, e).tocsr(), RTOL)
+    H.csr_values_close(api[0].get_mass_matrix(c, e), orc.mass_coo(c, e).tocsr(), RTOL)
+    c3, e3, _ = meshgen.unit_square(2)
+    e3 = np.vstack([e3, [[3, 3, 7]]])           # zero-area element with a repeated node
+    with np.errstate(all='ignore'):
+        ref = orc.mass_coo(c3, e3).tocsr()
+        H.csr_values_close(api[0].get_mass_matrix(c3, e3), ref, RTOL)
