@@ -103,12 +103,15 @@ fill_rows_kernel(int n_own, int rb, int exact,
   const int gbase = threadIdx.x & ~(GROUP - 1);
   const int a = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / GROUP);
   if (a >= n_own) return;
+  // the three loads that depend on the row id only are issued together: the
+  // kernel is bound by the latency of its dependent loads, not by bandwidth
   const unsigned long long v = __ldg(acc + a);
+  const int beg = __ldg(rec_off + a);
+  const int64_t base = __ldg(indptr + a);
   const int deg = (int)(unsigned)v;
   // group-uniform exits: empty rows; rows the slow / big kernels take
   if (deg == 0 || deg > GROUP) return;
   if (!exact && (unsigned)(v >> 32) != 0u) return;
-  const int beg = __ldg(rec_off + a);
   const int self = a + rb;
   const RowLane r = analyse_row(self, beg, deg, rec, gmask, lane8, shift, xch);
   if (!r.simple || (!exact && r.len != 1 + deg)) {
@@ -122,7 +125,6 @@ fill_rows_kernel(int n_own, int rb, int exact,
   s_vp[threadIdx.x] = vp;
   if (r.valid) s_vd[gbase + r.rk] = vd;  // canonical order: ascending `next`
   __syncwarp(gmask);
-  const int64_t base = __ldg(indptr + a);
   if (r.valid) {
     // column `next`: my (k,k+1) entry plus the (k,k+2) entry of the element
     // after me in the fan (two terms: order-free)

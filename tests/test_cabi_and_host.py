@@ -1,0 +1,91 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol that
+include/p1b200.h declares (no compute calls), host logic (cubature tables,
+scipy's index-dtype rule, error mapping)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from p1afempy_b200 import _lib, cubature
+from p1afempy_b200.device import scipy_index_dtype
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(REPO, 'include', 'p1b200.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(p1_[a-z0-9_]+)\s*\(', text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    names = declared_symbols()
+    assert len(names) >= 25
+    for name in names:
+        assert hasattr(lib, name), name
+    # and the Python binding knows all of them
+    assert set(names) == set(_lib.PROTOTYPES), set(names) ^ set(_lib.PROTOTYPES)
+
+
+def test_no_compute_without_gpu_is_loud():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    from p1afempy_b200 import solvers
+    with pytest.raises(_lib.P1Error):
+        solvers.get_stiffness_matrix(np.zeros((3, 2)), np.array([[0, 1, 2]]))
+    lib = _lib.load()
+    handle = ctypes.c_void_p()
+    assert lib.p1_ctx_create(0, ctypes.byref(handle)) != 0
+    assert _lib.last_error()
+
+
+def test_error_mapping():
+    assert _lib.check(0) is None
+    for code, exc in ((_lib.P1_EINDEX, IndexError), (_lib.P1_EINVAL, ValueError),
+                      (_lib.P1_ETOPOLOGY, ValueError), (_lib.P1_ECUDA, _lib.P1Error)):
+        with pytest.raises(exc):
+            _lib.check(code)
+
+
+def test_cubature_rules_integrate_monomials():
+    """weights sum to 1/2; MIDPOINT is (1/3,1/3); the DAYTAYLOR stand-in is
+    exact to total degree 6: int x^a y^b = a! b! / (a+b+2)!."""
+    from math import factorial
+    w, p = cubature.resolve_rule(cubature.CubatureRuleEnum.MIDPOINT)
+    assert np.array_equal(w, [0.5]) and np.allclose(p, [[1 / 3, 1 / 3]])
+    for rule, degree in ((cubature.CubatureRuleEnum.LAUFFER_LINEAR, 1),
+                         (cubature.CubatureRuleEnum.SMPLX1, 2),
+                         (cubature.CubatureRuleEnum.DAYTAYLOR, 6)):
+        w, p = cubature.resolve_rule(rule)
+        assert abs(w.sum() - 0.5) < 1e-15
+        for a in range(degree + 1):
+            for b in range(degree + 1 - a):
+                exact = factorial(a) * factorial(b) / factorial(a + b + 2)
+                assert abs(np.sum(w * p[:, 0] ** a * p[:, 1] ** b) - exact) < 1e-14
+
+
+def test_rule_is_data():
+    w, p = cubature.resolve_rule(([0.25, 0.25], [[0.2, 0.2], [0.4, 0.3]]))
+    assert w.dtype == np.float64 and p.shape == (2, 2)
+
+    class Holder:
+        weights = np.array([0.5])
+        integration_points = np.array([[1 / 3, 1 / 3]])
+    assert cubature.resolve_rule(Holder())[0].shape == (1,)
+    with pytest.raises(ValueError):
+        cubature.resolve_rule(([0.5, 0.5], [[0.1, 0.1]]))
+
+
+def test_scipy_index_dtype_rule():
+    """scipy: int32 unless max(nnz_coo, N) exceeds int32 (scipy/sparse/_coo.py:419);
+    checked against scipy itself at small sizes, by formula at the 256M point."""
+    from scipy.sparse import coo_matrix
+    e = np.array([[0, 1, 2]])
+    a = coo_matrix((np.ones(9), (np.repeat(e, 3), np.tile(e, 3).ravel()))).tocsr()
+    assert a.indices.dtype == scipy_index_dtype(1, 3, 3) == np.int32
+    assert scipy_index_dtype(67108864, 33562625, 33562625) == np.int32     # 64M mesh
+    assert scipy_index_dtype(268435456, 134234113, 134234113) == np.int64  # 256M mesh
