@@ -231,8 +231,10 @@ def run_b200(args):
 
     ctx, dev = context(local_rank)
     lib = _lib.load()
-    rows = (nn * rank // world, nn * (rank + 1) // world)
-    mesh = DeviceMesh(c, e, device=local_rank, rows=rows)
+    mesh = DeviceMesh(c, e, device=local_rank)
+    if world > 1:   # row ranges balanced by stored entries (p1_partition_rows)
+        bounds = mesh.balanced_rows(world)
+        mesh.set_rows((bounds[rank], bounds[rank + 1]))
     stream = torch.cuda.current_stream()
     nnz_all = torch.zeros(world, dtype=torch.int64, device='cuda')
 

@@ -89,6 +89,12 @@ int p1_plan_create(p1_ctx *ctx, const int32_t *elements, int64_t n_elements,
                    int64_t n_nodes, int64_t row_begin, int64_t row_end,
                    int flags, void *stream, p1_plan **out);
 int p1_plan_destroy(p1_plan *plan);
+/* Multi-GPU: world+1 row boundaries such that every range holds about the same
+ * number of stored entries (estimated from a strided sample of the elements;
+ * deterministic, so all ranks agree without communication).  SYNCHRONISES. */
+int p1_partition_rows(p1_ctx *ctx, const int32_t *elements, int64_t n_elements,
+                      int64_t n_nodes, int world, int64_t *boundaries_host,
+                      void *stream);
 /* nnz: stored entries in the owned rows; max_index: largest node index that
  * occurs in `elements` (the reference infers the shape of the stiffness and
  * mass matrices as max_index+1, solvers.py:46-47,153). */

@@ -47,6 +47,7 @@ PROTOTYPES = {
     'p1_widen_indices': [_vp, _vp, _i64, _vp, _vp],
     'p1_plan_create': [_vp, _vp, _i64, _i64, _i64, _i64, _int, _vp, C.POINTER(_vp)],
     'p1_plan_destroy': [_vp],
+    'p1_partition_rows': [_vp, _vp, _i64, _i64, _int, _vp, _vp],
     'p1_plan_info': [_vp, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64),
                      C.POINTER(_i64)],
     'p1_assemble_csr': [_vp, _int, _vp, _vp, _vp, _vp, _vp, _vp],

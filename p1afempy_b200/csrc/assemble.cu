@@ -23,12 +23,16 @@ constexpr int THREADS = 256;
 // ------------------------------------------------ per-element coefficients
 __global__ void __launch_bounds__(THREADS)
 elem_stiffness_kernel(const double2 *__restrict__ coords, const int *__restrict__ elements,
-                      int64_t M, double *__restrict__ abc) {
+                      int64_t M, int rb, int re, double *__restrict__ abc) {
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < M;
        t += (int64_t)gridDim.x * blockDim.x) {
-    const double2 z0 = __ldg(coords + __ldg(elements + 3 * t));
-    const double2 z1 = __ldg(coords + __ldg(elements + 3 * t + 1));
-    const double2 z2 = __ldg(coords + __ldg(elements + 3 * t + 2));
+    const int e0 = __ldg(elements + 3 * t), e1 = __ldg(elements + 3 * t + 1),
+              e2 = __ldg(elements + 3 * t + 2);
+    // only elements that touch an owned row are ever gathered (multi-GPU)
+    if (!((e0 >= rb && e0 < re) || (e1 >= rb && e1 < re) || (e2 >= rb && e2 < re))) continue;
+    const double2 z0 = __ldg(coords + e0);
+    const double2 z1 = __ldg(coords + e1);
+    const double2 z2 = __ldg(coords + e2);
     const double d21x = z1.x - z0.x, d21y = z1.y - z0.y;
     const double d31x = z2.x - z0.x, d31y = z2.y - z0.y;
     const double area4 = 4. * (0.5 * (d21x * d31y - d21y * d31x));
@@ -40,12 +44,15 @@ elem_stiffness_kernel(const double2 *__restrict__ coords, const int *__restrict_
 
 __global__ void __launch_bounds__(THREADS)
 elem_mass_kernel(const double2 *__restrict__ coords, const int *__restrict__ elements,
-                 int64_t M, double2 *__restrict__ on_off) {
+                 int64_t M, int rb, int re, double2 *__restrict__ on_off) {
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < M;
        t += (int64_t)gridDim.x * blockDim.x) {
-    const double2 z0 = __ldg(coords + __ldg(elements + 3 * t));
-    const double2 z1 = __ldg(coords + __ldg(elements + 3 * t + 1));
-    const double2 z2 = __ldg(coords + __ldg(elements + 3 * t + 2));
+    const int e0 = __ldg(elements + 3 * t), e1 = __ldg(elements + 3 * t + 1),
+              e2 = __ldg(elements + 3 * t + 2);
+    if (!((e0 >= rb && e0 < re) || (e1 >= rb && e1 < re) || (e2 >= rb && e2 < re))) continue;
+    const double2 z0 = __ldg(coords + e0);
+    const double2 z1 = __ldg(coords + e1);
+    const double2 z2 = __ldg(coords + e2);
     const double d21x = z1.x - z0.x, d21y = z1.y - z0.y;
     const double d31x = z2.x - z0.x, d31y = z2.y - z0.y;
     const double area = 0.5 * (d21x * d31y - d21y * d31x);
@@ -303,7 +310,8 @@ extern "C" int p1_assemble_csr(const p1_plan *plan, int op, const double *coords
       if (M > 0)
         P1_TIMED(ctx, "elem_coef", s,
                  elem_stiffness_kernel<<<eg, THREADS, 0, s>>>(
-                     (const double2 *)coords, plan->elements, M, coef));
+                     (const double2 *)coords, plan->elements, M, (int)plan->row_begin,
+                     (int)plan->row_end, coef));
       rc = launch_fill(plan, StiffnessOp{coef}, indices, data, s);
       break;
     case P1_OP_MASS:
@@ -312,7 +320,8 @@ extern "C" int p1_assemble_csr(const p1_plan *plan, int op, const double *coords
       if (M > 0)
         P1_TIMED(ctx, "elem_coef", s,
                  elem_mass_kernel<<<eg, THREADS, 0, s>>>(
-                     (const double2 *)coords, plan->elements, M, (double2 *)coef));
+                     (const double2 *)coords, plan->elements, M, (int)plan->row_begin,
+                     (int)plan->row_end, (double2 *)coef));
       rc = launch_fill(plan, MassOp{(const double2 *)coef}, indices, data, s);
       break;
     case P1_OP_LOCAL:

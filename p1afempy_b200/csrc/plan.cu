@@ -13,6 +13,7 @@
 // count = 1 atomic; scatter = 1 atomic (cursor preloaded with the row offset)
 // + 1 aligned 16 B store; rowlen = coalesced 16 B loads, shuffles only.
 #include "plan.cuh"
+#include <vector>
 
 namespace p1 {
 
@@ -248,9 +249,75 @@ int ensure_sorted(p1_plan *p, cudaStream_t s) {
   return P1_OK;
 }
 
+// ------------------------------------------------------ balanced row ranges
+__global__ void __launch_bounds__(THREADS)
+sample_hist_kernel(const int *__restrict__ elements, int64_t M, int N, int stride,
+                   int buckets, int *__restrict__ hist) {
+  // pseudo-random 1/stride sample: a strided one is biased, because the position
+  // of an element among its NVB siblings correlates with the age of its nodes
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < M;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    if (stride > 1 && (mix32((unsigned)t) % (unsigned)stride) != 0u) continue;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int e = __ldg(elements + 3 * t + k);
+      if ((unsigned)e < (unsigned)N)
+        atomicAdd(hist + (int)(((int64_t)e * buckets) / N), 1);
+    }
+  }
+}
+
 }  // namespace p1
 
 using namespace p1;
+
+// Row ranges with (nearly) equal numbers of stored entries, from a strided
+// sample of the elements: row i holds about 1 + #incident elements entries.
+// Deterministic in (elements, world): every rank computes the same answer
+// without communication.  boundaries_host receives world+1 row indices.
+extern "C" int p1_partition_rows(p1_ctx *ctx, const int32_t *elements,
+                                 int64_t n_elements, int64_t n_nodes, int world,
+                                 int64_t *boundaries_host, void *stream) {
+  P1_REQUIRE(ctx && boundaries_host && world >= 1, "bad argument");
+  P1_REQUIRE(n_elements >= 0 && n_nodes >= 0 && n_nodes <= 0x7fffffffLL, "bad size");
+  DeviceGuard guard(ctx->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int buckets = 8192;
+  const int stride = n_elements > (1 << 22) ? 16 : 1;
+  std::vector<int> h(buckets, 0);
+  if (n_elements > 0 && n_nodes > 0) {
+    int *hist = nullptr;
+    P1_TRY(pool_alloc(ctx, &hist, (size_t)buckets, s));
+    P1_CUDA(cudaMemsetAsync(hist, 0, buckets * sizeof(int), s));
+    sample_hist_kernel<<<min(grid_for(n_elements, THREADS), (unsigned)(ctx->sm_count * 16)),
+                         THREADS, 0, s>>>(elements, n_elements, (int)n_nodes, stride,
+                                          buckets, hist);
+    P1_CUDA(cudaMemcpyAsync(h.data(), hist, buckets * sizeof(int), cudaMemcpyDeviceToHost, s));
+    P1_CUDA(cudaStreamSynchronize(s));
+    pool_free(ctx, hist, s);
+  }
+  // weight of bucket b = rows in it + sampled incidences * stride
+  std::vector<double> cum(buckets + 1, 0.);
+  for (int b = 0; b < buckets; ++b) {
+    const int64_t lo = (int64_t)b * n_nodes / buckets, hi = (int64_t)(b + 1) * n_nodes / buckets;
+    cum[b + 1] = cum[b] + (double)(hi - lo) + (double)h[b] * stride;
+  }
+  boundaries_host[0] = 0;
+  boundaries_host[world] = n_nodes;
+  int b = 0;
+  for (int r = 1; r < world; ++r) {
+    const double target = cum[buckets] * r / world;
+    while (b < buckets - 1 && cum[b + 1] < target) ++b;
+    const int64_t lo = (int64_t)b * n_nodes / buckets, hi = (int64_t)(b + 1) * n_nodes / buckets;
+    const double w = cum[b + 1] - cum[b];
+    const double frac = w > 0 ? (target - cum[b]) / w : 0.;
+    int64_t row = lo + (int64_t)(frac * (double)(hi - lo));
+    if (row < boundaries_host[r - 1]) row = boundaries_host[r - 1];
+    if (row > n_nodes) row = n_nodes;
+    boundaries_host[r] = row;
+  }
+  return P1_OK;
+}
 
 extern "C" int p1_plan_create(p1_ctx *ctx, const int32_t *elements,
                               int64_t n_elements, int64_t n_nodes,

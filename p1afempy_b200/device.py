@@ -156,6 +156,19 @@ class DeviceMesh:
         self.nnz = None
         self.max_index = None
 
+    def balanced_rows(self, world):
+        """Row boundaries (world+1) with about equal numbers of stored entries
+        per range; deterministic, identical on every rank (p1_partition_rows)."""
+        out = np.zeros(world + 1, dtype=np.int64)
+        _lib.check(self._lib.p1_partition_rows(
+            self.ctx, _ptr(self.elements), self.n_elements, self.n_nodes, int(world),
+            out.ctypes.data_as(C.c_void_p), _stream(self.device)))
+        return [int(x) for x in out]
+
+    def set_rows(self, rows):
+        self.close()
+        self.rows = (int(rows[0]), int(rows[1]))
+
     # ------------------------------------------------------------------ plan
     @property
     def plan(self):

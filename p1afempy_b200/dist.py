@@ -88,9 +88,13 @@ class DistributedMesh:
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         n_nodes = int(coordinates.shape[0])
-        self.rows = partition_rows(n_nodes, self.world)[self.rank]
         self.n_nodes = n_nodes
-        self.local = DeviceMesh(coordinates, elements, device=device, rows=self.rows)
+        self.local = DeviceMesh(coordinates, elements, device=device)
+        # ranges balanced by stored entries, not by rows: in NVB numbering the
+        # early (coarse-level) nodes have twice the valence of the late ones
+        bounds = self.local.balanced_rows(self.world)
+        self.rows = (bounds[self.rank], bounds[self.rank + 1])
+        self.local.set_rows(self.rows)
 
     def stiffness_csr(self):
         return self.local.stiffness_csr()

@@ -41,6 +41,19 @@ def test_row_ranges_concatenate_to_reference(world):
     assert np.array_equal(got, whole.cpu().numpy())
 
 
+def test_balanced_partition():
+    from p1afempy_b200.device import DeviceMesh
+    c, e, _ = meshgen.unit_square(8)
+    with DeviceMesh(c, e) as mesh:
+        ip, _, _ = mesh.stiffness_csr()
+        indptr = ip.cpu().numpy().astype(np.int64)
+        for world in (1, 2, 4, 8):
+            b = mesh.balanced_rows(world)
+            assert b[0] == 0 and b[-1] == c.shape[0] and all(x <= y for x, y in zip(b, b[1:]))
+            share = np.diff(indptr[b])
+            assert share.max() <= 1.05 * share.mean() + 64, (world, share)
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(('127.0.0.1', 0))
