@@ -15,8 +15,8 @@
  *  - every function returns 0 on success or a negative P1_E* code; the text
  *    for the calling thread's last failure is p1_last_error();
  *  - inputs are never modified; outputs are caller-allocated; scratch memory
- *    comes from the context's stream-ordered pool and is released before the
- *    call returns (stream-ordered), except what a p1_plan keeps.
+ *    comes from the context's caching arena and goes back to it before the
+ *    call returns (reuse is stream-ordered), except what a p1_plan keeps.
  */
 #ifndef P1B200_H
 #define P1B200_H
