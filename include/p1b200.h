@@ -67,6 +67,11 @@ int p1_profile_enable(p1_ctx *ctx, int on);
 int p1_profile_reset(p1_ctx *ctx);
 int p1_profile_report(p1_ctx *ctx, char *buf, int64_t cap);
 
+/* P1_EINDEX unless every value lies in [0, n_nodes).  The per-triangle calls
+ * below gather by element index without checking; run this (or p1_plan_create,
+ * which checks too) on untrusted input first.  SYNCHRONISES. */
+int p1_check_indices(p1_ctx *ctx, const int32_t *indices, int64_t count,
+                     int64_t n_nodes, void *stream);
 /* int32 -> int64 widening of an index array (scipy switches the CSR index
  * dtype to int64 when max(9M, N) >= 2^31, scipy/sparse/_coo.py:419). */
 int p1_widen_indices(p1_ctx *ctx, const int32_t *src, int64_t count,
@@ -85,9 +90,20 @@ int p1_widen_indices(p1_ctx *ctx, const int32_t *src, int64_t count,
  * ---------------------------------------------------------------------- */
 #define P1_PLAN_DEFAULT 0
 #define P1_PLAN_EXACT 1     /* count the columns of every row by comparison   */
+#define P1_PLAN_KEEP_ELEMENTS 2 /* remember the element of every record: needed */
+                            /* to assemble a second operator on the same plan, */
+                            /* for load vectors, edge numbering and eta_R      */
 int p1_plan_create(p1_ctx *ctx, const int32_t *elements, int64_t n_elements,
                    int64_t n_nodes, int64_t row_begin, int64_t row_end,
                    int flags, void *stream, p1_plan **out);
+/* The cold path of one matrix: the scatter that groups the incidences also
+ * computes the local matrix of every element (once) and stores its rows in the
+ * records; assemble with P1_OP_STORED afterwards.  op/coords/local as for
+ * p1_assemble_csr. */
+int p1_plan_create_for(p1_ctx *ctx, const int32_t *elements, int64_t n_elements,
+                       int64_t n_nodes, int64_t row_begin, int64_t row_end,
+                       int flags, int op, const double *coords, const double *local,
+                       void *stream, p1_plan **out);
 int p1_plan_destroy(p1_plan *plan);
 /* Multi-GPU: world+1 row boundaries such that every range holds about the same
  * number of stored entries (estimated from a strided sample of the elements;
@@ -103,6 +119,8 @@ int p1_plan_info(const p1_plan *plan, int64_t *nnz, int64_t *max_index,
 
 /* What to assemble.  The value of local entry (r, c) of element T goes to
  * (row, col) = (elements[T][r], elements[T][c]). */
+#define P1_OP_STORED 0    /* the values the plan's records already hold
+                             (p1_plan_create_for, or the previous assemble)  */
 #define P1_OP_STIFFNESS 1 /* solvers.py:15-47   get_stiffness_matrix          */
 #define P1_OP_MASS 2      /* solvers.py:145-182 get_mass_matrix               */
 #define P1_OP_LOCAL 3     /* any 3x3 local matrix given per element, row-major
@@ -115,7 +133,9 @@ int p1_plan_info(const p1_plan *plan, int64_t *nnz, int64_t *max_index,
  *   data    : nnz float64; duplicates summed in increasing (element, vertex)
  * indptr and/or indices may be NULL (re-assembly on an unchanged mesh writes
  * values only).  `coords` (n_nodes x 2) is used by P1_OP_STIFFNESS/MASS,
- * `local` (n_elements x 9) by P1_OP_LOCAL. */
+ * `local` (n_elements x 9) by P1_OP_LOCAL; any op other than P1_OP_STORED
+ * recomputes the record values first and needs P1_PLAN_KEEP_ELEMENTS.
+ * Returns P1_ERETRY when the mesh contradicts a default plan (see above). */
 int p1_assemble_csr(const p1_plan *plan, int op, const double *coords,
                     const double *local, int32_t *indptr, int32_t *indices,
                     double *data, void *stream);

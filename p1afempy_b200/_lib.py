@@ -24,7 +24,9 @@ P1_ERETRY = -7
 
 PLAN_DEFAULT = 0
 PLAN_EXACT = 1
+PLAN_KEEP_ELEMENTS = 2
 
+OP_STORED = 0
 OP_STIFFNESS = 1
 OP_MASS = 2
 OP_LOCAL = 3
@@ -44,8 +46,11 @@ PROTOTYPES = {
     'p1_profile_reset': [_vp],
     'p1_profile_report': [_vp, C.c_char_p, _i64],
     'p1_narrow_indices': [_vp, _vp, _int, _i64, _vp, _vp],
+    'p1_check_indices': [_vp, _vp, _i64, _i64, _vp],
     'p1_widen_indices': [_vp, _vp, _i64, _vp, _vp],
     'p1_plan_create': [_vp, _vp, _i64, _i64, _i64, _i64, _int, _vp, C.POINTER(_vp)],
+    'p1_plan_create_for': [_vp, _vp, _i64, _i64, _i64, _i64, _int, _int, _vp, _vp, _vp,
+                           C.POINTER(_vp)],
     'p1_plan_destroy': [_vp],
     'p1_partition_rows': [_vp, _vp, _i64, _i64, _int, _vp, _vp],
     'p1_plan_info': [_vp, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64),

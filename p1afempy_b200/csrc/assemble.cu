@@ -1,105 +1,24 @@
-// assemble.cu -- numeric phase.
-//
-// Step 1 (one thread per triangle): the coefficients every entry of the local
-// 3x3 matrix derives from, computed ONCE per element with the reference's
-// arithmetic (compile with -fmad=false): /root/reference/p1afempy/
-// solvers.py:31-45 (stiffness: a, b, c), :176-181 (mass: area/6, area/12).
-// Local matrices of the generalised stiffness / weighted mass come as 9 values
-// per element (local_ops.cu).
-// Step 2: the owner of a CSR row gathers the entries (k,k), (k,k+1), (k,k+2)
-// of its incident elements, sums duplicates in a fixed order and writes the
+// assemble.cu -- numeric phase: the owner of a CSR row sums the entries its
+// records carry (written by the scatter, plan.cu: the local matrix of every
+// element is computed ONCE, by the thread that owns the element, with the
+// reference's arithmetic, plan.cuh: *Values) in a fixed order and writes the
 // finished row (sorted unique columns, explicit zeros kept).
 //
-// Fast path: 8 lanes per row, one record per lane, all-pairs comparison through
-// shared memory (plan.cuh: analyse_row).  HBM traffic per triangle: 12 B indices
-// + gathered coordinates + 24 B coefficients (step 1); 48 B records + 24 B
-// gathered coefficients + 42 B CSR output (step 2).
+// Fast path: 8 lanes per row, one 32-byte record per lane (one coalesced
+// 256-bit load), all-pairs comparison through shared memory (plan.cuh:
+// analyse_row).  HBM traffic per triangle: 96 B records + 42 B CSR output.
 #include "plan.cuh"
 
 namespace p1 {
 
 constexpr int THREADS = 256;
 
-// ------------------------------------------------ per-element coefficients
-__global__ void __launch_bounds__(THREADS)
-elem_stiffness_kernel(const double2 *__restrict__ coords, const int *__restrict__ elements,
-                      int64_t M, int rb, int re, double *__restrict__ abc) {
-  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < M;
-       t += (int64_t)gridDim.x * blockDim.x) {
-    const int e0 = __ldg(elements + 3 * t), e1 = __ldg(elements + 3 * t + 1),
-              e2 = __ldg(elements + 3 * t + 2);
-    // only elements that touch an owned row are ever gathered (multi-GPU)
-    if (!((e0 >= rb && e0 < re) || (e1 >= rb && e1 < re) || (e2 >= rb && e2 < re))) continue;
-    const double2 z0 = __ldg(coords + e0);
-    const double2 z1 = __ldg(coords + e1);
-    const double2 z2 = __ldg(coords + e2);
-    const double d21x = z1.x - z0.x, d21y = z1.y - z0.y;
-    const double d31x = z2.x - z0.x, d31y = z2.y - z0.y;
-    const double area4 = 4. * (0.5 * (d21x * d31y - d21y * d31x));
-    abc[3 * t] = (d21x * d31x + d21y * d31y) / area4;
-    abc[3 * t + 1] = (d31x * d31x + d31y * d31y) / area4;
-    abc[3 * t + 2] = (d21x * d21x + d21y * d21y) / area4;
-  }
-}
-
-__global__ void __launch_bounds__(THREADS)
-elem_mass_kernel(const double2 *__restrict__ coords, const int *__restrict__ elements,
-                 int64_t M, int rb, int re, double2 *__restrict__ on_off) {
-  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < M;
-       t += (int64_t)gridDim.x * blockDim.x) {
-    const int e0 = __ldg(elements + 3 * t), e1 = __ldg(elements + 3 * t + 1),
-              e2 = __ldg(elements + 3 * t + 2);
-    if (!((e0 >= rb && e0 < re) || (e1 >= rb && e1 < re) || (e2 >= rb && e2 < re))) continue;
-    const double2 z0 = __ldg(coords + e0);
-    const double2 z1 = __ldg(coords + e1);
-    const double2 z2 = __ldg(coords + e2);
-    const double d21x = z1.x - z0.x, d21y = z1.y - z0.y;
-    const double d31x = z2.x - z0.x, d31y = z2.y - z0.y;
-    const double area = 0.5 * (d21x * d31y - d21y * d31x);
-    on_off[t] = make_double2(area / 6., area / 12.);
-  }
-}
-
-// row k of the local matrix of element T: entries (k,k), (k,k+1), (k,k+2)
-struct StiffnessOp {
-  const double *__restrict__ abc;  // M x 3
-  __device__ __forceinline__ void row(int64_t T, int k, double &vd, double &vn,
-                                      double &vp) const {
-    const double a = __ldg(abc + 3 * T), b = __ldg(abc + 3 * T + 1),
-                 c = __ldg(abc + 3 * T + 2);
-    if (k == 0) { vd = -2. * a + b + c; vn = a - b; vp = a - c; }
-    else if (k == 1) { vd = b; vn = -a; vp = a - b; }
-    else { vd = c; vn = a - c; vp = -a; }
-  }
-};
-
-struct MassOp {
-  const double2 *__restrict__ on_off;  // M: (area/6, area/12)
-  __device__ __forceinline__ void row(int64_t T, int, double &vd, double &vn,
-                                      double &vp) const {
-    const double2 m = __ldg(on_off + T);
-    vd = m.x; vn = m.y; vp = m.y;
-  }
-};
-
-struct LocalOp {
-  const double *__restrict__ local;  // M x 9 row-major
-  __device__ __forceinline__ void row(int64_t T, int k, double &vd, double &vn,
-                                      double &vp) const {
-    const double *m = local + 9 * T + 3 * k;
-    vd = __ldg(m + k);
-    vn = __ldg(m + next_local(k));
-    vp = __ldg(m + prev_local(k));
-  }
-};
-
 // ------------------------------------------------------ fast path: 8 lanes/row
-template <class Op>
 __global__ void __launch_bounds__(THREADS)
 fill_rows_kernel(int n_own, int rb, int exact,
                  const unsigned long long *__restrict__ acc,
-                 const int *__restrict__ rec_off, const int4 *__restrict__ rec,
-                 const int *__restrict__ indptr, Op op, int *__restrict__ indices,
+                 const int *__restrict__ rec_off, const Rec *__restrict__ rec,
+                 const int *__restrict__ indptr, int *__restrict__ indices,
                  double *__restrict__ data, int *__restrict__ flags) {
   __shared__ int2 xch[THREADS];
   __shared__ double s_vp[THREADS];
@@ -127,20 +46,18 @@ fill_rows_kernel(int n_own, int rb, int exact,
     if (!exact && lane8 == 0) atomicOr(flags, FLAG_RETRY);
     return;
   }
-  double vd = 0., vn = 0., vp = 0.;
-  if (r.valid) op.row((int64_t)r.elem, r.k, vd, vn, vp);
-  s_vp[threadIdx.x] = vp;
-  if (r.valid) s_vd[gbase + r.rk] = vd;  // canonical order: ascending `next`
+  s_vp[threadIdx.x] = r.vp;
+  if (r.valid) s_vd[gbase + r.rk] = r.vd;  // canonical order: ascending `next`
   __syncwarp(gmask);
   if (r.valid) {
     // column `next`: my (k,k+1) entry plus the (k,k+2) entry of the element
     // after me in the fan (two terms: order-free)
-    const double off = r.mate < 0 ? vn : vn + s_vp[gbase + r.mate];
+    const double off = r.mate < 0 ? r.vn : r.vn + s_vp[gbase + r.mate];
     if (indices) indices[base + r.slot_nx] = r.nx;
     data[base + r.slot_nx] = off;
     if (r.extra) {
       if (indices) indices[base + r.slot_pv] = r.pv;
-      data[base + r.slot_pv] = vp;
+      data[base + r.slot_pv] = r.vp;
     }
   }
   if (lane8 == 0) {
@@ -176,11 +93,10 @@ __device__ __forceinline__ int insert_unique(int *cols, int n, int c) {
   return n + 1;
 }
 
-template <class Op>
 __global__ void __launch_bounds__(SLOW_THREADS)
 fill_slow_kernel(const int *__restrict__ slow_rows, int n_slow, int rb,
-                 const int *__restrict__ rec_off, const int4 *__restrict__ rec,
-                 const int *__restrict__ indptr, Op op, int *__restrict__ indices,
+                 const int *__restrict__ rec_off, const Rec *__restrict__ rec,
+                 const int *__restrict__ indptr, int *__restrict__ indices,
                  double *__restrict__ data) {
   __shared__ int cols_s[SLOW_THREADS * SLOW_COLS];
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -188,7 +104,7 @@ fill_slow_kernel(const int *__restrict__ slow_rows, int n_slow, int rb,
   const int a = slow_rows[idx];
   const int beg = rec_off[a], deg = rec_off[a + 1] - beg;
   const int self = a + rb;
-  const int4 *nb = rec + beg;
+  const Rec *nb = rec + beg;
   int *cs = cols_s + threadIdx.x * SLOW_COLS;
   int n = insert_unique(cs, 0, self);
   for (int i = 0; i < deg; ++i) {
@@ -202,38 +118,47 @@ fill_slow_kernel(const int *__restrict__ slow_rows, int n_slow, int rb,
     vs[j] = 0.;
   }
   const int js = lower_bound(cs, n, self);
-  // fixed summation order: ascending `next`, ties in stored order
+  // fixed summation order: ascending `next`, ties by `prev`
   for (int j = 0; j < n; ++j) {
     const int c = cs[j];
-    for (int i = 0; i < deg; ++i) {
-      const int4 p = nb[i];
-      if (rec_next(p) != c) continue;
-      double vd, vn, vp;
-      op.row((int64_t)rec_elem(p), rec_k(p), vd, vn, vp);
-      vs[js] += vd;
-      vs[j] += vn;
-      vs[lower_bound(cs, n, rec_prev(p))] += vp;
+    int last_pv = -1;
+    for (;;) {  // records with next == c in ascending prev order
+      int pick = -1, pick_pv = 0x7fffffff;
+      for (int i = 0; i < deg; ++i) {
+        if (rec_next(nb[i]) != c) continue;
+        const int pv = rec_prev(nb[i]);
+        if (pv > last_pv && pv < pick_pv) { pick = i; pick_pv = pv; }
+      }
+      if (pick < 0) break;
+      // every record with this (next, prev) pair (duplicates: identical elements)
+      for (int i = 0; i < deg; ++i) {
+        if (rec_next(nb[i]) != c || rec_prev(nb[i]) != pick_pv) continue;
+        const Rec p = nb[i];
+        vs[js] += p.vd;
+        vs[j] += p.vn;
+        vs[lower_bound(cs, n, pick_pv)] += p.vp;
+      }
+      last_pv = pick_pv;
     }
   }
 }
 
 // ------------------------------------------------ big path: one block per row
-__device__ __forceinline__ int big_candidate2(int self, const int4 *nb, int j) {
+__device__ __forceinline__ int big_candidate2(int self, const Rec *nb, int j) {
   if (j == 0) return self;
-  const int4 p = nb[(j - 1) >> 1];
+  const Rec p = nb[(j - 1) >> 1];
   return ((j - 1) & 1) ? rec_prev(p) : rec_next(p);
 }
 
-template <class Op>
 __global__ void __launch_bounds__(THREADS)
 fill_big_kernel(const int *__restrict__ big_rows, int rb,
-                const int *__restrict__ rec_off, const int4 *__restrict__ rec,
+                const int *__restrict__ rec_off, const Rec *__restrict__ rec,
                 const unsigned char *__restrict__ first,
-                const int *__restrict__ indptr, Op op, int *__restrict__ indices,
+                const int *__restrict__ indptr, int *__restrict__ indices,
                 double *__restrict__ data) {
   const int a = big_rows[blockIdx.x];
   const int beg = rec_off[a], deg = rec_off[a + 1] - beg;
-  const int4 *nb = rec + beg;
+  const Rec *nb = rec + beg;
   const unsigned char *fl = first + 2 * (int64_t)beg + a;
   const int self = a + rb;
   const int ncand = 2 * deg + 1;
@@ -245,95 +170,112 @@ fill_big_kernel(const int *__restrict__ big_rows, int rb,
     for (int i = 0; i < ncand; ++i)
       rank += fl[i] && big_candidate2(self, nb, i) < c;
     double sum = 0.;
-    for (int i = 0; i < deg; ++i) {  // records are in (element, vertex) order
-      const int4 p = nb[i];
+    for (int i = 0; i < deg; ++i) {  // records are in (next, prev) order
+      const Rec p = nb[i];
       const int px = rec_next(p), py = rec_prev(p);
-      if (c != self && px != c && py != c) continue;
-      double vd, vn, vp;
-      op.row((int64_t)rec_elem(p), rec_k(p), vd, vn, vp);
-      if (c == self) sum += vd;
-      if (px == c) sum += vn;
-      if (py == c) sum += vp;
+      if (c == self) sum += p.vd;
+      if (px == c) sum += p.vn;
+      if (py == c) sum += p.vp;
     }
     if (indices) indices[base + rank] = c;
     data[base + rank] = sum;
   }
 }
 
-template <class Op>
-int launch_fill(const p1_plan *p, Op op, int32_t *indices, double *data,
-                cudaStream_t s) {
-  const int n_own = (int)(p->row_end - p->row_begin);
-  const int rb = (int)p->row_begin;
-  if (n_own > 0)
-    P1_TIMED(p->ctx, "fill_rows", s,
-             (fill_rows_kernel<Op><<<grid_for((int64_t)n_own * GROUP, THREADS), THREADS, 0, s>>>(
-                 n_own, rb, p->exact ? 1 : 0, p->acc, p->rec_off, p->rec, p->indptr, op,
-                 indices, data, p->ctx->d_flags)));
-  if (p->n_slow > 0)
-    P1_TIMED(p->ctx, "fill_slow", s,
-             (fill_slow_kernel<Op><<<grid_for(p->n_slow, SLOW_THREADS), SLOW_THREADS, 0, s>>>(
-                 p->slow_rows, p->n_slow, rb, p->rec_off, p->rec, p->indptr, op, indices,
-                 data)));
-  if (p->n_big > 0)
-    fill_big_kernel<Op><<<p->n_big, THREADS, 0, s>>>(
-        p->big_rows, rb, p->rec_off, p->rec, p->big_first, p->indptr, op, indices, data);
-  P1_CUDA(cudaGetLastError());
-  return P1_OK;
+// ------------------------------------------- re-assembly: refresh the values
+template <class V>
+__global__ void __launch_bounds__(THREADS)
+refresh_kernel(const int *__restrict__ elements, int64_t n_rec,
+               Rec *__restrict__ rec, const int *__restrict__ rec_elem, V values) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_rec;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t t = rec_elem[i];
+    const int e[3] = {__ldg(elements + 3 * t), __ldg(elements + 3 * t + 1),
+                      __ldg(elements + 3 * t + 2)};
+    double v[3][3];
+    values.rows(t, e, v);
+    Rec r = rec[i];
+    const int k = rec_k(r);
+    r.vd = k == 0 ? v[0][0] : (k == 1 ? v[1][0] : v[2][0]);
+    r.vn = k == 0 ? v[0][1] : (k == 1 ? v[1][1] : v[2][1]);
+    r.vp = k == 0 ? v[0][2] : (k == 1 ? v[1][2] : v[2][2]);
+    store_rec(rec + i, r);
+  }
 }
 
 }  // namespace p1
 
 using namespace p1;
 
-extern "C" int p1_assemble_csr(const p1_plan *plan, int op, const double *coords,
+extern "C" int p1_assemble_csr(const p1_plan *cplan, int op, const double *coords,
                                const double *local, int32_t *indptr,
                                int32_t *indices, double *data, void *stream) {
-  P1_REQUIRE(plan, "null plan");
-  P1_REQUIRE(data || plan->nnz == 0, "null data");
+  P1_REQUIRE(cplan, "null plan");
+  P1_REQUIRE(data || cplan->nnz == 0, "null data");
+  p1_plan *plan = const_cast<p1_plan *>(cplan);
   p1_ctx *ctx = plan->ctx;
   DeviceGuard guard(ctx->device);
   cudaStream_t s = (cudaStream_t)stream;
-  const int64_t n_own = plan->row_end - plan->row_begin;
+  const int n_own = (int)(plan->row_end - plan->row_begin);
+  const int rb = (int)plan->row_begin;
   const int64_t M = plan->M;
+  if (op == P1_OP_STORED) {
+    if (plan->val_op == 0) {
+      set_error("p1_assemble_csr: P1_OP_STORED, but the plan was not created with "
+                "p1_plan_create_for and no operator has been assembled on it yet");
+      return P1_EINVAL;
+    }
+  } else {
+    // new coefficients on an existing plan: recompute the values in place
+    P1_TRY(require_elements(plan, "assembling a new operator on an existing plan"));
+    const unsigned rg = min(grid_for(plan->n_rec, THREADS), (unsigned)(ctx->sm_count * 32));
+    const double2 *xy = (const double2 *)coords;
+    switch (op) {
+      case P1_OP_STIFFNESS:
+      case P1_OP_MASS:
+        P1_REQUIRE(coords || M == 0, "stiffness/mass need coords");
+        break;
+      case P1_OP_LOCAL:
+        P1_REQUIRE(local || M == 0, "P1_OP_LOCAL needs the local matrices");
+        break;
+      default:
+        set_error("p1_assemble_csr: unknown op %d", op);
+        return P1_EINVAL;
+    }
+    if (plan->n_rec > 0) {
+      prof_begin(ctx, "refresh", s);
+      if (op == P1_OP_STIFFNESS)
+        refresh_kernel<<<rg, THREADS, 0, s>>>(plan->elements, plan->n_rec, plan->rec,
+                                              plan->rec_elem, StiffnessValues{xy});
+      else if (op == P1_OP_MASS)
+        refresh_kernel<<<rg, THREADS, 0, s>>>(plan->elements, plan->n_rec, plan->rec,
+                                              plan->rec_elem, MassValues{xy});
+      else
+        refresh_kernel<<<rg, THREADS, 0, s>>>(plan->elements, plan->n_rec, plan->rec,
+                                              plan->rec_elem, LocalValues{local});
+      prof_end(ctx, s);
+    }
+    plan->val_op = op;
+  }
   if (indptr)
-    P1_CUDA(cudaMemcpyAsync(indptr, plan->indptr, (n_own + 1) * sizeof(int),
+    P1_CUDA(cudaMemcpyAsync(indptr, plan->indptr, ((size_t)n_own + 1) * sizeof(int),
                             cudaMemcpyDeviceToDevice, s));
   P1_CUDA(cudaMemsetAsync(ctx->d_flags, 0, sizeof(int), s));
-  const unsigned eg = min(grid_for(M, THREADS), (unsigned)(ctx->sm_count * 32));
-  int rc = P1_OK;
-  double *coef = nullptr;
-  switch (op) {
-    case P1_OP_STIFFNESS:
-      P1_REQUIRE(coords || M == 0, "stiffness needs coords");
-      P1_TRY(pool_alloc(ctx, &coef, (size_t)3 * M, s));
-      if (M > 0)
-        P1_TIMED(ctx, "elem_coef", s,
-                 elem_stiffness_kernel<<<eg, THREADS, 0, s>>>(
-                     (const double2 *)coords, plan->elements, M, (int)plan->row_begin,
-                     (int)plan->row_end, coef));
-      rc = launch_fill(plan, StiffnessOp{coef}, indices, data, s);
-      break;
-    case P1_OP_MASS:
-      P1_REQUIRE(coords || M == 0, "mass needs coords");
-      P1_TRY(pool_alloc(ctx, &coef, (size_t)2 * M, s));
-      if (M > 0)
-        P1_TIMED(ctx, "elem_coef", s,
-                 elem_mass_kernel<<<eg, THREADS, 0, s>>>(
-                     (const double2 *)coords, plan->elements, M, (int)plan->row_begin,
-                     (int)plan->row_end, (double2 *)coef));
-      rc = launch_fill(plan, MassOp{(const double2 *)coef}, indices, data, s);
-      break;
-    case P1_OP_LOCAL:
-      P1_REQUIRE(local || M == 0, "P1_OP_LOCAL needs the local matrices");
-      rc = launch_fill(plan, LocalOp{local}, indices, data, s);
-      break;
-    default:
-      set_error("p1_assemble_csr: unknown op %d", op);
-      return P1_EINVAL;
-  }
-  pool_free(ctx, coef, s);
-  P1_TRY(rc);
+  if (n_own > 0)
+    P1_TIMED(ctx, "fill_rows", s,
+             (fill_rows_kernel<<<grid_for((int64_t)n_own * GROUP, THREADS), THREADS, 0, s>>>(
+                 n_own, rb, plan->exact ? 1 : 0, plan->acc, plan->rec_off, plan->rec,
+                 plan->indptr, indices, data, ctx->d_flags)));
+  if (plan->n_slow > 0)
+    P1_TIMED(ctx, "fill_slow", s,
+             (fill_slow_kernel<<<grid_for(plan->n_slow, SLOW_THREADS), SLOW_THREADS, 0, s>>>(
+                 plan->slow_rows, plan->n_slow, rb, plan->rec_off, plan->rec, plan->indptr,
+                 indices, data)));
+  if (plan->n_big > 0)
+    fill_big_kernel<<<plan->n_big, THREADS, 0, s>>>(
+        plan->big_rows, rb, plan->rec_off, plan->rec, plan->big_first, plan->indptr,
+        indices, data);
+  P1_CUDA(cudaGetLastError());
   if (!plan->exact) {
     // the closed-fan shortcut is verified while filling: read the verdict
     P1_CUDA(cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, sizeof(int),

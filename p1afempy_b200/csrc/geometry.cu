@@ -19,24 +19,23 @@ constexpr int THREADS = 256;
 
 __global__ void __launch_bounds__(THREADS)
 twin_kernel(int n_nodes, const int *__restrict__ rec_off,
-            const int4 *__restrict__ rec, int *__restrict__ twin,
-            int *__restrict__ flags) {
+            const Rec *__restrict__ rec, const int *__restrict__ rec_elem,
+            int *__restrict__ twin, int *__restrict__ flags) {
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= n_nodes) return;
   const int beg = rec_off[a], end = rec_off[a + 1];
   for (int i = beg; i < end; ++i) {
-    const int4 r = rec[i];
+    const Rec r = rec[i];
     const int target = rec_next(r);  // half-edge a -> target
     int found = -1, hits = 0;
     for (int s = beg; s < end; ++s)
       if (rec_prev(rec[s]) == target) { found = s; ++hits; }
-    const int64_t he = 3 * (int64_t)rec_elem(r) + rec_k(r);
+    const int64_t he = 3 * (int64_t)rec_elem[i] + rec_k(r);
     if (hits == 0) {
       twin[he] = -1;
       atomicAdd(flags + 1, 1);
     } else {
-      const int4 q = rec[found];
-      twin[he] = 3 * rec_elem(q) + prev_local(rec_k(q));
+      twin[he] = 3 * rec_elem[found] + prev_local(rec_k(rec[found]));
       if (hits > 1) atomicOr(flags, FLAG_NONMANIFOLD);
     }
     // the same directed edge twice is non-manifold as well
@@ -113,18 +112,19 @@ element_edges_kernel(const int *__restrict__ elements, int64_t M,
 // finds the element half-edge b0 -> b1 through the fan of b0
 __device__ __forceinline__ int64_t locate_halfedge(int b0, int b1,
                                                    const int *__restrict__ rec_off,
-                                                   const int4 *__restrict__ rec) {
+                                                   const Rec *__restrict__ rec,
+                                                   const int *__restrict__ rec_elem) {
   const int beg = rec_off[b0], end = rec_off[b0 + 1];
   for (int i = beg; i < end; ++i)
     if (rec_next(rec[i]) == b1)
-      return 3 * (int64_t)rec_elem(rec[i]) + rec_k(rec[i]);
+      return 3 * (int64_t)rec_elem[i] + rec_k(rec[i]);
   return -1;
 }
 
 __global__ void __launch_bounds__(THREADS)
 boundary_numbers_kernel(const int *__restrict__ bnd, int64_t K, int64_t M, int n_nodes,
-                        const int *__restrict__ rec_off, const int4 *__restrict__ rec,
-                        const int *__restrict__ num,
+                        const int *__restrict__ rec_off, const Rec *__restrict__ rec,
+                        const int *__restrict__ rec_elem, const int *__restrict__ num,
                         long long *__restrict__ element2edges,
                         long long *__restrict__ edge2nodes,
                         long long *__restrict__ boundary2edges, int *__restrict__ flags) {
@@ -135,7 +135,7 @@ boundary_numbers_kernel(const int *__restrict__ bnd, int64_t K, int64_t M, int n
     atomicOr(flags, FLAG_INDEX_RANGE);
     return;
   }
-  const int64_t h = locate_halfedge(b0, b1, rec_off, rec);
+  const int64_t h = locate_halfedge(b0, b1, rec_off, rec, rec_elem);
   if (h < 0) {
     atomicOr(flags, FLAG_BOUNDARY_MISS);
     boundary2edges[r] = -1;
@@ -186,8 +186,8 @@ eta_local_kernel(const double2 *__restrict__ coords, const double *__restrict__ 
 // mode 1: Dirichlet (indicators.py:79-80) jump  = 0
 __global__ void __launch_bounds__(THREADS)
 eta_boundary_kernel(int mode, const int *__restrict__ bnd, int64_t K, int n_nodes,
-                    const int *__restrict__ rec_off, const int4 *__restrict__ rec,
-                    const int *__restrict__ twin,
+                    const int *__restrict__ rec_off, const Rec *__restrict__ rec,
+                    const int *__restrict__ rec_elem, const int *__restrict__ twin,
                     const double *__restrict__ term, double *__restrict__ dudn,
                     int *__restrict__ flags) {
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -197,7 +197,7 @@ eta_boundary_kernel(int mode, const int *__restrict__ bnd, int64_t K, int n_node
     atomicOr(flags, FLAG_INDEX_RANGE);
     return;
   }
-  const int64_t h = locate_halfedge(b0, b1, rec_off, rec);
+  const int64_t h = locate_halfedge(b0, b1, rec_off, rec, rec_elem);
   if (h < 0) { atomicOr(flags, FLAG_BOUNDARY_MISS); return; }
   if (mode == 0) {
     dudn[h] = dudn[h] - term[r];
@@ -259,11 +259,12 @@ int ensure_twins(p1_plan *p, cudaStream_t s) {
   if (p->twin) return P1_OK;
   p1_ctx *ctx = p->ctx;
   P1_TRY(full_plan_required(p, "half-edge twins"));
+  P1_TRY(require_elements(p, "half-edge twins (edge numbering, eta_R)"));
   P1_TRY(pool_alloc(ctx, &p->twin, (size_t)(3 * p->M), s));
   P1_CUDA(cudaMemsetAsync(p->ctx->d_flags, 0, 4 * sizeof(int), s));
   if (p->N > 0)
     twin_kernel<<<grid_for(p->N, THREADS), THREADS, 0, s>>>(
-        (int)p->N, p->rec_off, p->rec, p->twin, p->ctx->d_flags);
+        (int)p->N, p->rec_off, p->rec, p->rec_elem, p->twin, p->ctx->d_flags);
   P1_CUDA(cudaGetLastError());
   P1_TRY(read_flags(p->ctx, s));
   if (p->ctx->h_flags[0] & FLAG_NONMANIFOLD) {
@@ -312,7 +313,7 @@ extern "C" int p1_geometric_data(const p1_plan *cplan, const int32_t *boundary_n
         p->elements, M, num, p->twin, (long long *)element2edges, (long long *)edge2nodes);
   if (K > 0)
     boundary_numbers_kernel<<<grid_for(K, THREADS), THREADS, 0, s>>>(
-        boundary_nodes, K, M, (int)p->N, p->rec_off, p->rec, num,
+        boundary_nodes, K, M, (int)p->N, p->rec_off, p->rec, p->rec_elem, num,
         (long long *)element2edges, (long long *)edge2nodes, (long long *)boundary2edges,
         ctx->d_flags);
   pool_free(ctx, num, s);
@@ -364,11 +365,11 @@ extern "C" int p1_eta_r(const p1_plan *cplan, const double *coords, const double
                                                      p->elements, M, dudn);
   if (n_neumann > 0)
     eta_boundary_kernel<<<grid_for(n_neumann, THREADS), THREADS, 0, s>>>(
-        0, neumann, n_neumann, (int)p->N, p->rec_off, p->rec, p->twin,
+        0, neumann, n_neumann, (int)p->N, p->rec_off, p->rec, p->rec_elem, p->twin,
         neumann_term, dudn, ctx->d_flags);
   if (n_dirichlet > 0)
     eta_boundary_kernel<<<grid_for(n_dirichlet, THREADS), THREADS, 0, s>>>(
-        1, dirichlet, n_dirichlet, (int)p->N, p->rec_off, p->rec, p->twin,
+        1, dirichlet, n_dirichlet, (int)p->N, p->rec_off, p->rec, p->rec_elem, p->twin,
         nullptr, dudn, ctx->d_flags);
   eta_final_kernel<<<egrid(ctx, M), THREADS, 0, s>>>((const double2 *)coords, p->elements,
                                                      M, p->twin, dudn, f_centroid, eta);

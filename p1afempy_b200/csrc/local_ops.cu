@@ -270,15 +270,15 @@ local_load_midpoint_kernel(const double2 *__restrict__ coords,
 // sequential np.bincount over elements.flatten() (solvers.py:593-596).
 __global__ void __launch_bounds__(THREADS)
 gather_load_kernel(int n_own, const int *__restrict__ rec_off,
-                   const int4 *__restrict__ rec, const double *__restrict__ L,
+                   const Rec *__restrict__ rec, const int *__restrict__ rec_elem,
+                   const double *__restrict__ L,
                    double *__restrict__ b) {
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= n_own) return;
   const int beg = rec_off[a], end = rec_off[a + 1];
   double sum = 0.;
   for (int i = beg; i < end; ++i) {
-    const int4 r = rec[i];
-    sum += __ldg(L + 3 * (int64_t)rec_elem(r) + rec_k(r));
+    sum += __ldg(L + 3 * (int64_t)rec_elem[i] + rec_k(rec[i]));
   }
   b[a] = sum;
 }
@@ -287,7 +287,8 @@ gather_load_kernel(int n_own, const int *__restrict__ rec_off,
 // (solvers.py:422-425)
 __global__ void __launch_bounds__(THREADS)
 gather_load_midpoint_kernel(int n_own, const int *__restrict__ rec_off,
-                            const int4 *__restrict__ rec,
+                            const Rec *__restrict__ rec,
+                            const int *__restrict__ rec_elem,
                             const double *__restrict__ share, double *__restrict__ b) {
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= n_own) return;
@@ -295,8 +296,7 @@ gather_load_midpoint_kernel(int n_own, const int *__restrict__ rec_off,
   double sum = 0.;
   for (int kk = 0; kk < 3; ++kk)
     for (int i = beg; i < end; ++i) {
-      const int4 r = rec[i];
-      if (rec_k(r) == kk) sum += __ldg(share + rec_elem(r));
+      if (rec_k(rec[i]) == kk) sum += __ldg(share + rec_elem[i]);
     }
   b[a] = sum;
 }
@@ -319,6 +319,14 @@ narrow_u32_kernel(const unsigned *__restrict__ src, int64_t n, int *__restrict__
 __global__ void __launch_bounds__(THREADS)
 widen_kernel(const int *__restrict__ src, int64_t n, long long *__restrict__ dst) {
   P1_FOR_ELEMENTS(i, n) dst[i] = src[i];
+}
+
+__global__ void __launch_bounds__(THREADS)
+check_indices_kernel(const int *__restrict__ idx, int64_t n, int limit,
+                     int *__restrict__ flags) {
+  bool bad = false;
+  P1_FOR_ELEMENTS(i, n) bad = bad || (unsigned)__ldg(idx + i) >= (unsigned)limit;
+  if (bad) atomicOr(flags, FLAG_INDEX_RANGE);
 }
 
 static inline unsigned egrid(const p1_ctx *ctx, int64_t n) {
@@ -355,6 +363,25 @@ extern "C" int p1_narrow_indices(p1_ctx *ctx, const void *src, int src_kind,
   else
     P1_REQUIRE(false, "src_kind must be 0 (int64), 1 (uint32) or 2 (int32)");
   P1_CUDA(cudaGetLastError());
+  return P1_OK;
+}
+
+extern "C" int p1_check_indices(p1_ctx *ctx, const int32_t *indices, int64_t count,
+                                int64_t n_nodes, void *stream) {
+  P1_REQUIRE(ctx && (count == 0 || indices), "null argument");
+  P1_REQUIRE(n_nodes >= 0 && n_nodes <= 0x7fffffffLL, "bad n_nodes");
+  DeviceGuard guard(ctx->device);
+  if (count == 0) return P1_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  P1_CUDA(cudaMemsetAsync(ctx->d_flags, 0, sizeof(int), s));
+  check_indices_kernel<<<egrid(ctx, count), THREADS, 0, s>>>(indices, count, (int)n_nodes,
+                                                            ctx->d_flags);
+  P1_CUDA(cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, sizeof(int), cudaMemcpyDeviceToHost, s));
+  P1_CUDA(cudaStreamSynchronize(s));
+  if (ctx->h_flags[0] & FLAG_INDEX_RANGE) {
+    set_error("index out of range [0, %lld)", (long long)n_nodes);
+    return P1_EINDEX;
+  }
   return P1_OK;
 }
 
@@ -533,7 +560,7 @@ extern "C" int p1_load_vector(const p1_plan *plan, const double *coords,
         (const double2 *)coords, plan->elements, M, fq, w, (const double2 *)pts, n_qp, L);
   if (n_own > 0)
     gather_load_kernel<<<grid_for(n_own, THREADS), THREADS, 0, s>>>(
-        n_own, plan->rec_off, plan->rec, L, b);
+        n_own, plan->rec_off, plan->rec, plan->rec_elem, L, b);
   pool_free(ctx, L, s);
   pool_free(ctx, w, s);
   pool_free(ctx, pts, s);
@@ -560,7 +587,7 @@ extern "C" int p1_load_vector_midpoint(const p1_plan *plan, const double *coords
         (const double2 *)coords, plan->elements, M, f_centroid, share);
   if (n_own > 0)
     gather_load_midpoint_kernel<<<grid_for(n_own, THREADS), THREADS, 0, s>>>(
-        n_own, plan->rec_off, plan->rec, share, b);
+        n_own, plan->rec_off, plan->rec, plan->rec_elem, share, b);
   pool_free(ctx, share, s);
   P1_CUDA(cudaGetLastError());
   return P1_OK;

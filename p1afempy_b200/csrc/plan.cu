@@ -79,10 +79,14 @@ split_kernel(int n_own, const unsigned long long *__restrict__ acc, int exact,
 }
 
 // -------------------------------------------------------------- scatter
-// cursor[a] starts at rec_off[a] and ends at rec_off[a+1].
+// cursor[a] starts at rec_off[a] and ends at rec_off[a+1].  The thread that
+// owns element t computes the element's local matrix ONCE (value source V) and
+// stores, for every owned vertex, one 32-byte record with one 256-bit store.
+template <class V>
 __global__ void __launch_bounds__(THREADS)
 scatter_kernel(const int *__restrict__ elements, int64_t M, int N, int rb, int re,
-               int *__restrict__ cursor, int4 *__restrict__ rec) {
+               int *__restrict__ cursor, Rec *__restrict__ rec,
+               int *__restrict__ rec_elem, V values) {
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < M;
        t += (int64_t)gridDim.x * blockDim.x) {
     int e[3];
@@ -92,12 +96,21 @@ scatter_kernel(const int *__restrict__ elements, int64_t M, int N, int rb, int r
     if ((unsigned)e[0] >= (unsigned)N || (unsigned)e[1] >= (unsigned)N ||
         (unsigned)e[2] >= (unsigned)N)
       continue;
+    const bool own0 = e[0] >= rb && e[0] < re, own1 = e[1] >= rb && e[1] < re,
+               own2 = e[2] >= rb && e[2] < re;
+    if (!(own0 || own1 || own2)) continue;  // multi-GPU: not my rows
+    double v[3][3];
+    values.rows(t, e, v);
 #pragma unroll
     for (int k = 0; k < 3; ++k)
-      if (e[k] >= rb && e[k] < re) {
+      if (k == 0 ? own0 : (k == 1 ? own1 : own2)) {
         const int pos = atomicAdd(cursor + (e[k] - rb), 1);
-        rec[pos] = make_int4(e[k == 2 ? 0 : k + 1],
-                             e[k == 0 ? 2 : k - 1] | (k << NODE_BITS), (int)t, 0);
+        Rec r;
+        r.nx = e[k == 2 ? 0 : k + 1];
+        r.pvk = e[k == 0 ? 2 : k - 1] | (k << NODE_BITS);
+        r.vd = v[k][0]; r.vn = v[k][1]; r.vp = v[k][2];
+        store_rec(rec + pos, r);
+        if (rec_elem) rec_elem[pos] = (int)t;
       }
   }
 }
@@ -107,7 +120,7 @@ scatter_kernel(const int *__restrict__ elements, int64_t M, int N, int rb, int r
 // are appended to slow_rows / big_rows and counted by the kernels below.
 __global__ void __launch_bounds__(THREADS)
 rowlen_kernel(int n_own, int rb, const int *__restrict__ rec_off,
-              const int4 *__restrict__ rec, int *__restrict__ rowlen,
+              const Rec *__restrict__ rec, int *__restrict__ rowlen,
               int *__restrict__ slow_rows, int *__restrict__ big_rows,
               int *__restrict__ counters /* [0] n_big, [1] n_slow */) {
   __shared__ int2 xch[THREADS];
@@ -136,14 +149,14 @@ rowlen_kernel(int n_own, int rb, const int *__restrict__ rec_off,
 // the few contiguous records stay in L1 while they are compared
 __global__ void __launch_bounds__(THREADS)
 rowlen_slow_kernel(const int *__restrict__ slow_rows, int n_slow, int rb,
-                   const int *__restrict__ rec_off, const int4 *__restrict__ rec,
+                   const int *__restrict__ rec_off, const Rec *__restrict__ rec,
                    int *__restrict__ rowlen) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n_slow) return;
   const int a = slow_rows[idx];
   const int beg = rec_off[a], deg = rec_off[a + 1] - beg;
   const int self = a + rb;
-  const int4 *nb = rec + beg;
+  const Rec *nb = rec + beg;
   int n = 1;
   for (int i = 0; i < deg; ++i) {
     const int x = rec_next(nb[i]), y = rec_prev(nb[i]);
@@ -160,40 +173,48 @@ rowlen_slow_kernel(const int *__restrict__ slow_rows, int n_slow, int rb,
 
 // Rows with more than DEG_BIG records: one block per row, O(deg^2) without
 // any capacity limit (pathological fans only; never on a shape-regular mesh).
+// Rank sort by (next, prev, k): the canonical order of the big path.
+__device__ __forceinline__ unsigned long long big_key(const Rec &r) {
+  return ((unsigned long long)(unsigned)r.nx << 32) | (unsigned)r.pvk;
+}
 __global__ void __launch_bounds__(THREADS)
 sort_big_kernel(const int *__restrict__ big_rows, const int *__restrict__ rec_off,
-                int4 *__restrict__ rec, int4 *__restrict__ tmp) {
+                Rec *__restrict__ rec, int *__restrict__ rec_elem,
+                Rec *__restrict__ tmp, int *__restrict__ tmp_elem) {
   const int a = big_rows[blockIdx.x];
   const int beg = rec_off[a], deg = rec_off[a + 1] - beg;
-  // rank sort by (element, vertex); records of one row are distinct
   for (int i = threadIdx.x; i < deg; i += blockDim.x) {
-    const int4 v = rec[beg + i];
-    const unsigned key = ((unsigned)v.z << 2) | (unsigned)rec_k(v);
+    const Rec v = rec[beg + i];
+    const unsigned long long key = big_key(v);
     int rank = 0;
     for (int j = 0; j < deg; ++j) {
-      const int4 q = rec[beg + j];
-      rank += (((unsigned)q.z << 2) | (unsigned)rec_k(q)) < key;
+      const unsigned long long kj = big_key(rec[beg + j]);
+      rank += kj < key || (kj == key && j < i);  // stable for identical keys
     }
     tmp[beg + rank] = v;
+    if (rec_elem) tmp_elem[beg + rank] = rec_elem[beg + i];
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < deg; i += blockDim.x) rec[beg + i] = tmp[beg + i];
+  for (int i = threadIdx.x; i < deg; i += blockDim.x) {
+    rec[beg + i] = tmp[beg + i];
+    if (rec_elem) rec_elem[beg + i] = tmp_elem[beg + i];
+  }
 }
 
 // candidate j of a big row: 0 = the row itself, 1+2i = next_i, 2+2i = prev_i
-__device__ __forceinline__ int big_candidate(int self, const int4 *nb, int j) {
+__device__ __forceinline__ int big_candidate(int self, const Rec *nb, int j) {
   if (j == 0) return self;
-  const int4 p = nb[(j - 1) >> 1];
+  const Rec p = nb[(j - 1) >> 1];
   return ((j - 1) & 1) ? rec_prev(p) : rec_next(p);
 }
 
 __global__ void __launch_bounds__(THREADS)
 rowlen_big_kernel(const int *__restrict__ big_rows, int rb,
-                  const int *__restrict__ rec_off, const int4 *__restrict__ rec,
+                  const int *__restrict__ rec_off, const Rec *__restrict__ rec,
                   unsigned char *__restrict__ first, int *__restrict__ rowlen) {
   const int a = big_rows[blockIdx.x];
   const int beg = rec_off[a], deg = rec_off[a + 1] - beg;
-  const int4 *nb = rec + beg;
+  const Rec *nb = rec + beg;
   unsigned char *fl = first + 2 * (int64_t)beg + a;
   const int ncand = 2 * deg + 1;
   int mine = 0;
@@ -216,35 +237,46 @@ rowlen_big_kernel(const int *__restrict__ big_rows, int rb,
 // ------------------------------------------------------ (T,k) row order
 __global__ void __launch_bounds__(THREADS)
 sort_rows_kernel(int n_own, const int *__restrict__ rec_off,
-                 const int4 *__restrict__ rec, int4 *__restrict__ out) {
+                 const Rec *__restrict__ rec, const int *__restrict__ rec_elem,
+                 Rec *__restrict__ out, int *__restrict__ out_elem) {
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= n_own) return;
   const int beg = rec_off[a], end = rec_off[a + 1];
   for (int i = beg; i < end; ++i) {
-    const int4 v = rec[i];
-    const unsigned key = ((unsigned)v.z << 2) | (unsigned)rec_k(v);
+    const Rec v = rec[i];
+    const unsigned key = ((unsigned)rec_elem[i] << 2) | (unsigned)rec_k(v);
     int rank = 0;
-    for (int j = beg; j < end; ++j) {
-      const int4 q = rec[j];
-      rank += (((unsigned)q.z << 2) | (unsigned)rec_k(q)) < key;
-    }
+    for (int j = beg; j < end; ++j)
+      rank += (((unsigned)rec_elem[j] << 2) | (unsigned)rec_k(rec[j])) < key;
     out[beg + rank] = v;
+    out_elem[beg + rank] = rec_elem[i];
   }
+}
+
+int require_elements(const p1_plan *p, const char *who) {
+  if (p->rec_elem) return P1_OK;
+  set_error("%s needs a plan created with P1_PLAN_KEEP_ELEMENTS", who);
+  return P1_EINVAL;
 }
 
 int ensure_sorted(p1_plan *p, cudaStream_t s) {
   if (p->sorted) return P1_OK;
+  P1_TRY(require_elements(p, "ordering records by (element, vertex)"));
   p1_ctx *ctx = p->ctx;
   const int n_own = (int)(p->row_end - p->row_begin);
-  int4 *r2 = nullptr;
+  Rec *r2 = nullptr;
+  int *e2 = nullptr;
   P1_TRY(pool_alloc(ctx, &r2, (size_t)p->n_rec, s));
+  P1_TRY(pool_alloc(ctx, &e2, (size_t)p->n_rec, s));
   if (n_own > 0)
     P1_TIMED(p->ctx, "sort_rows", s,
              sort_rows_kernel<<<grid_for(n_own, THREADS), THREADS, 0, s>>>(
-                 n_own, p->rec_off, p->rec, r2));
+                 n_own, p->rec_off, p->rec, p->rec_elem, r2, e2));
   P1_CUDA(cudaGetLastError());
   pool_free(ctx, p->rec, s);
+  pool_free(ctx, p->rec_elem, s);
   p->rec = r2;
+  p->rec_elem = e2;
   p->sorted = true;
   return P1_OK;
 }
@@ -319,10 +351,10 @@ extern "C" int p1_partition_rows(p1_ctx *ctx, const int32_t *elements,
   return P1_OK;
 }
 
-extern "C" int p1_plan_create(p1_ctx *ctx, const int32_t *elements,
-                              int64_t n_elements, int64_t n_nodes,
-                              int64_t row_begin, int64_t row_end, int flags,
-                              void *stream, p1_plan **out) {
+static int plan_build(p1_ctx *ctx, const int32_t *elements, int64_t n_elements,
+                      int64_t n_nodes, int64_t row_begin, int64_t row_end, int flags,
+                      int op, const double *coords, const double *local,
+                      void *stream, p1_plan **out) {
   P1_REQUIRE(ctx && out, "null ctx/out");
   P1_REQUIRE(n_elements >= 0 && n_nodes >= 0, "negative size");
   P1_REQUIRE(row_begin >= 0 && row_begin <= row_end && row_end <= n_nodes,
@@ -335,6 +367,12 @@ extern "C" int p1_plan_create(p1_ctx *ctx, const int32_t *elements,
     return P1_ERANGE;
   }
   P1_REQUIRE(elements || n_elements == 0, "null elements");
+  P1_REQUIRE(op == 0 || op == P1_OP_STIFFNESS || op == P1_OP_MASS || op == P1_OP_LOCAL,
+             "unknown op");
+  P1_REQUIRE(!(op == P1_OP_STIFFNESS || op == P1_OP_MASS) || coords || n_elements == 0,
+             "stiffness/mass need coords");
+  P1_REQUIRE(op != P1_OP_LOCAL || local || n_elements == 0,
+             "P1_OP_LOCAL needs the local matrices");
   DeviceGuard guard(ctx->device);
   cudaStream_t s = (cudaStream_t)stream;
   const int n_own = (int)(row_end - row_begin);
@@ -399,10 +437,29 @@ extern "C" int p1_plan_create(p1_ctx *ctx, const int32_t *elements,
   }
   p->n_rec = n_rec;
   if ((rc = pool_alloc(ctx, &p->rec, (size_t)n_rec, s))) return fail(rc);
+  if ((flags & P1_PLAN_KEEP_ELEMENTS) &&
+      (rc = pool_alloc(ctx, &p->rec_elem, (size_t)n_rec, s)))
+    return fail(rc);
   // cursor := row offsets (cnt is free again)
   cudaMemcpyAsync(cnt, p->rec_off, (size_t)n_own * sizeof(int), cudaMemcpyDeviceToDevice, s);
-  P1_TIMED(ctx, "scatter", s,
-           scatter_kernel<<<eg, THREADS, 0, s>>>(elements, M, N, rb, re, cnt, p->rec));
+  {
+    const double2 *xy = (const double2 *)coords;
+    prof_begin(ctx, "scatter", s);
+    if (op == P1_OP_STIFFNESS)
+      scatter_kernel<<<eg, THREADS, 0, s>>>(elements, M, N, rb, re, cnt, p->rec,
+                                            p->rec_elem, StiffnessValues{xy});
+    else if (op == P1_OP_MASS)
+      scatter_kernel<<<eg, THREADS, 0, s>>>(elements, M, N, rb, re, cnt, p->rec,
+                                            p->rec_elem, MassValues{xy});
+    else if (op == P1_OP_LOCAL)
+      scatter_kernel<<<eg, THREADS, 0, s>>>(elements, M, N, rb, re, cnt, p->rec,
+                                            p->rec_elem, LocalValues{local});
+    else
+      scatter_kernel<<<eg, THREADS, 0, s>>>(elements, M, N, rb, re, cnt, p->rec,
+                                            p->rec_elem, NoValues{});
+    prof_end(ctx, s);
+    p->val_op = op;
+  }
   if (p->exact && n_own > 0)
     P1_TIMED(ctx, "rowlen", s,
              rowlen_kernel<<<grid_for((int64_t)n_own * GROUP, THREADS), THREADS, 0, s>>>(
@@ -426,13 +483,18 @@ extern "C" int p1_plan_create(p1_ctx *ctx, const int32_t *elements,
     rowlen_slow_kernel<<<grid_for(p->n_slow, THREADS), THREADS, 0, s>>>(
         p->slow_rows, p->n_slow, rb, p->rec_off, p->rec, rowlen);
   if (p->n_big > 0) {
-    int4 *tmp = nullptr;
+    Rec *tmp = nullptr;
+    int *tmp_elem = nullptr;
     if ((rc = pool_alloc(ctx, &tmp, (size_t)n_rec, s)) ||
+        (rc = pool_alloc(ctx, &tmp_elem, (size_t)n_rec, s)) ||
         (rc = pool_alloc(ctx, &p->big_first, (size_t)(2 * n_rec + n_own + 1), s))) {
       pool_free(ctx, tmp, s);
+      pool_free(ctx, tmp_elem, s);
       return fail(rc);
     }
-    sort_big_kernel<<<p->n_big, THREADS, 0, s>>>(p->big_rows, p->rec_off, p->rec, tmp);
+    sort_big_kernel<<<p->n_big, THREADS, 0, s>>>(p->big_rows, p->rec_off, p->rec,
+                                                 p->rec_elem, tmp, tmp_elem);
+    pool_free(ctx, tmp_elem, s);
     rowlen_big_kernel<<<p->n_big, THREADS, 0, s>>>(p->big_rows, rb, p->rec_off,
                                                    p->rec, p->big_first, rowlen);
     pool_free(ctx, tmp, s);
@@ -454,11 +516,29 @@ extern "C" int p1_plan_create(p1_ctx *ctx, const int32_t *elements,
   return P1_OK;
 }
 
+extern "C" int p1_plan_create(p1_ctx *ctx, const int32_t *elements,
+                              int64_t n_elements, int64_t n_nodes,
+                              int64_t row_begin, int64_t row_end, int flags,
+                              void *stream, p1_plan **out) {
+  return plan_build(ctx, elements, n_elements, n_nodes, row_begin, row_end, flags, 0,
+                    nullptr, nullptr, stream, out);
+}
+
+extern "C" int p1_plan_create_for(p1_ctx *ctx, const int32_t *elements,
+                                  int64_t n_elements, int64_t n_nodes,
+                                  int64_t row_begin, int64_t row_end, int flags, int op,
+                                  const double *coords, const double *local,
+                                  void *stream, p1_plan **out) {
+  P1_REQUIRE(op != 0, "p1_plan_create_for needs an operator");
+  return plan_build(ctx, elements, n_elements, n_nodes, row_begin, row_end, flags, op,
+                    coords, local, stream, out);
+}
+
 extern "C" int p1_plan_destroy(p1_plan *p) {
   if (!p) return P1_OK;
   DeviceGuard guard(p->ctx->device);
-  void *blocks[] = {p->rec_off, p->rec, p->acc, p->indptr, p->slow_rows, p->big_rows,
-                    p->big_first, p->twin};
+  void *blocks[] = {p->rec_off, p->rec, p->rec_elem, p->acc, p->indptr, p->slow_rows,
+                    p->big_rows, p->big_first, p->twin};
   for (void *b : blocks) pool_free(p->ctx, b, p->stream);
   delete p;
   return P1_OK;

@@ -1,7 +1,19 @@
-// plan.cuh -- the p1_plan object and the 8-lane row analysis shared by the
-// symbolic (row length) and numeric (fill) kernels.
+// plan.cuh -- the p1_plan object, the 32-byte incidence record and the 8-lane
+// row analysis shared by the symbolic (row length) and numeric (fill) kernels.
 #pragma once
 #include "common.cuh"
+
+namespace p1 {
+// One record per (node, incident element): exactly one 32-byte sector, written
+// with one 256-bit store by the scatter and read with one 256-bit load per lane.
+//   nx  : next vertex of the element after this node
+//   pvk : previous vertex | local index k of this node in the element << 29
+//   vd, vn, vp : entries (k,k), (k,k+1), (k,k+2) of the element's local matrix
+struct __align__(32) Rec {
+  int nx, pvk;
+  double vd, vn, vp;
+};
+}  // namespace p1
 
 struct p1_plan {
   p1_ctx *ctx;
@@ -13,15 +25,16 @@ struct p1_plan {
   int64_t nnz;
   int max_index;
   int *rec_off;        // n_own+1 : node -> first record
-  int4 *rec;           // n_rec   : x = next node, y = prev node | k<<29, z = element,
-                       //           w = 0; arrival order within a row until `sorted`
+  p1::Rec *rec;        // n_rec   : arrival order within a row until `sorted`
+  int *rec_elem;       // n_rec   : element of the record (P1_PLAN_KEEP_ELEMENTS) or null
+  int val_op;          // which operator's values the records hold (0 = none)
   bool sorted;         // records of every row ascending in (element, vertex)
   bool exact;          // row lengths from the all-pairs kernel (no hash shortcut)
   unsigned long long *acc;  // n_own: low 32 bits = #records, high 32 bits = sum over the
                        // records of hash(next) - hash(prev): 0 for a closed fan
   int *indptr;         // n_own+1
-  int *slow_rows;      // rows the 8-lane kernels do not take: more than 8 records
-                       // or repeated neighbours (non-manifold / degenerate)
+  int *slow_rows;      // rows the 8-lane kernels do not take: open fans, more than 8
+                       // records, repeated neighbours (non-manifold / degenerate)
   int n_slow;
   int *big_rows;       // rows with more than DEG_BIG records
   int n_big;
@@ -40,25 +53,46 @@ __host__ __device__ __forceinline__ unsigned mix32(unsigned x) {
 
 constexpr int GROUP = 8;      // lanes per row in the fast kernels = max records
 constexpr int DEG_BIG = 40;   // rows with more records take the block-per-row path
-// node ids must leave the top 3 bits of an int free (k is packed into rec.y)
+// node ids must leave the top 3 bits of an int free (k is packed into pvk)
 constexpr int NODE_BITS = 29;
 constexpr int NODE_MASK = (1 << NODE_BITS) - 1;
 
 __device__ __forceinline__ int next_local(int k) { return k == 2 ? 0 : k + 1; }
 __device__ __forceinline__ int prev_local(int k) { return k == 0 ? 2 : k - 1; }
-__device__ __forceinline__ int rec_next(const int4 &r) { return r.x; }
-__device__ __forceinline__ int rec_prev(const int4 &r) { return r.y & NODE_MASK; }
-__device__ __forceinline__ int rec_k(const int4 &r) { return (int)((unsigned)r.y >> NODE_BITS); }
-__device__ __forceinline__ int rec_elem(const int4 &r) { return r.z; }
+__device__ __forceinline__ int rec_next(const Rec &r) { return r.nx; }
+__device__ __forceinline__ int rec_prev(const Rec &r) { return r.pvk & NODE_MASK; }
+__device__ __forceinline__ int rec_k(const Rec &r) { return (int)((unsigned)r.pvk >> NODE_BITS); }
+
+// sm_100a has 256-bit global loads/stores (LDG.E.256 / STG.E.256)
+__device__ __forceinline__ void store_rec(Rec *p, const Rec &r) {
+  asm volatile("st.global.v4.b64 [%0], {%1,%2,%3,%4};"
+               :: "l"(p), "l"(((long long)(unsigned)r.pvk << 32) | (unsigned)r.nx),
+                  "l"(__double_as_longlong(r.vd)), "l"(__double_as_longlong(r.vn)),
+                  "l"(__double_as_longlong(r.vp))
+               : "memory");
+}
+__device__ __forceinline__ Rec load_rec(const Rec *p) {
+  long long a, b, c, d;
+  asm volatile("ld.global.v4.b64 {%0,%1,%2,%3}, [%4];"
+               : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+  Rec r;
+  r.nx = (int)(unsigned)(a & 0xffffffffll);
+  r.pvk = (int)(unsigned)((unsigned long long)a >> 32);
+  r.vd = __longlong_as_double(b);
+  r.vn = __longlong_as_double(c);
+  r.vp = __longlong_as_double(d);
+  return r;
+}
 
 // What one lane of an 8-lane group knows about "its" record and its row after
-// the all-pairs comparison (shuffles only).  A row is `simple` when it has at
-// most 8 records, all `next` distinct, all `prev` distinct and none equal to
-// the row itself -- every row of an edge-manifold mesh of valence <= 8.
+// the all-pairs comparison.  A row is `simple` when it has at most 8 records,
+// all `next` distinct, all `prev` distinct and none equal to the row itself --
+// every row of an edge-manifold mesh of valence <= 8.
 struct RowLane {
   bool valid;     // this lane holds a record
   bool simple;    // group-uniform
-  int nx, pv, k, elem;
+  int nx, pv, k;
+  double vd, vn, vp;
   int rk;         // rank of nx among the row's nexts = canonical record order
   int src;        // lane whose next == my prev (the element before me), or -1
   int mate;       // lane whose prev == my next (the element after me), or -1
@@ -72,17 +106,18 @@ struct RowLane {
 // per lane saturate the ADU pipe -- measured 93 % -- while broadcast LDS is
 // one wavefront per warp.)
 __device__ __forceinline__ RowLane analyse_row(int self, int beg, int deg,
-                                               const int4 *__restrict__ rec,
+                                               const Rec *__restrict__ rec,
                                                unsigned gmask, int lane8, int shift,
                                                int2 *xch) {
   RowLane o;
   o.valid = lane8 < deg && deg <= GROUP;
-  int4 r = make_int4(-1, -2, 0, 0);
-  if (o.valid) r = __ldg(rec + beg + lane8);
-  o.nx = rec_next(r);
+  Rec r;
+  r.nx = -1; r.pvk = 0; r.vd = r.vn = r.vp = 0.;
+  if (o.valid) r = load_rec(rec + beg + lane8);
+  o.nx = r.nx;
   o.pv = o.valid ? rec_prev(r) : -2;
   o.k = rec_k(r);
-  o.elem = rec_elem(r);
+  o.vd = r.vd; o.vn = r.vn; o.vp = r.vp;
   int2 *grp = xch + (threadIdx.x & ~(GROUP - 1));
   grp[lane8] = make_int2(o.nx, o.pv);
   __syncwarp(gmask);
@@ -129,5 +164,57 @@ int ensure_twins(p1_plan *plan, cudaStream_t s);
 // puts the records of every row into ascending (element, vertex) order: the
 // order of the reference's sequential np.bincount (load vectors)
 int ensure_sorted(p1_plan *plan, cudaStream_t s);
+// error unless the plan was created with P1_PLAN_KEEP_ELEMENTS
+int require_elements(const p1_plan *plan, const char *who);
+
+// ---- value sources for the scatter / refresh kernels (assemble.cu) ----------
+// rows(t, e, v): v[k][0..2] = entries (k,k), (k,k+1), (k,k+2) of element t
+struct NoValues {
+  __device__ __forceinline__ void rows(int64_t, const int *, double (*v)[3]) const {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) v[k][0] = v[k][1] = v[k][2] = 0.;
+  }
+};
+struct StiffnessValues {  // solvers.py:31-45
+  const double2 *__restrict__ coords;
+  __device__ __forceinline__ void rows(int64_t, const int *e, double (*v)[3]) const {
+    const double2 z0 = __ldg(coords + e[0]), z1 = __ldg(coords + e[1]),
+                  z2 = __ldg(coords + e[2]);
+    const double d21x = z1.x - z0.x, d21y = z1.y - z0.y;
+    const double d31x = z2.x - z0.x, d31y = z2.y - z0.y;
+    const double area4 = 4. * (0.5 * (d21x * d31y - d21y * d31x));
+    const double a = (d21x * d31x + d21y * d31y) / area4;
+    const double b = (d31x * d31x + d31y * d31y) / area4;
+    const double c = (d21x * d21x + d21y * d21y) / area4;
+    v[0][0] = -2. * a + b + c; v[0][1] = a - b; v[0][2] = a - c;
+    v[1][0] = b;               v[1][1] = -a;    v[1][2] = a - b;
+    v[2][0] = c;               v[2][1] = a - c; v[2][2] = -a;
+  }
+};
+struct MassValues {  // solvers.py:176-181
+  const double2 *__restrict__ coords;
+  __device__ __forceinline__ void rows(int64_t, const int *e, double (*v)[3]) const {
+    const double2 z0 = __ldg(coords + e[0]), z1 = __ldg(coords + e[1]),
+                  z2 = __ldg(coords + e[2]);
+    const double d21x = z1.x - z0.x, d21y = z1.y - z0.y;
+    const double d31x = z2.x - z0.x, d31y = z2.y - z0.y;
+    const double area = 0.5 * (d21x * d31y - d21y * d31x);
+    const double on = area / 6., off = area / 12.;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { v[k][0] = on; v[k][1] = off; v[k][2] = off; }
+  }
+};
+struct LocalValues {  // 3x3 local matrix given per element, row-major
+  const double *__restrict__ local;
+  __device__ __forceinline__ void rows(int64_t t, const int *, double (*v)[3]) const {
+    const double *m = local + 9 * t;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      v[k][0] = __ldg(m + 3 * k + k);
+      v[k][1] = __ldg(m + 3 * k + (k == 2 ? 0 : k + 1));
+      v[k][2] = __ldg(m + 3 * k + (k == 0 ? 2 : k - 1));
+    }
+  }
+};
 
 }  // namespace p1

@@ -128,11 +128,14 @@ class DeviceMesh:
     ``elements`` (node -> incident elements, CSR row pointer).
 
     rows=(begin, end) restricts the plan to a contiguous row range (one rank of
-    a multi-GPU assembly); everything else is identical.
+    a multi-GPU assembly); everything else is identical.  reuse=True keeps the
+    plan across assemble() calls (new coefficients on the same mesh only
+    recompute the values); the default rebuilds it, which is what the
+    reference's stateless functions do.
     """
 
     def __init__(self, coordinates, elements, device=None, rows=None,
-                 n_nodes=None):
+                 n_nodes=None, reuse=False, check=True):
         self.ctx, self.device = context(device)
         self._lib = _lib.load()
         self.elements = to_device_indices(elements, self.device, self.ctx)
@@ -151,10 +154,17 @@ class DeviceMesh:
         self.n_nodes = int(n_nodes)
         self.n_elements = int(self.elements.shape[0])
         self.rows = (0, self.n_nodes) if rows is None else (int(rows[0]), int(rows[1]))
+        self.reuse = bool(reuse)
         self._plan = None
+        self._plan_keeps_elements = False
         self._exact = False
         self.nnz = None
         self.max_index = None
+        if check and self.elements.numel():
+            # every kernel gathers by element index: reject bad input up front
+            _lib.check(self._lib.p1_check_indices(
+                self.ctx, _ptr(self.elements), self.elements.numel(), self.n_nodes,
+                _stream(self.device)))
 
     def balanced_rows(self, world):
         """Row boundaries (world+1) with about equal numbers of stored entries
@@ -170,21 +180,40 @@ class DeviceMesh:
         self.rows = (int(rows[0]), int(rows[1]))
 
     # ------------------------------------------------------------------ plan
+    def _flags(self, keep):
+        return ((_lib.PLAN_EXACT if self._exact else 0)
+                | (_lib.PLAN_KEEP_ELEMENTS if keep else 0))
+
+    def _adopt(self, handle, keep):
+        self._plan = handle
+        self._plan_keeps_elements = keep
+        nnz, mx = C.c_int64(), C.c_int64()
+        _lib.check(self._lib.p1_plan_info(handle, C.byref(nnz), C.byref(mx), None, None))
+        self.nnz, self.max_index = nnz.value, mx.value
+
     @property
     def plan(self):
+        """Symbolic plan that remembers the element of every record (what load
+        vectors, edge numbering and eta_R need)."""
+        if self._plan is not None and not self._plan_keeps_elements:
+            self.close()
         if self._plan is None:
             handle = C.c_void_p()
             _lib.check(self._lib.p1_plan_create(
                 self.ctx, _ptr(self.elements), self.n_elements, self.n_nodes,
-                self.rows[0], self.rows[1],
-                _lib.PLAN_EXACT if self._exact else _lib.PLAN_DEFAULT,
-                _stream(self.device), C.byref(handle)))
-            self._plan = handle
-            nnz, mx = C.c_int64(), C.c_int64()
-            _lib.check(self._lib.p1_plan_info(handle, C.byref(nnz), C.byref(mx),
-                                              None, None))
-            self.nnz, self.max_index = nnz.value, mx.value
+                self.rows[0], self.rows[1], self._flags(True), _stream(self.device),
+                C.byref(handle)))
+            self._adopt(handle, True)
         return self._plan
+
+    def _plan_for(self, op, local):
+        """Cold path of one matrix: scatter and local matrices in one kernel."""
+        handle = C.c_void_p()
+        _lib.check(self._lib.p1_plan_create_for(
+            self.ctx, _ptr(self.elements), self.n_elements, self.n_nodes,
+            self.rows[0], self.rows[1], self._flags(self.reuse), op, _ptr(self.coords),
+            _ptr(local), _stream(self.device), C.byref(handle)))
+        self._adopt(handle, self.reuse)
 
     def close(self):
         if self._plan is not None:
@@ -211,14 +240,19 @@ class DeviceMesh:
         """-> (indptr, indices, data) CUDA tensors over the owned rows.
         pattern=False skips the index arrays (re-assembly on the same mesh)."""
         for attempt in (0, 1):
-            plan = self.plan
+            if self._plan is not None and self._plan_keeps_elements:
+                run_op = op                      # refresh the values in place
+            else:
+                self.close()
+                self._plan_for(op, local)
+                run_op = _lib.OP_STORED
             n_own = self.rows[1] - self.rows[0]
             data = self._empty(self.nnz)
             indptr = self._empty(n_own + 1, torch.int32) if pattern else None
             indices = self._empty(self.nnz, torch.int32) if pattern else None
             rc = self._lib.p1_assemble_csr(
-                plan, op, _ptr(self.coords), _ptr(local), _ptr(indptr), _ptr(indices),
-                _ptr(data), _stream(self.device))
+                self._plan, run_op, _ptr(self.coords), _ptr(local), _ptr(indptr),
+                _ptr(indices), _ptr(data), _stream(self.device))
             if rc == _lib.P1_ERETRY and attempt == 0 and not self._exact:
                 # non-manifold vertex / degenerate element: the closed-fan
                 # shortcut of the default plan does not hold; count exactly
@@ -226,6 +260,8 @@ class DeviceMesh:
                 self._exact = True
                 continue
             _lib.check(rc)
+            if not self.reuse:
+                self.close()
             return indptr, indices, data
 
     def stiffness_csr(self, pattern=True):

@@ -15,7 +15,6 @@ def compute_eta_r(x, coordinates, elements, dirichlet, neumann, f, g):
     element centroids) and ``g`` (at the Neumann edge midpoints) run on the
     host, everything else on the device."""
     with DeviceMesh(coordinates, elements) as mesh:
-        mesh.plan  # noqa: B018  range check
         d = to_device_indices(np.asarray(dirichlet).reshape(-1, 2), mesh.device,
                               mesh.ctx)
         n = to_device_indices(np.asarray(neumann).reshape(-1, 2), mesh.device,

@@ -12,7 +12,6 @@ __all__ = ['get_area', 'get_directional_vectors', 'provide_geometric_data']
 def get_area(coordinates, elements):
     """Signed element areas (mesh.py:10-28)."""
     with DeviceMesh(coordinates, elements) as mesh:
-        mesh.plan  # noqa: B018  range check
         area, _, _ = mesh.geometry(area=True, vectors=False)
         return to_host(area)
 
@@ -20,7 +19,6 @@ def get_area(coordinates, elements):
 def get_directional_vectors(coordinates, elements):
     """(d21, d31): vertex0->vertex1 and vertex0->vertex2 (mesh.py:31-51)."""
     with DeviceMesh(coordinates, elements) as mesh:
-        mesh.plan  # noqa: B018
         _, d21, d31 = mesh.geometry(area=False, vectors=True)
         return to_host(d21), to_host(d31)
 

@@ -66,7 +66,6 @@ def get_mass_matrix(coordinates, elements):
 def get_mass_matrix_elements(coordinates, elements):
     """(I, J, D) triplets in the reference's order (solvers.py:156-182)."""
     with DeviceMesh(coordinates, elements) as mesh:
-        _check_range(mesh)
         rows, cols, vals = mesh.triplets(stiffness=False)
         kind = np.asarray(elements).dtype
         i, j = to_host(rows), to_host(cols)
@@ -75,19 +74,12 @@ def get_mass_matrix_elements(coordinates, elements):
         return i, j, to_host(vals)
 
 
-def _check_range(mesh):
-    """Kernels that gather by element index without a plan rely on the range
-    check the plan performs."""
-    mesh.plan  # noqa: B018  (raises IndexError on out-of-range indices)
-
-
 def get_general_stiffness_matrix(coordinates, elements, a_11, a_12, a_21, a_22,
                                  cubature_rule):
     """Stiffness matrix of -div(A(x) grad u) (solvers.py:278-377) as CSR with
     explicit shape (N, N)."""
     weights, points = resolve_rule(cubature_rule)
     with DeviceMesh(coordinates, elements) as mesh:
-        _check_range(mesh)
         xq = mesh.quadrature_points(points)
         q11, q12, q21, q22 = _callback_at_points((a_11, a_12, a_21, a_22), xq)
         del xq
@@ -100,11 +92,11 @@ def get_weighted_mass_matrix(coordinates, elements, current_iterate, phi,
     """M_ij = int phi(u_h) phi_i phi_j (solvers.py:50-142) as CSR (N, N)."""
     weights, points = resolve_rule(cubature_rule)
     with DeviceMesh(coordinates, elements) as mesh:
-        _check_range(mesh)
         u = np.asarray(current_iterate, dtype=np.float64).reshape(-1)
-        if u.shape[0] < mesh.max_index + 1:
+        top = int(mesh.elements.max().item()) if mesh.n_elements else -1
+        if u.shape[0] < top + 1:
             raise IndexError('current_iterate has %d entries, elements reference '
-                             'node %d' % (u.shape[0], mesh.max_index))
+                             'node %d' % (u.shape[0], top))
         if u.shape[0] != mesh.n_nodes:   # numpy would only read what it needs
             u = np.concatenate([u, np.zeros(max(0, mesh.n_nodes - u.shape[0]))])[:mesh.n_nodes]
         uq = to_host(mesh.nodal_at_quadrature(u, points))
@@ -123,7 +115,6 @@ def get_right_hand_side(coordinates, elements, f, cubature_rule=None):
             coordinates=coordinates, elements=elements, f=f,
             cubature_rule=cubature_rule)
     with DeviceMesh(coordinates, elements) as mesh:
-        _check_range(mesh)
         cent = to_host(mesh.centroids())
         fc = _values_on_host(f, cent, mesh.n_elements)
         return to_host(mesh.load_vector_midpoint(fc))
@@ -134,6 +125,5 @@ def get_right_hand_side_using_quadrature_rule(coordinates, elements, f,
     """Load vector with a cubature rule (solvers.py:540-598)."""
     weights, points = resolve_rule(cubature_rule)
     with DeviceMesh(coordinates, elements) as mesh:
-        _check_range(mesh)
         (fq,) = _callback_at_points((f,), mesh.quadrature_points(points))
         return to_host(mesh.load_vector(fq, weights, points))

