@@ -13,58 +13,154 @@ namespace p1 {
 
 constexpr int THREADS = 256;
 
-// ------------------------------------------------------ fast path: 8 lanes/row
-__global__ void __launch_bounds__(THREADS)
+// ---------------------------------------------------- fast path: thread per row
+// One block = FR consecutive rows.  Their records form one contiguous range:
+// the block loads it with coalesced 256-bit loads and transposes it into
+// shared memory (field arrays); thread t then owns row row0+t: it pulls its
+// <= 8 records into registers, does the all-pairs comparison fully unrolled
+// (rank of every column, the mate record sharing each off-diagonal entry,
+// verification that the fan is closed and repeat-free), builds the row in a
+// shared-memory image of the block's contiguous CSR span, and the block
+// streams the image out with coalesced stores.
+constexpr int FR = 128;          // rows per block = threads per block
+constexpr int CAP_REC = 1024;    // records staged per block (8 per row)
+constexpr int CAP_OUT = 1280;    // CSR entries staged per block (9 per regular row + slack)
+
+__global__ void __launch_bounds__(FR)
 fill_rows_kernel(int n_own, int rb, int exact,
                  const unsigned long long *__restrict__ acc,
                  const int *__restrict__ rec_off, const Rec *__restrict__ rec,
                  const int *__restrict__ indptr, int *__restrict__ indices,
                  double *__restrict__ data, int *__restrict__ flags) {
-  __shared__ int2 xch[THREADS];
-  __shared__ double s_vp[THREADS];
-  __shared__ double s_vd[THREADS];
-  const int lane = threadIdx.x & 31, lane8 = lane & (GROUP - 1);
-  const int shift = lane & ~(GROUP - 1);
-  const unsigned gmask = 0xffu << shift;
-  const int gbase = threadIdx.x & ~(GROUP - 1);
-  const int a = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / GROUP);
-  if (a >= n_own) return;
-  // the three loads that depend on the row id only are issued together: the
-  // kernel is bound by the latency of its dependent loads, not by bandwidth
-  const unsigned long long v = __ldg(acc + a);
-  const int beg = __ldg(rec_off + a);
-  const int64_t base = __ldg(indptr + a);
-  const int deg = (int)(unsigned)v;
-  // group-uniform exits: empty rows; rows the slow / big kernels take
-  if (deg == 0 || deg > GROUP) return;
-  if (!exact && (unsigned)(v >> 32) != 0u) return;
-  const int self = a + rb;
-  const RowLane r = analyse_row(self, beg, deg, rec, gmask, lane8, shift, xch);
-  if (!r.simple || (!exact && r.len != 1 + deg)) {
-    // exact plan: the row is in slow_rows.  Hash plan: the shortcut
-    // "closed fan => 1 + #records columns" does not hold for this row.
-    if (!exact && lane8 == 0) atomicOr(flags, FLAG_RETRY);
-    return;
+  __shared__ int nx_s[CAP_REC];
+  __shared__ int pv_s[CAP_REC];
+  __shared__ double vd_s[CAP_REC];
+  __shared__ double vn_s[CAP_REC];
+  __shared__ double vp_s[CAP_REC];
+  __shared__ int cols_s[CAP_OUT];
+  __shared__ double vals_s[CAP_OUT];
+  const int tid = threadIdx.x;
+  const int row0 = blockIdx.x * FR;
+  const int nrows = min(FR, n_own - row0);
+  const int rbeg = __ldg(rec_off + row0), rend = __ldg(rec_off + row0 + nrows);
+  const int obeg = __ldg(indptr + row0), oend = __ldg(indptr + row0 + nrows);
+  const int nrec = rend - rbeg, span = oend - obeg;
+  const bool in_staged = nrec <= CAP_REC, out_staged = span <= CAP_OUT;  // block-uniform
+  // per-row scalars (issued before the staging loop: independent loads)
+  int deg = 0, beg = 0, ob = 0;
+  unsigned hash = 0;
+  if (tid < nrows) {
+    const unsigned long long v = __ldg(acc + row0 + tid);
+    deg = (int)(unsigned)v;
+    hash = (unsigned)(v >> 32);
+    beg = __ldg(rec_off + row0 + tid);
+    ob = __ldg(indptr + row0 + tid);
   }
-  s_vp[threadIdx.x] = r.vp;
-  if (r.valid) s_vd[gbase + r.rk] = r.vd;  // canonical order: ascending `next`
-  __syncwarp(gmask);
-  if (r.valid) {
-    // column `next`: my (k,k+1) entry plus the (k,k+2) entry of the element
-    // after me in the fan (two terms: order-free)
-    const double off = r.mate < 0 ? r.vn : r.vn + s_vp[gbase + r.mate];
-    if (indices) indices[base + r.slot_nx] = r.nx;
-    data[base + r.slot_nx] = off;
-    if (r.extra) {
-      if (indices) indices[base + r.slot_pv] = r.pv;
-      data[base + r.slot_pv] = r.vp;
+  if (in_staged) {
+    for (int j = tid; j < nrec; j += FR) {
+      const Rec r = load_rec(rec + rbeg + j);
+      nx_s[j] = r.nx;
+      pv_s[j] = rec_prev(r);
+      vd_s[j] = r.vd;
+      vn_s[j] = r.vn;
+      vp_s[j] = r.vp;
     }
   }
-  if (lane8 == 0) {
-    double diag = 0.;
-    for (int q = 0; q < deg; ++q) diag += s_vd[gbase + q];
-    if (indices) indices[base + r.slot_self] = self;
-    data[base + r.slot_self] = diag;
+  __syncthreads();
+  bool process = deg >= 1 && deg <= GROUP && (exact || hash == 0u);
+  const int self = row0 + tid + rb;
+  int nx[GROUP], pv[GROUP], slot[GROUP];
+  double vd[GROUP], vn[GROUP], vp[GROUP], mvp[GROUP];
+  int slot_self = 0;
+  if (process) {
+#pragma unroll
+    for (int i = 0; i < GROUP; ++i) {
+      nx[i] = 0x7fffffff - i;  // never below a valid column, never equal to one
+      pv[i] = -2 - i;
+      vd[i] = vn[i] = vp[i] = 0.;
+      if (i < deg) {
+        if (in_staged) {
+          const int j = beg - rbeg + i;
+          nx[i] = nx_s[j]; pv[i] = pv_s[j];
+          vd[i] = vd_s[j]; vn[i] = vn_s[j]; vp[i] = vp_s[j];
+        } else {
+          const Rec r = load_rec(rec + beg + i);
+          nx[i] = r.nx; pv[i] = rec_prev(r);
+          vd[i] = r.vd; vn[i] = r.vn; vp[i] = r.vp;
+        }
+      }
+    }
+    // all pairs, in registers
+    bool ok = true;
+    slot_self = 0;
+#pragma unroll
+    for (int i = 0; i < GROUP; ++i) {
+      int below = 0;
+      bool mated = false;
+      mvp[i] = 0.;
+#pragma unroll
+      for (int j = 0; j < GROUP; ++j) {
+        below += nx[j] < nx[i];
+        if (pv[j] == nx[i]) { mvp[i] = vp[j]; mated = true; }
+        if (j > i) ok = ok && nx[j] != nx[i] && pv[j] != pv[i];
+      }
+      const bool live = i < deg;
+      // closed, repeat-free fan: every next has a mate, nothing equals the row
+      ok = ok && (!live || (mated && nx[i] != self && pv[i] != self));
+      slot[i] = below + (self < nx[i]);
+      slot_self += live && nx[i] < self;
+    }
+    if (!ok) {
+      // exact plan: the row is in slow_rows.  Hash plan: the shortcut
+      // "closed fan => 1 + #records columns" does not hold for this row.
+      if (!exact) atomicOr(flags, FLAG_RETRY);
+      process = false;
+    }
+  }
+  if (process) {
+    if (out_staged) {
+      int *cs = cols_s + (ob - obeg);
+      double *vs = vals_s + (ob - obeg);
+      // diagonal in a fixed order: park the (k,k) entries at their columns and
+      // add them up in ascending column order
+#pragma unroll
+      for (int i = 0; i < GROUP; ++i)
+        if (i < deg) vs[slot[i]] = vd[i];
+      double diag = 0.;
+      for (int q = 0; q <= deg; ++q)
+        if (q != slot_self) diag += vs[q];
+#pragma unroll
+      for (int i = 0; i < GROUP; ++i)
+        if (i < deg) { cs[slot[i]] = nx[i]; vs[slot[i]] = vn[i] + mvp[i]; }
+      cs[slot_self] = self;
+      vs[slot_self] = diag;
+    } else {
+      // oversize block (irregular rows inside): same construction in place
+      double *vs = data + ob;
+#pragma unroll
+      for (int i = 0; i < GROUP; ++i)
+        if (i < deg) vs[slot[i]] = vd[i];
+      double diag = 0.;
+      for (int q = 0; q <= deg; ++q)
+        if (q != slot_self) diag += vs[q];
+#pragma unroll
+      for (int i = 0; i < GROUP; ++i)
+        if (i < deg) {
+          if (indices) indices[ob + slot[i]] = nx[i];
+          vs[slot[i]] = vn[i] + mvp[i];
+        }
+      if (indices) indices[ob + slot_self] = self;
+      vs[slot_self] = diag;
+    }
+  }
+  __syncthreads();
+  if (out_staged) {
+    // rows the slow / big kernels own get whatever the image holds here; those
+    // kernels run afterwards on the same stream and overwrite them
+    for (int i = tid; i < span; i += FR) {
+      if (indices) indices[(int64_t)obeg + i] = cols_s[i];
+      data[(int64_t)obeg + i] = vals_s[i];
+    }
   }
 }
 
@@ -263,7 +359,7 @@ extern "C" int p1_assemble_csr(const p1_plan *cplan, int op, const double *coord
   P1_CUDA(cudaMemsetAsync(ctx->d_flags, 0, sizeof(int), s));
   if (n_own > 0)
     P1_TIMED(ctx, "fill_rows", s,
-             (fill_rows_kernel<<<grid_for((int64_t)n_own * GROUP, THREADS), THREADS, 0, s>>>(
+             (fill_rows_kernel<<<grid_for(n_own, FR), FR, 0, s>>>(
                  n_own, rb, plan->exact ? 1 : 0, plan->acc, plan->rec_off, plan->rec,
                  plan->indptr, indices, data, ctx->d_flags)));
   if (plan->n_slow > 0)

@@ -136,7 +136,7 @@ rowlen_kernel(int n_own, int rb, const int *__restrict__ rec_off,
   }
   const RowLane r = analyse_row(a + rb, beg, deg, rec, gmask, lane8, shift, xch);
   if (lane8 != 0) return;
-  if (r.simple) {
+  if (r.simple && r.len == 1 + deg) {  // closed, repeat-free fan: the fast fill takes it
     rowlen[a] = r.len;
   } else if (deg > DEG_BIG) {
     big_rows[atomicAdd(counters, 1)] = a;
