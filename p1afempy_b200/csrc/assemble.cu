@@ -14,39 +14,34 @@ namespace p1 {
 constexpr int THREADS = 256;
 
 // ---------------------------------------------------- fast path: thread per row
-// One block = FR consecutive rows.  Their records form one contiguous range:
-// the block loads it with coalesced 256-bit loads and transposes it into
-// shared memory (field arrays); thread t then owns row row0+t: it pulls its
-// <= 8 records into registers, does the all-pairs comparison fully unrolled
-// (rank of every column, the mate record sharing each off-diagonal entry,
-// verification that the fan is closed and repeat-free), builds the row in a
-// shared-memory image of the block's contiguous CSR span, and the block
-// streams the image out with coalesced stores.
+// Thread t of a block owns row row0+t.  It pulls its <= 8 records straight into
+// registers -- a record is exactly one 32-byte sector, so a per-thread 256-bit
+// load wastes nothing (staging the records through shared memory was measured
+// slower: bank conflicts on the per-row reads) -- does the all-pairs comparison
+// fully unrolled (rank of every column, the mate record sharing each
+// off-diagonal entry, verification that the fan is closed and repeat-free),
+// builds the row in a shared-memory image of the block's contiguous CSR span,
+// and the block streams the image out with coalesced stores.
+#ifndef P1_FILL_MIN_BLOCKS
+#define P1_FILL_MIN_BLOCKS 5
+#endif
 constexpr int FR = 128;          // rows per block = threads per block
-constexpr int CAP_REC = 1024;    // records staged per block (8 per row)
 constexpr int CAP_OUT = 1280;    // CSR entries staged per block (9 per regular row + slack)
 
-__global__ void __launch_bounds__(FR)
+__global__ void __launch_bounds__(FR, P1_FILL_MIN_BLOCKS)
 fill_rows_kernel(int n_own, int rb, int exact,
                  const unsigned long long *__restrict__ acc,
                  const int *__restrict__ rec_off, const Rec *__restrict__ rec,
                  const int *__restrict__ indptr, int *__restrict__ indices,
                  double *__restrict__ data, int *__restrict__ flags) {
-  __shared__ int nx_s[CAP_REC];
-  __shared__ int pv_s[CAP_REC];
-  __shared__ double vd_s[CAP_REC];
-  __shared__ double vn_s[CAP_REC];
-  __shared__ double vp_s[CAP_REC];
   __shared__ int cols_s[CAP_OUT];
   __shared__ double vals_s[CAP_OUT];
   const int tid = threadIdx.x;
   const int row0 = blockIdx.x * FR;
   const int nrows = min(FR, n_own - row0);
-  const int rbeg = __ldg(rec_off + row0), rend = __ldg(rec_off + row0 + nrows);
   const int obeg = __ldg(indptr + row0), oend = __ldg(indptr + row0 + nrows);
-  const int nrec = rend - rbeg, span = oend - obeg;
-  const bool in_staged = nrec <= CAP_REC, out_staged = span <= CAP_OUT;  // block-uniform
-  // per-row scalars (issued before the staging loop: independent loads)
+  const int span = oend - obeg;
+  const bool out_staged = span <= CAP_OUT;  // block-uniform
   int deg = 0, beg = 0, ob = 0;
   unsigned hash = 0;
   if (tid < nrows) {
@@ -56,17 +51,6 @@ fill_rows_kernel(int n_own, int rb, int exact,
     beg = __ldg(rec_off + row0 + tid);
     ob = __ldg(indptr + row0 + tid);
   }
-  if (in_staged) {
-    for (int j = tid; j < nrec; j += FR) {
-      const Rec r = load_rec(rec + rbeg + j);
-      nx_s[j] = r.nx;
-      pv_s[j] = rec_prev(r);
-      vd_s[j] = r.vd;
-      vn_s[j] = r.vn;
-      vp_s[j] = r.vp;
-    }
-  }
-  __syncthreads();
   bool process = deg >= 1 && deg <= GROUP && (exact || hash == 0u);
   const int self = row0 + tid + rb;
   int nx[GROUP], pv[GROUP], slot[GROUP];
@@ -79,20 +63,13 @@ fill_rows_kernel(int n_own, int rb, int exact,
       pv[i] = -2 - i;
       vd[i] = vn[i] = vp[i] = 0.;
       if (i < deg) {
-        if (in_staged) {
-          const int j = beg - rbeg + i;
-          nx[i] = nx_s[j]; pv[i] = pv_s[j];
-          vd[i] = vd_s[j]; vn[i] = vn_s[j]; vp[i] = vp_s[j];
-        } else {
-          const Rec r = load_rec(rec + beg + i);
-          nx[i] = r.nx; pv[i] = rec_prev(r);
-          vd[i] = r.vd; vn[i] = r.vn; vp[i] = r.vp;
-        }
+        const Rec r = load_rec(rec + beg + i);
+        nx[i] = r.nx; pv[i] = rec_prev(r);
+        vd[i] = r.vd; vn[i] = r.vn; vp[i] = r.vp;
       }
     }
     // all pairs, in registers
     bool ok = true;
-    slot_self = 0;
 #pragma unroll
     for (int i = 0; i < GROUP; ++i) {
       int below = 0;
@@ -118,40 +95,27 @@ fill_rows_kernel(int n_own, int rb, int exact,
     }
   }
   if (process) {
-    if (out_staged) {
-      int *cs = cols_s + (ob - obeg);
-      double *vs = vals_s + (ob - obeg);
-      // diagonal in a fixed order: park the (k,k) entries at their columns and
-      // add them up in ascending column order
+    // staged: the row is built in the block's image; otherwise (irregular rows
+    // inside the block made the span oversize) directly in the output
+    int *cs = out_staged ? cols_s + (ob - obeg) : indices + ob;
+    double *vs = out_staged ? vals_s + (ob - obeg) : data + ob;
+    const bool put_cols = out_staged || indices != nullptr;
+    // diagonal in a fixed order: park the (k,k) entries at their columns and
+    // add them up in ascending column order
 #pragma unroll
-      for (int i = 0; i < GROUP; ++i)
-        if (i < deg) vs[slot[i]] = vd[i];
-      double diag = 0.;
-      for (int q = 0; q <= deg; ++q)
-        if (q != slot_self) diag += vs[q];
+    for (int i = 0; i < GROUP; ++i)
+      if (i < deg) vs[slot[i]] = vd[i];
+    double diag = 0.;
+    for (int q = 0; q <= deg; ++q)
+      if (q != slot_self) diag += vs[q];
 #pragma unroll
-      for (int i = 0; i < GROUP; ++i)
-        if (i < deg) { cs[slot[i]] = nx[i]; vs[slot[i]] = vn[i] + mvp[i]; }
-      cs[slot_self] = self;
-      vs[slot_self] = diag;
-    } else {
-      // oversize block (irregular rows inside): same construction in place
-      double *vs = data + ob;
-#pragma unroll
-      for (int i = 0; i < GROUP; ++i)
-        if (i < deg) vs[slot[i]] = vd[i];
-      double diag = 0.;
-      for (int q = 0; q <= deg; ++q)
-        if (q != slot_self) diag += vs[q];
-#pragma unroll
-      for (int i = 0; i < GROUP; ++i)
-        if (i < deg) {
-          if (indices) indices[ob + slot[i]] = nx[i];
-          vs[slot[i]] = vn[i] + mvp[i];
-        }
-      if (indices) indices[ob + slot_self] = self;
-      vs[slot_self] = diag;
-    }
+    for (int i = 0; i < GROUP; ++i)
+      if (i < deg) {
+        if (put_cols) cs[slot[i]] = nx[i];
+        vs[slot[i]] = vn[i] + mvp[i];
+      }
+    if (put_cols) cs[slot_self] = self;
+    vs[slot_self] = diag;
   }
   __syncthreads();
   if (out_staged) {
