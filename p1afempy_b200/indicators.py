@@ -3,9 +3,10 @@
 from __future__ import annotations
 
 import numpy as np
+import torch
 
 from .device import DeviceMesh, to_device_indices, to_host
-from .solvers import _values_on_host
+from .solvers import _callback_at
 
 __all__ = ['compute_eta_r']
 
@@ -22,7 +23,8 @@ def compute_eta_r(x, coordinates, elements, dirichlet, neumann, f, g):
         term = None
         if n.shape[0] > 0:
             length, mid = mesh.boundary_edges(n)
-            gm = _values_on_host(g, to_host(mid), n.shape[0])
-            term = to_host(length) * gm
-        fc = _values_on_host(f, to_host(mesh.centroids()), mesh.n_elements)
+            gm = _callback_at(g, mid)
+            # |E| * g(midpoint), indicators.py:74-76 (one multiplication either way)
+            term = (length * gm) if isinstance(gm, torch.Tensor) else to_host(length) * gm
+        fc = _callback_at(f, mesh.centroids())
         return to_host(mesh.eta_r(x, d, n, term, fc))

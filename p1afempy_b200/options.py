@@ -1,0 +1,17 @@
+"""Run-time options of the drop-in layer.
+
+callbacks = 'host'   (default) user callbacks (f, g, a_ij, phi) are evaluated
+                     by numpy on the host on exactly the arrays the reference
+                     would pass them: results are bit-identical to the
+                     reference wherever the assembly is.
+callbacks = 'device' callbacks are first tried on a device-resident ndarray
+                     stand-in (p1afempy_b200.devarray); no point array crosses
+                     PCIe.  Transcendentals then come from CUDA's libm, so
+                     values agree with the reference to ~1e-15 relative instead
+                     of bit for bit.  Callbacks the stand-in cannot express
+                     fall back to the host one by one.
+Set with ``p1afempy_b200.options.callbacks = 'device'`` or P1_CALLBACKS=device.
+"""
+import os
+
+callbacks = os.environ.get('P1_CALLBACKS', 'host')

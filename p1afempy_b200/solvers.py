@@ -10,7 +10,9 @@ from __future__ import annotations
 
 import numpy as np
 
-from . import _lib
+import torch
+
+from . import _lib, devarray, options
 from .cubature import resolve_rule
 from .device import DeviceMesh, to_host
 
@@ -33,15 +35,35 @@ def _values_on_host(fn, points_host, n):
 
 
 def _callback_at_points(fns, xq):
-    """fns evaluated at every quadrature point set; xq: CUDA (n_qp, M, 2).
-    -> list of host arrays (n_qp, M), one per callback."""
-    pts = to_host(xq)
-    n_qp, m = pts.shape[0], pts.shape[1]
-    outs = [np.empty((n_qp, m)) for _ in fns]
-    for q in range(n_qp):
-        for o, fn in zip(outs, fns):
-            o[q] = _values_on_host(fn, pts[q], m)
+    """fns evaluated at every quadrature point set; xq: CUDA (n_qp, M, 2) or
+    (n_qp, M).  -> list of (n_qp, M) arrays, one per callback: CUDA tensors in
+    'device' mode (options.callbacks), host arrays otherwise."""
+    n_qp, m = xq.shape[0], xq.shape[1]
+    outs = [None] * len(fns)
+    todo = list(range(len(fns)))
+    if options.callbacks == 'device':
+        for j in list(todo):
+            vals = []
+            for q in range(n_qp):
+                v = devarray.evaluate(fns[j], xq[q], m)
+                if v is None:
+                    break
+                vals.append(v)
+            else:
+                outs[j] = torch.stack(vals) if vals else xq.new_empty((0, m))
+                todo.remove(j)
+    if todo:   # host evaluation of the remaining callbacks (only the callbacks)
+        pts = to_host(xq)
+        for j in todo:
+            outs[j] = np.empty((n_qp, m))
+            for q in range(n_qp):
+                outs[j][q] = _values_on_host(fns[j], pts[q], m)
     return outs
+
+
+def _callback_at(fn, points):
+    """One callback on one CUDA point/value array (n, 2) or (n,) -> (n,)."""
+    return _callback_at_points((fn,), points[None])[0][0]
 
 
 def _need_inferable(mesh):
@@ -99,10 +121,7 @@ def get_weighted_mass_matrix(coordinates, elements, current_iterate, phi,
                              'node %d' % (u.shape[0], top))
         if u.shape[0] != mesh.n_nodes:   # numpy would only read what it needs
             u = np.concatenate([u, np.zeros(max(0, mesh.n_nodes - u.shape[0]))])[:mesh.n_nodes]
-        uq = to_host(mesh.nodal_at_quadrature(u, points))
-        phiq = np.empty_like(uq)
-        for q in range(uq.shape[0]):
-            phiq[q] = _values_on_host(phi, uq[q], uq.shape[1])
+        (phiq,) = _callback_at_points((phi,), mesh.nodal_at_quadrature(u, points))
         return mesh.to_scipy(*mesh.weighted_mass_csr(phiq, weights, points),
                              inferred_shape=False)
 
@@ -115,8 +134,7 @@ def get_right_hand_side(coordinates, elements, f, cubature_rule=None):
             coordinates=coordinates, elements=elements, f=f,
             cubature_rule=cubature_rule)
     with DeviceMesh(coordinates, elements) as mesh:
-        cent = to_host(mesh.centroids())
-        fc = _values_on_host(f, cent, mesh.n_elements)
+        fc = _callback_at(f, mesh.centroids())
         return to_host(mesh.load_vector_midpoint(fc))
 
 

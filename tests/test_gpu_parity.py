@@ -340,3 +340,41 @@ def test_pinched_vertex_falls_back_to_exact_plan(api):
     with np.errstate(all='ignore'):
         ref = orc.mass_coo(c3, e3).tocsr()
         H.csr_values_close(api[0].get_mass_matrix(c3, e3), ref, RTOL)
+
+
+def test_device_callbacks(api):
+    """options.callbacks='device': the reference's callbacks run unchanged on a
+    device-resident ndarray stand-in; values agree to 1e-12 (CUDA libm instead
+    of glibc), index arrays stay bit-exact; callbacks the stand-in cannot
+    express (boolean-mask assignment: helpers_laplace.g) fall back to the host."""
+    from p1afempy_b200 import options
+    solvers, mesh, indicators = api
+    c, e, b = H.perturbed_square(5)
+    rule = cubature.CubatureRuleEnum.DAYTAYLOR
+    w, p = cubature.resolve_rule(rule)
+    u = H.u_nodal(c)
+    options.callbacks = 'device'
+    try:
+        gen = solvers.get_general_stiffness_matrix(c, e, H.a11, H.a12, H.a21, H.a22, rule)
+        wm = solvers.get_weighted_mass_matrix(c, e, u, H.phi, rule)
+        rhs = solvers.get_right_hand_side(c, e, H.f_load, cubature_rule=rule)
+        rhs0 = solvers.get_right_hand_side(c, e, H.f_load)
+        minus_one = lambda r: -np.ones(r.shape[0])   # noqa: E731  (host result, uploaded)
+        zero = lambda r: np.zeros(r.shape[0])        # noqa: E731
+        ident = solvers.get_general_stiffness_matrix(c, e, minus_one, zero, zero,
+                                                     minus_one, rule)
+        dirichlet, neumann = np.vstack(b)[:40], np.vstack(b)[40:]
+        x = u + 0.1 * c[:, 0]
+        eta = indicators.compute_eta_r(x, c, e, dirichlet, neumann, L.f, L.g)
+    finally:
+        options.callbacks = 'host'
+    H.csr_values_close(gen, orc.general_stiffness_coo(c, e, H.a11, H.a12, H.a21, H.a22,
+                                                      w, p).tocsr(), RTOL)
+    H.csr_values_close(wm, orc.weighted_mass_coo(c, e, u, H.phi, w, p).tocsr(), RTOL)
+    ref = orc.load_vector_cubature(c, e, H.f_load, w, p)
+    assert np.abs(rhs - ref).max() <= 1e-12 * np.abs(ref).max()
+    ref0 = orc.load_vector_midpoint(c, e, H.f_load)
+    assert np.abs(rhs0 - ref0).max() <= 1e-12 * np.abs(ref0).max()
+    assert np.allclose(ident.toarray(), solvers.get_stiffness_matrix(c, e).toarray())
+    ref_eta = orc.eta_r(x, c, e, dirichlet, neumann, L.f, L.g)
+    assert np.abs(eta - ref_eta).max() <= 1e-12 * np.abs(ref_eta).max()
