@@ -148,6 +148,19 @@ def read_peaks():
         return 6650.0, 'fallback (B200_PROFILING.md)'
 
 
+def ncu_traffic(kernel, level):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel`
+    from the committed `ncu --set full` capture (profiles/traffic.json; taken
+    on this workload at this level), or None when there is no capture."""
+    try:
+        with open(os.path.join(REPO, 'profiles', 'traffic.json')) as fh:
+            table = json.load(fh)
+        entry = table.get('level_%d' % level, {}).get(kernel)
+        return int(entry['dram_bytes']) if entry else None
+    except (OSError, ValueError, KeyError):
+        return None
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path
     (oracle port, pinned bit-identical to /root/reference) on host cores."""
@@ -293,7 +306,8 @@ def run_b200(args):
     # ---- roofline of the dominant kernel (live CUDA-event timing)
     peak, peak_src = read_peaks()
     alg = algorithmic_bytes(m, nn, nnz)
-    launches = sum(n for _, n in prof.values())
+    # kernels per timed span: a scan is reduce + scan-of-sums + downsweep
+    launches = sum(n * (3 if k == 'scan' else 1) for k, (_, n) in prof.items())
     dom = max(prof, key=lambda k: prof[k][0]) if prof else None
     kernel_ms = {k: v[0] / max(1, v[1]) * (v[1] / args.steps) for k, v in prof.items()}
     roof = None
@@ -301,7 +315,8 @@ def run_b200(args):
         dom_ms = prof[dom][0] / args.steps
         achieved = alg / world / (dom_ms * 1e-3) / 1e9
         roof = {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak,
-                'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
+                'unit': 'GB/s', 'frac': achieved / peak,
+                'traffic': ncu_traffic(dom, level) if world == 1 else None,
                 'peak_source': peak_src, 'kernel_ms_per_step': dom_ms,
                 'algorithmic_bytes_per_launch': alg // world,
                 'whole_step': {'achieved': alg / (ms_step * 1e-3) / 1e9,
