@@ -193,8 +193,8 @@ extern "C" int p1_ctx_create(int device, p1_ctx **out) {
   ctx->h_flags = nullptr;
   ctx->prof = nullptr;
   ctx->arena = new p1_arena();
-  if (cudaMalloc((void **)&ctx->d_flags, 4 * sizeof(int)) != cudaSuccess ||
-      cudaMallocHost((void **)&ctx->h_flags, 4 * sizeof(int)) != cudaSuccess) {
+  if (cudaMalloc((void **)&ctx->d_flags, 8 * sizeof(int)) != cudaSuccess ||
+      cudaMallocHost((void **)&ctx->h_flags, 8 * sizeof(int)) != cudaSuccess) {
     set_error("p1_ctx_create: allocation failed: %s",
               cudaGetErrorString(cudaGetLastError()));
     p1_ctx_destroy(ctx);

@@ -30,8 +30,7 @@ constexpr int CAP_OUT = 1280;    // CSR entries staged per block (9 per regular 
 
 __global__ void __launch_bounds__(FR, P1_FILL_MIN_BLOCKS)
 fill_rows_kernel(int n_own, int rb, int exact,
-                 const unsigned long long *__restrict__ acc,
-                 const int *__restrict__ rec_off, const Rec *__restrict__ rec,
+                 const unsigned long long *__restrict__ acc, const Rec *__restrict__ rec,
                  const int *__restrict__ indptr, int *__restrict__ indices,
                  double *__restrict__ data, int *__restrict__ flags) {
   __shared__ int cols_s[CAP_OUT];
@@ -42,15 +41,15 @@ fill_rows_kernel(int n_own, int rb, int exact,
   const int obeg = __ldg(indptr + row0), oend = __ldg(indptr + row0 + nrows);
   const int span = oend - obeg;
   const bool out_staged = span <= CAP_OUT;  // block-uniform
-  int deg = 0, beg = 0, ob = 0;
+  int deg = 0, ob = 0;
   unsigned hash = 0;
   if (tid < nrows) {
     const unsigned long long v = __ldg(acc + row0 + tid);
     deg = (int)(unsigned)v;
     hash = (unsigned)(v >> 32);
-    beg = __ldg(rec_off + row0 + tid);
     ob = __ldg(indptr + row0 + tid);
   }
+  const Rec *row = rec + (int64_t)(row0 + tid) * GROUP;  // the row's 8 slots
   bool process = deg >= 1 && deg <= GROUP && (exact || hash == 0u);
   const int self = row0 + tid + rb;
   int nx[GROUP], pv[GROUP], slot[GROUP];
@@ -63,7 +62,7 @@ fill_rows_kernel(int n_own, int rb, int exact,
       pv[i] = -2 - i;
       vd[i] = vn[i] = vp[i] = 0.;
       if (i < deg) {
-        const Rec r = load_rec(rec + beg + i);
+        const Rec r = load_rec(row + i);
         nx[i] = r.nx; pv[i] = rec_prev(r);
         vd[i] = r.vd; vn[i] = r.vn; vp[i] = r.vp;
       }
@@ -154,17 +153,16 @@ __device__ __forceinline__ int insert_unique(int *cols, int n, int c) {
 }
 
 __global__ void __launch_bounds__(SLOW_THREADS)
-fill_slow_kernel(const int *__restrict__ slow_rows, int n_slow, int rb,
-                 const int *__restrict__ rec_off, const Rec *__restrict__ rec,
+fill_slow_kernel(const int *__restrict__ slow_rows, int n_slow, int rb, Rows rows,
                  const int *__restrict__ indptr, int *__restrict__ indices,
                  double *__restrict__ data) {
   __shared__ int cols_s[SLOW_THREADS * SLOW_COLS];
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n_slow) return;
   const int a = slow_rows[idx];
-  const int beg = rec_off[a], deg = rec_off[a + 1] - beg;
+  const int deg = rows.deg(a);
   const int self = a + rb;
-  const Rec *nb = rec + beg;
+  const Rec *nb = rows.ptr(a, deg);
   int *cs = cols_s + threadIdx.x * SLOW_COLS;
   int n = insert_unique(cs, 0, self);
   for (int i = 0; i < deg; ++i) {
@@ -211,15 +209,14 @@ __device__ __forceinline__ int big_candidate2(int self, const Rec *nb, int j) {
 }
 
 __global__ void __launch_bounds__(THREADS)
-fill_big_kernel(const int *__restrict__ big_rows, int rb,
-                const int *__restrict__ rec_off, const Rec *__restrict__ rec,
+fill_big_kernel(const int *__restrict__ big_rows, int rb, Rows rows,
                 const unsigned char *__restrict__ first,
                 const int *__restrict__ indptr, int *__restrict__ indices,
                 double *__restrict__ data) {
   const int a = big_rows[blockIdx.x];
-  const int beg = rec_off[a], deg = rec_off[a + 1] - beg;
-  const Rec *nb = rec + beg;
-  const unsigned char *fl = first + 2 * (int64_t)beg + a;
+  const int deg = rows.deg(a);
+  const Rec *nb = rows.ptr(a, deg);
+  const unsigned char *fl = first + 2 * (int64_t)rows.ovf_off[a] + a;
   const int self = a + rb;
   const int ncand = 2 * deg + 1;
   const int64_t base = indptr[a];
@@ -243,12 +240,18 @@ fill_big_kernel(const int *__restrict__ big_rows, int rb,
 }
 
 // ------------------------------------------- re-assembly: refresh the values
+// `live` = number of valid records per group of 8 slots (null: all n valid)
 template <class V>
 __global__ void __launch_bounds__(THREADS)
-refresh_kernel(const int *__restrict__ elements, int64_t n_rec,
-               Rec *__restrict__ rec, const int *__restrict__ rec_elem, V values) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_rec;
+refresh_kernel(const int *__restrict__ elements, int64_t n,
+               const unsigned long long *__restrict__ live, Rec *__restrict__ rec,
+               const int *__restrict__ rec_elem, V values) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x) {
+    if (live) {
+      const unsigned deg = (unsigned)live[i >> 3];
+      if (deg > (unsigned)GROUP || (unsigned)(i & 7) >= deg) continue;
+    }
     const int64_t t = rec_elem[i];
     const int e[3] = {__ldg(elements + 3 * t), __ldg(elements + 3 * t + 1),
                       __ldg(elements + 3 * t + 2)};
@@ -261,6 +264,20 @@ refresh_kernel(const int *__restrict__ elements, int64_t n_rec,
     r.vp = k == 0 ? v[0][2] : (k == 1 ? v[1][2] : v[2][2]);
     store_rec(rec + i, r);
   }
+}
+
+template <class V>
+static void launch_refresh(p1_plan *plan, V values, cudaStream_t s) {
+  p1_ctx *ctx = plan->ctx;
+  const int64_t n_slots = (plan->row_end - plan->row_begin) * GROUP;
+  if (n_slots > 0)
+    refresh_kernel<<<min(grid_for(n_slots, THREADS), (unsigned)(ctx->sm_count * 32)), THREADS,
+                     0, s>>>(plan->elements, n_slots, plan->acc, plan->rec, plan->rec_elem,
+                             values);
+  if (plan->n_ovf > 0)
+    refresh_kernel<<<min(grid_for(plan->n_ovf, THREADS), (unsigned)(ctx->sm_count * 32)),
+                     THREADS, 0, s>>>(plan->elements, plan->n_ovf, nullptr, plan->ovf_rec,
+                                      plan->ovf_elem, values);
 }
 
 }  // namespace p1
@@ -288,7 +305,6 @@ extern "C" int p1_assemble_csr(const p1_plan *cplan, int op, const double *coord
   } else {
     // new coefficients on an existing plan: recompute the values in place
     P1_TRY(require_elements(plan, "assembling a new operator on an existing plan"));
-    const unsigned rg = min(grid_for(plan->n_rec, THREADS), (unsigned)(ctx->sm_count * 32));
     const double2 *xy = (const double2 *)coords;
     switch (op) {
       case P1_OP_STIFFNESS:
@@ -302,19 +318,11 @@ extern "C" int p1_assemble_csr(const p1_plan *cplan, int op, const double *coord
         set_error("p1_assemble_csr: unknown op %d", op);
         return P1_EINVAL;
     }
-    if (plan->n_rec > 0) {
-      prof_begin(ctx, "refresh", s);
-      if (op == P1_OP_STIFFNESS)
-        refresh_kernel<<<rg, THREADS, 0, s>>>(plan->elements, plan->n_rec, plan->rec,
-                                              plan->rec_elem, StiffnessValues{xy});
-      else if (op == P1_OP_MASS)
-        refresh_kernel<<<rg, THREADS, 0, s>>>(plan->elements, plan->n_rec, plan->rec,
-                                              plan->rec_elem, MassValues{xy});
-      else
-        refresh_kernel<<<rg, THREADS, 0, s>>>(plan->elements, plan->n_rec, plan->rec,
-                                              plan->rec_elem, LocalValues{local});
-      prof_end(ctx, s);
-    }
+    prof_begin(ctx, "refresh", s);
+    if (op == P1_OP_STIFFNESS) launch_refresh(plan, StiffnessValues{xy}, s);
+    else if (op == P1_OP_MASS) launch_refresh(plan, MassValues{xy}, s);
+    else launch_refresh(plan, LocalValues{local}, s);
+    prof_end(ctx, s);
     plan->val_op = op;
   }
   if (indptr)
@@ -324,17 +332,16 @@ extern "C" int p1_assemble_csr(const p1_plan *cplan, int op, const double *coord
   if (n_own > 0)
     P1_TIMED(ctx, "fill_rows", s,
              (fill_rows_kernel<<<grid_for(n_own, FR), FR, 0, s>>>(
-                 n_own, rb, plan->exact ? 1 : 0, plan->acc, plan->rec_off, plan->rec,
-                 plan->indptr, indices, data, ctx->d_flags)));
+                 n_own, rb, plan->exact ? 1 : 0, plan->acc, plan->rec, plan->indptr, indices,
+                 data, ctx->d_flags)));
   if (plan->n_slow > 0)
     P1_TIMED(ctx, "fill_slow", s,
              (fill_slow_kernel<<<grid_for(plan->n_slow, SLOW_THREADS), SLOW_THREADS, 0, s>>>(
-                 plan->slow_rows, plan->n_slow, rb, plan->rec_off, plan->rec, plan->indptr,
-                 indices, data)));
+                 plan->slow_rows, plan->n_slow, rb, rows_of(plan), plan->indptr, indices,
+                 data)));
   if (plan->n_big > 0)
     fill_big_kernel<<<plan->n_big, THREADS, 0, s>>>(
-        plan->big_rows, rb, plan->rec_off, plan->rec, plan->big_first, plan->indptr,
-        indices, data);
+        plan->big_rows, rb, rows_of(plan), plan->big_first, plan->indptr, indices, data);
   P1_CUDA(cudaGetLastError());
   if (!plan->exact) {
     // the closed-fan shortcut is verified while filling: read the verdict

@@ -18,12 +18,12 @@ constexpr int THREADS = 256;
 // [2] #forward entries, [3] #backward entries
 
 __global__ void __launch_bounds__(THREADS)
-twin_kernel(int n_nodes, const int *__restrict__ rec_off,
-            const Rec *__restrict__ rec, const int *__restrict__ rec_elem,
-            int *__restrict__ twin, int *__restrict__ flags) {
+twin_kernel(int n_nodes, Rows rows, int *__restrict__ twin, int *__restrict__ flags) {
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= n_nodes) return;
-  const int beg = rec_off[a], end = rec_off[a + 1];
+  const int end = rows.deg(a), beg = 0;
+  const Rec *rec = rows.ptr(a, end);
+  const int *rec_elem = rows.elem(a, end);
   for (int i = beg; i < end; ++i) {
     const Rec r = rec[i];
     const int target = rec_next(r);  // half-edge a -> target
@@ -111,11 +111,11 @@ element_edges_kernel(const int *__restrict__ elements, int64_t M,
 
 // finds the element half-edge b0 -> b1 through the fan of b0
 __device__ __forceinline__ int64_t locate_halfedge(int b0, int b1,
-                                                   const int *__restrict__ rec_off,
-                                                   const Rec *__restrict__ rec,
-                                                   const int *__restrict__ rec_elem) {
-  const int beg = rec_off[b0], end = rec_off[b0 + 1];
-  for (int i = beg; i < end; ++i)
+                                                   const Rows &rows) {
+  const int end = rows.deg(b0);
+  const Rec *rec = rows.ptr(b0, end);
+  const int *rec_elem = rows.elem(b0, end);
+  for (int i = 0; i < end; ++i)
     if (rec_next(rec[i]) == b1)
       return 3 * (int64_t)rec_elem[i] + rec_k(rec[i]);
   return -1;
@@ -123,8 +123,7 @@ __device__ __forceinline__ int64_t locate_halfedge(int b0, int b1,
 
 __global__ void __launch_bounds__(THREADS)
 boundary_numbers_kernel(const int *__restrict__ bnd, int64_t K, int64_t M, int n_nodes,
-                        const int *__restrict__ rec_off, const Rec *__restrict__ rec,
-                        const int *__restrict__ rec_elem, const int *__restrict__ num,
+                        Rows rows, const int *__restrict__ num,
                         long long *__restrict__ element2edges,
                         long long *__restrict__ edge2nodes,
                         long long *__restrict__ boundary2edges, int *__restrict__ flags) {
@@ -135,7 +134,7 @@ boundary_numbers_kernel(const int *__restrict__ bnd, int64_t K, int64_t M, int n
     atomicOr(flags, FLAG_INDEX_RANGE);
     return;
   }
-  const int64_t h = locate_halfedge(b0, b1, rec_off, rec, rec_elem);
+  const int64_t h = locate_halfedge(b0, b1, rows);
   if (h < 0) {
     atomicOr(flags, FLAG_BOUNDARY_MISS);
     boundary2edges[r] = -1;
@@ -186,8 +185,7 @@ eta_local_kernel(const double2 *__restrict__ coords, const double *__restrict__ 
 // mode 1: Dirichlet (indicators.py:79-80) jump  = 0
 __global__ void __launch_bounds__(THREADS)
 eta_boundary_kernel(int mode, const int *__restrict__ bnd, int64_t K, int n_nodes,
-                    const int *__restrict__ rec_off, const Rec *__restrict__ rec,
-                    const int *__restrict__ rec_elem, const int *__restrict__ twin,
+                    Rows rows, const int *__restrict__ twin,
                     const double *__restrict__ term, double *__restrict__ dudn,
                     int *__restrict__ flags) {
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -197,7 +195,7 @@ eta_boundary_kernel(int mode, const int *__restrict__ bnd, int64_t K, int n_node
     atomicOr(flags, FLAG_INDEX_RANGE);
     return;
   }
-  const int64_t h = locate_halfedge(b0, b1, rec_off, rec, rec_elem);
+  const int64_t h = locate_halfedge(b0, b1, rows);
   if (h < 0) { atomicOr(flags, FLAG_BOUNDARY_MISS); return; }
   if (mode == 0) {
     dudn[h] = dudn[h] - term[r];
@@ -241,7 +239,7 @@ static inline unsigned egrid(const p1_ctx *ctx, int64_t n) {
 }
 
 static int read_flags(p1_ctx *ctx, cudaStream_t s) {
-  P1_CUDA(cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, 4 * sizeof(int),
+  P1_CUDA(cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, 8 * sizeof(int),
                           cudaMemcpyDeviceToHost, s));
   P1_CUDA(cudaStreamSynchronize(s));
   return P1_OK;
@@ -261,10 +259,10 @@ int ensure_twins(p1_plan *p, cudaStream_t s) {
   P1_TRY(full_plan_required(p, "half-edge twins"));
   P1_TRY(require_elements(p, "half-edge twins (edge numbering, eta_R)"));
   P1_TRY(pool_alloc(ctx, &p->twin, (size_t)(3 * p->M), s));
-  P1_CUDA(cudaMemsetAsync(p->ctx->d_flags, 0, 4 * sizeof(int), s));
+  P1_CUDA(cudaMemsetAsync(p->ctx->d_flags, 0, 8 * sizeof(int), s));
   if (p->N > 0)
     twin_kernel<<<grid_for(p->N, THREADS), THREADS, 0, s>>>(
-        (int)p->N, p->rec_off, p->rec, p->rec_elem, p->twin, p->ctx->d_flags);
+        (int)p->N, rows_of(p), p->twin, p->ctx->d_flags);
   P1_CUDA(cudaGetLastError());
   P1_TRY(read_flags(p->ctx, s));
   if (p->ctx->h_flags[0] & FLAG_NONMANIFOLD) {
@@ -302,7 +300,7 @@ extern "C" int p1_geometric_data(const p1_plan *cplan, const int32_t *boundary_n
   const int64_t total = 3 * M + K;
   int *num = nullptr;
   P1_TRY(pool_alloc(ctx, &num, (size_t)total + 1, s));
-  P1_CUDA(cudaMemsetAsync(ctx->d_flags, 0, 4 * sizeof(int), s));
+  P1_CUDA(cudaMemsetAsync(ctx->d_flags, 0, 8 * sizeof(int), s));
   if (total > 0)
     forward_flags_kernel<<<egrid(ctx, total), THREADS, 0, s>>>(
         p->elements, M, boundary_nodes, K, num, ctx->d_flags);
@@ -313,7 +311,7 @@ extern "C" int p1_geometric_data(const p1_plan *cplan, const int32_t *boundary_n
         p->elements, M, num, p->twin, (long long *)element2edges, (long long *)edge2nodes);
   if (K > 0)
     boundary_numbers_kernel<<<grid_for(K, THREADS), THREADS, 0, s>>>(
-        boundary_nodes, K, M, (int)p->N, p->rec_off, p->rec, p->rec_elem, num,
+        boundary_nodes, K, M, (int)p->N, rows_of(p), num,
         (long long *)element2edges, (long long *)edge2nodes, (long long *)boundary2edges,
         ctx->d_flags);
   pool_free(ctx, num, s);
@@ -360,16 +358,16 @@ extern "C" int p1_eta_r(const p1_plan *cplan, const double *coords, const double
   if (M == 0) return P1_OK;
   double *dudn = nullptr;
   P1_TRY(pool_alloc(ctx, &dudn, (size_t)(3 * M), s));
-  P1_CUDA(cudaMemsetAsync(ctx->d_flags, 0, 4 * sizeof(int), s));
+  P1_CUDA(cudaMemsetAsync(ctx->d_flags, 0, 8 * sizeof(int), s));
   eta_local_kernel<<<egrid(ctx, M), THREADS, 0, s>>>((const double2 *)coords, x,
                                                      p->elements, M, dudn);
   if (n_neumann > 0)
     eta_boundary_kernel<<<grid_for(n_neumann, THREADS), THREADS, 0, s>>>(
-        0, neumann, n_neumann, (int)p->N, p->rec_off, p->rec, p->rec_elem, p->twin,
+        0, neumann, n_neumann, (int)p->N, rows_of(p), p->twin,
         neumann_term, dudn, ctx->d_flags);
   if (n_dirichlet > 0)
     eta_boundary_kernel<<<grid_for(n_dirichlet, THREADS), THREADS, 0, s>>>(
-        1, dirichlet, n_dirichlet, (int)p->N, p->rec_off, p->rec, p->rec_elem, p->twin,
+        1, dirichlet, n_dirichlet, (int)p->N, rows_of(p), p->twin,
         nullptr, dudn, ctx->d_flags);
   eta_final_kernel<<<egrid(ctx, M), THREADS, 0, s>>>((const double2 *)coords, p->elements,
                                                      M, p->twin, dudn, f_centroid, eta);

@@ -269,13 +269,13 @@ local_load_midpoint_kernel(const double2 *__restrict__ coords,
 // b[a] = sum over the node's records in (element, vertex) order == the
 // sequential np.bincount over elements.flatten() (solvers.py:593-596).
 __global__ void __launch_bounds__(THREADS)
-gather_load_kernel(int n_own, const int *__restrict__ rec_off,
-                   const Rec *__restrict__ rec, const int *__restrict__ rec_elem,
-                   const double *__restrict__ L,
+gather_load_kernel(int n_own, Rows rows, const double *__restrict__ L,
                    double *__restrict__ b) {
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= n_own) return;
-  const int beg = rec_off[a], end = rec_off[a + 1];
+  const int end = rows.deg(a), beg = 0;
+  const Rec *rec = rows.ptr(a, end);
+  const int *rec_elem = rows.elem(a, end);
   double sum = 0.;
   for (int i = beg; i < end; ++i) {
     sum += __ldg(L + 3 * (int64_t)rec_elem[i] + rec_k(rec[i]));
@@ -286,13 +286,13 @@ gather_load_kernel(int n_own, const int *__restrict__ rec_off,
 // order (vertex, element) == np.bincount over elements.flatten('F')
 // (solvers.py:422-425)
 __global__ void __launch_bounds__(THREADS)
-gather_load_midpoint_kernel(int n_own, const int *__restrict__ rec_off,
-                            const Rec *__restrict__ rec,
-                            const int *__restrict__ rec_elem,
-                            const double *__restrict__ share, double *__restrict__ b) {
+gather_load_midpoint_kernel(int n_own, Rows rows, const double *__restrict__ share,
+                            double *__restrict__ b) {
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= n_own) return;
-  const int beg = rec_off[a], end = rec_off[a + 1];
+  const int end = rows.deg(a), beg = 0;
+  const Rec *rec = rows.ptr(a, end);
+  const int *rec_elem = rows.elem(a, end);
   double sum = 0.;
   for (int kk = 0; kk < 3; ++kk)
     for (int i = beg; i < end; ++i) {
@@ -560,7 +560,7 @@ extern "C" int p1_load_vector(const p1_plan *plan, const double *coords,
         (const double2 *)coords, plan->elements, M, fq, w, (const double2 *)pts, n_qp, L);
   if (n_own > 0)
     gather_load_kernel<<<grid_for(n_own, THREADS), THREADS, 0, s>>>(
-        n_own, plan->rec_off, plan->rec, plan->rec_elem, L, b);
+        n_own, rows_of(plan), L, b);
   pool_free(ctx, L, s);
   pool_free(ctx, w, s);
   pool_free(ctx, pts, s);
@@ -587,7 +587,7 @@ extern "C" int p1_load_vector_midpoint(const p1_plan *plan, const double *coords
         (const double2 *)coords, plan->elements, M, f_centroid, share);
   if (n_own > 0)
     gather_load_midpoint_kernel<<<grid_for(n_own, THREADS), THREADS, 0, s>>>(
-        n_own, plan->rec_off, plan->rec, plan->rec_elem, share, b);
+        n_own, rows_of(plan), share, b);
   pool_free(ctx, share, s);
   P1_CUDA(cudaGetLastError());
   return P1_OK;

@@ -1,5 +1,5 @@
 // plan.cu -- symbolic phase: node -> incident (element, vertex) records with
-// their neighbour pair, and the CSR row pointer.
+// their neighbour pair and local-matrix row, and the CSR row pointer.
 //
 // Replaces, for the assembly hot path, what scipy derives on every
 // coo_matrix(...).tocsr() call: coo_tocsr (counting sort by row),
@@ -8,10 +8,12 @@
 // (node, element) incidences instead of the 9M triplets: row i of any P1
 // matrix has the columns {i} U {next, prev vertex of every element at i}.
 //
-// The kernels here are bound by L2 transactions (one 32 B sector per random
-// access), not by HBM bytes, so the layout minimises accesses per incidence:
-// count = 1 atomic; scatter = 1 atomic (cursor preloaded with the row offset)
-// + 1 aligned 16 B store; rowlen = coalesced 16 B loads, shuffles only.
+// These kernels are bound by the SM's LSU rate for divergent accesses (about one
+// 32 B sector per lane per 1.1-1.3 cycles: 201M incidences -> ~0.75 ms per
+// access at 64M triangles), not by HBM bytes, so the layout minimises accesses
+// per incidence: ONE 64-bit atomic (slot number + closed-fan hash; row a owns
+// the fixed slots rec[8a..8a+7], so there is no counting pass, no offset scan)
+// and ONE 256-bit store.
 #include "plan.cuh"
 #include <vector>
 
@@ -19,17 +21,23 @@ namespace p1 {
 
 constexpr int THREADS = 256;
 
-// ---------------------------------------------------------------- count
-// One 64-bit atomic per incidence: low word counts the records of the node,
-// high word sums hash(next) - hash(prev).  The nexts and prevs of a closed fan
-// are the same set, so the high word of an interior node ends up 0; a non-zero
-// high word marks the rows whose length is not simply 1 + #records (open fans
-// = boundary nodes, O(sqrt(M)) of them).  The shortcut is verified row by row
-// when the matrix is filled (FLAG_RETRY), so a hash coincidence cannot go
-// unnoticed.
+// -------------------------------------------------------------- scatter
+// The thread that owns element t computes the element's local matrix ONCE
+// (value source V) and stores, for every owned vertex, one 32-byte record.
+//   OVERFLOW == false: slot = old value of the row's counter; slots >= 8 are
+//                      dropped here (their row is redone by the overflow pass).
+//                      The atomic also accumulates hash(next) - hash(prev): the
+//                      nexts and prevs of a closed fan are the same set, so an
+//                      interior node ends at 0; a non-zero word marks the rows
+//                      whose length is not 1 + #records (open fans = boundary
+//                      nodes).  Verified row by row when the matrix is filled.
+//   OVERFLOW == true : only rows with more than 8 records; compact storage.
+template <class V, bool OVERFLOW>
 __global__ void __launch_bounds__(THREADS)
-count_kernel(const int *__restrict__ elements, int64_t M, int N, int rb, int re,
-             unsigned long long *__restrict__ acc, int *__restrict__ flags) {
+scatter_kernel(const int *__restrict__ elements, int64_t M, int N, int rb, int re,
+               unsigned long long *__restrict__ acc, Rec *__restrict__ rec,
+               int *__restrict__ rec_elem, int *__restrict__ cursor, V values,
+               int *__restrict__ flags) {
   int mx = -1;
   bool bad = false;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < M;
@@ -44,126 +52,140 @@ count_kernel(const int *__restrict__ elements, int64_t M, int N, int rb, int re,
       continue;
     }
     mx = max(mx, max(e[0], max(e[1], e[2])));
-    const unsigned h[3] = {mix32((unsigned)e[0]), mix32((unsigned)e[1]),
-                           mix32((unsigned)e[2])};
+    bool own[3];
 #pragma unroll
-    for (int k = 0; k < 3; ++k)
-      if (e[k] >= rb && e[k] < re) {
-        const unsigned d = h[k == 2 ? 0 : k + 1] - h[k == 0 ? 2 : k - 1];
-        atomicAdd(acc + (e[k] - rb), ((unsigned long long)d << 32) + 1ull);
-      }
-  }
-  mx = __reduce_max_sync(0xffffffffu, mx);
-  if ((threadIdx.x & 31) == 0 && mx >= 0) atomicMax(flags + 1, mx);
-  if (bad) atomicOr(flags, FLAG_INDEX_RANGE);
-}
-
-// acc -> per-row record count (for the record offsets) and, unless `exact`,
-// the row length of every regular row; irregular rows are listed.
-__global__ void __launch_bounds__(THREADS)
-split_kernel(int n_own, const unsigned long long *__restrict__ acc, int exact,
-             int *__restrict__ cnt, int *__restrict__ rowlen,
-             int *__restrict__ slow_rows, int *__restrict__ big_rows,
-             int *__restrict__ counters /* [0] n_big, [1] n_slow */) {
-  const int a = blockIdx.x * blockDim.x + threadIdx.x;
-  if (a >= n_own) return;
-  const unsigned long long v = acc[a];
-  const int deg = (int)(unsigned)v;
-  cnt[a] = deg;
-  if (exact) return;
-  if (deg == 0) { rowlen[a] = 0; return; }
-  if ((unsigned)(v >> 32) == 0u && deg <= GROUP) { rowlen[a] = 1 + deg; return; }
-  rowlen[a] = 0;  // written by rowlen_slow_kernel / rowlen_big_kernel
-  if (deg > DEG_BIG) big_rows[atomicAdd(counters, 1)] = a;
-  else slow_rows[atomicAdd(counters + 1, 1)] = a;
-}
-
-// -------------------------------------------------------------- scatter
-// cursor[a] starts at rec_off[a] and ends at rec_off[a+1].  The thread that
-// owns element t computes the element's local matrix ONCE (value source V) and
-// stores, for every owned vertex, one 32-byte record with one 256-bit store.
-template <class V>
-__global__ void __launch_bounds__(THREADS)
-scatter_kernel(const int *__restrict__ elements, int64_t M, int N, int rb, int re,
-               int *__restrict__ cursor, Rec *__restrict__ rec,
-               int *__restrict__ rec_elem, V values) {
-  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < M;
-       t += (int64_t)gridDim.x * blockDim.x) {
-    int e[3];
-    e[0] = __ldg(elements + 3 * t);
-    e[1] = __ldg(elements + 3 * t + 1);
-    e[2] = __ldg(elements + 3 * t + 2);
-    if ((unsigned)e[0] >= (unsigned)N || (unsigned)e[1] >= (unsigned)N ||
-        (unsigned)e[2] >= (unsigned)N)
-      continue;
-    const bool own0 = e[0] >= rb && e[0] < re, own1 = e[1] >= rb && e[1] < re,
-               own2 = e[2] >= rb && e[2] < re;
-    if (!(own0 || own1 || own2)) continue;  // multi-GPU: not my rows
+    for (int k = 0; k < 3; ++k) {
+      own[k] = e[k] >= rb && e[k] < re;
+      if (OVERFLOW && own[k]) own[k] = (unsigned)acc[e[k] - rb] > (unsigned)GROUP;
+    }
+    if (!(own[0] || own[1] || own[2])) continue;  // not my rows
     double v[3][3];
     values.rows(t, e, v);
 #pragma unroll
     for (int k = 0; k < 3; ++k)
-      if (k == 0 ? own0 : (k == 1 ? own1 : own2)) {
-        const int pos = atomicAdd(cursor + (e[k] - rb), 1);
+      if (own[k]) {
+        const int a = e[k] - rb;
+        const int nx = e[k == 2 ? 0 : k + 1], pv = e[k == 0 ? 2 : k - 1];
+        int64_t pos;
+        if (OVERFLOW) {
+          pos = atomicAdd(cursor + a, 1);
+        } else {
+          const unsigned d = mix32((unsigned)nx) - mix32((unsigned)pv);
+          const unsigned slot =
+              (unsigned)atomicAdd(acc + a, ((unsigned long long)d << 32) + 1ull);
+          if (slot >= (unsigned)GROUP) continue;
+          pos = (int64_t)a * GROUP + slot;
+        }
         Rec r;
-        r.nx = e[k == 2 ? 0 : k + 1];
-        r.pvk = e[k == 0 ? 2 : k - 1] | (k << NODE_BITS);
+        r.nx = nx;
+        r.pvk = pv | (k << NODE_BITS);
         r.vd = v[k][0]; r.vn = v[k][1]; r.vp = v[k][2];
         store_rec(rec + pos, r);
         if (rec_elem) rec_elem[pos] = (int)t;
       }
   }
+  if (!OVERFLOW) {
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    if ((threadIdx.x & 31) == 0 && mx >= 0) atomicMax(flags + 1, mx);
+    if (bad) atomicOr(flags, FLAG_INDEX_RANGE);
+  }
 }
 
-// --------------------------------------------------------------- rowlen
-// 8 lanes per owned row (see analyse_row); rows the fast path does not take
-// are appended to slow_rows / big_rows and counted by the kernels below.
+template <bool OVERFLOW>
+static void launch_scatter(p1_ctx *ctx, unsigned grid, cudaStream_t s, int op,
+                           const int *elements, int64_t M, int N, int rb, int re,
+                           unsigned long long *acc, Rec *rec, int *rec_elem, int *cursor,
+                           const double *coords, const double *local) {
+  const double2 *xy = (const double2 *)coords;
+  int *fl = ctx->d_flags;
+  if (op == P1_OP_STIFFNESS)
+    scatter_kernel<StiffnessValues, OVERFLOW><<<grid, THREADS, 0, s>>>(
+        elements, M, N, rb, re, acc, rec, rec_elem, cursor, StiffnessValues{xy}, fl);
+  else if (op == P1_OP_MASS)
+    scatter_kernel<MassValues, OVERFLOW><<<grid, THREADS, 0, s>>>(
+        elements, M, N, rb, re, acc, rec, rec_elem, cursor, MassValues{xy}, fl);
+  else if (op == P1_OP_LOCAL)
+    scatter_kernel<LocalValues, OVERFLOW><<<grid, THREADS, 0, s>>>(
+        elements, M, N, rb, re, acc, rec, rec_elem, cursor, LocalValues{local}, fl);
+  else
+    scatter_kernel<NoValues, OVERFLOW><<<grid, THREADS, 0, s>>>(
+        elements, M, N, rb, re, acc, rec, rec_elem, cursor, NoValues{}, fl);
+}
+
+// ---------------------------------------------------------------- split
+// counters: [0] n_big, [1] n_slow, [2] rows with more than 8 records
 __global__ void __launch_bounds__(THREADS)
-rowlen_kernel(int n_own, int rb, const int *__restrict__ rec_off,
-              const Rec *__restrict__ rec, int *__restrict__ rowlen,
+split_kernel(int n_own, const unsigned long long *__restrict__ acc,
+             int *__restrict__ rowlen, int *__restrict__ slow_rows,
+             int *__restrict__ big_rows, int *__restrict__ counters) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= n_own) return;
+  const unsigned long long v = acc[a];
+  const int deg = (int)(unsigned)v;
+  if (deg == 0) { rowlen[a] = 0; return; }
+  if ((unsigned)(v >> 32) == 0u && deg <= GROUP) { rowlen[a] = 1 + deg; return; }
+  rowlen[a] = 0;  // written by rowlen_slow_kernel / rowlen_big_kernel
+  if (deg > GROUP) atomicAdd(counters + 2, 1);
+  if (deg > DEG_BIG) big_rows[atomicAdd(counters, 1)] = a;
+  else slow_rows[atomicAdd(counters + 1, 1)] = a;
+}
+
+// exact plans: 8 lanes per row, all-pairs (plan.cuh: analyse_row)
+__global__ void __launch_bounds__(THREADS)
+rowlen_kernel(int n_own, int rb, Rows rows, int *__restrict__ rowlen,
               int *__restrict__ slow_rows, int *__restrict__ big_rows,
-              int *__restrict__ counters /* [0] n_big, [1] n_slow */) {
+              int *__restrict__ counters) {
   __shared__ int2 xch[THREADS];
   const int lane = threadIdx.x & 31, lane8 = lane & (GROUP - 1);
   const int shift = lane & ~(GROUP - 1);
   const unsigned gmask = 0xffu << shift;
   const int a = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / GROUP);
   if (a >= n_own) return;
-  const int beg = __ldg(rec_off + a), deg = __ldg(rec_off + a + 1) - beg;
+  const int deg = rows.deg(a);
   if (deg == 0) {
     if (lane8 == 0) rowlen[a] = 0;
     return;
   }
-  const RowLane r = analyse_row(a + rb, beg, deg, rec, gmask, lane8, shift, xch);
+  const RowLane r = analyse_row(a + rb, rows.rec + (int64_t)a * GROUP, deg, gmask, lane8,
+                                shift, xch);
   if (lane8 != 0) return;
   if (r.simple && r.len == 1 + deg) {  // closed, repeat-free fan: the fast fill takes it
     rowlen[a] = r.len;
-  } else if (deg > DEG_BIG) {
-    big_rows[atomicAdd(counters, 1)] = a;
-  } else {
-    slow_rows[atomicAdd(counters + 1, 1)] = a;
+    return;
   }
+  rowlen[a] = 0;
+  if (deg > GROUP) atomicAdd(counters + 2, 1);
+  if (deg > DEG_BIG) big_rows[atomicAdd(counters, 1)] = a;
+  else slow_rows[atomicAdd(counters + 1, 1)] = a;
+}
+
+__global__ void __launch_bounds__(THREADS)
+overflow_count_kernel(int n_own, const unsigned long long *__restrict__ acc,
+                      int *__restrict__ cnt) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= n_own) return;
+  const int deg = (int)(unsigned)acc[a];
+  cnt[a] = deg > GROUP ? deg : 0;
 }
 
 // distinct values of {self} U {next_i} U {prev_i}, any number of records;
 // the few contiguous records stay in L1 while they are compared
 __global__ void __launch_bounds__(THREADS)
-rowlen_slow_kernel(const int *__restrict__ slow_rows, int n_slow, int rb,
-                   const int *__restrict__ rec_off, const Rec *__restrict__ rec,
+rowlen_slow_kernel(const int *__restrict__ slow_rows, int n_slow, int rb, Rows rows,
                    int *__restrict__ rowlen) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n_slow) return;
   const int a = slow_rows[idx];
-  const int beg = rec_off[a], deg = rec_off[a + 1] - beg;
+  const int deg = rows.deg(a);
   const int self = a + rb;
-  const Rec *nb = rec + beg;
+  const Rec *nb = rows.ptr(a, deg);
   int n = 1;
   for (int i = 0; i < deg; ++i) {
     const int x = rec_next(nb[i]), y = rec_prev(nb[i]);
     bool fx = x != self, fy = y != self && y != x;
     for (int j = 0; j < deg; ++j) {
       const int qx = rec_next(nb[j]), qy = rec_prev(nb[j]);
-      fx = fx && !(j < i && qx == x);           // an earlier next equals it
+      fx = fx && !(j < i && qx == x);             // an earlier next equals it
       fy = fy && qx != y && !(j < i && qy == y);  // any next / an earlier prev
     }
     n += fx + fy;
@@ -178,26 +200,28 @@ __device__ __forceinline__ unsigned long long big_key(const Rec &r) {
   return ((unsigned long long)(unsigned)r.nx << 32) | (unsigned)r.pvk;
 }
 __global__ void __launch_bounds__(THREADS)
-sort_big_kernel(const int *__restrict__ big_rows, const int *__restrict__ rec_off,
-                Rec *__restrict__ rec, int *__restrict__ rec_elem,
-                Rec *__restrict__ tmp, int *__restrict__ tmp_elem) {
+sort_big_kernel(const int *__restrict__ big_rows, Rows rows, Rec *__restrict__ tmp,
+                int *__restrict__ tmp_elem) {
   const int a = big_rows[blockIdx.x];
-  const int beg = rec_off[a], deg = rec_off[a + 1] - beg;
+  const int deg = rows.deg(a);
+  Rec *row = rows.ptr(a, deg);
+  int *el = rows.ovf_elem ? rows.elem(a, deg) : nullptr;
+  const int64_t off = rows.ovf_off[a];
   for (int i = threadIdx.x; i < deg; i += blockDim.x) {
-    const Rec v = rec[beg + i];
+    const Rec v = row[i];
     const unsigned long long key = big_key(v);
     int rank = 0;
     for (int j = 0; j < deg; ++j) {
-      const unsigned long long kj = big_key(rec[beg + j]);
+      const unsigned long long kj = big_key(row[j]);
       rank += kj < key || (kj == key && j < i);  // stable for identical keys
     }
-    tmp[beg + rank] = v;
-    if (rec_elem) tmp_elem[beg + rank] = rec_elem[beg + i];
+    tmp[off + rank] = v;
+    if (el) tmp_elem[off + rank] = el[i];
   }
   __syncthreads();
   for (int i = threadIdx.x; i < deg; i += blockDim.x) {
-    rec[beg + i] = tmp[beg + i];
-    if (rec_elem) rec_elem[beg + i] = tmp_elem[beg + i];
+    row[i] = tmp[off + i];
+    if (el) el[i] = tmp_elem[off + i];
   }
 }
 
@@ -209,13 +233,12 @@ __device__ __forceinline__ int big_candidate(int self, const Rec *nb, int j) {
 }
 
 __global__ void __launch_bounds__(THREADS)
-rowlen_big_kernel(const int *__restrict__ big_rows, int rb,
-                  const int *__restrict__ rec_off, const Rec *__restrict__ rec,
+rowlen_big_kernel(const int *__restrict__ big_rows, int rb, Rows rows,
                   unsigned char *__restrict__ first, int *__restrict__ rowlen) {
   const int a = big_rows[blockIdx.x];
-  const int beg = rec_off[a], deg = rec_off[a + 1] - beg;
-  const Rec *nb = rec + beg;
-  unsigned char *fl = first + 2 * (int64_t)beg + a;
+  const int deg = rows.deg(a);
+  const Rec *nb = rows.ptr(a, deg);
+  unsigned char *fl = first + 2 * (int64_t)rows.ovf_off[a] + a;
   const int ncand = 2 * deg + 1;
   int mine = 0;
   for (int j = threadIdx.x; j < ncand; j += blockDim.x) {
@@ -236,20 +259,22 @@ rowlen_big_kernel(const int *__restrict__ big_rows, int rb,
 
 // ------------------------------------------------------ (T,k) row order
 __global__ void __launch_bounds__(THREADS)
-sort_rows_kernel(int n_own, const int *__restrict__ rec_off,
-                 const Rec *__restrict__ rec, const int *__restrict__ rec_elem,
-                 Rec *__restrict__ out, int *__restrict__ out_elem) {
+sort_rows_kernel(int n_own, Rows in, Rows out) {
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= n_own) return;
-  const int beg = rec_off[a], end = rec_off[a + 1];
-  for (int i = beg; i < end; ++i) {
-    const Rec v = rec[i];
-    const unsigned key = ((unsigned)rec_elem[i] << 2) | (unsigned)rec_k(v);
+  const int deg = in.deg(a);
+  const Rec *r = in.ptr(a, deg);
+  const int *el = in.elem(a, deg);
+  Rec *ro = out.ptr(a, deg);
+  int *eo = out.elem(a, deg);
+  for (int i = 0; i < deg; ++i) {
+    const Rec v = r[i];
+    const unsigned key = ((unsigned)el[i] << 2) | (unsigned)rec_k(v);
     int rank = 0;
-    for (int j = beg; j < end; ++j)
-      rank += (((unsigned)rec_elem[j] << 2) | (unsigned)rec_k(rec[j])) < key;
-    out[beg + rank] = v;
-    out_elem[beg + rank] = rec_elem[i];
+    for (int j = 0; j < deg; ++j)
+      rank += (((unsigned)el[j] << 2) | (unsigned)rec_k(r[j])) < key;
+    ro[rank] = v;
+    eo[rank] = el[i];
   }
 }
 
@@ -264,19 +289,25 @@ int ensure_sorted(p1_plan *p, cudaStream_t s) {
   P1_TRY(require_elements(p, "ordering records by (element, vertex)"));
   p1_ctx *ctx = p->ctx;
   const int n_own = (int)(p->row_end - p->row_begin);
-  Rec *r2 = nullptr;
-  int *e2 = nullptr;
-  P1_TRY(pool_alloc(ctx, &r2, (size_t)p->n_rec, s));
-  P1_TRY(pool_alloc(ctx, &e2, (size_t)p->n_rec, s));
+  Rows in = rows_of(p), out = in;
+  out.rec = nullptr; out.rec_elem = nullptr; out.ovf_rec = nullptr; out.ovf_elem = nullptr;
+  int rc = P1_OK;
+  if ((rc = pool_alloc(ctx, &out.rec, (size_t)n_own * GROUP, s)) ||
+      (rc = pool_alloc(ctx, &out.rec_elem, (size_t)n_own * GROUP, s)) ||
+      (p->n_ovf > 0 && ((rc = pool_alloc(ctx, &out.ovf_rec, (size_t)p->n_ovf, s)) ||
+                        (rc = pool_alloc(ctx, &out.ovf_elem, (size_t)p->n_ovf, s))))) {
+    pool_free(ctx, out.rec, s); pool_free(ctx, out.rec_elem, s);
+    pool_free(ctx, out.ovf_rec, s); pool_free(ctx, out.ovf_elem, s);
+    return rc;
+  }
   if (n_own > 0)
     P1_TIMED(p->ctx, "sort_rows", s,
-             sort_rows_kernel<<<grid_for(n_own, THREADS), THREADS, 0, s>>>(
-                 n_own, p->rec_off, p->rec, p->rec_elem, r2, e2));
+             sort_rows_kernel<<<grid_for(n_own, THREADS), THREADS, 0, s>>>(n_own, in, out));
   P1_CUDA(cudaGetLastError());
-  pool_free(ctx, p->rec, s);
-  pool_free(ctx, p->rec_elem, s);
-  p->rec = r2;
-  p->rec_elem = e2;
+  pool_free(ctx, p->rec, s); pool_free(ctx, p->rec_elem, s);
+  pool_free(ctx, p->ovf_rec, s); pool_free(ctx, p->ovf_elem, s);
+  p->rec = out.rec; p->rec_elem = out.rec_elem;
+  p->ovf_rec = out.ovf_rec; p->ovf_elem = out.ovf_elem;
   p->sorted = true;
   return P1_OK;
 }
@@ -379,6 +410,7 @@ static int plan_build(p1_ctx *ctx, const int32_t *elements, int64_t n_elements,
   const int rb = (int)row_begin, re = (int)row_end;
   const int N = (int)n_nodes;
   const int64_t M = n_elements;
+  const bool keep = (flags & P1_PLAN_KEEP_ELEMENTS) != 0;
 
   p1_plan *p = new p1_plan();
   memset(p, 0, sizeof(*p));
@@ -388,123 +420,107 @@ static int plan_build(p1_ctx *ctx, const int32_t *elements, int64_t n_elements,
   *out = nullptr;
 
   int rc = P1_OK;
-  int *cnt = nullptr, *rowlen = nullptr;
+  int *rowlen = nullptr, *cnt = nullptr;
   auto fail = [&](int code) {
-    pool_free(ctx, cnt, s);
     pool_free(ctx, rowlen, s);
+    pool_free(ctx, cnt, s);
     p1_plan_destroy(p);
     return code;
   };
-
-  // flags: [0] status, [1] max index, [2] n_big, [3] n_slow
-  if (cudaMemsetAsync(ctx->d_flags, 0, 4 * sizeof(int), s) != cudaSuccess ||
-      cudaMemsetAsync(ctx->d_flags + 1, 0xff, sizeof(int), s) != cudaSuccess) {
-    set_error("p1_plan_create: memset failed");
+  auto cuda_fail = [&](const char *what) {
+    set_error("p1_plan_create: %s: %s", what, cudaGetErrorString(cudaGetLastError()));
     return fail(P1_ECUDA);
-  }
-  if ((rc = pool_alloc(ctx, &p->rec_off, (size_t)n_own + 1, s))) return fail(rc);
-  if ((rc = pool_alloc(ctx, &p->indptr, (size_t)n_own + 1, s))) return fail(rc);
-  if ((rc = pool_alloc(ctx, &cnt, (size_t)n_own + 1, s))) return fail(rc);
-  if ((rc = pool_alloc(ctx, &rowlen, (size_t)n_own + 1, s))) return fail(rc);
+  };
+
+  // flags: [0] status, [1] max index, [2] n_big, [3] n_slow, [4] rows with > 8 records
+  if (cudaMemsetAsync(ctx->d_flags, 0, 8 * sizeof(int), s) != cudaSuccess ||
+      cudaMemsetAsync(ctx->d_flags + 1, 0xff, sizeof(int), s) != cudaSuccess)
+    return cuda_fail("memset");
   if ((rc = pool_alloc(ctx, &p->acc, (size_t)n_own + 1, s))) return fail(rc);
+  if ((rc = pool_alloc(ctx, &p->rec, (size_t)n_own * GROUP, s))) return fail(rc);
+  if (keep && (rc = pool_alloc(ctx, &p->rec_elem, (size_t)n_own * GROUP, s))) return fail(rc);
+  if ((rc = pool_alloc(ctx, &p->indptr, (size_t)n_own + 1, s))) return fail(rc);
+  if ((rc = pool_alloc(ctx, &rowlen, (size_t)n_own + 1, s))) return fail(rc);
   if ((rc = pool_alloc(ctx, &p->slow_rows, (size_t)n_own + 1, s))) return fail(rc);
-  if ((rc = pool_alloc(ctx, &p->big_rows, (size_t)((3 * M) / (DEG_BIG + 1) < n_own ? (3 * M) / (DEG_BIG + 1) : n_own) + 1, s)))
-    return fail(rc);
+  {
+    const int64_t cap = (3 * M) / (DEG_BIG + 1);
+    if ((rc = pool_alloc(ctx, &p->big_rows, (size_t)(cap < n_own ? cap : n_own) + 1, s)))
+      return fail(rc);
+  }
   cudaMemsetAsync(p->acc, 0, ((size_t)n_own + 1) * sizeof(unsigned long long), s);
 
   const unsigned eg = min(grid_for(M, THREADS), (unsigned)(ctx->sm_count * 32));
-  P1_TIMED(ctx, "count", s,
-           count_kernel<<<eg, THREADS, 0, s>>>(elements, M, N, rb, re, p->acc,
-                                               ctx->d_flags));
-  if (n_own > 0)
-    P1_TIMED(ctx, "split", s,
-             split_kernel<<<grid_for(n_own, THREADS), THREADS, 0, s>>>(
-                 n_own, p->acc, p->exact ? 1 : 0, cnt, rowlen, p->slow_rows,
-                 p->big_rows, ctx->d_flags + 2));
-  if ((rc = exclusive_scan_i32(ctx, cnt, p->rec_off, n_own, true, s))) return fail(rc);
-  // n_rec is needed on the host to size rec; for the whole matrix it is 3M,
-  // for a row range it is read back
-  int64_t n_rec = 3 * M;
-  if (!(rb == 0 && re == N)) {
-    int h = 0;
-    cudaMemcpyAsync(&h, p->rec_off + n_own, sizeof(int), cudaMemcpyDeviceToHost, s);
-    if (cudaStreamSynchronize(s) != cudaSuccess) {
-      set_error("p1_plan_create: sync failed: %s",
-                cudaGetErrorString(cudaGetLastError()));
-      return fail(P1_ECUDA);
-    }
-    n_rec = h;
-  }
-  p->n_rec = n_rec;
-  if ((rc = pool_alloc(ctx, &p->rec, (size_t)n_rec, s))) return fail(rc);
-  if ((flags & P1_PLAN_KEEP_ELEMENTS) &&
-      (rc = pool_alloc(ctx, &p->rec_elem, (size_t)n_rec, s)))
-    return fail(rc);
-  // cursor := row offsets (cnt is free again)
-  cudaMemcpyAsync(cnt, p->rec_off, (size_t)n_own * sizeof(int), cudaMemcpyDeviceToDevice, s);
-  {
-    const double2 *xy = (const double2 *)coords;
-    prof_begin(ctx, "scatter", s);
-    if (op == P1_OP_STIFFNESS)
-      scatter_kernel<<<eg, THREADS, 0, s>>>(elements, M, N, rb, re, cnt, p->rec,
-                                            p->rec_elem, StiffnessValues{xy});
-    else if (op == P1_OP_MASS)
-      scatter_kernel<<<eg, THREADS, 0, s>>>(elements, M, N, rb, re, cnt, p->rec,
-                                            p->rec_elem, MassValues{xy});
-    else if (op == P1_OP_LOCAL)
-      scatter_kernel<<<eg, THREADS, 0, s>>>(elements, M, N, rb, re, cnt, p->rec,
-                                            p->rec_elem, LocalValues{local});
+  prof_begin(ctx, "scatter", s);
+  launch_scatter<false>(ctx, eg, s, op, elements, M, N, rb, re, p->acc, p->rec,
+                        p->rec_elem, nullptr, coords, local);
+  prof_end(ctx, s);
+  p->val_op = op;
+  const Rows rows0 = rows_of(p);
+  if (n_own > 0) {
+    if (p->exact)
+      P1_TIMED(ctx, "rowlen", s,
+               rowlen_kernel<<<grid_for((int64_t)n_own * GROUP, THREADS), THREADS, 0, s>>>(
+                   n_own, rb, rows0, rowlen, p->slow_rows, p->big_rows, ctx->d_flags + 2));
     else
-      scatter_kernel<<<eg, THREADS, 0, s>>>(elements, M, N, rb, re, cnt, p->rec,
-                                            p->rec_elem, NoValues{});
-    prof_end(ctx, s);
-    p->val_op = op;
+      P1_TIMED(ctx, "split", s,
+               split_kernel<<<grid_for(n_own, THREADS), THREADS, 0, s>>>(
+                   n_own, p->acc, rowlen, p->slow_rows, p->big_rows, ctx->d_flags + 2));
   }
-  if (p->exact && n_own > 0)
-    P1_TIMED(ctx, "rowlen", s,
-             rowlen_kernel<<<grid_for((int64_t)n_own * GROUP, THREADS), THREADS, 0, s>>>(
-                 n_own, rb, p->rec_off, p->rec, rowlen, p->slow_rows, p->big_rows,
-                 ctx->d_flags + 2));
-  cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, 4 * sizeof(int),
-                  cudaMemcpyDeviceToHost, s);
-  if (cudaStreamSynchronize(s) != cudaSuccess) {
-    set_error("p1_plan_create: %s", cudaGetErrorString(cudaGetLastError()));
-    return fail(P1_ECUDA);
-  }
+  cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, 8 * sizeof(int), cudaMemcpyDeviceToHost, s);
+  if (cudaStreamSynchronize(s) != cudaSuccess) return cuda_fail("scatter");
   if (ctx->h_flags[0] & FLAG_INDEX_RANGE) {
-    set_error("p1_plan_create: element index out of range [0, %lld)",
-              (long long)n_nodes);
+    set_error("p1_plan_create: element index out of range [0, %lld)", (long long)n_nodes);
     return fail(P1_EINDEX);
   }
   p->max_index = ctx->h_flags[1];
   p->n_big = ctx->h_flags[2];
   p->n_slow = ctx->h_flags[3];
+  if (ctx->h_flags[4] > 0) {
+    // some rows have more than 8 records: give them compact storage and redo
+    // their incidences (a second pass over the elements; never on an NVB mesh)
+    if ((rc = pool_alloc(ctx, &cnt, (size_t)n_own + 1, s))) return fail(rc);
+    if ((rc = pool_alloc(ctx, &p->ovf_off, (size_t)n_own + 1, s))) return fail(rc);
+    overflow_count_kernel<<<grid_for(n_own, THREADS), THREADS, 0, s>>>(n_own, p->acc, cnt);
+    if ((rc = exclusive_scan_i32(ctx, cnt, p->ovf_off, n_own, true, s))) return fail(rc);
+    int h = 0;
+    cudaMemcpyAsync(&h, p->ovf_off + n_own, sizeof(int), cudaMemcpyDeviceToHost, s);
+    if (cudaStreamSynchronize(s) != cudaSuccess) return cuda_fail("overflow scan");
+    p->n_ovf = h;
+    if ((rc = pool_alloc(ctx, &p->ovf_rec, (size_t)p->n_ovf, s))) return fail(rc);
+    if (keep && (rc = pool_alloc(ctx, &p->ovf_elem, (size_t)p->n_ovf, s))) return fail(rc);
+    cudaMemcpyAsync(cnt, p->ovf_off, (size_t)n_own * sizeof(int), cudaMemcpyDeviceToDevice, s);
+    prof_begin(ctx, "scatter_overflow", s);
+    launch_scatter<true>(ctx, eg, s, op, elements, M, N, rb, re, p->acc, p->ovf_rec,
+                         p->ovf_elem, cnt, coords, local);
+    prof_end(ctx, s);
+    pool_free(ctx, cnt, s);
+    cnt = nullptr;
+  }
+  const Rows rows = rows_of(p);
   if (p->n_slow > 0)
     rowlen_slow_kernel<<<grid_for(p->n_slow, THREADS), THREADS, 0, s>>>(
-        p->slow_rows, p->n_slow, rb, p->rec_off, p->rec, rowlen);
+        p->slow_rows, p->n_slow, rb, rows, rowlen);
   if (p->n_big > 0) {
     Rec *tmp = nullptr;
     int *tmp_elem = nullptr;
-    if ((rc = pool_alloc(ctx, &tmp, (size_t)n_rec, s)) ||
-        (rc = pool_alloc(ctx, &tmp_elem, (size_t)n_rec, s)) ||
-        (rc = pool_alloc(ctx, &p->big_first, (size_t)(2 * n_rec + n_own + 1), s))) {
+    if ((rc = pool_alloc(ctx, &tmp, (size_t)p->n_ovf, s)) ||
+        (rc = pool_alloc(ctx, &tmp_elem, (size_t)p->n_ovf, s)) ||
+        (rc = pool_alloc(ctx, &p->big_first, (size_t)(2 * p->n_ovf + n_own + 1), s))) {
       pool_free(ctx, tmp, s);
       pool_free(ctx, tmp_elem, s);
       return fail(rc);
     }
-    sort_big_kernel<<<p->n_big, THREADS, 0, s>>>(p->big_rows, p->rec_off, p->rec,
-                                                 p->rec_elem, tmp, tmp_elem);
-    pool_free(ctx, tmp_elem, s);
-    rowlen_big_kernel<<<p->n_big, THREADS, 0, s>>>(p->big_rows, rb, p->rec_off,
-                                                   p->rec, p->big_first, rowlen);
+    sort_big_kernel<<<p->n_big, THREADS, 0, s>>>(p->big_rows, rows, tmp, tmp_elem);
+    rowlen_big_kernel<<<p->n_big, THREADS, 0, s>>>(p->big_rows, rb, rows, p->big_first,
+                                                   rowlen);
     pool_free(ctx, tmp, s);
+    pool_free(ctx, tmp_elem, s);
   }
   if ((rc = exclusive_scan_i32(ctx, rowlen, p->indptr, n_own, true, s))) return fail(rc);
   int h_nnz = 0;
   cudaMemcpyAsync(&h_nnz, p->indptr + n_own, sizeof(int), cudaMemcpyDeviceToHost, s);
-  pool_free(ctx, cnt, s);
   pool_free(ctx, rowlen, s);
-  cnt = rowlen = nullptr;
+  rowlen = nullptr;
   cudaError_t e = cudaStreamSynchronize(s);
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) {
@@ -537,8 +553,8 @@ extern "C" int p1_plan_create_for(p1_ctx *ctx, const int32_t *elements,
 extern "C" int p1_plan_destroy(p1_plan *p) {
   if (!p) return P1_OK;
   DeviceGuard guard(p->ctx->device);
-  void *blocks[] = {p->rec_off, p->rec, p->rec_elem, p->acc, p->indptr, p->slow_rows,
-                    p->big_rows, p->big_first, p->twin};
+  void *blocks[] = {p->acc, p->rec, p->rec_elem, p->ovf_off, p->ovf_rec, p->ovf_elem,
+                    p->indptr, p->slow_rows, p->big_rows, p->big_first, p->twin};
   for (void *b : blocks) pool_free(p->ctx, b, p->stream);
   delete p;
   return P1_OK;

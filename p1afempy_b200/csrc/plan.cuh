@@ -21,24 +21,30 @@ struct p1_plan {
   const int32_t *elements;  // borrowed, M x 3 (must outlive the plan)
   int64_t M, N;
   int64_t row_begin, row_end;  // owned rows
-  int64_t n_rec;               // incident (element, vertex) records of owned rows
   int64_t nnz;
   int max_index;
-  int *rec_off;        // n_own+1 : node -> first record
-  p1::Rec *rec;        // n_rec   : arrival order within a row until `sorted`
-  int *rec_elem;       // n_rec   : element of the record (P1_PLAN_KEEP_ELEMENTS) or null
+  // Records: row a owns the 8 slots rec[8a .. 8a+7] (256 B); its slot number comes
+  // from the same atomic that counts it, so there is no counting pass and no
+  // offset array.  Rows with more than 8 records (none on an NVB mesh) keep ALL
+  // their records in the compact overflow area instead: ovf_rec[ovf_off[a] ..].
+  unsigned long long *acc;  // n_own: low 32 bits = #records, high 32 bits = sum over the
+                       // records of hash(next) - hash(prev): 0 for a closed fan
+  p1::Rec *rec;        // 8 * n_own
+  int *rec_elem;       // 8 * n_own: element of the record (P1_PLAN_KEEP_ELEMENTS) or null
+  int *ovf_off;        // n_own+1 (only when some row overflows) or null
+  p1::Rec *ovf_rec;    // n_ovf
+  int *ovf_elem;       // n_ovf or null
+  int64_t n_ovf;
   int val_op;          // which operator's values the records hold (0 = none)
   bool sorted;         // records of every row ascending in (element, vertex)
   bool exact;          // row lengths from the all-pairs kernel (no hash shortcut)
-  unsigned long long *acc;  // n_own: low 32 bits = #records, high 32 bits = sum over the
-                       // records of hash(next) - hash(prev): 0 for a closed fan
   int *indptr;         // n_own+1
-  int *slow_rows;      // rows the 8-lane kernels do not take: open fans, more than 8
+  int *slow_rows;      // rows the fast fill does not take: open fans, more than 8
                        // records, repeated neighbours (non-manifold / degenerate)
   int n_slow;
   int *big_rows;       // rows with more than DEG_BIG records
   int n_big;
-  unsigned char *big_first;  // scratch flags for big rows (2*n_rec+n_own) or null
+  unsigned char *big_first;  // scratch flags for big rows (2*n_ovf+n_own) or null
   int *twin;           // lazily built: 3M, twin half-edge id T'*3+k' or -1
   int64_t n_open;      // half-edges without twin (valid once twin is built)
 };
@@ -62,6 +68,26 @@ __device__ __forceinline__ int prev_local(int k) { return k == 0 ? 2 : k - 1; }
 __device__ __forceinline__ int rec_next(const Rec &r) { return r.nx; }
 __device__ __forceinline__ int rec_prev(const Rec &r) { return r.pvk & NODE_MASK; }
 __device__ __forceinline__ int rec_k(const Rec &r) { return (int)((unsigned)r.pvk >> NODE_BITS); }
+
+// Where the records of a row live (see p1_plan).
+struct Rows {
+  const unsigned long long *acc;
+  Rec *rec;
+  int *rec_elem;
+  const int *ovf_off;
+  Rec *ovf_rec;
+  int *ovf_elem;
+  __device__ __forceinline__ int deg(int a) const { return (int)(unsigned)acc[a]; }
+  __device__ __forceinline__ Rec *ptr(int a, int deg) const {
+    return deg <= 8 ? rec + (int64_t)a * 8 : ovf_rec + ovf_off[a];
+  }
+  __device__ __forceinline__ int *elem(int a, int deg) const {
+    return deg <= 8 ? rec_elem + (int64_t)a * 8 : ovf_elem + ovf_off[a];
+  }
+};
+inline Rows rows_of(const p1_plan *p) {
+  return Rows{p->acc, p->rec, p->rec_elem, p->ovf_off, p->ovf_rec, p->ovf_elem};
+}
 
 // sm_100a has 256-bit global loads/stores (LDG.E.256 / STG.E.256)
 __device__ __forceinline__ void store_rec(Rec *p, const Rec &r) {
@@ -105,15 +131,14 @@ struct RowLane {
 // group exchange (next, prev) through it.  (Shuffles would do, but 16 of them
 // per lane saturate the ADU pipe -- measured 93 % -- while broadcast LDS is
 // one wavefront per warp.)
-__device__ __forceinline__ RowLane analyse_row(int self, int beg, int deg,
-                                               const Rec *__restrict__ rec,
+__device__ __forceinline__ RowLane analyse_row(int self, const Rec *row, int deg,
                                                unsigned gmask, int lane8, int shift,
                                                int2 *xch) {
   RowLane o;
   o.valid = lane8 < deg && deg <= GROUP;
   Rec r;
   r.nx = -1; r.pvk = 0; r.vd = r.vn = r.vp = 0.;
-  if (o.valid) r = load_rec(rec + beg + lane8);
+  if (o.valid) r = load_rec(row + lane8);
   o.nx = r.nx;
   o.pv = o.valid ? rec_prev(r) : -2;
   o.k = rec_k(r);
