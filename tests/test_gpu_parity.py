@@ -378,3 +378,68 @@ def test_device_callbacks(api):
     assert np.allclose(ident.toarray(), solvers.get_stiffness_matrix(c, e).toarray())
     ref_eta = orc.eta_r(x, c, e, dirichlet, neumann, L.f, L.g)
     assert np.abs(eta - ref_eta).max() <= 1e-12 * np.abs(ref_eta).max()
+
+
+@pytest.mark.parametrize('n', [9, 12, 41, 60, 300])
+def test_fans_of_every_size_class(api, n):
+    """Valence 9..40: overflow storage + one thread per row; > 40: one block per
+    row.  All operators that walk the fans."""
+    ang = 2 * np.pi * np.arange(n) / n
+    c = np.vstack([[0., 0.], np.column_stack([np.cos(ang), np.sin(ang)])])
+    c[1:] *= (1 + 0.1 * np.sin(5 * ang))[:, None]
+    e = np.column_stack([np.zeros(n, dtype=int), 1 + np.arange(n), 1 + (np.arange(n) + 1) % n])
+    rim = np.column_stack([1 + np.arange(n), 1 + (np.arange(n) + 1) % n])
+    H.csr_values_close(api[0].get_stiffness_matrix(c, e), orc.stiffness_coo(c, e).tocsr(), RTOL)
+    w, p = cubature.resolve_rule(cubature.CubatureRuleEnum.SMPLX1)
+    H.csr_values_close(
+        api[0].get_general_stiffness_matrix(c, e, H.a11, H.a12, H.a21, H.a22, (w, p)),
+        orc.general_stiffness_coo(c, e, H.a11, H.a12, H.a21, H.a22, w, p).tocsr(), RTOL)
+    assert np.array_equal(api[0].get_right_hand_side(c, e, H.f_load, (w, p)),
+                          orc.load_vector_cubature(c, e, H.f_load, w, p))
+    e2e, e2n, b2e = api[1].provide_geometric_data(e, [rim])
+    o2e, o2n, ob2e = orc.geometric_data(e, [rim])
+    assert np.array_equal(e2e, o2e) and np.array_equal(e2n, o2n) and np.array_equal(b2e[0], ob2e[0])
+    x = H.u_nodal(c) + c[:, 1]
+    assert np.array_equal(
+        api[2].compute_eta_r(x, c, e, rim, np.zeros((0, 2), dtype=int), H.f_load, H.g_neu),
+        orc.eta_r(x, c, e, rim, np.zeros((0, 2), dtype=int), H.f_load, H.g_neu))
+
+
+def test_unstructured_delaunay_mesh(api):
+    """A mesh that is NOT in NVB order: random points, Delaunay triangulation,
+    valences 3..12 (rows with more than 8 incidences take the overflow pass),
+    node numbering without any locality."""
+    from scipy.spatial import Delaunay
+    rng = np.random.default_rng(7)
+    pts = np.vstack([rng.random((4000, 2)),
+                     [[0., 0.], [1., 0.], [1., 1.], [0., 1.]]])
+    tri = Delaunay(pts)
+    e = tri.simplices.astype(np.int64)
+    # counter-clockwise orientation, like every mesh of the reference
+    d1, d2 = pts[e[:, 1]] - pts[e[:, 0]], pts[e[:, 2]] - pts[e[:, 0]]
+    flip = (d1[:, 0] * d2[:, 1] - d1[:, 1] * d2[:, 0]) < 0
+    e[flip] = e[flip][:, [0, 2, 1]]
+    valence = np.bincount(e.reshape(-1))
+    assert valence.max() > 8
+    H.csr_values_close(api[0].get_stiffness_matrix(pts, e), orc.stiffness_coo(pts, e).tocsr(), 1e-11)
+    H.csr_values_close(api[0].get_mass_matrix(pts, e), orc.mass_coo(pts, e).tocsr(), RTOL)
+    w, p = cubature.resolve_rule(cubature.CubatureRuleEnum.DAYTAYLOR)
+    u = H.u_nodal(pts)
+    H.csr_values_close(api[0].get_weighted_mass_matrix(pts, e, u, H.phi, (w, p)),
+                       orc.weighted_mass_coo(pts, e, u, H.phi, w, p).tocsr(), RTOL)
+    assert np.array_equal(api[0].get_right_hand_side(pts, e, H.f_load, (w, p)),
+                          orc.load_vector_cubature(pts, e, H.f_load, w, p))
+    assert np.array_equal(api[0].get_right_hand_side(pts, e, H.f_load),
+                          orc.load_vector_midpoint(pts, e, H.f_load))
+    # boundary = edges that occur once, oriented like their element
+    he = np.vstack([e[:, [0, 1]], e[:, [1, 2]], e[:, [2, 0]]])
+    key = np.sort(he, axis=1)
+    _, inv, cnt = np.unique(key, axis=0, return_inverse=True, return_counts=True)
+    bnd = he[cnt[np.asarray(inv).reshape(-1)] == 1]
+    e2e, e2n, b2e = api[1].provide_geometric_data(e, [bnd])
+    o2e, o2n, ob2e = orc.geometric_data(e, [bnd])
+    assert np.array_equal(e2e, o2e) and np.array_equal(e2n, o2n) and np.array_equal(b2e[0], ob2e[0])
+    x = u + 0.3 * pts[:, 0]
+    none = np.zeros((0, 2), dtype=int)
+    assert np.array_equal(api[2].compute_eta_r(x, pts, e, bnd, none, H.f_load, H.g_neu),
+                          orc.eta_r(x, pts, e, bnd, none, H.f_load, H.g_neu))
