@@ -104,6 +104,16 @@ int p1_plan_create_for(p1_ctx *ctx, const int32_t *elements, int64_t n_elements,
                        int64_t n_nodes, int64_t row_begin, int64_t row_end,
                        int flags, int op, const double *coords, const double *local,
                        void *stream, p1_plan **out);
+/* Multi-GPU with balanced ownership: of the chunks of 2^chunk_log2 consecutive
+ * rows, rank r owns those with chunk index % world == r; its local rows are the
+ * owned chunks in ascending order (p1_plan_rows of them).  Every rank then holds
+ * the same mix of old, high-valence and new nodes.  Interleaving the ranks'
+ * pieces chunk by chunk gives the reference CSR bit for bit. */
+int p1_plan_create_interleaved(p1_ctx *ctx, const int32_t *elements, int64_t n_elements,
+                               int64_t n_nodes, int chunk_log2, int world, int rank,
+                               int flags, int op, const double *coords,
+                               const double *local, void *stream, p1_plan **out);
+int64_t p1_plan_rows(const p1_plan *plan); /* rows the plan owns (length of indptr - 1) */
 int p1_plan_destroy(p1_plan *plan);
 /* Multi-GPU: world+1 row boundaries such that every range holds about the same
  * number of stored entries (estimated from a strided sample of the elements;

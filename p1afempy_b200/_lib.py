@@ -51,6 +51,9 @@ PROTOTYPES = {
     'p1_plan_create': [_vp, _vp, _i64, _i64, _i64, _i64, _int, _vp, C.POINTER(_vp)],
     'p1_plan_create_for': [_vp, _vp, _i64, _i64, _i64, _i64, _int, _int, _vp, _vp, _vp,
                            C.POINTER(_vp)],
+    'p1_plan_create_interleaved': [_vp, _vp, _i64, _i64, _int, _int, _int, _int, _int, _vp,
+                                   _vp, _vp, C.POINTER(_vp)],
+    'p1_plan_rows': [_vp],
     'p1_plan_destroy': [_vp],
     'p1_partition_rows': [_vp, _vp, _i64, _i64, _int, _vp, _vp],
     'p1_plan_info': [_vp, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64),
@@ -73,7 +76,7 @@ PROTOTYPES = {
     'p1_eta_r': [_vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp],
     'p1_boundary_edges': [_vp, _vp, _vp, _i64, _vp, _vp, _vp],
 }
-_RESTYPES = {'p1_last_error': C.c_char_p}
+_RESTYPES = {'p1_last_error': C.c_char_p, 'p1_plan_rows': _i64}
 
 _lib = None
 _lock = threading.Lock()

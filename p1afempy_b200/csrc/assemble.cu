@@ -29,7 +29,7 @@ constexpr int FR = 128;          // rows per block = threads per block
 constexpr int CAP_OUT = 1280;    // CSR entries staged per block (9 per regular row + slack)
 
 __global__ void __launch_bounds__(FR, P1_FILL_MIN_BLOCKS)
-fill_rows_kernel(int n_own, int rb, int exact,
+fill_rows_kernel(int n_own, Own own, int exact,
                  const unsigned long long *__restrict__ acc, const Rec *__restrict__ rec,
                  const int *__restrict__ indptr, int *__restrict__ indices,
                  double *__restrict__ data, int *__restrict__ flags) {
@@ -51,7 +51,7 @@ fill_rows_kernel(int n_own, int rb, int exact,
   }
   const Rec *row = rec + (int64_t)(row0 + tid) * GROUP;  // the row's 8 slots
   bool process = deg >= 1 && deg <= GROUP && (exact || hash == 0u);
-  const int self = row0 + tid + rb;
+  const int self = own.global(row0 + tid);
   int nx[GROUP], pv[GROUP], slot[GROUP];
   double vd[GROUP], vn[GROUP], vp[GROUP], mvp[GROUP];
   int slot_self = 0;
@@ -153,7 +153,7 @@ __device__ __forceinline__ int insert_unique(int *cols, int n, int c) {
 }
 
 __global__ void __launch_bounds__(SLOW_THREADS)
-fill_slow_kernel(const int *__restrict__ slow_rows, int n_slow, int rb, Rows rows,
+fill_slow_kernel(const int *__restrict__ slow_rows, int n_slow, Own own, Rows rows,
                  const int *__restrict__ indptr, int *__restrict__ indices,
                  double *__restrict__ data) {
   __shared__ int cols_s[SLOW_THREADS * SLOW_COLS];
@@ -161,7 +161,7 @@ fill_slow_kernel(const int *__restrict__ slow_rows, int n_slow, int rb, Rows row
   if (idx >= n_slow) return;
   const int a = slow_rows[idx];
   const int deg = rows.deg(a);
-  const int self = a + rb;
+  const int self = own.global(a);
   const Rec *nb = rows.ptr(a, deg);
   int *cs = cols_s + threadIdx.x * SLOW_COLS;
   int n = insert_unique(cs, 0, self);
@@ -209,7 +209,7 @@ __device__ __forceinline__ int big_candidate2(int self, const Rec *nb, int j) {
 }
 
 __global__ void __launch_bounds__(THREADS)
-fill_big_kernel(const int *__restrict__ big_rows, int rb, Rows rows,
+fill_big_kernel(const int *__restrict__ big_rows, Own own, Rows rows,
                 const unsigned char *__restrict__ first,
                 const int *__restrict__ indptr, int *__restrict__ indices,
                 double *__restrict__ data) {
@@ -217,7 +217,7 @@ fill_big_kernel(const int *__restrict__ big_rows, int rb, Rows rows,
   const int deg = rows.deg(a);
   const Rec *nb = rows.ptr(a, deg);
   const unsigned char *fl = first + 2 * (int64_t)rows.ovf_off[a] + a;
-  const int self = a + rb;
+  const int self = own.global(a);
   const int ncand = 2 * deg + 1;
   const int64_t base = indptr[a];
   for (int j = threadIdx.x; j < ncand; j += blockDim.x) {
@@ -269,7 +269,7 @@ refresh_kernel(const int *__restrict__ elements, int64_t n,
 template <class V>
 static void launch_refresh(p1_plan *plan, V values, cudaStream_t s) {
   p1_ctx *ctx = plan->ctx;
-  const int64_t n_slots = (plan->row_end - plan->row_begin) * GROUP;
+  const int64_t n_slots = plan->n_own * GROUP;
   if (n_slots > 0)
     refresh_kernel<<<min(grid_for(n_slots, THREADS), (unsigned)(ctx->sm_count * 32)), THREADS,
                      0, s>>>(plan->elements, n_slots, plan->acc, plan->rec, plan->rec_elem,
@@ -293,8 +293,8 @@ extern "C" int p1_assemble_csr(const p1_plan *cplan, int op, const double *coord
   p1_ctx *ctx = plan->ctx;
   DeviceGuard guard(ctx->device);
   cudaStream_t s = (cudaStream_t)stream;
-  const int n_own = (int)(plan->row_end - plan->row_begin);
-  const int rb = (int)plan->row_begin;
+  const int n_own = (int)plan->n_own;
+  const Own own = plan->own;
   const int64_t M = plan->M;
   if (op == P1_OP_STORED) {
     if (plan->val_op == 0) {
@@ -332,16 +332,16 @@ extern "C" int p1_assemble_csr(const p1_plan *cplan, int op, const double *coord
   if (n_own > 0)
     P1_TIMED(ctx, "fill_rows", s,
              (fill_rows_kernel<<<grid_for(n_own, FR), FR, 0, s>>>(
-                 n_own, rb, plan->exact ? 1 : 0, plan->acc, plan->rec, plan->indptr, indices,
+                 n_own, own, plan->exact ? 1 : 0, plan->acc, plan->rec, plan->indptr, indices,
                  data, ctx->d_flags)));
   if (plan->n_slow > 0)
     P1_TIMED(ctx, "fill_slow", s,
              (fill_slow_kernel<<<grid_for(plan->n_slow, SLOW_THREADS), SLOW_THREADS, 0, s>>>(
-                 plan->slow_rows, plan->n_slow, rb, rows_of(plan), plan->indptr, indices,
+                 plan->slow_rows, plan->n_slow, own, rows_of(plan), plan->indptr, indices,
                  data)));
   if (plan->n_big > 0)
     fill_big_kernel<<<plan->n_big, THREADS, 0, s>>>(
-        plan->big_rows, rb, rows_of(plan), plan->big_first, plan->indptr, indices, data);
+        plan->big_rows, own, rows_of(plan), plan->big_first, plan->indptr, indices, data);
   P1_CUDA(cudaGetLastError());
   if (!plan->exact) {
     // the closed-fan shortcut is verified while filling: read the verdict

@@ -246,7 +246,7 @@ static int read_flags(p1_ctx *ctx, cudaStream_t s) {
 }
 
 static int full_plan_required(const p1_plan *p, const char *who) {
-  if (p->row_begin != 0 || p->row_end != p->N) {
+  if (p->row_begin != 0 || p->row_end != p->N || p->own.world != 1) {
     set_error("%s needs a plan over all rows", who);
     return P1_EINVAL;
   }

@@ -544,7 +544,7 @@ extern "C" int p1_load_vector(const p1_plan *plan, const double *coords,
                               void *stream) {
   P1_REQUIRE(plan && weights_host && points_host && n_qp > 0, "bad plan/rule");
   const int64_t M = plan->M;
-  const int n_own = (int)(plan->row_end - plan->row_begin);
+  const int n_own = (int)plan->n_own;
   P1_REQUIRE(n_own == 0 || b, "null b");
   P1_REQUIRE(M == 0 || (coords && fq), "null argument");
   p1_ctx *ctx = plan->ctx;
@@ -573,7 +573,7 @@ extern "C" int p1_load_vector_midpoint(const p1_plan *plan, const double *coords
                                        void *stream) {
   P1_REQUIRE(plan, "null plan");
   const int64_t M = plan->M;
-  const int n_own = (int)(plan->row_end - plan->row_begin);
+  const int n_own = (int)plan->n_own;
   P1_REQUIRE(n_own == 0 || b, "null b");
   P1_REQUIRE(M == 0 || (coords && f_centroid), "null argument");
   p1_ctx *ctx = plan->ctx;

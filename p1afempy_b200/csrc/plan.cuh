@@ -13,6 +13,46 @@ struct __align__(32) Rec {
   int nx, pvk;
   double vd, vn, vp;
 };
+
+// Which rows a plan owns, and the local <-> global row numbering.
+//   contiguous : rows [rb, re)                                   (world == 1)
+//   interleaved: of the chunks of 2^cshift rows inside [rb, re), those with
+//                chunk index % world == rank; local rows are the owned chunks
+//                in ascending order.  Every rank then holds the same mix of
+//                old (high-valence) and new nodes: balanced in every respect.
+struct Own {
+  int rb, re, cshift, world, rank;
+  int wshift;  // log2(world) when world is a power of two, else -1
+  __host__ __device__ __forceinline__ bool owns(int e, int &a) const {
+    const unsigned x = (unsigned)(e - rb);
+    if (x >= (unsigned)(re - rb)) return false;
+    if (world == 1) { a = (int)x; return true; }
+    const unsigned q = x >> cshift;
+    unsigned owner, mine;  // the scatter tests 3 vertices of every element: keep it cheap
+    if (wshift >= 0) { owner = q & ((1u << wshift) - 1u); mine = q >> wshift; }
+    else { owner = q % (unsigned)world; mine = q / (unsigned)world; }
+    if ((int)owner != rank) return false;
+    a = (int)((mine << cshift) | (x & ((1u << cshift) - 1u)));
+    return true;
+  }
+  __host__ __device__ __forceinline__ int global(int a) const {
+    if (world == 1) return a + rb;
+    const unsigned q = (unsigned)a >> cshift;
+    return rb + (int)(((q * (unsigned)world + (unsigned)rank) << cshift) |
+                      ((unsigned)a & ((1u << cshift) - 1u)));
+  }
+  // number of owned rows
+  __host__ int64_t count() const {
+    const int64_t n = (int64_t)re - rb;
+    if (world == 1) return n;
+    const int64_t c = (int64_t)1 << cshift;
+    const int64_t full = n / c, tail = n % c;
+    int64_t mine = (full / world) * c + ((full % world) > rank ? c : 0);
+    if (tail && (full % world) == rank) mine += tail;
+    return mine;
+  }
+};
+
 }  // namespace p1
 
 struct p1_plan {
@@ -20,7 +60,9 @@ struct p1_plan {
   cudaStream_t stream;      // the stream the plan was built on (frees are ordered on it)
   const int32_t *elements;  // borrowed, M x 3 (must outlive the plan)
   int64_t M, N;
-  int64_t row_begin, row_end;  // owned rows
+  int64_t row_begin, row_end;  // row range the ownership is defined on
+  p1::Own own;                 // which of those rows this plan owns
+  int64_t n_own;               // number of owned (= local) rows
   int64_t nnz;
   int max_index;
   // Records: row a owns the 8 slots rec[8a .. 8a+7] (256 B); its slot number comes

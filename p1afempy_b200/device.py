@@ -135,7 +135,7 @@ class DeviceMesh:
     """
 
     def __init__(self, coordinates, elements, device=None, rows=None,
-                 n_nodes=None, reuse=False, check=True):
+                 n_nodes=None, reuse=False, check=True, interleave=None):
         self.ctx, self.device = context(device)
         self._lib = _lib.load()
         self.elements = to_device_indices(elements, self.device, self.ctx)
@@ -154,6 +154,11 @@ class DeviceMesh:
         self.n_nodes = int(n_nodes)
         self.n_elements = int(self.elements.shape[0])
         self.rows = (0, self.n_nodes) if rows is None else (int(rows[0]), int(rows[1]))
+        # (world, rank, chunk_log2): own the row chunks with index % world == rank
+        self.interleave = None if interleave is None else tuple(int(x) for x in interleave)
+        if self.interleave is not None and rows is not None:
+            raise ValueError('rows= and interleave= are mutually exclusive')
+        self.n_rows = self.rows[1] - self.rows[0]     # owned rows; final once planned
         self.reuse = bool(reuse)
         self._plan = None
         self._plan_keeps_elements = False
@@ -187,9 +192,31 @@ class DeviceMesh:
     def _adopt(self, handle, keep):
         self._plan = handle
         self._plan_keeps_elements = keep
+        self.n_rows = int(self._lib.p1_plan_rows(handle))
         nnz, mx = C.c_int64(), C.c_int64()
         _lib.check(self._lib.p1_plan_info(handle, C.byref(nnz), C.byref(mx), None, None))
         self.nnz, self.max_index = nnz.value, mx.value
+
+    def _create(self, keep, op, local):
+        handle = C.c_void_p()
+        if self.interleave is not None:
+            world, rank, chunk_log2 = self.interleave
+            rc = self._lib.p1_plan_create_interleaved(
+                self.ctx, _ptr(self.elements), self.n_elements, self.n_nodes, chunk_log2,
+                world, rank, self._flags(keep), op, _ptr(self.coords) if op else None,
+                _ptr(local), _stream(self.device), C.byref(handle))
+        elif op:
+            rc = self._lib.p1_plan_create_for(
+                self.ctx, _ptr(self.elements), self.n_elements, self.n_nodes,
+                self.rows[0], self.rows[1], self._flags(keep), op, _ptr(self.coords),
+                _ptr(local), _stream(self.device), C.byref(handle))
+        else:
+            rc = self._lib.p1_plan_create(
+                self.ctx, _ptr(self.elements), self.n_elements, self.n_nodes,
+                self.rows[0], self.rows[1], self._flags(keep), _stream(self.device),
+                C.byref(handle))
+        _lib.check(rc)
+        self._adopt(handle, keep)
 
     @property
     def plan(self):
@@ -198,22 +225,25 @@ class DeviceMesh:
         if self._plan is not None and not self._plan_keeps_elements:
             self.close()
         if self._plan is None:
-            handle = C.c_void_p()
-            _lib.check(self._lib.p1_plan_create(
-                self.ctx, _ptr(self.elements), self.n_elements, self.n_nodes,
-                self.rows[0], self.rows[1], self._flags(True), _stream(self.device),
-                C.byref(handle)))
-            self._adopt(handle, True)
+            self._create(True, 0, None)
         return self._plan
 
     def _plan_for(self, op, local):
         """Cold path of one matrix: scatter and local matrices in one kernel."""
-        handle = C.c_void_p()
-        _lib.check(self._lib.p1_plan_create_for(
-            self.ctx, _ptr(self.elements), self.n_elements, self.n_nodes,
-            self.rows[0], self.rows[1], self._flags(self.reuse), op, _ptr(self.coords),
-            _ptr(local), _stream(self.device), C.byref(handle)))
-        self._adopt(handle, self.reuse)
+        self._create(self.reuse, op, local)
+
+    def global_rows(self):
+        """Global row index of every local row (int64 CUDA tensor)."""
+        dev = torch.device('cuda', self.device)
+        if self.interleave is None:
+            return torch.arange(self.rows[0], self.rows[1], dtype=torch.int64, device=dev)
+        world, rank, c = self.interleave
+        n = self.n_nodes
+        chunks = torch.arange(rank, max(rank, (n + (1 << c) - 1) >> c), world, dtype=torch.int64,
+                              device=dev)
+        rows = (chunks[:, None] << c) + torch.arange(1 << c, dtype=torch.int64, device=dev)
+        rows = rows.reshape(-1)
+        return rows[rows < n]
 
     def close(self):
         if self._plan is not None:
@@ -246,7 +276,7 @@ class DeviceMesh:
                 self.close()
                 self._plan_for(op, local)
                 run_op = _lib.OP_STORED
-            n_own = self.rows[1] - self.rows[0]
+            n_own = self.n_rows
             data = self._empty(self.nnz)
             indptr = self._empty(n_own + 1, torch.int32) if pattern else None
             indices = self._empty(self.nnz, torch.int32) if pattern else None
@@ -352,7 +382,8 @@ class DeviceMesh:
     def load_vector(self, fq, weights, points):
         w, p = _host_f64(weights), _host_f64(points)
         fq = to_device_f64(fq, self.device, (w.shape[0], self.n_elements))
-        b = self._empty(self.rows[1] - self.rows[0])
+        self.plan  # noqa: B018  (fixes n_rows)
+        b = self._empty(self.n_rows)
         _lib.check(self._lib.p1_load_vector(
             self.plan, _ptr(self.coords), _ptr(fq), w.ctypes.data_as(C.c_void_p),
             p.ctypes.data_as(C.c_void_p), w.shape[0], _ptr(b), _stream(self.device)))
@@ -360,7 +391,8 @@ class DeviceMesh:
 
     def load_vector_midpoint(self, f_centroid):
         fc = to_device_f64(f_centroid, self.device, (self.n_elements,))
-        b = self._empty(self.rows[1] - self.rows[0])
+        self.plan  # noqa: B018
+        b = self._empty(self.n_rows)
         _lib.check(self._lib.p1_load_vector_midpoint(
             self.plan, _ptr(self.coords), _ptr(fc), _ptr(b), _stream(self.device)))
         return b
@@ -413,7 +445,7 @@ class DeviceMesh:
         (solvers.py:140-141,375-376); index dtype by scipy's rule."""
         from scipy.sparse import csr_matrix
         n = (self.max_index + 1) if inferred_shape else self.n_nodes
-        if self.rows != (0, self.n_nodes):
+        if self.rows != (0, self.n_nodes) or self.interleave is not None:
             raise ValueError('to_scipy needs a plan over all rows')
         idx_dtype = scipy_index_dtype(self.n_elements, n, n)
         ip = indptr[:n + 1]

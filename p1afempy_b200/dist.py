@@ -1,33 +1,46 @@
 """Multi-GPU assembly on one box: one process per GPU (torch.distributed,
-NCCL over NVLink/NVSwitch), rows of the matrix split into contiguous ranges of
-the ORIGINAL node numbering, so that the per-rank CSR pieces concatenated in
-rank order ARE the reference CSR bit for bit.
+NCCL over NVLink/NVSwitch).  The rows of the matrix are dealt out to the ranks
+in chunks of 2^chunk_log2 consecutive rows of the ORIGINAL node numbering
+(chunk c belongs to rank c % world), so that the ranks' CSR pieces interleaved
+chunk by chunk ARE the reference CSR bit for bit, and
+every rank holds the same mix of old (high-valence) and new nodes.
 
 Design: inputs replicated, owner filter.  Every rank holds (coordinates,
 elements) -- 1.3 GB at 64M triangles, nothing next to 180 GB -- and builds the
-plan for its own rows only: the count/scatter kernels scan all M elements
-(12 B per triangle each) and keep the incidences whose node is owned; records,
-row pointer, fill and output scale 1/G.  No partial sums cross GPUs, hence no
-data-path collective and results are independent of G; the only collective
-is the all-gather of per-rank nnz that turns local row pointers into global
-ones (and, on request, the gather of the pieces onto one rank).
+plan for its own rows only: the scatter kernel scans all M elements (12 B per
+triangle) and keeps, and computes, only the incidences whose node is owned;
+records, row pointer, fill and output scale 1/G.  No partial sums cross GPUs,
+hence no data-path collective and results are independent of G; the only
+collectives are size exchanges and, on request, the gather of the pieces onto
+one rank.
 
 The host-side logic below is backend-agnostic (gloo on CPU in the tests).
 """
 from __future__ import annotations
 
-import numpy as np
 import torch
 import torch.distributed as dist
 
+DEFAULT_CHUNK_LOG2 = 12
+
 
 def partition_rows(n_rows: int, world: int):
-    """Contiguous, balanced row ranges [(begin, end)] * world."""
+    """Contiguous, balanced row ranges [(begin, end)] * world (by row count)."""
     return [(n_rows * r // world, n_rows * (r + 1) // world) for r in range(world)]
 
 
+def interleaved_rows(n_rows: int, world: int, rank: int, chunk_log2: int, device=None):
+    """Global row ids owned by `rank`: chunks rank, rank+world, ... in order."""
+    chunks = torch.arange(rank, max(rank, (n_rows + (1 << chunk_log2) - 1) >> chunk_log2), world,
+                          dtype=torch.int64, device=device)
+    rows = (chunks[:, None] << chunk_log2) + torch.arange(1 << chunk_log2, dtype=torch.int64,
+                                                          device=device)
+    rows = rows.reshape(-1)
+    return rows[rows < n_rows]
+
+
 def nnz_offsets(local_nnz: int, device=None, group=None):
-    """-> (offset of this rank's first entry, total nnz, per-rank nnz)."""
+    """-> (sum of nnz of lower ranks, total nnz, per-rank nnz)."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     mine = torch.tensor([int(local_nnz)], dtype=torch.int64, device=device)
@@ -38,63 +51,73 @@ def nnz_offsets(local_nnz: int, device=None, group=None):
     return int(starts[rank]), int(every.sum()), [int(x) for x in every]
 
 
-def gather_csr(indptr, indices, data, n_rows, root=0, group=None):
-    """Concatenates the row-range pieces on `root`.
+def _place(g_indptr, g_indices, g_data, rows, indptr, indices, data):
+    """Copies one piece (local CSR over the global rows `rows`) into place."""
+    lens = (indptr[1:] - indptr[:-1]).to(torch.int64)
+    start = g_indptr[rows].to(torch.int64)
+    dest = torch.repeat_interleave(start - indptr[:-1].to(torch.int64), lens) + \
+        torch.arange(indices.numel(), dtype=torch.int64, device=indices.device)
+    g_indices[dest] = indices
+    g_data[dest] = data
 
-    indptr: local row pointer (rows_owned+1, starting at 0), indices, data:
-    torch tensors on the rank's device.  Returns (indptr, indices, data) of the
-    whole matrix on root (same device/dtypes), None elsewhere."""
+
+def gather_csr(indptr, indices, data, rows, n_rows, root=0, group=None):
+    """Assembles the whole matrix on `root` from the ranks' pieces.
+
+    indptr: local row pointer (len(rows)+1, starting at 0); rows: the global
+    row id of every local row (any disjoint cover of range(n_rows) over the
+    ranks: contiguous ranges or interleaved chunks).  Returns (indptr, indices,
+    data) on root (same device/dtypes), None elsewhere."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     dev = data.device
-    offset, total, every = nnz_offsets(data.numel(), device=dev, group=group)
-    rows = torch.tensor([indptr.numel() - 1], dtype=torch.int64, device=dev)
-    all_rows = torch.zeros(world, dtype=torch.int64, device=dev)
-    dist.all_gather_into_tensor(all_rows, rows, group=group)
-    all_rows = [int(x) for x in all_rows.cpu()]
-    assert sum(all_rows) == n_rows, (all_rows, n_rows)
+    sizes = torch.tensor([rows.numel(), data.numel()], dtype=torch.int64, device=dev)
+    every = torch.zeros(2 * world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(every, sizes, group=group)
+    every = every.cpu().reshape(world, 2)
+    assert int(every[:, 0].sum()) == n_rows, (every, n_rows)
+    total = int(every[:, 1].sum())
     if rank != root:
-        dist.send((indptr[:-1] + offset).contiguous(), dst=root, group=group)
-        dist.send(indices.contiguous(), dst=root, group=group)
-        dist.send(data.contiguous(), dst=root, group=group)
+        for t in (rows, indptr, indices, data):
+            dist.send(t.contiguous(), dst=root, group=group)
         return None
-    g_indptr = torch.empty(n_rows + 1, dtype=indptr.dtype, device=dev)
+    pieces = []
+    for r in range(world):
+        if r == root:
+            pieces.append((rows, indptr, indices, data))
+            continue
+        nr, nz = int(every[r, 0]), int(every[r, 1])
+        bufs = (torch.empty(nr, dtype=rows.dtype, device=dev),
+                torch.empty(nr + 1, dtype=indptr.dtype, device=dev),
+                torch.empty(nz, dtype=indices.dtype, device=dev),
+                torch.empty(nz, dtype=data.dtype, device=dev))
+        for t in bufs:
+            dist.recv(t, src=r, group=group)
+        pieces.append(bufs)
+    lens = torch.zeros(n_rows, dtype=torch.int64, device=dev)
+    for prow, pptr, _, _ in pieces:
+        lens[prow] = (pptr[1:] - pptr[:-1]).to(torch.int64)
+    g_indptr = torch.zeros(n_rows + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(lens, 0, out=g_indptr[1:])
     g_indices = torch.empty(total, dtype=indices.dtype, device=dev)
     g_data = torch.empty(total, dtype=data.dtype, device=dev)
-    row0, nz0 = 0, 0
-    for r in range(world):
-        rs, ns = slice(row0, row0 + all_rows[r]), slice(nz0, nz0 + every[r])
-        if r == root:
-            g_indptr[rs] = indptr[:-1] + offset
-            g_indices[ns] = indices
-            g_data[ns] = data
-        else:
-            for buf in (g_indptr[rs], g_indices[ns], g_data[ns]):
-                tmp = torch.empty_like(buf)
-                dist.recv(tmp, src=r, group=group)
-                buf.copy_(tmp)
-        row0 += all_rows[r]
-        nz0 += every[r]
-    g_indptr[n_rows] = total
-    return g_indptr, g_indices, g_data
+    for piece in pieces:
+        _place(g_indptr, g_indices, g_data, *piece)
+    return g_indptr.to(indptr.dtype), g_indices, g_data
 
 
 class DistributedMesh:
     """The calling rank's share of a mesh replicated on every GPU."""
 
-    def __init__(self, coordinates, elements, device=None, group=None):
+    def __init__(self, coordinates, elements, device=None, group=None,
+                 chunk_log2=DEFAULT_CHUNK_LOG2):
         from .device import DeviceMesh
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
-        n_nodes = int(coordinates.shape[0])
-        self.n_nodes = n_nodes
-        self.local = DeviceMesh(coordinates, elements, device=device)
-        # ranges balanced by stored entries, not by rows: in NVB numbering the
-        # early (coarse-level) nodes have twice the valence of the late ones
-        bounds = self.local.balanced_rows(self.world)
-        self.rows = (bounds[self.rank], bounds[self.rank + 1])
-        self.local.set_rows(self.rows)
+        self.n_nodes = int(coordinates.shape[0])
+        self.local = DeviceMesh(coordinates, elements, device=device,
+                                interleave=(self.world, self.rank, chunk_log2))
 
     def stiffness_csr(self):
         return self.local.stiffness_csr()
@@ -102,13 +125,12 @@ class DistributedMesh:
     def mass_csr(self):
         return self.local.mass_csr()
 
-    def offsets(self):
-        return nnz_offsets(self.local.nnz, device=self.local.coords.device,
-                           group=self.group)
+    def global_rows(self):
+        return self.local.global_rows()
 
     def gather(self, indptr, indices, data, root=0):
-        return gather_csr(indptr, indices, data, self.n_nodes, root=root,
-                          group=self.group)
+        return gather_csr(indptr, indices, data, self.global_rows(), self.n_nodes,
+                          root=root, group=self.group)
 
     def close(self):
         self.local.close()

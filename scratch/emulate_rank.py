@@ -9,9 +9,8 @@ c, e = generate_mesh(level)
 n = c.shape[0]
 ctx, dev = context(0)
 lib = _lib.load()
-m0 = DeviceMesh(c, e); bounds = m0.balanced_rows(world); print(bounds)
 for rank in (0, world // 2, world - 1):
-    mesh = DeviceMesh(c, e, rows=(bounds[rank], bounds[rank + 1]))
+    mesh = DeviceMesh(c, e, interleave=(world, rank, 12))
     for _ in range(3):
         out = mesh.stiffness_csr()
     torch.cuda.synchronize()

@@ -22,7 +22,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, result_path):
+def _worker(rank, world, port, result_path, layout):
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
     dist.init_process_group('gloo', rank=rank, world_size=world)
@@ -31,14 +31,18 @@ def _worker(rank, world, port, result_path):
         c = meshgen.perturb_interior(c, b, 0.01)
         ref = orc.stiffness_coo(c, e).tocsr()
         n = ref.shape[0]
-        lo, hi = pdist.partition_rows(n, world)[rank]
-        piece = ref[lo:hi]
+        if layout == 'contiguous':
+            lo, hi = pdist.partition_rows(n, world)[rank]
+            rows = torch.arange(lo, hi, dtype=torch.int64)
+        else:
+            rows = pdist.interleaved_rows(n, world, rank, 5)
+        piece = ref[rows.numpy()]
         indptr = torch.from_numpy(piece.indptr.astype(np.int32))
         indices = torch.from_numpy(piece.indices.astype(np.int32))
         data = torch.from_numpy(piece.data.copy())
         offset, total, every = pdist.nnz_offsets(data.numel())
-        assert total == ref.nnz and offset == ref.indptr[lo]
-        out = pdist.gather_csr(indptr, indices, data, n, root=0)
+        assert total == ref.nnz
+        out = pdist.gather_csr(indptr, indices, data, rows, n, root=0)
         if rank == 0:
             gi, gx, gd = (t.numpy() for t in out)
             ok = (np.array_equal(gi, ref.indptr) and np.array_equal(gx, ref.indices)
@@ -51,11 +55,24 @@ def _worker(rank, world, port, result_path):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('world', [2, 3])
-def test_row_pieces_concatenate_to_reference(tmp_path, world):
+@pytest.mark.parametrize('world,layout', [(2, 'contiguous'), (2, 'interleaved'),
+                                          (3, 'interleaved')])
+def test_row_pieces_assemble_to_reference(tmp_path, world, layout):
     result = tmp_path / 'result.txt'
-    mp.spawn(_worker, args=(world, _free_port(), str(result)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), str(result), layout), nprocs=world,
+             join=True)
     assert result.read_text() == 'ok'
+
+
+def test_interleaved_rows_cover_everything():
+    for n in (1, 7, 100, 4097, 33562625):
+        for w in (1, 2, 8):
+            for c in (0, 3, 12):
+                if n > 10 ** 6 and c < 12:
+                    continue
+                got = torch.cat([pdist.interleaved_rows(n, w, r, c) for r in range(w)])
+                assert got.numel() == n and torch.equal(torch.sort(got).values,
+                                                         torch.arange(n))
 
 
 def test_partition_rows_covers_everything():
