@@ -252,7 +252,7 @@ refresh_kernel(const int *__restrict__ elements, int64_t n,
       const unsigned deg = (unsigned)live[i >> 3];
       if (deg > (unsigned)GROUP || (unsigned)(i & 7) >= deg) continue;
     }
-    const int64_t t = rec_elem[i];
+    const int64_t t = rec_elem[i] >> 2;
     const int e[3] = {__ldg(elements + 3 * t), __ldg(elements + 3 * t + 1),
                       __ldg(elements + 3 * t + 2)};
     double v[3][3];

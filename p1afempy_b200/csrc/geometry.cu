@@ -17,31 +17,73 @@ constexpr int THREADS = 256;
 // flags layout in ctx->d_flags: [0] status bits, [1] #half-edges without twin,
 // [2] #forward entries, [3] #backward entries
 
+// half-edge id 3*T + k from a record's element code (T << 2) | k
+__device__ __forceinline__ int halfedge_of(int code) { return 3 * (code >> 2) + (code & 3); }
+
 __global__ void __launch_bounds__(THREADS)
 twin_kernel(int n_nodes, Rows rows, int *__restrict__ twin, int *__restrict__ flags) {
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= n_nodes) return;
-  const int end = rows.deg(a), beg = 0;
-  const Rec *rec = rows.ptr(a, end);
-  const int *rec_elem = rows.elem(a, end);
-  for (int i = beg; i < end; ++i) {
-    const Rec r = rec[i];
-    const int target = rec_next(r);  // half-edge a -> target
-    int found = -1, hits = 0;
-    for (int s = beg; s < end; ++s)
-      if (rec_prev(rec[s]) == target) { found = s; ++hits; }
-    const int64_t he = 3 * (int64_t)rec_elem[i] + rec_k(r);
-    if (hits == 0) {
-      twin[he] = -1;
-      atomicAdd(flags + 1, 1);
-    } else {
-      twin[he] = 3 * rec_elem[found] + prev_local(rec_k(rec[found]));
-      if (hits > 1) atomicOr(flags, FLAG_NONMANIFOLD);
+  const int deg = rows.deg(a);
+  if (deg == 0) return;
+  const Rec *rec = rows.ptr(a, deg);
+  const int *code = rows.elem(a, deg);
+  int open_edges = 0;
+  bool nonmanifold = false;
+  if (deg <= GROUP) {
+    // the row's records and element codes in registers, all pairs unrolled
+    int nx[GROUP], pv[GROUP], cd[GROUP];
+    const int4 c0 = __ldg(reinterpret_cast<const int4 *>(code));
+    const int4 c1 = __ldg(reinterpret_cast<const int4 *>(code) + 1);
+    const int cc[GROUP] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+#pragma unroll
+    for (int i = 0; i < GROUP; ++i) {
+      nx[i] = -1 - i; pv[i] = -20 - i; cd[i] = cc[i];
+      if (i < deg) {
+        const Rec r = load_rec(rec + i);
+        nx[i] = r.nx; pv[i] = rec_prev(r);
+      }
     }
-    // the same directed edge twice is non-manifold as well
-    for (int s = i + 1; s < end; ++s)
-      if (rec_next(rec[s]) == target) atomicOr(flags, FLAG_NONMANIFOLD);
+#pragma unroll
+    for (int i = 0; i < GROUP; ++i) {
+      int found = -1, hits = 0;
+#pragma unroll
+      for (int s = 0; s < GROUP; ++s) {
+        if (pv[s] == nx[i]) { found = cd[s]; ++hits; }
+        if (s > i && nx[s] == nx[i]) nonmanifold = true;  // same directed edge twice
+      }
+      if (i < deg) {
+        const int he = halfedge_of(cd[i]);
+        if (hits == 0) {
+          twin[he] = -1;
+          ++open_edges;
+        } else {
+          // the twin (target -> a) is edge prev(k_s) of the matching element
+          twin[he] = 3 * (found >> 2) + prev_local(found & 3);
+          nonmanifold = nonmanifold || hits > 1;
+        }
+      }
+    }
+  } else {
+    for (int i = 0; i < deg; ++i) {
+      const int target = rec_next(rec[i]);
+      int found = -1, hits = 0;
+      for (int s = 0; s < deg; ++s)
+        if (rec_prev(rec[s]) == target) { found = code[s]; ++hits; }
+      const int he = halfedge_of(code[i]);
+      if (hits == 0) {
+        twin[he] = -1;
+        ++open_edges;
+      } else {
+        twin[he] = 3 * (found >> 2) + prev_local(found & 3);
+        nonmanifold = nonmanifold || hits > 1;
+      }
+      for (int s = i + 1; s < deg; ++s)
+        if (rec_next(rec[s]) == target) nonmanifold = true;
+    }
   }
+  if (open_edges) atomicAdd(flags + 1, open_edges);
+  if (nonmanifold) atomicOr(flags, FLAG_NONMANIFOLD);
 }
 
 // position p of the reference's concatenated half-edge list:
@@ -117,7 +159,7 @@ __device__ __forceinline__ int64_t locate_halfedge(int b0, int b1,
   const int *rec_elem = rows.elem(b0, end);
   for (int i = 0; i < end; ++i)
     if (rec_next(rec[i]) == b1)
-      return 3 * (int64_t)rec_elem[i] + rec_k(rec[i]);
+      return (int64_t)halfedge_of(rec_elem[i]);
   return -1;
 }
 
@@ -261,8 +303,8 @@ int ensure_twins(p1_plan *p, cudaStream_t s) {
   P1_TRY(pool_alloc(ctx, &p->twin, (size_t)(3 * p->M), s));
   P1_CUDA(cudaMemsetAsync(p->ctx->d_flags, 0, 8 * sizeof(int), s));
   if (p->N > 0)
-    twin_kernel<<<grid_for(p->N, THREADS), THREADS, 0, s>>>(
-        (int)p->N, rows_of(p), p->twin, p->ctx->d_flags);
+    P1_TIMED(ctx, "twin", s, twin_kernel<<<grid_for(p->N, THREADS), THREADS, 0, s>>>(
+        (int)p->N, rows_of(p), p->twin, p->ctx->d_flags));
   P1_CUDA(cudaGetLastError());
   P1_TRY(read_flags(p->ctx, s));
   if (p->ctx->h_flags[0] & FLAG_NONMANIFOLD) {
@@ -302,13 +344,16 @@ extern "C" int p1_geometric_data(const p1_plan *cplan, const int32_t *boundary_n
   P1_TRY(pool_alloc(ctx, &num, (size_t)total + 1, s));
   P1_CUDA(cudaMemsetAsync(ctx->d_flags, 0, 8 * sizeof(int), s));
   if (total > 0)
-    forward_flags_kernel<<<egrid(ctx, total), THREADS, 0, s>>>(
-        p->elements, M, boundary_nodes, K, num, ctx->d_flags);
+    P1_TIMED(ctx, "edge_flags", s,
+             forward_flags_kernel<<<egrid(ctx, total), THREADS, 0, s>>>(
+                 p->elements, M, boundary_nodes, K, num, ctx->d_flags));
   int rc = exclusive_scan_i32(ctx, num, num, total, true, s);
   if (rc) { pool_free(ctx, num, s); return rc; }
   if (M > 0)
-    element_edges_kernel<<<egrid(ctx, 3 * M), THREADS, 0, s>>>(
-        p->elements, M, num, p->twin, (long long *)element2edges, (long long *)edge2nodes);
+    P1_TIMED(ctx, "edge_numbers", s,
+             element_edges_kernel<<<egrid(ctx, 3 * M), THREADS, 0, s>>>(
+                 p->elements, M, num, p->twin, (long long *)element2edges,
+                 (long long *)edge2nodes));
   if (K > 0)
     boundary_numbers_kernel<<<grid_for(K, THREADS), THREADS, 0, s>>>(
         boundary_nodes, K, M, (int)p->N, rows_of(p), num,
@@ -359,8 +404,9 @@ extern "C" int p1_eta_r(const p1_plan *cplan, const double *coords, const double
   double *dudn = nullptr;
   P1_TRY(pool_alloc(ctx, &dudn, (size_t)(3 * M), s));
   P1_CUDA(cudaMemsetAsync(ctx->d_flags, 0, 8 * sizeof(int), s));
-  eta_local_kernel<<<egrid(ctx, M), THREADS, 0, s>>>((const double2 *)coords, x,
-                                                     p->elements, M, dudn);
+  P1_TIMED(ctx, "eta_local", s,
+           eta_local_kernel<<<egrid(ctx, M), THREADS, 0, s>>>((const double2 *)coords, x,
+                                                              p->elements, M, dudn));
   if (n_neumann > 0)
     eta_boundary_kernel<<<grid_for(n_neumann, THREADS), THREADS, 0, s>>>(
         0, neumann, n_neumann, (int)p->N, rows_of(p), p->twin,
@@ -369,8 +415,9 @@ extern "C" int p1_eta_r(const p1_plan *cplan, const double *coords, const double
     eta_boundary_kernel<<<grid_for(n_dirichlet, THREADS), THREADS, 0, s>>>(
         1, dirichlet, n_dirichlet, (int)p->N, rows_of(p), p->twin,
         nullptr, dudn, ctx->d_flags);
-  eta_final_kernel<<<egrid(ctx, M), THREADS, 0, s>>>((const double2 *)coords, p->elements,
-                                                     M, p->twin, dudn, f_centroid, eta);
+  P1_TIMED(ctx, "eta_final", s,
+           eta_final_kernel<<<egrid(ctx, M), THREADS, 0, s>>>(
+               (const double2 *)coords, p->elements, M, p->twin, dudn, f_centroid, eta));
   pool_free(ctx, dudn, s);
   P1_CUDA(cudaGetLastError());
   P1_TRY(read_flags(ctx, s));

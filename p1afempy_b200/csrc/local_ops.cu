@@ -266,38 +266,74 @@ local_load_midpoint_kernel(const double2 *__restrict__ coords,
 }
 
 // ------------------------------------------------------ per-node gathers
-// b[a] = sum over the node's records in (element, vertex) order == the
-// sequential np.bincount over elements.flatten() (solvers.py:593-596).
-__global__ void __launch_bounds__(THREADS)
-gather_load_kernel(int n_own, Rows rows, const double *__restrict__ L,
-                   double *__restrict__ b) {
-  const int a = blockIdx.x * blockDim.x + threadIdx.x;
-  if (a >= n_own) return;
-  const int end = rows.deg(a), beg = 0;
-  const Rec *rec = rows.ptr(a, end);
-  const int *rec_elem = rows.elem(a, end);
-  double sum = 0.;
-  for (int i = beg; i < end; ++i) {
-    sum += __ldg(L + 3 * (int64_t)rec_elem[i] + rec_k(rec[i]));
-  }
-  b[a] = sum;
+// b[a] = sum of the node's local contributions in the ORDER of the reference's
+// sequential np.bincount: ascending (element, vertex) for the cubature rule
+// (bincount over elements.flatten(), solvers.py:593-596), ascending (vertex,
+// element) for the legacy rule (elements.flatten('F'), solvers.py:422-425).
+// The row's <= 8 element codes (T << 2 | k) are one 32-byte sector: they are
+// sorted in registers, nothing is written back.
+__device__ __forceinline__ unsigned gather_key(int code, bool vertex_major) {
+  const unsigned c = (unsigned)code;
+  return vertex_major ? ((c & 3u) << 29) | (c >> 2) : c;
 }
 
-// order (vertex, element) == np.bincount over elements.flatten('F')
-// (solvers.py:422-425)
+template <bool VERTEX_MAJOR, int STRIDE>
 __global__ void __launch_bounds__(THREADS)
-gather_load_midpoint_kernel(int n_own, Rows rows, const double *__restrict__ share,
-                            double *__restrict__ b) {
+gather_nodes_kernel(int n_own, Rows rows, const double *__restrict__ L,
+                    double *__restrict__ b) {
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= n_own) return;
-  const int end = rows.deg(a), beg = 0;
-  const Rec *rec = rows.ptr(a, end);
-  const int *rec_elem = rows.elem(a, end);
+  const int deg = rows.deg(a);
   double sum = 0.;
-  for (int kk = 0; kk < 3; ++kk)
-    for (int i = beg; i < end; ++i) {
-      if (rec_k(rec[i]) == kk) sum += __ldg(share + rec_elem[i]);
+  if (deg == 0) { b[a] = sum; return; }
+  const int *code = rows.elem(a, deg);
+  if (deg <= GROUP) {
+    const int4 c0 = __ldg(reinterpret_cast<const int4 *>(code));
+    const int4 c1 = __ldg(reinterpret_cast<const int4 *>(code) + 1);
+    const int cc[GROUP] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+    unsigned key[GROUP];
+#pragma unroll
+    for (int i = 0; i < GROUP; ++i)
+      key[i] = i < deg ? gather_key(cc[i], VERTEX_MAJOR) : 0xffffffffu;
+    // rank by counting (keys of one row are distinct), then add in rank order
+    int rank[GROUP];
+#pragma unroll
+    for (int i = 0; i < GROUP; ++i) {
+      rank[i] = 0;
+#pragma unroll
+      for (int j = 0; j < GROUP; ++j) rank[i] += key[j] < key[i];
     }
+    double val[GROUP];
+#pragma unroll
+    for (int i = 0; i < GROUP; ++i) {
+      val[i] = 0.;
+      if (i < deg) {
+        const int t = cc[i] >> 2, k = cc[i] & 3;
+        val[i] = __ldg(L + (STRIDE == 3 ? 3 * (int64_t)t + k : (int64_t)t));
+      }
+    }
+    for (int q = 0; q < deg; ++q) {
+#pragma unroll
+      for (int i = 0; i < GROUP; ++i)
+        if (rank[i] == q) sum += val[i];
+    }
+  } else {
+    // more than 8 incidences: selection by key, no scratch
+    unsigned last = 0;
+    bool first = true;
+    for (int q = 0; q < deg; ++q) {
+      unsigned best = 0xffffffffu;
+      int pick = 0;
+      for (int i = 0; i < deg; ++i) {
+        const unsigned key = gather_key(code[i], VERTEX_MAJOR);
+        if ((first || key > last) && key < best) { best = key; pick = code[i]; }
+      }
+      const int t = pick >> 2, k = pick & 3;
+      sum += __ldg(L + (STRIDE == 3 ? 3 * (int64_t)t + k : (int64_t)t));
+      last = best;
+      first = false;
+    }
+  }
   b[a] = sum;
 }
 
@@ -550,17 +586,20 @@ extern "C" int p1_load_vector(const p1_plan *plan, const double *coords,
   p1_ctx *ctx = plan->ctx;
   DeviceGuard guard(ctx->device);
   cudaStream_t s = (cudaStream_t)stream;
-  P1_TRY(ensure_sorted(const_cast<p1_plan *>(plan), s));
+  P1_TRY(require_elements(plan, "p1_load_vector"));
   double *w = nullptr, *pts = nullptr, *L = nullptr;
   P1_TRY(upload_small(ctx, &w, weights_host, (size_t)n_qp, s));
   P1_TRY(upload_small(ctx, &pts, points_host, (size_t)2 * n_qp, s));
   P1_TRY(pool_alloc(ctx, &L, (size_t)3 * M, s));
   if (M > 0)
-    local_load_kernel<<<egrid(plan->ctx, M), THREADS, 0, s>>>(
-        (const double2 *)coords, plan->elements, M, fq, w, (const double2 *)pts, n_qp, L);
+    P1_TIMED(ctx, "load_local", s,
+             local_load_kernel<<<egrid(plan->ctx, M), THREADS, 0, s>>>(
+                 (const double2 *)coords, plan->elements, M, fq, w, (const double2 *)pts, n_qp,
+                 L));
   if (n_own > 0)
-    gather_load_kernel<<<grid_for(n_own, THREADS), THREADS, 0, s>>>(
-        n_own, rows_of(plan), L, b);
+    P1_TIMED(ctx, "load_gather", s,
+             (gather_nodes_kernel<false, 3><<<grid_for(n_own, THREADS), THREADS, 0, s>>>(
+                 n_own, rows_of(plan), L, b)));
   pool_free(ctx, L, s);
   pool_free(ctx, w, s);
   pool_free(ctx, pts, s);
@@ -579,14 +618,14 @@ extern "C" int p1_load_vector_midpoint(const p1_plan *plan, const double *coords
   p1_ctx *ctx = plan->ctx;
   DeviceGuard guard(ctx->device);
   cudaStream_t s = (cudaStream_t)stream;
-  P1_TRY(ensure_sorted(const_cast<p1_plan *>(plan), s));
+  P1_TRY(require_elements(plan, "p1_load_vector_midpoint"));
   double *share = nullptr;
   P1_TRY(pool_alloc(ctx, &share, (size_t)M, s));
   if (M > 0)
     local_load_midpoint_kernel<<<egrid(plan->ctx, M), THREADS, 0, s>>>(
         (const double2 *)coords, plan->elements, M, f_centroid, share);
   if (n_own > 0)
-    gather_load_midpoint_kernel<<<grid_for(n_own, THREADS), THREADS, 0, s>>>(
+    gather_nodes_kernel<true, 1><<<grid_for(n_own, THREADS), THREADS, 0, s>>>(
         n_own, rows_of(plan), share, b);
   pool_free(ctx, share, s);
   P1_CUDA(cudaGetLastError());

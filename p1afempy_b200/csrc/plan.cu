@@ -76,7 +76,7 @@ __device__ __forceinline__ void scatter_element(int64_t t, const int (&e)[3], in
       r.pvk = pv | (k << NODE_BITS);
       r.vd = v[k][0]; r.vn = v[k][1]; r.vp = v[k][2];
       store_rec(rec + pos, r);
-      if (rec_elem) rec_elem[pos] = (int)t;
+      if (rec_elem) rec_elem[pos] = (int)((t << 2) | k);
     }
 }
 
@@ -283,59 +283,10 @@ rowlen_big_kernel(const int *__restrict__ big_rows, Own own, Rows rows,
   if (threadIdx.x == 0) rowlen[a] = total;
 }
 
-// ------------------------------------------------------ (T,k) row order
-__global__ void __launch_bounds__(THREADS)
-sort_rows_kernel(int n_own, Rows in, Rows out) {
-  const int a = blockIdx.x * blockDim.x + threadIdx.x;
-  if (a >= n_own) return;
-  const int deg = in.deg(a);
-  const Rec *r = in.ptr(a, deg);
-  const int *el = in.elem(a, deg);
-  Rec *ro = out.ptr(a, deg);
-  int *eo = out.elem(a, deg);
-  for (int i = 0; i < deg; ++i) {
-    const Rec v = r[i];
-    const unsigned key = ((unsigned)el[i] << 2) | (unsigned)rec_k(v);
-    int rank = 0;
-    for (int j = 0; j < deg; ++j)
-      rank += (((unsigned)el[j] << 2) | (unsigned)rec_k(r[j])) < key;
-    ro[rank] = v;
-    eo[rank] = el[i];
-  }
-}
-
 int require_elements(const p1_plan *p, const char *who) {
   if (p->rec_elem) return P1_OK;
   set_error("%s needs a plan created with P1_PLAN_KEEP_ELEMENTS", who);
   return P1_EINVAL;
-}
-
-int ensure_sorted(p1_plan *p, cudaStream_t s) {
-  if (p->sorted) return P1_OK;
-  P1_TRY(require_elements(p, "ordering records by (element, vertex)"));
-  p1_ctx *ctx = p->ctx;
-  const int n_own = (int)p->n_own;
-  Rows in = rows_of(p), out = in;
-  out.rec = nullptr; out.rec_elem = nullptr; out.ovf_rec = nullptr; out.ovf_elem = nullptr;
-  int rc = P1_OK;
-  if ((rc = pool_alloc(ctx, &out.rec, (size_t)n_own * GROUP, s)) ||
-      (rc = pool_alloc(ctx, &out.rec_elem, (size_t)n_own * GROUP, s)) ||
-      (p->n_ovf > 0 && ((rc = pool_alloc(ctx, &out.ovf_rec, (size_t)p->n_ovf, s)) ||
-                        (rc = pool_alloc(ctx, &out.ovf_elem, (size_t)p->n_ovf, s))))) {
-    pool_free(ctx, out.rec, s); pool_free(ctx, out.rec_elem, s);
-    pool_free(ctx, out.ovf_rec, s); pool_free(ctx, out.ovf_elem, s);
-    return rc;
-  }
-  if (n_own > 0)
-    P1_TIMED(p->ctx, "sort_rows", s,
-             sort_rows_kernel<<<grid_for(n_own, THREADS), THREADS, 0, s>>>(n_own, in, out));
-  P1_CUDA(cudaGetLastError());
-  pool_free(ctx, p->rec, s); pool_free(ctx, p->rec_elem, s);
-  pool_free(ctx, p->ovf_rec, s); pool_free(ctx, p->ovf_elem, s);
-  p->rec = out.rec; p->rec_elem = out.rec_elem;
-  p->ovf_rec = out.ovf_rec; p->ovf_elem = out.ovf_elem;
-  p->sorted = true;
-  return P1_OK;
 }
 
 // ------------------------------------------------------ balanced row ranges
@@ -419,10 +370,10 @@ static int plan_build(p1_ctx *ctx, const int32_t *elements, int64_t n_elements,
              "row range outside [0, n_nodes]");
   P1_REQUIRE(world >= 1 && rank >= 0 && rank < world && chunk_log2 >= 0 && chunk_log2 < 31,
              "bad interleave");
-  if (n_nodes > (int64_t)NODE_MASK || n_elements >= (1LL << 30) ||
+  if (n_nodes > (int64_t)NODE_MASK || n_elements >= (1LL << 29) ||
       3 * n_elements + n_nodes > 0x7fffffffLL) {
     set_error("p1_plan_create: mesh too large for int32 device indices "
-              "(M=%lld N=%lld; limits: N < 2^29, 3M+N < 2^31)",
+              "(M=%lld N=%lld; limits: N < 2^29, M < 2^29, 3M+N < 2^31)",
               (long long)n_elements, (long long)n_nodes);
     return P1_ERANGE;
   }

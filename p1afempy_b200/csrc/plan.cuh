@@ -72,13 +72,13 @@ struct p1_plan {
   unsigned long long *acc;  // n_own: low 32 bits = #records, high 32 bits = sum over the
                        // records of hash(next) - hash(prev): 0 for a closed fan
   p1::Rec *rec;        // 8 * n_own
-  int *rec_elem;       // 8 * n_own: element of the record (P1_PLAN_KEEP_ELEMENTS) or null
+  int *rec_elem;       // 8 * n_own: (element << 2) | k of the record
+                       // (P1_PLAN_KEEP_ELEMENTS) or null
   int *ovf_off;        // n_own+1 (only when some row overflows) or null
   p1::Rec *ovf_rec;    // n_ovf
   int *ovf_elem;       // n_ovf or null
   int64_t n_ovf;
   int val_op;          // which operator's values the records hold (0 = none)
-  bool sorted;         // records of every row ascending in (element, vertex)
   bool exact;          // row lengths from the all-pairs kernel (no hash shortcut)
   int *indptr;         // n_own+1
   int *slow_rows;      // rows the fast fill does not take: open fans, more than 8
@@ -228,9 +228,6 @@ __device__ __forceinline__ RowLane analyse_row(int self, const Rec *row, int deg
 }
 
 int ensure_twins(p1_plan *plan, cudaStream_t s);
-// puts the records of every row into ascending (element, vertex) order: the
-// order of the reference's sequential np.bincount (load vectors)
-int ensure_sorted(p1_plan *plan, cudaStream_t s);
 // error unless the plan was created with P1_PLAN_KEEP_ELEMENTS
 int require_elements(const p1_plan *plan, const char *who);
 
