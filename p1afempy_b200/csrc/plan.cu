@@ -83,6 +83,7 @@ __device__ __forceinline__ void scatter_element(int64_t t, const int (&e)[3], in
 // `vec` != 0: elements is 16-byte aligned; a thread then reads 4 triangles =
 // 12 indices as three 128-bit loads (the scalar form reads 12 B at stride 12 B
 // and spends 0.45 ms just scanning 64M triangles).
+// (forcing more resident blocks was measured: 40 or 32 registers spill and lose)
 template <class V, bool OVERFLOW>
 __global__ void __launch_bounds__(THREADS)
 scatter_kernel(const int *__restrict__ elements, int64_t M, int N, Own own, int vec,
