@@ -443,3 +443,44 @@ def test_unstructured_delaunay_mesh(api):
     none = np.zeros((0, 2), dtype=int)
     assert np.array_equal(api[2].compute_eta_r(x, pts, e, bnd, none, H.f_load, H.g_neu),
                           orc.eta_r(x, pts, e, bnd, none, H.f_load, H.g_neu))
+
+
+def test_device_resident_api_and_plan_reuse():
+    """DeviceMesh: torch CUDA tensors in, CSR triple of CUDA tensors out; with
+    reuse=True a second operator on the same mesh only refreshes the record
+    values (overflow rows included: Delaunay mesh with valence > 8)."""
+    import torch
+    from scipy.spatial import Delaunay
+    from p1afempy_b200.device import DeviceMesh
+    rng = np.random.default_rng(11)
+    pts = np.vstack([rng.random((3000, 2)), [[0., 0.], [1., 0.], [1., 1.], [0., 1.]]])
+    e = Delaunay(pts).simplices.astype(np.int64)
+    d1, d2 = pts[e[:, 1]] - pts[e[:, 0]], pts[e[:, 2]] - pts[e[:, 0]]
+    flip = (d1[:, 0] * d2[:, 1] - d1[:, 1] * d2[:, 0]) < 0
+    e[flip] = e[flip][:, [0, 2, 1]]
+    assert np.bincount(e.reshape(-1)).max() > 8
+    ct = torch.from_numpy(pts).cuda()
+    et = torch.from_numpy(e.astype(np.int32)).cuda()
+    ref_a = orc.stiffness_coo(pts, e).tocsr()
+    ref_m = orc.mass_coo(pts, e).tocsr()
+    w, p = cubature.resolve_rule(cubature.CubatureRuleEnum.DAYTAYLOR)
+    ref_g = orc.general_stiffness_coo(pts, e, H.a11, H.a12, H.a21, H.a22, w, p).tocsr()
+    with DeviceMesh(ct, et, reuse=True) as mesh:
+        ip, ix, a = mesh.stiffness_csr()
+        assert ip.is_cuda and ix.dtype == torch.int32 and a.dtype == torch.float64
+        assert np.array_equal(ip.cpu().numpy(), ref_a.indptr)
+        assert np.array_equal(ix.cpu().numpy(), ref_a.indices)
+        assert np.abs(a.cpu().numpy() - ref_a.data).max() <= 1e-11 * np.abs(ref_a.data).max()
+        plan_before = mesh._plan.value
+        none_ip, none_ix, m = mesh.mass_csr(pattern=False)       # values only
+        assert none_ip is None and none_ix is None and mesh._plan.value == plan_before
+        assert np.abs(m.cpu().numpy() - ref_m.data).max() <= 1e-12 * np.abs(ref_m.data).max()
+        xq = mesh.quadrature_points(p)
+        qs = [torch.from_numpy(np.stack([f(xq[q].cpu().numpy()) for q in range(len(w))])).cuda()
+              for f in (H.a11, H.a12, H.a21, H.a22)]
+        _, _, g = mesh.general_stiffness_csr(*qs, w, pattern=False)
+        assert np.abs(g.cpu().numpy() - ref_g.data).max() <= 1e-11 * np.abs(ref_g.data).max()
+        # and the vector / edge consumers work on the same (element-keeping) plan
+        fc = torch.from_numpy(H.f_load(mesh.centroids().cpu().numpy())).cuda()
+        b = mesh.load_vector_midpoint(fc)
+        assert np.array_equal(b.cpu().numpy(), orc.load_vector_midpoint(pts, e, H.f_load))
