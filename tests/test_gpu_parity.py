@@ -484,3 +484,36 @@ def test_device_resident_api_and_plan_reuse():
         fc = torch.from_numpy(H.f_load(mesh.centroids().cpu().numpy())).cuda()
         b = mesh.load_vector_midpoint(fc)
         assert np.array_equal(b.cpu().numpy(), orc.load_vector_midpoint(pts, e, H.f_load))
+
+
+def test_empty_and_tiny_inputs(api):
+    """Empty element arrays (the reference: scipy cannot infer a shape ->
+    ValueError; explicit-shape builders return empty matrices) and a single
+    triangle."""
+    solvers, mesh, indicators = api
+    c = np.array([[0., 0.], [1., 0.], [0., 1.]])
+    none = np.zeros((0, 3), dtype=np.int64)
+    with pytest.raises(ValueError):
+        solvers.get_stiffness_matrix(c, none)
+    w, p = cubature.resolve_rule(cubature.CubatureRuleEnum.MIDPOINT)
+    g = solvers.get_general_stiffness_matrix(c, none, H.a11, H.a12, H.a21, H.a22, (w, p))
+    assert g.shape == (3, 3) and g.nnz == 0
+    assert np.array_equal(solvers.get_right_hand_side(c, none, H.f_load), np.zeros(3))
+    assert np.array_equal(solvers.get_right_hand_side(c, none, H.f_load, (w, p)), np.zeros(3))
+    one = np.array([[0, 1, 2]])
+    H.csr_values_close(solvers.get_stiffness_matrix(c, one), orc.stiffness_coo(c, one).tocsr(), RTOL)
+    H.csr_values_close(solvers.get_mass_matrix(c, one), orc.mass_coo(c, one).tocsr(), RTOL)
+    assert np.array_equal(solvers.get_right_hand_side(c, one, H.f_load),
+                          orc.load_vector_midpoint(c, one, H.f_load))
+    edges = np.array([[0, 1], [1, 2], [2, 0]])
+    e2e, e2n, b2e = mesh.provide_geometric_data(one, [edges])
+    o2e, o2n, ob2e = orc.geometric_data(one, [edges])
+    assert np.array_equal(e2e, o2e) and np.array_equal(e2n, o2n) and np.array_equal(b2e[0], ob2e[0])
+    x = np.array([0., 1., 2.])
+    assert np.array_equal(
+        indicators.compute_eta_r(x, c, one, edges[:2], edges[2:], H.f_load, H.g_neu),
+        orc.eta_r(x, c, one, edges[:2], edges[2:], H.f_load, H.g_neu))
+    # a clockwise triangle: negative area propagates exactly like in numpy
+    cw = np.array([[0, 2, 1]])
+    H.csr_values_close(solvers.get_mass_matrix(c, cw), orc.mass_coo(c, cw).tocsr(), RTOL)
+    assert solvers.get_mass_matrix(c, cw).data.max() < 0
