@@ -248,13 +248,12 @@ def run_b200(args):
     mesh = DeviceMesh(c, e, device=local_rank,
                       interleave=(world, rank, 12) if world > 1 else None)
     stream = torch.cuda.current_stream()
-    nnz_all = torch.zeros(world, dtype=torch.int64, device='cuda')
+    nnz_all = torch.zeros(world, dtype=torch.int32, device='cuda')
 
     def step():
         ip, ix, data = mesh.stiffness_csr()   # cold: plan + fill, nothing cached
-        if world > 1:                      # global row-pointer offsets
-            mine = torch.tensor([mesh.nnz], dtype=torch.int64, device='cuda')
-            dist.all_gather_into_tensor(nnz_all, mine)
+        if world > 1:   # global row-pointer offsets: every rank learns every rank's nnz
+            dist.all_gather_into_tensor(nnz_all, ip[-1:])   # (ip[-1] = local nnz, on device)
         return ip, ix, data
 
     for _ in range(args.warmup):
@@ -290,7 +289,7 @@ def run_b200(args):
         tmax = torch.tensor([ms_total], dtype=torch.float64, device='cuda')
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         ms_total = float(tmax.item())
-        total_nnz = int(nnz_all.sum().item())
+        total_nnz = int(nnz_all.to(torch.int64).sum().item())
         assert total_nnz == nnz, (total_nnz, nnz)
     ms_step = ms_total / args.steps
     value = m / (ms_step * 1e-3) / 1e6
