@@ -198,12 +198,15 @@ overflow_count_kernel(int n_own, const unsigned long long *__restrict__ acc,
 // distinct values of {self} U {next_i} U {prev_i}, any number of records;
 // the few contiguous records stay in L1 while they are compared
 __global__ void __launch_bounds__(THREADS)
-rowlen_slow_kernel(const int *__restrict__ slow_rows, int n_slow, Own own, Rows rows,
-                   int *__restrict__ rowlen) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n_slow) return;
+rowlen_slow_kernel(const int *__restrict__ slow_rows, const int *__restrict__ n_slow_dev,
+                   Own own, Rows rows, int *__restrict__ rowlen) {
+  // the list length is read on the device: the host has not synchronised yet
+  const int n_slow = *n_slow_dev;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_slow;
+       idx += gridDim.x * blockDim.x) {
   const int a = slow_rows[idx];
   const int deg = rows.deg(a);
+  if (deg > GROUP && !rows.ovf_rec) continue;  // redone after the overflow pass
   const int self = own.global(a);
   const Rec *nb = rows.ptr(a, deg);
   int n = 1;
@@ -218,6 +221,7 @@ rowlen_slow_kernel(const int *__restrict__ slow_rows, int n_slow, Own own, Rows 
     n += fx + fy;
   }
   rowlen[a] = n;
+  }
 }
 
 // Rows with more than DEG_BIG records: one block per row, O(deg^2) without
@@ -451,8 +455,26 @@ static int plan_build(p1_ctx *ctx, const int32_t *elements, int64_t n_elements,
                split_kernel<<<grid_for(n_own, THREADS), THREADS, 0, s>>>(
                    n_own, p->acc, rowlen, p->slow_rows, p->big_rows, ctx->d_flags + 2));
   }
-  cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, 8 * sizeof(int), cudaMemcpyDeviceToHost, s);
-  if (cudaStreamSynchronize(s) != cudaSuccess) return cuda_fail("scatter");
+  // Common case (no row with more than 8 records): ONE synchronisation per plan.
+  // The boundary rows are counted with the list length read on the device.
+  const unsigned sg = (unsigned)(ctx->sm_count * 4);
+  int h_nnz = 0;
+  auto finish = [&]() -> int {   // slow rows -> scan -> read flags and nnz
+    rowlen_slow_kernel<<<sg, THREADS, 0, s>>>(p->slow_rows, ctx->d_flags + 3, own, rows_of(p),
+                                              rowlen);
+    int r = exclusive_scan_i32(ctx, rowlen, p->indptr, n_own, true, s);
+    if (r) return r;
+    cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, 8 * sizeof(int), cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(&h_nnz, p->indptr + n_own, sizeof(int), cudaMemcpyDeviceToHost, s);
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) {
+      set_error("p1_plan_create: %s", cudaGetErrorString(e));
+      return P1_ECUDA;
+    }
+    return P1_OK;
+  };
+  if ((rc = finish())) return fail(rc);
   if (ctx->h_flags[0] & FLAG_INDEX_RANGE) {
     set_error("p1_plan_create: element index out of range [0, %lld)", (long long)n_nodes);
     return fail(P1_EINDEX);
@@ -480,38 +502,27 @@ static int plan_build(p1_ctx *ctx, const int32_t *elements, int64_t n_elements,
     prof_end(ctx, s);
     pool_free(ctx, cnt, s);
     cnt = nullptr;
-  }
-  const Rows rows = rows_of(p);
-  if (p->n_slow > 0)
-    rowlen_slow_kernel<<<grid_for(p->n_slow, THREADS), THREADS, 0, s>>>(
-        p->slow_rows, p->n_slow, own, rows, rowlen);
-  if (p->n_big > 0) {
-    Rec *tmp = nullptr;
-    int *tmp_elem = nullptr;
-    if ((rc = pool_alloc(ctx, &tmp, (size_t)p->n_ovf, s)) ||
-        (rc = pool_alloc(ctx, &tmp_elem, (size_t)p->n_ovf, s)) ||
-        (rc = pool_alloc(ctx, &p->big_first, (size_t)(2 * p->n_ovf + n_own + 1), s))) {
+    const Rows rows = rows_of(p);
+    if (p->n_big > 0) {
+      Rec *tmp = nullptr;
+      int *tmp_elem = nullptr;
+      if ((rc = pool_alloc(ctx, &tmp, (size_t)p->n_ovf, s)) ||
+          (rc = pool_alloc(ctx, &tmp_elem, (size_t)p->n_ovf, s)) ||
+          (rc = pool_alloc(ctx, &p->big_first, (size_t)(2 * p->n_ovf + n_own + 1), s))) {
+        pool_free(ctx, tmp, s);
+        pool_free(ctx, tmp_elem, s);
+        return fail(rc);
+      }
+      sort_big_kernel<<<p->n_big, THREADS, 0, s>>>(p->big_rows, rows, tmp, tmp_elem);
+      rowlen_big_kernel<<<p->n_big, THREADS, 0, s>>>(p->big_rows, own, rows, p->big_first,
+                                                     rowlen);
       pool_free(ctx, tmp, s);
       pool_free(ctx, tmp_elem, s);
-      return fail(rc);
     }
-    sort_big_kernel<<<p->n_big, THREADS, 0, s>>>(p->big_rows, rows, tmp, tmp_elem);
-    rowlen_big_kernel<<<p->n_big, THREADS, 0, s>>>(p->big_rows, own, rows, p->big_first,
-                                                   rowlen);
-    pool_free(ctx, tmp, s);
-    pool_free(ctx, tmp_elem, s);
+    if ((rc = finish())) return fail(rc);  // slow rows again (now with their records), rescan
   }
-  if ((rc = exclusive_scan_i32(ctx, rowlen, p->indptr, n_own, true, s))) return fail(rc);
-  int h_nnz = 0;
-  cudaMemcpyAsync(&h_nnz, p->indptr + n_own, sizeof(int), cudaMemcpyDeviceToHost, s);
   pool_free(ctx, rowlen, s);
   rowlen = nullptr;
-  cudaError_t e = cudaStreamSynchronize(s);
-  if (e == cudaSuccess) e = cudaGetLastError();
-  if (e != cudaSuccess) {
-    set_error("p1_plan_create: %s", cudaGetErrorString(e));
-    return fail(P1_ECUDA);
-  }
   p->nnz = h_nnz;
   *out = p;
   return P1_OK;
