@@ -104,6 +104,20 @@ int p1_plan_create_for(p1_ctx *ctx, const int32_t *elements, int64_t n_elements,
                        int64_t n_nodes, int64_t row_begin, int64_t row_end,
                        int flags, int op, const double *coords, const double *local,
                        void *stream, p1_plan **out);
+/* Generalised stiffness / weighted mass with the quadrature sums and the local
+ * matrix evaluated inside the scatter (no [M x 9] array through HBM).  Device
+ * arrays are [n_qp x M], qp-major; the rule is given on the host. */
+typedef struct p1_quad_args {
+  const double *a11q, *a12q, *a21q, *a22q; /* P1_OP_GENERAL                    */
+  const double *phiq;                      /* P1_OP_WEIGHTED                   */
+  const double *weights_host;              /* n_qp                             */
+  const double *points_host;               /* n_qp x 2 (eta, xi); WEIGHTED only */
+  int n_qp;
+} p1_quad_args;
+int p1_plan_create_quad(p1_ctx *ctx, const int32_t *elements, int64_t n_elements,
+                        int64_t n_nodes, int64_t row_begin, int64_t row_end,
+                        int flags, int op, const double *coords,
+                        const p1_quad_args *args, void *stream, p1_plan **out);
 /* Multi-GPU with balanced ownership: of the chunks of 2^chunk_log2 consecutive
  * rows, rank r owns those with chunk index % world == r; its local rows are the
  * owned chunks in ascending order (p1_plan_rows of them).  Every rank then holds
@@ -133,6 +147,9 @@ int p1_plan_info(const p1_plan *plan, int64_t *nnz, int64_t *max_index,
                              (p1_plan_create_for, or the previous assemble)  */
 #define P1_OP_STIFFNESS 1 /* solvers.py:15-47   get_stiffness_matrix          */
 #define P1_OP_MASS 2      /* solvers.py:145-182 get_mass_matrix               */
+#define P1_OP_GENERAL 4   /* solvers.py:278-377: local matrices computed inside the
+                             scatter from p1_quad_args (p1_plan_create_quad only) */
+#define P1_OP_WEIGHTED 5  /* solvers.py:50-142: likewise                       */
 #define P1_OP_LOCAL 3     /* any 3x3 local matrix given per element, row-major
                              local[T*9 + 3*r + c] (general stiffness, weighted
                              mass after p1_local_* below)                     */

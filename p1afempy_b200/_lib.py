@@ -30,10 +30,18 @@ OP_STORED = 0
 OP_STIFFNESS = 1
 OP_MASS = 2
 OP_LOCAL = 3
+OP_GENERAL = 4
+OP_WEIGHTED = 5
 
 _vp = C.c_void_p
 _i64 = C.c_int64
 _int = C.c_int
+
+class QuadArgs(C.Structure):
+    """p1_quad_args (include/p1b200.h)."""
+    _fields_ = [('a11q', _vp), ('a12q', _vp), ('a21q', _vp), ('a22q', _vp), ('phiq', _vp),
+                ('weights_host', _vp), ('points_host', _vp), ('n_qp', _int)]
+
 
 # name -> argtypes; every function returns int unless listed in _RESTYPES
 PROTOTYPES = {
@@ -51,6 +59,8 @@ PROTOTYPES = {
     'p1_plan_create': [_vp, _vp, _i64, _i64, _i64, _i64, _int, _vp, C.POINTER(_vp)],
     'p1_plan_create_for': [_vp, _vp, _i64, _i64, _i64, _i64, _int, _int, _vp, _vp, _vp,
                            C.POINTER(_vp)],
+    'p1_plan_create_quad': [_vp, _vp, _i64, _i64, _i64, _i64, _int, _int, _vp,
+                            C.POINTER(QuadArgs), _vp, C.POINTER(_vp)],
     'p1_plan_create_interleaved': [_vp, _vp, _i64, _i64, _int, _int, _int, _int, _int, _vp,
                                    _vp, _vp, C.POINTER(_vp)],
     'p1_plan_rows': [_vp],

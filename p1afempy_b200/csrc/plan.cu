@@ -121,11 +121,25 @@ template <bool OVERFLOW>
 static void launch_scatter(p1_ctx *ctx, unsigned grid, cudaStream_t s, int op,
                            const int *elements, int64_t M, int N, Own own,
                            unsigned long long *acc, Rec *rec, int *rec_elem, int *cursor,
-                           const double *coords, const double *local) {
+                           const double *coords, const double *local,
+                           const p1_quad_args *qa, const double *d_weights,
+                           const double *d_points) {
   const double2 *xy = (const double2 *)coords;
   int *fl = ctx->d_flags;
-  const int vec = ((uintptr_t)elements & 15) == 0;
-  if (op == P1_OP_STIFFNESS)
+  // 4 triangles per thread; not for the source that streams four [n_qp x M] arrays,
+  // which wants consecutive lanes on consecutive triangles (measured at 64M: 24.5 ms
+  // with, 12.5 ms without; the unfused route through p1_local_general_stiffness is
+  // 12.1 ms, so the drop-in layer uses that one)
+  const int vec = ((uintptr_t)elements & 15) == 0 && op != P1_OP_GENERAL;
+  if (op == P1_OP_GENERAL)
+    scatter_kernel<GeneralValues, OVERFLOW><<<grid, THREADS, 0, s>>>(
+        elements, M, N, own, vec, acc, rec, rec_elem, cursor,
+        GeneralValues{xy, qa->a11q, qa->a12q, qa->a21q, qa->a22q, d_weights, qa->n_qp, M}, fl);
+  else if (op == P1_OP_WEIGHTED)
+    scatter_kernel<WeightedValues, OVERFLOW><<<grid, THREADS, 0, s>>>(
+        elements, M, N, own, vec, acc, rec, rec_elem, cursor,
+        WeightedValues{xy, qa->phiq, d_weights, (const double2 *)d_points, qa->n_qp, M}, fl);
+  else if (op == P1_OP_STIFFNESS)
     scatter_kernel<StiffnessValues, OVERFLOW><<<grid, THREADS, 0, s>>>(
         elements, M, N, own, vec, acc, rec, rec_elem, cursor, StiffnessValues{xy}, fl);
   else if (op == P1_OP_MASS)
@@ -368,7 +382,7 @@ static int plan_build(p1_ctx *ctx, const int32_t *elements, int64_t n_elements,
                       int64_t n_nodes, int64_t row_begin, int64_t row_end, int chunk_log2,
                       int world, int rank, int flags,
                       int op, const double *coords, const double *local,
-                      void *stream, p1_plan **out) {
+                      const p1_quad_args *qa, void *stream, p1_plan **out) {
   P1_REQUIRE(ctx && out, "null ctx/out");
   P1_REQUIRE(n_elements >= 0 && n_nodes >= 0, "negative size");
   P1_REQUIRE(row_begin >= 0 && row_begin <= row_end && row_end <= n_nodes,
@@ -383,10 +397,16 @@ static int plan_build(p1_ctx *ctx, const int32_t *elements, int64_t n_elements,
     return P1_ERANGE;
   }
   P1_REQUIRE(elements || n_elements == 0, "null elements");
-  P1_REQUIRE(op == 0 || op == P1_OP_STIFFNESS || op == P1_OP_MASS || op == P1_OP_LOCAL,
-             "unknown op");
-  P1_REQUIRE(!(op == P1_OP_STIFFNESS || op == P1_OP_MASS) || coords || n_elements == 0,
-             "stiffness/mass need coords");
+  P1_REQUIRE(op == 0 || op == P1_OP_STIFFNESS || op == P1_OP_MASS || op == P1_OP_LOCAL ||
+                 op == P1_OP_GENERAL || op == P1_OP_WEIGHTED, "unknown op");
+  const bool quad = op == P1_OP_GENERAL || op == P1_OP_WEIGHTED;
+  P1_REQUIRE(!(op == P1_OP_STIFFNESS || op == P1_OP_MASS || quad) || coords ||
+                 n_elements == 0, "this operator needs coords");
+  P1_REQUIRE(!quad || (qa && qa->n_qp > 0 && qa->weights_host), "bad p1_quad_args");
+  P1_REQUIRE(op != P1_OP_GENERAL || n_elements == 0 ||
+                 (qa->a11q && qa->a12q && qa->a21q && qa->a22q), "null coefficient array");
+  P1_REQUIRE(op != P1_OP_WEIGHTED || (qa->points_host && (n_elements == 0 || qa->phiq)),
+             "null phiq/points");
   P1_REQUIRE(op != P1_OP_LOCAL || local || n_elements == 0,
              "P1_OP_LOCAL needs the local matrices");
   DeviceGuard guard(ctx->device);
@@ -410,9 +430,12 @@ static int plan_build(p1_ctx *ctx, const int32_t *elements, int64_t n_elements,
 
   int rc = P1_OK;
   int *rowlen = nullptr, *cnt = nullptr;
+  double *d_weights = nullptr, *d_points = nullptr;
   auto fail = [&](int code) {
     pool_free(ctx, rowlen, s);
     pool_free(ctx, cnt, s);
+    pool_free(ctx, d_weights, s);
+    pool_free(ctx, d_points, s);
     p1_plan_destroy(p);
     return code;
   };
@@ -439,9 +462,23 @@ static int plan_build(p1_ctx *ctx, const int32_t *elements, int64_t n_elements,
   cudaMemsetAsync(p->acc, 0, ((size_t)n_own + 1) * sizeof(unsigned long long), s);
 
   const unsigned eg = min(grid_for(M, THREADS), (unsigned)(ctx->sm_count * 32));
+  if (quad) {  // the rule travels to the device once
+    if ((rc = pool_alloc(ctx, &d_weights, (size_t)qa->n_qp, s))) return fail(rc);
+    if ((rc = pool_alloc(ctx, &d_points, (size_t)2 * qa->n_qp, s))) return fail(rc);
+    cudaMemcpyAsync(d_weights, qa->weights_host, qa->n_qp * sizeof(double),
+                    cudaMemcpyHostToDevice, s);
+    if (qa->points_host)
+      cudaMemcpyAsync(d_points, qa->points_host, 2 * qa->n_qp * sizeof(double),
+                      cudaMemcpyHostToDevice, s);
+  }
+  auto free_rule = [&]() {
+    pool_free(ctx, d_weights, s);
+    pool_free(ctx, d_points, s);
+    d_weights = d_points = nullptr;
+  };
   prof_begin(ctx, "scatter", s);
   launch_scatter<false>(ctx, eg, s, op, elements, M, N, own, p->acc, p->rec,
-                        p->rec_elem, nullptr, coords, local);
+                        p->rec_elem, nullptr, coords, local, qa, d_weights, d_points);
   prof_end(ctx, s);
   p->val_op = op;
   const Rows rows0 = rows_of(p);
@@ -498,7 +535,7 @@ static int plan_build(p1_ctx *ctx, const int32_t *elements, int64_t n_elements,
     cudaMemcpyAsync(cnt, p->ovf_off, (size_t)n_own * sizeof(int), cudaMemcpyDeviceToDevice, s);
     prof_begin(ctx, "scatter_overflow", s);
     launch_scatter<true>(ctx, eg, s, op, elements, M, N, own, p->acc, p->ovf_rec,
-                         p->ovf_elem, cnt, coords, local);
+                         p->ovf_elem, cnt, coords, local, qa, d_weights, d_points);
     prof_end(ctx, s);
     pool_free(ctx, cnt, s);
     cnt = nullptr;
@@ -523,6 +560,7 @@ static int plan_build(p1_ctx *ctx, const int32_t *elements, int64_t n_elements,
   }
   pool_free(ctx, rowlen, s);
   rowlen = nullptr;
+  free_rule();
   p->nnz = h_nnz;
   *out = p;
   return P1_OK;
@@ -533,7 +571,7 @@ extern "C" int p1_plan_create(p1_ctx *ctx, const int32_t *elements,
                               int64_t row_begin, int64_t row_end, int flags,
                               void *stream, p1_plan **out) {
   return plan_build(ctx, elements, n_elements, n_nodes, row_begin, row_end, 0, 1, 0, flags,
-                    0, nullptr, nullptr, stream, out);
+                    0, nullptr, nullptr, nullptr, stream, out);
 }
 
 extern "C" int p1_plan_create_for(p1_ctx *ctx, const int32_t *elements,
@@ -542,8 +580,19 @@ extern "C" int p1_plan_create_for(p1_ctx *ctx, const int32_t *elements,
                                   const double *coords, const double *local,
                                   void *stream, p1_plan **out) {
   P1_REQUIRE(op != 0, "p1_plan_create_for needs an operator");
+  P1_REQUIRE(op != P1_OP_GENERAL && op != P1_OP_WEIGHTED, "use p1_plan_create_quad");
   return plan_build(ctx, elements, n_elements, n_nodes, row_begin, row_end, 0, 1, 0, flags,
-                    op, coords, local, stream, out);
+                    op, coords, local, nullptr, stream, out);
+}
+
+extern "C" int p1_plan_create_quad(p1_ctx *ctx, const int32_t *elements, int64_t n_elements,
+                                   int64_t n_nodes, int64_t row_begin, int64_t row_end,
+                                   int flags, int op, const double *coords,
+                                   const p1_quad_args *args, void *stream, p1_plan **out) {
+  P1_REQUIRE(op == P1_OP_GENERAL || op == P1_OP_WEIGHTED,
+             "p1_plan_create_quad: op must be P1_OP_GENERAL or P1_OP_WEIGHTED");
+  return plan_build(ctx, elements, n_elements, n_nodes, row_begin, row_end, 0, 1, 0, flags,
+                    op, coords, nullptr, args, stream, out);
 }
 
 extern "C" int p1_plan_create_interleaved(p1_ctx *ctx, const int32_t *elements,
@@ -551,8 +600,10 @@ extern "C" int p1_plan_create_interleaved(p1_ctx *ctx, const int32_t *elements,
                                           int chunk_log2, int world, int rank, int flags,
                                           int op, const double *coords, const double *local,
                                           void *stream, p1_plan **out) {
+  P1_REQUIRE(op != P1_OP_GENERAL && op != P1_OP_WEIGHTED,
+             "interleaved plans take P1_OP_LOCAL for these operators");
   return plan_build(ctx, elements, n_elements, n_nodes, 0, n_nodes, chunk_log2, world, rank,
-                    flags, op, coords, local, stream, out);
+                    flags, op, coords, local, nullptr, stream, out);
 }
 
 extern "C" int64_t p1_plan_rows(const p1_plan *p) { return p ? p->n_own : -1; }

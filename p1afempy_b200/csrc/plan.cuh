@@ -281,4 +281,81 @@ struct LocalValues {  // 3x3 local matrix given per element, row-major
   }
 };
 
+// solvers.py:306-366 evaluated inside the scatter: the quadrature sums of the
+// four coefficients ([n_qp x M] arrays) and the local matrix never touch HBM
+// as an [M x 9] array.
+struct GeneralValues {
+  const double2 *__restrict__ coords;
+  const double *__restrict__ a11q, *__restrict__ a12q, *__restrict__ a21q,
+      *__restrict__ a22q;
+  const double *__restrict__ weights;  // device, n_qp
+  int n_qp;
+  int64_t M;
+  __device__ __forceinline__ void rows(int64_t t, const int *e, double (*v)[3]) const {
+    const double2 z0 = __ldg(coords + e[0]), z1 = __ldg(coords + e[1]),
+                  z2 = __ldg(coords + e[2]);
+    const double dz1x = z1.x - z0.x, dz1y = z1.y - z0.y;
+    const double dz2x = z2.x - z0.x, dz2y = z2.y - z0.y;
+    const double alpha = dz2y, beta = -dz2x, gamma = -dz1y, delta = dz1x;
+    const double areas = 0.5 * (dz1x * dz2y - dz1y * dz2x);
+    double a = 0., b = 0., c = 0., d = 0.;
+    for (int q = 0; q < n_qp; ++q) {
+      const double w = __ldg(weights + q);
+      const int64_t i = (int64_t)q * M + t;
+      a += w * __ldg(a11q + i);
+      b += w * __ldg(a12q + i);
+      c += w * __ldg(a21q + i);
+      d += w * __ldg(a22q + i);
+    }
+    const double pre = -1. / (2. * areas);
+    const double b11 = pre * (a * alpha * alpha + b * beta * alpha +
+                              c * alpha * beta + d * beta * beta);
+    const double b12 = pre * (a * alpha * gamma + b * delta * alpha +
+                              c * gamma * beta + d * beta * delta);
+    const double b21 = pre * (a * alpha * gamma + b * beta * gamma +
+                              c * alpha * delta + d * beta * delta);
+    const double b22 = pre * (a * gamma * gamma + b * delta * gamma +
+                              c * gamma * delta + d * delta * delta);
+    // local matrix m[3r+c] (solvers.py:356-366); v[k] = (m[k][k], m[k][k+1], m[k][k+2])
+    v[0][0] = b11 + b12 + b21 + b22; v[0][1] = -(b11 + b21); v[0][2] = -(b12 + b22);
+    v[1][0] = b11;                   v[1][1] = b12;          v[1][2] = -(b11 + b12);
+    v[2][0] = b22;                   v[2][1] = -(b21 + b22); v[2][2] = b21;
+  }
+};
+
+// solvers.py:86-129 evaluated inside the scatter
+struct WeightedValues {
+  const double2 *__restrict__ coords;
+  const double *__restrict__ phiq;     // [n_qp x M]
+  const double *__restrict__ weights;  // device, n_qp
+  const double2 *__restrict__ points;  // device, n_qp (eta, xi)
+  int n_qp;
+  int64_t M;
+  __device__ __forceinline__ void rows(int64_t t, const int *e, double (*v)[3]) const {
+    const double2 z0 = __ldg(coords + e[0]), z1 = __ldg(coords + e[1]),
+                  z2 = __ldg(coords + e[2]);
+    const double dz1x = z1.x - z0.x, dz1y = z1.y - z0.y;
+    const double dz2x = z2.x - z0.x, dz2y = z2.y - z0.y;
+    const double areas = 0.5 * (dz1x * dz2y - dz1y * dz2x);
+    double m[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) m[k] = 0.;
+    for (int q = 0; q < n_qp; ++q) {
+      const double2 pt = __ldg(points + q);
+      const double h[3] = {1 - pt.x - pt.y, pt.x, pt.y};
+      const double base = 2 * areas * __ldg(weights + q) * __ldg(phiq + (int64_t)q * M + t);
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int l = 0; l < 3; ++l) m[3 * k + l] += base * h[k] * h[l];
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      v[k][0] = m[3 * k + k];
+      v[k][1] = m[3 * k + (k == 2 ? 0 : k + 1)];
+      v[k][2] = m[3 * k + (k == 0 ? 2 : k - 1)];
+    }
+  }
+};
+
 }  // namespace p1

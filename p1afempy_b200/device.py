@@ -232,6 +232,31 @@ class DeviceMesh:
         """Cold path of one matrix: scatter and local matrices in one kernel."""
         self._create(self.reuse, op, local)
 
+    def _assemble_quad(self, op, args, keepalive, pattern):
+        """Cold generalised stiffness / weighted mass: quadrature sums and local
+        matrices inside the scatter (p1_plan_create_quad), then P1_OP_STORED."""
+        for attempt in (0, 1):
+            self.close()
+            handle = C.c_void_p()
+            _lib.check(self._lib.p1_plan_create_quad(
+                self.ctx, _ptr(self.elements), self.n_elements, self.n_nodes,
+                self.rows[0], self.rows[1], self._flags(False), op, _ptr(self.coords),
+                C.byref(args), _stream(self.device), C.byref(handle)))
+            self._adopt(handle, False)
+            data = self._empty(self.nnz)
+            indptr = self._empty(self.n_rows + 1, torch.int32) if pattern else None
+            indices = self._empty(self.nnz, torch.int32) if pattern else None
+            rc = self._lib.p1_assemble_csr(self._plan, _lib.OP_STORED, None, None,
+                                           _ptr(indptr), _ptr(indices), _ptr(data),
+                                           _stream(self.device))
+            if rc == _lib.P1_ERETRY and attempt == 0 and not self._exact:
+                self._exact = True
+                continue
+            _lib.check(rc)
+            self.close()
+            del keepalive
+            return indptr, indices, data
+
     def global_rows(self):
         """Global row index of every local row (int64 CUDA tensor)."""
         dev = torch.device('cuda', self.device)
@@ -300,13 +325,20 @@ class DeviceMesh:
     def mass_csr(self, pattern=True):
         return self.assemble(_lib.OP_MASS, pattern=pattern)
 
-    def general_stiffness_csr(self, a11q, a12q, a21q, a22q, weights, pattern=True):
+    def general_stiffness_csr(self, a11q, a12q, a21q, a22q, weights, pattern=True,
+                              fused=False):
         """a_ij_q: (n_qp, M) CUDA float64 values of the coefficients at the
         quadrature points (see ``quadrature_points``)."""
         w = _host_f64(weights)
-        local = self._empty((self.n_elements, 9))
         qs = [to_device_f64(a, self.device, (w.shape[0], self.n_elements))
               for a in (a11q, a12q, a21q, a22q)]
+        if fused and not self.reuse and self.interleave is None:
+            # measured slower than the two-step route at 64M (12.5 vs 12.1 ms): four
+            # streamed arrays per triangle do not mix well with the scatter's atomics
+            args = _lib.QuadArgs(qs[0].data_ptr(), qs[1].data_ptr(), qs[2].data_ptr(),
+                                 qs[3].data_ptr(), None, w.ctypes.data, None, w.shape[0])
+            return self._assemble_quad(_lib.OP_GENERAL, args, (qs, w), pattern)
+        local = self._empty((self.n_elements, 9))
         _lib.check(self._lib.p1_local_general_stiffness(
             self.ctx, _ptr(self.coords), _ptr(self.elements), self.n_elements,
             _ptr(qs[0]), _ptr(qs[1]), _ptr(qs[2]), _ptr(qs[3]),
@@ -316,8 +348,12 @@ class DeviceMesh:
 
     def weighted_mass_csr(self, phiq, weights, points, pattern=True):
         w, p = _host_f64(weights), _host_f64(points)
-        local = self._empty((self.n_elements, 9))
         phiq = to_device_f64(phiq, self.device, (w.shape[0], self.n_elements))
+        if not self.reuse and self.interleave is None:
+            args = _lib.QuadArgs(None, None, None, None, phiq.data_ptr(), w.ctypes.data,
+                                 p.ctypes.data, w.shape[0])
+            return self._assemble_quad(_lib.OP_WEIGHTED, args, (phiq, w, p), pattern)
+        local = self._empty((self.n_elements, 9))
         _lib.check(self._lib.p1_local_weighted_mass(
             self.ctx, _ptr(self.coords), _ptr(self.elements), self.n_elements,
             _ptr(phiq), w.ctypes.data_as(C.c_void_p), p.ctypes.data_as(C.c_void_p),

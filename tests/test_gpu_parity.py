@@ -480,6 +480,12 @@ def test_device_resident_api_and_plan_reuse():
               for f in (H.a11, H.a12, H.a21, H.a22)]
         _, _, g = mesh.general_stiffness_csr(*qs, w, pattern=False)
         assert np.abs(g.cpu().numpy() - ref_g.data).max() <= 1e-11 * np.abs(ref_g.data).max()
+    with DeviceMesh(ct, et) as cold:     # quadrature sums inside the scatter
+        gip, gix, g2 = cold.general_stiffness_csr(*qs, w, fused=True)
+        assert np.array_equal(gix.cpu().numpy(), ref_g.indices)
+        assert np.array_equal(g2.cpu().numpy(), g.cpu().numpy())      # same arithmetic
+    with DeviceMesh(ct, et, reuse=True) as mesh:
+        mesh.stiffness_csr()
         # and the vector / edge consumers work on the same (element-keeping) plan
         fc = torch.from_numpy(H.f_load(mesh.centroids().cpu().numpy())).cuda()
         b = mesh.load_vector_midpoint(fc)
