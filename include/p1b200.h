@@ -223,6 +223,16 @@ int p1_load_vector(const p1_plan *plan, const double *coords,
                    const double *fq, const double *weights_host,
                    const double *points_host, int n_qp, double *b,
                    void *stream);
+/* solvers.py:429-472 integrate_composition_nonlinear_with_fem (SURVEY.md 8(f),
+ * "next" rank 1): sum over the triangles of sum_q w_q * fq[q*M+T] * 2. * area_T,
+ * fq = f(u_q) with u_q from p1_nodal_at_quadrature.  The load vector of the
+ * composition (solvers.py:475-537) is p1_load_vector fed with the same fq.
+ * Fixed-order summation tree; SYNCHRONISES (the result is a host scalar). */
+int p1_integrate_quadrature(p1_ctx *ctx, const double *coords, const int32_t *elements,
+                            int64_t n_elements, const double *fq,
+                            const double *weights_host, int n_qp, double *result_host,
+                            void *stream);
+
 /* solvers.py:414-426 legacy centroid rule; f_centroid[T]; summation order
  * per node = (vertex, element), as bincount over elements.flatten('F'). */
 int p1_load_vector_midpoint(const p1_plan *plan, const double *coords,

@@ -291,6 +291,39 @@ def load_vector_cubature(coordinates, elements, f, weights, points):
 
 
 # --------------------------------------------------------------------------
+# non-linear cousins  (reference: p1afempy/solvers.py:429-537) -- SURVEY.md
+# section 8(f), rank 1 of the "next" rows
+# --------------------------------------------------------------------------
+
+def integrate_composition(f, u, coordinates, elements, weights, points):
+    """int_Omega f(u_h) dx, solvers.py:457-472: per element
+    L += w * f(u_q) * 2. * areas (left to right), then np.sum(L)."""
+    areas = signed_area(coordinates, elements)
+    acc = np.zeros(elements.shape[0], dtype=float)
+    for w, (eta, xi) in zip(weights, points):
+        uq = (u[elements[:, 0]] * (1 - eta - xi) + u[elements[:, 1]] * eta
+              + u[elements[:, 2]] * xi)
+        acc += w * f(uq) * 2. * areas
+    return np.sum(acc)
+
+
+def load_vector_composition(f, u, coordinates, elements, weights, points):
+    """F_i = int f(u_h) phi_i, solvers.py:504-537: as the cubature load vector
+    with f evaluated at u_q = u0*(1.-eta-xi) + u1*eta + u2*xi."""
+    areas = signed_area(coordinates, elements)
+    n_el = elements.shape[0]
+    u0, u1, u2 = u[elements[:, 0]], u[elements[:, 1]], u[elements[:, 2]]
+    acc = np.zeros((n_el, 3))
+    col_area = areas.reshape(n_el, 1)
+    for w, (eta, xi) in zip(weights, points):
+        hat = np.array([1. - eta - xi, eta, xi])
+        uq = u0 * (1. - eta - xi) + u1 * eta + u2 * xi
+        acc += 2. * w * col_area * hat * f(uq).reshape(n_el, 1)
+    return np.bincount(elements.reshape(-1), weights=acc.reshape(-1),
+                       minlength=coordinates.shape[0])
+
+
+# --------------------------------------------------------------------------
 # edge numbering  (reference: p1afempy/mesh.py:87-161)
 # --------------------------------------------------------------------------
 

@@ -79,6 +79,8 @@ PROTOTYPES = {
                                    _vp, _int, _vp, _vp],
     'p1_local_weighted_mass': [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _int, _vp,
                                _vp],
+    'p1_integrate_quadrature': [_vp, _vp, _vp, _i64, _vp, _vp, _int, C.POINTER(C.c_double),
+                                _vp],
     'p1_load_vector': [_vp, _vp, _vp, _vp, _vp, _int, _vp, _vp],
     'p1_load_vector_midpoint': [_vp, _vp, _vp, _vp, _vp],
     'p1_geometric_data': [_vp, _vp, _vp, _int, _vp, _vp, _vp, C.POINTER(_i64),

@@ -265,6 +265,55 @@ local_load_midpoint_kernel(const double2 *__restrict__ coords,
   }
 }
 
+// ------------------------------------------------ integral of f(u_h)
+// solvers.py:457-472: L[t] += w * f(u_q) * 2. * areas (left to right); the sum
+// over the elements is a fixed-order tree (numpy's pairwise sum differs in the
+// last bits; the integral is a scalar with tolerance 1e-12).
+__global__ void __launch_bounds__(THREADS)
+integrate_kernel(const double2 *__restrict__ coords, const int *__restrict__ elements,
+                 int64_t M, const double *__restrict__ fq,
+                 const double *__restrict__ weights, int n_qp,
+                 double *__restrict__ partial) {
+  __shared__ double red[THREADS];
+  double acc = 0.;
+  // every block owns a fixed contiguous slice, every thread a fixed stride in it:
+  // the summation order depends on (M, grid) only
+  const int64_t per_block = (M + gridDim.x - 1) / gridDim.x;
+  const int64_t lo = (int64_t)blockIdx.x * per_block;
+  const int64_t hi = lo + per_block < M ? lo + per_block : M;
+  for (int64_t t = lo + threadIdx.x; t < hi; t += THREADS) {
+    const Verts v = load_verts(elements, coords, t);
+    const double px = v.z1.x - v.z0.x, py = v.z1.y - v.z0.y;
+    const double qx = v.z2.x - v.z0.x, qy = v.z2.y - v.z0.y;
+    const double area = 0.5 * (px * qy - py * qx);
+    double l = 0.;
+    for (int q = 0; q < n_qp; ++q)
+      l += weights[q] * __ldg(fq + (int64_t)q * M + t) * 2. * area;
+    acc += l;
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = THREADS / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = red[0];
+}
+
+__global__ void __launch_bounds__(THREADS)
+sum_partials_kernel(const double *__restrict__ partial, int n, double *__restrict__ out) {
+  __shared__ double red[THREADS];
+  double acc = 0.;
+  for (int i = threadIdx.x; i < n; i += THREADS) acc += partial[i];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = THREADS / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = red[0];
+}
+
 // ------------------------------------------------------ per-node gathers
 // b[a] = sum of the node's local contributions in the ORDER of the reference's
 // sequential np.bincount: ascending (element, vertex) for the cubature rule
@@ -570,6 +619,32 @@ extern "C" int p1_local_weighted_mass(p1_ctx *ctx, const double *coords,
       (const double2 *)coords, elements, M, phiq, w, (const double2 *)pts, n_qp, local);
   pool_free(ctx, w, s);
   pool_free(ctx, pts, s);
+  P1_CUDA(cudaGetLastError());
+  return P1_OK;
+}
+
+extern "C" int p1_integrate_quadrature(p1_ctx *ctx, const double *coords,
+                                       const int32_t *elements, int64_t M,
+                                       const double *fq, const double *weights_host,
+                                       int n_qp, double *result_host, void *stream) {
+  P1_REQUIRE(ctx && weights_host && n_qp > 0 && result_host, "bad argument");
+  P1_REQUIRE(M == 0 || (coords && elements && fq), "null argument");
+  DeviceGuard guard(ctx->device);
+  *result_host = 0.;
+  if (M == 0) return P1_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int blocks = 1024;  // fixed: the summation tree must not depend on the device
+  double *w = nullptr, *partial = nullptr;
+  P1_TRY(upload_small(ctx, &w, weights_host, (size_t)n_qp, s));
+  P1_TRY(pool_alloc(ctx, &partial, (size_t)blocks + 1, s));
+  integrate_kernel<<<blocks, THREADS, 0, s>>>((const double2 *)coords, elements, M, fq, w,
+                                             n_qp, partial);
+  sum_partials_kernel<<<1, THREADS, 0, s>>>(partial, blocks, partial + blocks);
+  P1_CUDA(cudaMemcpyAsync(result_host, partial + blocks, sizeof(double),
+                          cudaMemcpyDeviceToHost, s));
+  P1_CUDA(cudaStreamSynchronize(s));
+  pool_free(ctx, w, s);
+  pool_free(ctx, partial, s);
   P1_CUDA(cudaGetLastError());
   return P1_OK;
 }

@@ -425,6 +425,16 @@ class DeviceMesh:
             p.ctypes.data_as(C.c_void_p), w.shape[0], _ptr(b), _stream(self.device)))
         return b
 
+    def integrate(self, fq, weights):
+        """sum_T sum_q w_q fq[q][T] 2|T| (host float)."""
+        w = _host_f64(weights)
+        fq = to_device_f64(fq, self.device, (w.shape[0], self.n_elements))
+        out = C.c_double()
+        _lib.check(self._lib.p1_integrate_quadrature(
+            self.ctx, _ptr(self.coords), _ptr(self.elements), self.n_elements, _ptr(fq),
+            w.ctypes.data_as(C.c_void_p), w.shape[0], C.byref(out), _stream(self.device)))
+        return out.value
+
     def load_vector_midpoint(self, f_centroid):
         fc = to_device_f64(f_centroid, self.device, (self.n_elements,))
         self.plan  # noqa: B018

@@ -18,7 +18,9 @@ from .device import DeviceMesh, to_host
 
 __all__ = ['get_stiffness_matrix', 'get_mass_matrix', 'get_mass_matrix_elements',
            'get_general_stiffness_matrix', 'get_weighted_mass_matrix',
-           'get_right_hand_side', 'get_right_hand_side_using_quadrature_rule']
+           'get_right_hand_side', 'get_right_hand_side_using_quadrature_rule',
+           'integrate_composition_nonlinear_with_fem',
+           'get_load_vector_of_composition_nonlinear_with_fem']
 
 
 def _values_on_host(fn, points_host, n):
@@ -144,4 +146,33 @@ def get_right_hand_side_using_quadrature_rule(coordinates, elements, f,
     weights, points = resolve_rule(cubature_rule)
     with DeviceMesh(coordinates, elements) as mesh:
         (fq,) = _callback_at_points((f,), mesh.quadrature_points(points))
+        return to_host(mesh.load_vector(fq, weights, points))
+
+
+def _nodal_checked(mesh, u):
+    u = np.asarray(u, dtype=np.float64).reshape(-1)
+    top = int(mesh.elements.max().item()) if mesh.n_elements else -1
+    if u.shape[0] < top + 1:
+        raise IndexError('u has %d entries, elements reference node %d' % (u.shape[0], top))
+    if u.shape[0] != mesh.n_nodes:
+        u = np.concatenate([u, np.zeros(max(0, mesh.n_nodes - u.shape[0]))])[:mesh.n_nodes]
+    return u
+
+
+def integrate_composition_nonlinear_with_fem(f, u, coordinates, elements, cubature_rule):
+    """int_Omega f(u_h) dx for a P1 function u_h (solvers.py:429-472)."""
+    weights, points = resolve_rule(cubature_rule)
+    with DeviceMesh(coordinates, elements) as mesh:
+        uq = mesh.nodal_at_quadrature(_nodal_checked(mesh, u), points)
+        (fq,) = _callback_at_points((f,), uq)
+        return mesh.integrate(fq, weights)
+
+
+def get_load_vector_of_composition_nonlinear_with_fem(f, u, coordinates, elements,
+                                                      cubature_rule):
+    """F_i = int_Omega f(u_h) phi_i dx (solvers.py:475-537)."""
+    weights, points = resolve_rule(cubature_rule)
+    with DeviceMesh(coordinates, elements) as mesh:
+        uq = mesh.nodal_at_quadrature(_nodal_checked(mesh, u), points)
+        (fq,) = _callback_at_points((f,), uq)
         return to_host(mesh.load_vector(fq, weights, points))

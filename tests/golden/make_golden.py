@@ -66,6 +66,12 @@ def full_case(name, c, e, bnds):
                                  c, e, u, H.phi, rule)))
         out['rhs_' + rname] = ref.solvers.get_right_hand_side(
             c, e, H.f_load, cubature_rule=rule)
+        out['nl_load_' + rname] = \
+            ref.solvers.get_load_vector_of_composition_nonlinear_with_fem(
+                f=H.f_nl, u=u, coordinates=c, elements=e, cubature_rule=rule)
+        out['nl_integral_' + rname] = np.array(
+            ref.solvers.integrate_composition_nonlinear_with_fem(
+                f=H.f_nl, u=u, coordinates=c, elements=e, cubature_rule=rule))
     out['rhs_legacy'] = ref.solvers.get_right_hand_side(c, e, H.f_load)
     e2e, e2n, b2e = ref.mesh.provide_geometric_data(e, [dirichlet, neumann])
     out.update(element2edges=e2e, edge2nodes=e2n, dir2edges=b2e[0],

@@ -41,6 +41,7 @@ def a22(r): return -(2. + np.sin(np.pi * r[:, 1]))
 def phi(u): return 1. + u ** 2
 def f_load(r): return np.sin(2. * np.pi * r[:, 0]) * np.cos(3. * np.pi * r[:, 1]) + 1.
 def g_neu(r): return np.cos(r[:, 0]) - 0.5 * r[:, 1]
+def f_nl(x): return 1.7 * x ** 2 + 0.3 * x ** 3
 def u_nodal(c): return np.sin(np.pi * c[:, 0]) * np.sin(np.pi * c[:, 1])
 
 

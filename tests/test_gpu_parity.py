@@ -523,3 +523,29 @@ def test_empty_and_tiny_inputs(api):
     cw = np.array([[0, 2, 1]])
     H.csr_values_close(solvers.get_mass_matrix(c, cw), orc.mass_coo(c, cw).tocsr(), RTOL)
     assert solvers.get_mass_matrix(c, cw).data.max() < 0
+
+
+def test_nonlinear_cousins(api, mesh_case):
+    """load vector of f(u_h) (bit-exact) and the
+    integral of f(u_h) (fixed-order tree vs numpy's pairwise sum: 1e-12)."""
+    c, e, _ = mesh_case
+    u = H.u_nodal(c)
+    for rule in ('MIDPOINT', 'DAYTAYLOR'):
+        r = cubature.CubatureRuleEnum[rule]
+        w, p = cubature.resolve_rule(r)
+        got = api[0].get_load_vector_of_composition_nonlinear_with_fem(H.f_nl, u, c, e, r)
+        assert np.array_equal(got, orc.load_vector_composition(H.f_nl, u, c, e, w, p))
+        val = api[0].integrate_composition_nonlinear_with_fem(H.f_nl, u, c, e, r)
+        ref = orc.integrate_composition(H.f_nl, u, c, e, w, p)
+        assert abs(val - ref) <= 1e-12 * abs(ref)
+
+
+def test_nonlinear_cousins_against_reference_fixture(api):
+    g = load('graded')
+    c, e, u = g['coordinates'], g['elements'], g['u']
+    rule = (g['rule_DAYTAYLOR_w'], g['rule_DAYTAYLOR_p'])
+    assert np.array_equal(
+        api[0].get_load_vector_of_composition_nonlinear_with_fem(H.f_nl, u, c, e, rule),
+        g['nl_load_DAYTAYLOR'])
+    val = api[0].integrate_composition_nonlinear_with_fem(H.f_nl, u, c, e, rule)
+    assert abs(val - float(g['nl_integral_DAYTAYLOR'])) <= 1e-12 * abs(val)

@@ -45,6 +45,9 @@ def test_full_case_bit_exact(case):
                  csr_of(g, 'wmass_' + r))
         assert np.array_equal(orc.load_vector_cubature(c, e, H.f_load, w, p),
                               g['rhs_' + r])
+        assert np.array_equal(orc.load_vector_composition(H.f_nl, u, c, e, w, p),
+                              g['nl_load_' + r])
+        assert orc.integrate_composition(H.f_nl, u, c, e, w, p) == float(g['nl_integral_' + r])
     assert np.array_equal(orc.load_vector_midpoint(c, e, H.f_load),
                           g['rhs_legacy'])
     e2e, e2n, b2e = orc.geometric_data(e, [g['dirichlet'], g['neumann']])

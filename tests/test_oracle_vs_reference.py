@@ -98,6 +98,20 @@ def test_load_vector(ref, mesh, rule):
     assert np.array_equal(mine, theirs)
 
 
+@pytest.mark.parametrize('rule', RULES)
+def test_nonlinear_cousins(ref, mesh, rule):
+    c, e, _ = mesh
+    u = H.u_nodal(c)
+    w, p = cubature.resolve_rule(rule)
+    assert np.array_equal(
+        orc.load_vector_composition(H.f_nl, u, c, e, w, p),
+        ref.solvers.get_load_vector_of_composition_nonlinear_with_fem(
+            f=H.f_nl, u=u, coordinates=c, elements=e, cubature_rule=rule))
+    assert orc.integrate_composition(H.f_nl, u, c, e, w, p) == \
+        ref.solvers.integrate_composition_nonlinear_with_fem(
+            f=H.f_nl, u=u, coordinates=c, elements=e, cubature_rule=rule)
+
+
 def _split_boundary(b):
     """dirichlet = first ~60 % of the edges, neumann = the rest."""
     allb = np.vstack(b)
