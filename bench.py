@@ -11,9 +11,9 @@ S(L) (unit square cut by its centre, L uniform NVB refinements; L=12 is the
 plan (node->element lists, row pointer) + numeric fill, nothing cached between
 steps.  Prints ONE JSON line (see the contract in the task description).
 
-N > 1 (torchrun): every rank holds the mesh and assembles a contiguous range of
-rows (strong scaling of one 64M mesh; no data-path collective, only the
-all-gather of per-rank nnz that turns local row pointers into global ones).
+N > 1 (torchrun): every rank holds the mesh and assembles its share of the rows
+(chunks of 4096 rows dealt round-robin; strong scaling of one 64M mesh; no
+data-path collective, only the all-gather of per-rank nnz).
 """
 import argparse
 import json
@@ -220,25 +220,13 @@ def run_b200(args):
     level = args.level
     m, nn, nnz = mesh_counts(level)
 
-    # ---- synthetic input: the mesh the reference's refineNVB would produce
+    # ---- synthetic input: the mesh the reference's refineNVB would produce,
+    # generated on the device (meshgen.unit_square_device: bit-identical to the
+    # host generator, tests/test_gpu_dist.py), every rank for itself
+    from p1afempy_b200 import meshgen
     t0 = time.perf_counter()
-    shared = '/dev/shm/p1_bench_S%d' % level
-    keep = {args.ref_level: None} if args.ref_level < level else {}
-    if world == 1:
-        c, e = generate_mesh(level, keep)
-    else:
-        if rank == 0:
-            c, e = generate_mesh(level, keep)
-            np.save(shared + '_c.npy', c)
-            np.save(shared + '_e.npy', e.astype(np.int32))
-        dist.barrier()
-        if rank != 0:
-            c = np.load(shared + '_c.npy')
-            e = np.load(shared + '_e.npy')
-        dist.barrier()
-        if rank == 0:
-            os.unlink(shared + '_c.npy')
-            os.unlink(shared + '_e.npy')
+    c, e, _ = meshgen.unit_square_device(level, device=local_rank)
+    torch.cuda.synchronize()
     gen_s = time.perf_counter() - t0
     assert e.shape[0] == m and c.shape[0] == nn
 
@@ -323,11 +311,11 @@ def run_b200(args):
 
     # ---- end to end through the drop-in call: pinned host numpy in, scipy out
     e2e = None
-    if world == 1:
+    if world == 1 and not args.no_e2e:
         hc = torch.empty(c.shape, dtype=torch.float64, pin_memory=True)
-        he = torch.empty(e.shape, dtype=torch.int64, pin_memory=True)
-        hc.numpy()[...] = c
-        he.numpy()[...] = e
+        he = torch.empty(e.shape, dtype=torch.int64, pin_memory=True)   # what numpy users hold
+        hc.copy_(c)
+        he.copy_(e)
         cn, en = hc.numpy(), he.numpy()
         n_e2e = max(1, min(args.steps, 3))
         a = solvers.get_stiffness_matrix(cn, en)      # warm-up (pinned pool, pages)
@@ -352,7 +340,7 @@ def run_b200(args):
     cpu = None
     if world == 1 and not args.no_cpu:
         rl = args.ref_level if args.ref_level < level else level
-        rc, re_ = keep.get(rl) or (c, e)
+        rc, re_ = generate_mesh(rl)
         times = time_reference(rc, re_, 3, 1)
         model, ncpu, naff = cpu_info()
         cpu = {'value': re_.shape[0] / float(np.mean(times)) / 1e6, 'unit': UNIT,
@@ -396,6 +384,8 @@ def main():
     ap.add_argument('--ref-level', type=int, default=10,
                     help='mesh of the bounded CPU sample (10 = 4M triangles)')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true',
+                    help='skip the host-buffer leg (256M: 25 GB of pinned host memory)')
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == 'b200':
         args.warmup = 3

@@ -187,3 +187,54 @@ def perturb_interior(coordinates, boundaries, scale, seed=0):
     shift = rng.uniform(-scale, scale, size=coordinates.shape)
     out[~fixed] += shift[~fixed]
     return out
+
+
+# ---------------------------------------------------------------------------
+# device-side uniform refinement (benchmark meshes beyond what the host can hold)
+# ---------------------------------------------------------------------------
+
+def refine_uniform_device(coords, elements, boundaries):
+    """One NVB step with EVERY element marked, on the GPU.
+
+    coords (N,2) float64, elements (M,3) int32, boundaries: list of (K,2) int32
+    CUDA tensors.  Same output as ``refine_nvb(c, e, arange(M), b)`` (hence as
+    the reference's ``refineNVB``), bit for bit: the edge numbering comes from
+    ``p1_geometric_data`` (the device implementation of
+    mesh.provide_geometric_data), the rest is index arithmetic
+    (refinement.py:593-716, case bisec(3) for every element)."""
+    import torch
+    from .device import DeviceMesh
+    n = coords.shape[0]
+    with DeviceMesh(None, elements, n_nodes=n, check=False) as mesh:
+        e2e, e2n, b2e = mesh.geometric_data(boundaries)
+    mid = (coords[e2n[:, 0]] + coords[e2n[:, 1]]) / 2.
+    new_coords = torch.cat([coords, mid])
+    del mid, e2n
+    nn = (e2e + n).to(torch.int32)
+    del e2e
+    v0, v1, v2 = elements[:, 0], elements[:, 1], elements[:, 2]
+    m0, m1, m2 = nn[:, 0], nn[:, 1], nn[:, 2]
+    children = torch.stack([
+        torch.stack([m0, v2, m2], 1), torch.stack([v0, m0, m2], 1),
+        torch.stack([m0, v1, m1], 1), torch.stack([v2, m0, m1], 1)], 1)
+    new_elements = children.reshape(-1, 3).contiguous()
+    new_boundaries = []
+    for b, be in zip(boundaries, b2e):
+        mids = (be + n).to(torch.int32)
+        new_boundaries.append(torch.cat([torch.stack([b[:, 0], mids], 1),
+                                         torch.stack([mids, b[:, 1]], 1)]).contiguous())
+    return new_coords, new_elements, new_boundaries
+
+
+def unit_square_device(k: int, device=None, host_levels: int = 6):
+    """S(k) as CUDA tensors (coords float64, elements int32, [boundary] int32):
+    the first levels on the host, the rest refined on the device."""
+    import torch
+    dev = torch.device('cuda', torch.cuda.current_device() if device is None else device)
+    c, e, b = unit_square(min(k, host_levels))
+    ct = torch.from_numpy(c).to(dev)
+    et = torch.from_numpy(e.astype(np.int32)).to(dev)
+    bt = [torch.from_numpy(x.astype(np.int32)).to(dev) for x in b]
+    for _ in range(max(0, k - host_levels)):
+        ct, et, bt = refine_uniform_device(ct, et, bt)
+    return ct, et, bt

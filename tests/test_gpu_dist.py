@@ -119,3 +119,13 @@ def test_two_ranks_nccl(tmp_path):
     result = tmp_path / 'r.txt'
     mp.spawn(_nccl_worker, args=(2, _free_port(), str(result)), nprocs=2, join=True)
     assert result.read_text() == 'ok'
+
+
+def test_device_mesh_generator_matches_host():
+    """meshgen.unit_square_device == meshgen.unit_square (== the reference's
+    refineNVB, tests/test_meshgen_vs_reference.py) bit for bit."""
+    c, e, b = meshgen.unit_square(8)
+    ct, et, bt = meshgen.unit_square_device(8, host_levels=3)
+    assert np.array_equal(ct.cpu().numpy(), c)
+    assert np.array_equal(et.cpu().numpy(), e)
+    assert np.array_equal(bt[0].cpu().numpy(), b[0])
