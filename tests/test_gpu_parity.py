@@ -549,3 +549,39 @@ def test_nonlinear_cousins_against_reference_fixture(api):
         g['nl_load_DAYTAYLOR'])
     val = api[0].integrate_composition_nonlinear_with_fem(H.f_nl, u, c, e, rule)
     assert abs(val - float(g['nl_integral_DAYTAYLOR'])) <= 1e-12 * abs(val)
+
+
+def test_adaptive_lshape_loop(api):
+    """Config C4 at test size: L-shaped domain, nodal
+    interpolant of r^(2/3) sin(2 theta/3) about the re-entrant corner, eta_R on
+    the GPU drives Doerfler marking (theta = 0.5, stable descending sort) and
+    NVB refinement; at every step eta_R equals the oracle bit for bit and the
+    mesh grades towards the corner."""
+    solvers, mesh, indicators = api
+    c, e, b = meshgen.refine_uniform(*meshgen.l_shape(), times=3)
+    dirichlet_of = lambda bs: np.vstack(bs)               # noqa: E731
+    none = np.zeros((0, 2), dtype=int)
+
+    def singular(r):
+        x, y = r[:, 0] - 1., r[:, 1] - 1.
+        theta = np.mod(np.arctan2(y, x) - np.pi / 2., 2. * np.pi)   # 0 along the edge x=1, y>1
+        return np.hypot(x, y) ** (2. / 3.) * np.sin(2. * theta / 3.)
+    zero = lambda r: np.zeros(r.shape[0])                 # noqa: E731
+    sizes = []
+    for _ in range(7):
+        x = singular(c)
+        eta = indicators.compute_eta_r(x, c, e, dirichlet_of(b), none, zero, zero)
+        assert np.array_equal(eta, orc.eta_r(x, c, e, dirichlet_of(b), none, zero, zero))
+        order = np.argsort(-eta, kind='stable')
+        csum = np.cumsum(eta[order])
+        marked = order[:int(np.searchsorted(csum, 0.5 * csum[-1])) + 1]
+        sizes.append(e.shape[0])
+        c, e, b = meshgen.refine_nvb(c, e, marked, b)
+    assert sizes[-1] > sizes[0]
+    # the estimator concentrates the refinement at the re-entrant corner
+    cent = (c[e[:, 0]] + c[e[:, 1]] + c[e[:, 2]]) / 3.
+    area = np.abs(orc.signed_area(c, e))
+    near = np.hypot(cent[:, 0] - 1., cent[:, 1] - 1.) < 0.1
+    assert area[near].min() < 0.01 * area[~near].max()
+    a = solvers.get_stiffness_matrix(c, e)
+    H.csr_values_close(a, orc.stiffness_coo(c, e).tocsr(), RTOL)
