@@ -23,10 +23,13 @@ constexpr int THREADS = 256;
 // builds the row in a shared-memory image of the block's contiguous CSR span,
 // and the block streams the image out with coalesced stores.
 #ifndef P1_FILL_MIN_BLOCKS
-#define P1_FILL_MIN_BLOCKS 5
+#define P1_FILL_MIN_BLOCKS 20
 #endif
-constexpr int FR = 128;          // rows per block = threads per block
-constexpr int CAP_OUT = 1280;    // CSR entries staged per block (9 per regular row + slack)
+#ifndef P1_FILL_ROWS
+#define P1_FILL_ROWS 32
+#endif
+constexpr int FR = P1_FILL_ROWS;  // rows per block = threads per block
+constexpr int CAP_OUT = FR * 10;  // CSR entries staged per block (9 per regular row + slack)
 
 __global__ void __launch_bounds__(FR, P1_FILL_MIN_BLOCKS)
 fill_rows_kernel(int n_own, Own own, int exact,
