@@ -20,6 +20,13 @@
 namespace p1 {
 
 constexpr int THREADS = 256;
+#ifndef P1_SCATTER_THREADS
+#define P1_SCATTER_THREADS 256
+#endif
+#ifndef P1_SCATTER_WAVES
+#define P1_SCATTER_WAVES 32
+#endif
+constexpr int SC_THREADS = P1_SCATTER_THREADS;  // scatter block size
 
 // -------------------------------------------------------------- scatter
 // The thread that owns element t computes the element's local matrix ONCE
@@ -85,7 +92,7 @@ __device__ __forceinline__ void scatter_element(int64_t t, const int (&e)[3], in
 // and spends 0.45 ms just scanning 64M triangles).
 // (forcing more resident blocks was measured: 40 or 32 registers spill and lose)
 template <class V, bool OVERFLOW>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(SC_THREADS)
 scatter_kernel(const int *__restrict__ elements, int64_t M, int N, Own own, int vec,
                unsigned long long *__restrict__ acc, Rec *__restrict__ rec,
                int *__restrict__ rec_elem, int *__restrict__ cursor, V values,
@@ -132,24 +139,24 @@ static void launch_scatter(p1_ctx *ctx, unsigned grid, cudaStream_t s, int op,
   // 12.1 ms, so the drop-in layer uses that one)
   const int vec = ((uintptr_t)elements & 15) == 0 && op != P1_OP_GENERAL;
   if (op == P1_OP_GENERAL)
-    scatter_kernel<GeneralValues, OVERFLOW><<<grid, THREADS, 0, s>>>(
+    scatter_kernel<GeneralValues, OVERFLOW><<<grid, SC_THREADS, 0, s>>>(
         elements, M, N, own, vec, acc, rec, rec_elem, cursor,
         GeneralValues{xy, qa->a11q, qa->a12q, qa->a21q, qa->a22q, d_weights, qa->n_qp, M}, fl);
   else if (op == P1_OP_WEIGHTED)
-    scatter_kernel<WeightedValues, OVERFLOW><<<grid, THREADS, 0, s>>>(
+    scatter_kernel<WeightedValues, OVERFLOW><<<grid, SC_THREADS, 0, s>>>(
         elements, M, N, own, vec, acc, rec, rec_elem, cursor,
         WeightedValues{xy, qa->phiq, d_weights, (const double2 *)d_points, qa->n_qp, M}, fl);
   else if (op == P1_OP_STIFFNESS)
-    scatter_kernel<StiffnessValues, OVERFLOW><<<grid, THREADS, 0, s>>>(
+    scatter_kernel<StiffnessValues, OVERFLOW><<<grid, SC_THREADS, 0, s>>>(
         elements, M, N, own, vec, acc, rec, rec_elem, cursor, StiffnessValues{xy}, fl);
   else if (op == P1_OP_MASS)
-    scatter_kernel<MassValues, OVERFLOW><<<grid, THREADS, 0, s>>>(
+    scatter_kernel<MassValues, OVERFLOW><<<grid, SC_THREADS, 0, s>>>(
         elements, M, N, own, vec, acc, rec, rec_elem, cursor, MassValues{xy}, fl);
   else if (op == P1_OP_LOCAL)
-    scatter_kernel<LocalValues, OVERFLOW><<<grid, THREADS, 0, s>>>(
+    scatter_kernel<LocalValues, OVERFLOW><<<grid, SC_THREADS, 0, s>>>(
         elements, M, N, own, vec, acc, rec, rec_elem, cursor, LocalValues{local}, fl);
   else
-    scatter_kernel<NoValues, OVERFLOW><<<grid, THREADS, 0, s>>>(
+    scatter_kernel<NoValues, OVERFLOW><<<grid, SC_THREADS, 0, s>>>(
         elements, M, N, own, vec, acc, rec, rec_elem, cursor, NoValues{}, fl);
 }
 
