@@ -585,3 +585,28 @@ def test_adaptive_lshape_loop(api):
     assert area[near].min() < 0.01 * area[~near].max()
     a = solvers.get_stiffness_matrix(c, e)
     H.csr_values_close(a, orc.stiffness_coo(c, e).tocsr(), RTOL)
+
+
+def test_random_element_soups(api):
+    """Differential fuzzing of the row machinery: random triples over a few
+    nodes (non-manifold, repeated vertices, duplicated triangles, both
+    orientations) -- the reference just sums triplets, so must we.  The mass
+    matrix has no division by the area, so every value stays finite."""
+    rng = np.random.default_rng(2024)
+    for trial in range(120):
+        n = int(rng.integers(3, 14))
+        m = int(rng.integers(1, 40))
+        c = rng.random((n, 2))
+        e = rng.integers(0, n, size=(m, 3))
+        if trial % 3 == 0:                       # proper triangles only
+            e = np.array([rng.choice(n, size=3, replace=False) for _ in range(m)])
+        ref = orc.mass_coo(c, e).tocsr()
+        got = api[0].get_mass_matrix(c, e)
+        assert got.shape == ref.shape, trial
+        assert np.array_equal(got.indptr, ref.indptr), trial
+        assert np.array_equal(got.indices, ref.indices), trial
+        # both orientations cancel: measure against the size of the contributions
+        scale = np.abs(orc.mass_triplets(c, e)[2]).max()
+        assert np.abs(got.data - ref.data).max() <= 1e-12 * scale, trial
+        b = api[0].get_right_hand_side(c, e, H.f_load)
+        assert np.array_equal(b, orc.load_vector_midpoint(c, e, H.f_load)), trial
