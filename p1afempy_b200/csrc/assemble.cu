@@ -259,7 +259,13 @@ refresh_kernel(const int *__restrict__ elements, int64_t n,
     const int e[3] = {__ldg(elements + 3 * t), __ldg(elements + 3 * t + 1),
                       __ldg(elements + 3 * t + 2)};
     double v[3][3];
-    values.rows(t, e, v);
+    double2 z0 = make_double2(0., 0.), z1 = z0, z2 = z0;
+    if constexpr (V::needs_xy) {
+      z0 = __ldg(values.coords + e[0]);
+      z1 = __ldg(values.coords + e[1]);
+      z2 = __ldg(values.coords + e[2]);
+    }
+    values.rows(t, e, z0, z1, z2, v);
     Rec r = rec[i];
     const int k = rec_k(r);
     r.vd = k == 0 ? v[0][0] : (k == 1 ? v[1][0] : v[2][0]);

@@ -62,7 +62,13 @@ __device__ __forceinline__ void scatter_element(int64_t t, const int (&e)[3], in
   }
   if (!(mine[0] || mine[1] || mine[2])) return;  // not my rows
   double v[3][3];
-  values.rows(t, e, v);
+  double2 z0 = make_double2(0., 0.), z1 = z0, z2 = z0;
+  if constexpr (V::needs_xy) {
+    z0 = __ldg(values.coords + e[0]);
+    z1 = __ldg(values.coords + e[1]);
+    z2 = __ldg(values.coords + e[2]);
+  }
+  values.rows(t, e, z0, z1, z2, v);
 #pragma unroll
   for (int k = 0; k < 3; ++k)
     if (mine[k]) {
@@ -87,11 +93,103 @@ __device__ __forceinline__ void scatter_element(int64_t t, const int (&e)[3], in
     }
 }
 
+// Two consecutive triangles at once: NVB siblings share two of their three
+// vertices, so the 6 vertex references are grouped in registers -- one
+// coordinate gather and one atomic per DISTINCT node (typically 4 instead of 6).
+// The kernel is bound by LSU operations per lane; the 15 comparisons are free.
+template <class V>
+__device__ __forceinline__ void scatter_pair(int64_t t, const int (&id)[6], int N,
+                                             const Own &own,
+                                             unsigned long long *__restrict__ acc,
+                                             Rec *__restrict__ rec,
+                                             int *__restrict__ rec_elem, const V &values,
+                                             int &mx, bool &bad) {
+  bool valid[2], touched[2], mine[6];
+  int row[6];
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    valid[j] = (unsigned)id[3 * j] < (unsigned)N && (unsigned)id[3 * j + 1] < (unsigned)N &&
+               (unsigned)id[3 * j + 2] < (unsigned)N;
+    bad = bad || !valid[j];
+    touched[j] = false;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int i = 3 * j + k;
+      row[i] = 0;
+      mine[i] = valid[j] && own.owns(id[i], row[i]);
+      touched[j] = touched[j] || mine[i];
+      if (valid[j]) mx = max(mx, id[i]);
+    }
+  }
+  if (!(touched[0] || touched[1])) return;
+  double2 z[6];
+  if constexpr (V::needs_xy) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      z[i] = make_double2(0., 0.);
+      bool dup = false;
+#pragma unroll
+      for (int j = 0; j < i; ++j)
+        if (touched[j / 3] && id[j] == id[i]) { z[i] = z[j]; dup = true; }
+      if (touched[i / 3] && !dup) z[i] = __ldg(values.coords + id[i]);
+    }
+  }
+  unsigned slot[6], base[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    base[i] = 0;
+    bool leader = mine[i];
+    unsigned rank = 0;
+#pragma unroll
+    for (int j = 0; j < i; ++j)
+      if (mine[i] && mine[j] && row[j] == row[i]) { leader = false; ++rank; base[i] = base[j]; }
+    if (leader) {
+      const int ej = i / 3, ek = i - 3 * ej;
+      unsigned cnt = 1;
+      unsigned h = mix32((unsigned)id[3 * ej + (ek == 2 ? 0 : ek + 1)]) -
+                   mix32((unsigned)id[3 * ej + (ek == 0 ? 2 : ek - 1)]);
+#pragma unroll
+      for (int j = i + 1; j < 6; ++j)
+        if (mine[j] && row[j] == row[i]) {
+          const int fj = j / 3, fk = j - 3 * fj;
+          ++cnt;
+          h += mix32((unsigned)id[3 * fj + (fk == 2 ? 0 : fk + 1)]) -
+               mix32((unsigned)id[3 * fj + (fk == 0 ? 2 : fk - 1)]);
+        }
+      base[i] = (unsigned)atomicAdd(acc + row[i], ((unsigned long long)h << 32) + cnt);
+    }
+    slot[i] = mine[i] ? base[i] + rank : 0xffu;
+  }
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    if (!touched[j]) continue;
+    const int e[3] = {id[3 * j], id[3 * j + 1], id[3 * j + 2]};
+    double v[3][3];
+    values.rows(t + j, e, z[3 * j], z[3 * j + 1], z[3 * j + 2], v);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int i = 3 * j + k;
+      if (slot[i] >= (unsigned)GROUP) continue;
+      const int64_t pos = (int64_t)row[i] * GROUP + slot[i];
+      Rec rc;
+      rc.nx = e[k == 2 ? 0 : k + 1];
+      rc.pvk = e[k == 0 ? 2 : k - 1] | (k << NODE_BITS);
+      rc.vd = v[k][0]; rc.vn = v[k][1]; rc.vp = v[k][2];
+      store_rec(rec + pos, rc);
+      if (rec_elem) rec_elem[pos] = (int)(((t + j) << 2) | k);
+    }
+  }
+}
+
 // `vec` != 0: elements is 16-byte aligned; a thread then reads 4 triangles =
 // 12 indices as three 128-bit loads (the scalar form reads 12 B at stride 12 B
 // and spends 0.45 ms just scanning 64M triangles).
 // (forcing more resident blocks was measured: 40 or 32 registers spill and lose)
-template <class V, bool OVERFLOW>
+// PAIRS: group the references of two consecutive triangles (scatter_pair).  Pays
+// when most references are owned (one GPU: 2.58 -> 2.20 ms at 64M); with 1/8 of the
+// rows owned there is little to group and the extra registers cost more (0.76 ->
+// 1.01 ms), so multi-GPU plans use the plain form.
+template <class V, bool OVERFLOW, bool PAIRS>
 __global__ void __launch_bounds__(SC_THREADS)
 scatter_kernel(const int *__restrict__ elements, int64_t M, int N, Own own, int vec,
                unsigned long long *__restrict__ acc, Rec *__restrict__ rec,
@@ -105,6 +203,12 @@ scatter_kernel(const int *__restrict__ elements, int64_t M, int N, Own own, int 
   const int4 *e4 = reinterpret_cast<const int4 *>(elements);
   for (int64_t g = tid; g < quads; g += stride) {
     const int4 p = __ldg(e4 + 3 * g), q = __ldg(e4 + 3 * g + 1), r = __ldg(e4 + 3 * g + 2);
+    if constexpr (!OVERFLOW && PAIRS) {
+      const int ab[6] = {p.x, p.y, p.z, p.w, q.x, q.y}, cd[6] = {q.z, q.w, r.x, r.y, r.z, r.w};
+      scatter_pair<V>(4 * g, ab, N, own, acc, rec, rec_elem, values, mx, bad);
+      scatter_pair<V>(4 * g + 2, cd, N, own, acc, rec, rec_elem, values, mx, bad);
+      continue;
+    }
     const int ea[3] = {p.x, p.y, p.z}, eb[3] = {p.w, q.x, q.y}, ec[3] = {q.z, q.w, r.x},
               ed[3] = {r.y, r.z, r.w};
     scatter_element<V, OVERFLOW>(4 * g, ea, N, own, acc, rec, rec_elem, cursor, values, mx, bad);
@@ -124,6 +228,18 @@ scatter_kernel(const int *__restrict__ elements, int64_t M, int N, Own own, int 
   }
 }
 
+template <class V, bool OVERFLOW>
+static void launch_one(bool pairs, unsigned grid, cudaStream_t s, const int *elements, int64_t M,
+                       int N, Own own, int vec, unsigned long long *acc, Rec *rec,
+                       int *rec_elem, int *cursor, V values, int *fl) {
+  if (pairs && !OVERFLOW)
+    scatter_kernel<V, OVERFLOW, true><<<grid, SC_THREADS, 0, s>>>(
+        elements, M, N, own, vec, acc, rec, rec_elem, cursor, values, fl);
+  else
+    scatter_kernel<V, OVERFLOW, false><<<grid, SC_THREADS, 0, s>>>(
+        elements, M, N, own, vec, acc, rec, rec_elem, cursor, values, fl);
+}
+
 template <bool OVERFLOW>
 static void launch_scatter(p1_ctx *ctx, unsigned grid, cudaStream_t s, int op,
                            const int *elements, int64_t M, int N, Own own,
@@ -138,26 +254,27 @@ static void launch_scatter(p1_ctx *ctx, unsigned grid, cudaStream_t s, int op,
   // with, 12.5 ms without; the unfused route through p1_local_general_stiffness is
   // 12.1 ms, so the drop-in layer uses that one)
   const int vec = ((uintptr_t)elements & 15) == 0 && op != P1_OP_GENERAL;
+  // all rows owned, and a source that does not stream [n_qp x M] arrays
+  const bool pairs = own.world == 1 && own.re - own.rb == N && op != P1_OP_WEIGHTED &&
+                     op != P1_OP_GENERAL;
   if (op == P1_OP_GENERAL)
-    scatter_kernel<GeneralValues, OVERFLOW><<<grid, SC_THREADS, 0, s>>>(
-        elements, M, N, own, vec, acc, rec, rec_elem, cursor,
-        GeneralValues{xy, qa->a11q, qa->a12q, qa->a21q, qa->a22q, d_weights, qa->n_qp, M}, fl);
+    launch_one<GeneralValues, OVERFLOW>(pairs, grid, s, elements, M, N, own, vec, acc, rec, rec_elem,
+            cursor, GeneralValues{xy, qa->a11q, qa->a12q, qa->a21q, qa->a22q, d_weights, qa->n_qp, M}, fl);
   else if (op == P1_OP_WEIGHTED)
-    scatter_kernel<WeightedValues, OVERFLOW><<<grid, SC_THREADS, 0, s>>>(
-        elements, M, N, own, vec, acc, rec, rec_elem, cursor,
-        WeightedValues{xy, qa->phiq, d_weights, (const double2 *)d_points, qa->n_qp, M}, fl);
+    launch_one<WeightedValues, OVERFLOW>(pairs, grid, s, elements, M, N, own, vec, acc, rec, rec_elem,
+            cursor, WeightedValues{xy, qa->phiq, d_weights, (const double2 *)d_points, qa->n_qp, M}, fl);
   else if (op == P1_OP_STIFFNESS)
-    scatter_kernel<StiffnessValues, OVERFLOW><<<grid, SC_THREADS, 0, s>>>(
-        elements, M, N, own, vec, acc, rec, rec_elem, cursor, StiffnessValues{xy}, fl);
+    launch_one<StiffnessValues, OVERFLOW>(pairs, grid, s, elements, M, N, own, vec, acc, rec, rec_elem,
+            cursor, StiffnessValues{xy}, fl);
   else if (op == P1_OP_MASS)
-    scatter_kernel<MassValues, OVERFLOW><<<grid, SC_THREADS, 0, s>>>(
-        elements, M, N, own, vec, acc, rec, rec_elem, cursor, MassValues{xy}, fl);
+    launch_one<MassValues, OVERFLOW>(pairs, grid, s, elements, M, N, own, vec, acc, rec, rec_elem,
+            cursor, MassValues{xy}, fl);
   else if (op == P1_OP_LOCAL)
-    scatter_kernel<LocalValues, OVERFLOW><<<grid, SC_THREADS, 0, s>>>(
-        elements, M, N, own, vec, acc, rec, rec_elem, cursor, LocalValues{local}, fl);
+    launch_one<LocalValues, OVERFLOW>(pairs, grid, s, elements, M, N, own, vec, acc, rec, rec_elem,
+            cursor, LocalValues{local}, fl);
   else
-    scatter_kernel<NoValues, OVERFLOW><<<grid, SC_THREADS, 0, s>>>(
-        elements, M, N, own, vec, acc, rec, rec_elem, cursor, NoValues{}, fl);
+    launch_one<NoValues, OVERFLOW>(pairs, grid, s, elements, M, N, own, vec, acc, rec, rec_elem,
+            cursor, NoValues{}, fl);
 }
 
 // ---------------------------------------------------------------- split

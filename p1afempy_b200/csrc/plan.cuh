@@ -232,18 +232,22 @@ int ensure_twins(p1_plan *plan, cudaStream_t s);
 int require_elements(const p1_plan *plan, const char *who);
 
 // ---- value sources for the scatter / refresh kernels (assemble.cu) ----------
-// rows(t, e, v): v[k][0..2] = entries (k,k), (k,k+1), (k,k+2) of element t
+// rows(t, e, z0, z1, z2, v): v[k][0..2] = entries (k,k), (k,k+1), (k,k+2) of
+// element t; z0..z2 are the vertex coordinates (supplied by the caller, who can
+// share them between neighbouring triangles) when needs_xy
 struct NoValues {
-  __device__ __forceinline__ void rows(int64_t, const int *, double (*v)[3]) const {
+  static constexpr bool needs_xy = false;
+  __device__ __forceinline__ void rows(int64_t, const int *, double2, double2, double2,
+                                       double (*v)[3]) const {
 #pragma unroll
     for (int k = 0; k < 3; ++k) v[k][0] = v[k][1] = v[k][2] = 0.;
   }
 };
 struct StiffnessValues {  // solvers.py:31-45
+  static constexpr bool needs_xy = true;
   const double2 *__restrict__ coords;
-  __device__ __forceinline__ void rows(int64_t, const int *e, double (*v)[3]) const {
-    const double2 z0 = __ldg(coords + e[0]), z1 = __ldg(coords + e[1]),
-                  z2 = __ldg(coords + e[2]);
+  __device__ __forceinline__ void rows(int64_t, const int *, double2 z0, double2 z1,
+                                       double2 z2, double (*v)[3]) const {
     const double d21x = z1.x - z0.x, d21y = z1.y - z0.y;
     const double d31x = z2.x - z0.x, d31y = z2.y - z0.y;
     const double area4 = 4. * (0.5 * (d21x * d31y - d21y * d31x));
@@ -256,10 +260,10 @@ struct StiffnessValues {  // solvers.py:31-45
   }
 };
 struct MassValues {  // solvers.py:176-181
+  static constexpr bool needs_xy = true;
   const double2 *__restrict__ coords;
-  __device__ __forceinline__ void rows(int64_t, const int *e, double (*v)[3]) const {
-    const double2 z0 = __ldg(coords + e[0]), z1 = __ldg(coords + e[1]),
-                  z2 = __ldg(coords + e[2]);
+  __device__ __forceinline__ void rows(int64_t, const int *, double2 z0, double2 z1,
+                                       double2 z2, double (*v)[3]) const {
     const double d21x = z1.x - z0.x, d21y = z1.y - z0.y;
     const double d31x = z2.x - z0.x, d31y = z2.y - z0.y;
     const double area = 0.5 * (d21x * d31y - d21y * d31x);
@@ -269,8 +273,10 @@ struct MassValues {  // solvers.py:176-181
   }
 };
 struct LocalValues {  // 3x3 local matrix given per element, row-major
+  static constexpr bool needs_xy = false;
   const double *__restrict__ local;
-  __device__ __forceinline__ void rows(int64_t t, const int *, double (*v)[3]) const {
+  __device__ __forceinline__ void rows(int64_t t, const int *, double2, double2, double2,
+                                       double (*v)[3]) const {
     const double *m = local + 9 * t;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -285,15 +291,15 @@ struct LocalValues {  // 3x3 local matrix given per element, row-major
 // four coefficients ([n_qp x M] arrays) and the local matrix never touch HBM
 // as an [M x 9] array.
 struct GeneralValues {
+  static constexpr bool needs_xy = true;
   const double2 *__restrict__ coords;
   const double *__restrict__ a11q, *__restrict__ a12q, *__restrict__ a21q,
       *__restrict__ a22q;
   const double *__restrict__ weights;  // device, n_qp
   int n_qp;
   int64_t M;
-  __device__ __forceinline__ void rows(int64_t t, const int *e, double (*v)[3]) const {
-    const double2 z0 = __ldg(coords + e[0]), z1 = __ldg(coords + e[1]),
-                  z2 = __ldg(coords + e[2]);
+  __device__ __forceinline__ void rows(int64_t t, const int *, double2 z0, double2 z1,
+                                       double2 z2, double (*v)[3]) const {
     const double dz1x = z1.x - z0.x, dz1y = z1.y - z0.y;
     const double dz2x = z2.x - z0.x, dz2y = z2.y - z0.y;
     const double alpha = dz2y, beta = -dz2x, gamma = -dz1y, delta = dz1x;
@@ -325,15 +331,15 @@ struct GeneralValues {
 
 // solvers.py:86-129 evaluated inside the scatter
 struct WeightedValues {
+  static constexpr bool needs_xy = true;
   const double2 *__restrict__ coords;
   const double *__restrict__ phiq;     // [n_qp x M]
   const double *__restrict__ weights;  // device, n_qp
   const double2 *__restrict__ points;  // device, n_qp (eta, xi)
   int n_qp;
   int64_t M;
-  __device__ __forceinline__ void rows(int64_t t, const int *e, double (*v)[3]) const {
-    const double2 z0 = __ldg(coords + e[0]), z1 = __ldg(coords + e[1]),
-                  z2 = __ldg(coords + e[2]);
+  __device__ __forceinline__ void rows(int64_t t, const int *, double2 z0, double2 z1,
+                                       double2 z2, double (*v)[3]) const {
     const double dz1x = z1.x - z0.x, dz1y = z1.y - z0.y;
     const double dz2x = z2.x - z0.x, dz2y = z2.y - z0.y;
     const double areas = 0.5 * (dz1x * dz2y - dz1y * dz2x);
