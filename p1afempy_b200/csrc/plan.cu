@@ -189,11 +189,11 @@ __device__ __forceinline__ void scatter_pair(int64_t t, const int (&id)[6], int 
 // when most references are owned (one GPU: 2.58 -> 2.20 ms at 64M); with 1/8 of the
 // rows owned there is little to group and the extra registers cost more (0.76 ->
 // 1.01 ms), so multi-GPU plans use the plain form.
-#ifndef P1_SCATTER_PAIR_BLOCKS
-#define P1_SCATTER_PAIR_BLOCKS 1
-#endif
+// (register allocation of the PAIRS form, measured at 64M: 80 registers 2.20 ms --
+// what ptxas picks without a min-blocks hint --, 99 registers 2.74 ms, 64 with
+// spills 2.35 ms, 48 with spills 2.82 ms)
 template <class V, bool OVERFLOW, bool PAIRS>
-__global__ void __launch_bounds__(SC_THREADS, PAIRS ? P1_SCATTER_PAIR_BLOCKS : 1)
+__global__ void __launch_bounds__(SC_THREADS)
 scatter_kernel(const int *__restrict__ elements, int64_t M, int N, Own own, int vec,
                unsigned long long *__restrict__ acc, Rec *__restrict__ rec,
                int *__restrict__ rec_elem, int *__restrict__ cursor, V values,
