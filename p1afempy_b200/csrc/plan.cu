@@ -15,6 +15,7 @@
 // the fixed slots rec[8a..8a+7], so there is no counting pass, no offset scan)
 // and ONE 256-bit store.
 #include "plan.cuh"
+#include <stdlib.h>
 #include <vector>
 
 namespace p1 {
@@ -258,8 +259,9 @@ static void launch_scatter(p1_ctx *ctx, unsigned grid, cudaStream_t s, int op,
   // 12.1 ms, so the drop-in layer uses that one)
   const int vec = ((uintptr_t)elements & 15) == 0 && op != P1_OP_GENERAL;
   // all rows owned, and a source that does not stream [n_qp x M] arrays
-  const bool pairs = own.world == 1 && own.re - own.rb == N && op != P1_OP_WEIGHTED &&
-                     op != P1_OP_GENERAL;
+  bool pairs = own.world == 1 && own.re - own.rb == N && op != P1_OP_WEIGHTED &&
+               op != P1_OP_GENERAL;
+  if (const char *force = getenv("P1_SCATTER_PAIRS")) pairs = force[0] == '1';  // experiments
   if (op == P1_OP_GENERAL)
     launch_one<GeneralValues, OVERFLOW>(pairs, grid, s, elements, M, N, own, vec, acc, rec, rec_elem,
             cursor, GeneralValues{xy, qa->a11q, qa->a12q, qa->a21q, qa->a22q, d_weights, qa->n_qp, M}, fl);
