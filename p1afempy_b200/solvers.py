@@ -20,7 +20,8 @@ __all__ = ['get_stiffness_matrix', 'get_mass_matrix', 'get_mass_matrix_elements'
            'get_general_stiffness_matrix', 'get_weighted_mass_matrix',
            'get_right_hand_side', 'get_right_hand_side_using_quadrature_rule',
            'integrate_composition_nonlinear_with_fem',
-           'get_load_vector_of_composition_nonlinear_with_fem']
+           'get_load_vector_of_composition_nonlinear_with_fem',
+           'apply_neumann', 'solve_laplace']
 
 
 def _values_on_host(fn, points_host, n):
@@ -176,3 +177,49 @@ def get_load_vector_of_composition_nonlinear_with_fem(f, u, coordinates, element
         uq = mesh.nodal_at_quadrature(_nodal_checked(mesh, u), points)
         (fq,) = _callback_at_points((f,), uq)
         return to_host(mesh.load_vector(fq, weights, points))
+
+
+# ---------------------------------------------------------------------------
+# The reference's driver on top of the accelerated path (SURVEY.md section 8(f),
+# "next" rank 2: the consumer side).  Host orchestration exactly as in
+# /root/reference/p1afempy/solvers.py:601-697; assembly and load vector run on
+# the GPU, the sparse direct solve stays scipy's, as in the reference.
+# ---------------------------------------------------------------------------
+
+def apply_neumann(neumann_bc, coordinates, g, b):
+    """b + Neumann contributions (solvers.py:601-618): every boundary edge adds
+    |E| g(midpoint) / 2 to both of its nodes (sequential bincount order)."""
+    neumann_bc = np.asarray(neumann_bc)
+    cn1 = coordinates[neumann_bc[:, 0], :]
+    cn2 = coordinates[neumann_bc[:, 1], :]
+    gm = _values_on_host(g, (cn1 + cn2) / 2, neumann_bc.shape[0])
+    share = np.sqrt(np.sum(np.square(cn2 - cn1), axis=1)) * gm / 2.
+    return b + np.bincount(
+        np.concatenate([neumann_bc[:, 0], neumann_bc[:, 1]]).astype(np.int64),
+        weights=np.concatenate([share, share]), minlength=b.size)
+
+
+def solve_laplace(coordinates, elements, dirichlet, neumann, f, g, uD,
+                  cubature_rule=None):
+    """-Laplace u = f with mixed boundary conditions (solvers.py:621-697).
+    Returns (x, energy)."""
+    from scipy.sparse import csc_matrix
+    from scipy.sparse.linalg import spsolve
+    coordinates = np.asarray(coordinates, dtype=np.float64)
+    n = coordinates.shape[0]
+    x = np.zeros(n)
+    a = get_stiffness_matrix(coordinates=coordinates, elements=elements)
+    if a.shape[0] < n:                      # trailing unused nodes (inferred shape)
+        raise ValueError('solve_laplace: every node must belong to an element')
+    fixed = np.unique(np.asarray(dirichlet))
+    x[fixed] = _values_on_host(uD, coordinates[fixed, :], fixed.shape[0])
+    b = get_right_hand_side(coordinates=coordinates, elements=elements, f=f,
+                            cubature_rule=cubature_rule) - a.dot(x)
+    neumann = np.asarray(neumann)
+    if neumann.size > 0:
+        b = apply_neumann(neumann_bc=neumann, coordinates=coordinates, g=g, b=b)
+    free = np.setdiff1d(np.arange(0, n), fixed, assume_unique=True)
+    a = csc_matrix(a)
+    x[free] = spsolve(a[free, :][:, free], b[free], use_umfpack=True)
+    energy = x.dot(a.dot(x))
+    return x, energy

@@ -610,3 +610,23 @@ def test_random_element_soups(api):
         assert np.abs(got.data - ref.data).max() <= 1e-12 * scale, trial
         b = api[0].get_right_hand_side(c, e, H.f_load)
         assert np.array_equal(b, orc.load_vector_midpoint(c, e, H.f_load)), trial
+
+
+def test_solve_laplace_matlab_golden(api):
+    """The reference's own end-to-end tests on the drop-in functions:
+    test_solver.py:20-57 (x and energy of MATLAB's p1afem after 3 NVB
+    refinements) and test_indicators.py:12-55 (eta_R after 2)."""
+    solvers, _, indicators = api
+    g = load('laplace_example')
+    x3, energy3 = solvers.solve_laplace(
+        coordinates=g['coordinates3'], elements=g['elements3'], dirichlet=g['dirichlet3'],
+        neumann=g['neumann3'], f=L.f, g=L.g, uD=L.uD)
+    assert np.allclose(x3, g['x_matlab'])
+    assert np.isclose(energy3, g['energy_matlab'])
+    assert np.allclose(x3, g['x3_reference'], rtol=1e-12, atol=1e-14)
+    x2, _ = solvers.solve_laplace(
+        coordinates=g['coordinates'], elements=g['elements'], dirichlet=g['dirichlet'],
+        neumann=g['neumann'], f=L.f, g=L.g, uD=L.uD)
+    eta = indicators.compute_eta_r(x2, g['coordinates'], g['elements'], g['dirichlet'],
+                                   g['neumann'], L.f, L.g)
+    assert np.allclose(eta, g['eta_matlab'])
