@@ -630,3 +630,32 @@ def test_solve_laplace_matlab_golden(api):
     eta = indicators.compute_eta_r(x2, g['coordinates'], g['elements'], g['dirichlet'],
                                    g['neumann'], L.f, L.g)
     assert np.allclose(eta, g['eta_matlab'])
+
+
+def test_weighted_mass_closed_form(api):
+    """test_get_weighted_mass_matrix.py:20-96 of the reference on the drop-in:
+    u^T M(phi(u)) u for a pyramid function and a degree-4 polynomial phi equals
+    a closed form on every refined mesh (needs a rule exact to degree 6)."""
+    coefficients = [34.3, 12.4, 1.4, 0.45, 0.332]
+    u_star = 12.
+    c = np.array([[-1., -1.], [1., -1.], [1., 1.], [-1., 1.], [0., 0.]])
+    e = np.array([[0, 4, 3], [0, 1, 4], [1, 2, 4], [4, 2, 3]])
+    b = [np.array([[0, 1], [1, 2], [2, 3], [3, 0]])]
+    u = np.array([0., 0., 0., 0., u_star])
+
+    def phi(x):
+        out = np.zeros(x.shape[0])
+        for k, a in enumerate(coefficients):
+            out += a * x ** k
+        return out
+    exact = 8. * u_star ** 2 * sum(a * u_star ** k / ((k + 3.) * (k + 4.))
+                                   for k, a in enumerate(coefficients))
+    for _ in range(5):
+        # refineNVB with to_embed: new nodes take the mean of their edge's ends
+        e2e, e2n, _ = meshgen.number_edges(e, b)
+        u = np.concatenate([u, (u[e2n[:, 0]] + u[e2n[:, 1]]) / 2.])
+        c, e, b = meshgen.refine_nvb(c, e, np.arange(e.shape[0]), b)
+        m = api[0].get_weighted_mass_matrix(coordinates=c, elements=e, current_iterate=u,
+                                            phi=phi,
+                                            cubature_rule=cubature.CubatureRuleEnum.DAYTAYLOR)
+        assert abs(u.dot(m.dot(u)) - exact) < 5e-8 * abs(exact)
