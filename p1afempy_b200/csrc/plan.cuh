@@ -132,8 +132,14 @@ inline Rows rows_of(const p1_plan *p) {
 }
 
 // sm_100a has 256-bit global loads/stores (LDG.E.256 / STG.E.256)
+#ifndef P1_REC_ST
+#define P1_REC_ST "st.global.v4.b64"
+#endif
+#ifndef P1_REC_LD
+#define P1_REC_LD "ld.global.v4.b64"
+#endif
 __device__ __forceinline__ void store_rec(Rec *p, const Rec &r) {
-  asm volatile("st.global.v4.b64 [%0], {%1,%2,%3,%4};"
+  asm volatile(P1_REC_ST " [%0], {%1,%2,%3,%4};"
                :: "l"(p), "l"(((long long)(unsigned)r.pvk << 32) | (unsigned)r.nx),
                   "l"(__double_as_longlong(r.vd)), "l"(__double_as_longlong(r.vn)),
                   "l"(__double_as_longlong(r.vp))
@@ -141,7 +147,7 @@ __device__ __forceinline__ void store_rec(Rec *p, const Rec &r) {
 }
 __device__ __forceinline__ Rec load_rec(const Rec *p) {
   long long a, b, c, d;
-  asm volatile("ld.global.v4.b64 {%0,%1,%2,%3}, [%4];"
+  asm volatile(P1_REC_LD " {%0,%1,%2,%3}, [%4];"
                : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
   Rec r;
   r.nx = (int)(unsigned)(a & 0xffffffffll);
