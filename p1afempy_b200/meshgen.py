@@ -238,3 +238,71 @@ def unit_square_device(k: int, device=None, host_levels: int = 6):
     for _ in range(max(0, k - host_levels)):
         ct, et, bt = refine_uniform_device(ct, et, bt)
     return ct, et, bt
+
+
+def refine_nvb_device(coords, elements, marked, boundaries):
+    """Newest vertex bisection of the MARKED elements on the GPU; same output as
+    ``refine_nvb`` / the reference's ``refineNVB`` (refinement.py:508-718), bit
+    for bit.  coords (N,2) float64, elements (M,3) int32, marked int64 indices,
+    boundaries: list of (K,2) int32 -- all CUDA tensors.
+
+    The edge numbering is ``p1_geometric_data`` (CUDA); closure, numbering of the
+    new nodes and child generation are tensor index arithmetic.  This is mesh
+    infrastructure for device-resident adaptive loops and large benchmark
+    meshes, not part of the assembly path."""
+    import torch
+    from .device import DeviceMesh
+    n, m = coords.shape[0], elements.shape[0]
+    dev = coords.device
+    with DeviceMesh(None, elements, n_nodes=n, check=False) as mesh:
+        e2e, e2n, b2e = mesh.geometric_data(boundaries)
+    split = torch.zeros(e2n.shape[0], dtype=torch.bool, device=dev)
+    split[e2e[marked].reshape(-1)] = True
+    while True:  # closure: a split edge forces the reference edge of its elements
+        flags = split[e2e]
+        need = ~flags[:, 0] & (flags[:, 1] | flags[:, 2])
+        if not bool(need.any()):
+            break
+        split[e2e[need, 0]] = True
+    chosen = torch.nonzero(split).reshape(-1)
+    new_id = torch.zeros(e2n.shape[0], dtype=torch.int64, device=dev)
+    new_id[chosen] = n + torch.arange(chosen.numel(), dtype=torch.int64, device=dev)
+    mid = (coords[e2n[chosen, 0]] + coords[e2n[chosen, 1]]) / 2.
+    new_coords = torch.cat([coords, mid])
+    new_boundaries = []
+    for b, be in zip(boundaries, b2e):
+        if b.numel():
+            nn_b = new_id[be]
+            hit = torch.nonzero(nn_b).reshape(-1)
+            if hit.numel():
+                mids = nn_b[hit].to(torch.int32)
+                b = torch.cat([b[nn_b == 0], torch.stack([b[hit, 0], mids], 1),
+                               torch.stack([mids, b[hit, 1]], 1)]).contiguous()
+        new_boundaries.append(b)
+    nn = new_id[e2e]
+    s0, s1, s2 = nn[:, 0] != 0, nn[:, 1] != 0, nn[:, 2] != 0
+    kinds = {'b1': s0 & ~s1 & ~s2, 'b12': s0 & s1 & ~s2, 'b13': s0 & ~s1 & s2,
+             'b123': s0 & s1 & s2}
+    n_child = torch.ones(m, dtype=torch.int64, device=dev)
+    n_child[kinds['b1']] = 2
+    n_child[kinds['b12']] = 3
+    n_child[kinds['b13']] = 3
+    n_child[kinds['b123']] = 4
+    first = torch.cumsum(n_child, 0) - n_child
+    out = torch.zeros((int(n_child.sum()), 3), dtype=torch.int32, device=dev)
+    keep = ~s0
+    out[first[keep]] = elements[keep]
+    nn = nn.to(torch.int32)
+    v0, v1, v2 = elements[:, 0], elements[:, 1], elements[:, 2]
+    m0, m1, m2 = nn[:, 0], nn[:, 1], nn[:, 2]
+
+    def put(sel, children):
+        base = first[sel]
+        for j, (a, b_, c) in enumerate(children):
+            out[base + j] = torch.stack([a[sel], b_[sel], c[sel]], 1)
+
+    put(kinds['b1'], [(v2, v0, m0), (v1, v2, m0)])
+    put(kinds['b12'], [(v2, v0, m0), (m0, v1, m1), (v2, m0, m1)])
+    put(kinds['b13'], [(m0, v2, m2), (v0, m0, m2), (v1, v2, m0)])
+    put(kinds['b123'], [(m0, v2, m2), (v0, m0, m2), (m0, v1, m1), (v2, m0, m1)])
+    return new_coords, out, new_boundaries

@@ -129,3 +129,23 @@ def test_device_mesh_generator_matches_host():
     assert np.array_equal(ct.cpu().numpy(), c)
     assert np.array_equal(et.cpu().numpy(), e)
     assert np.array_equal(bt[0].cpu().numpy(), b[0])
+
+
+def test_device_refine_nvb_matches_host():
+    """meshgen.refine_nvb_device == meshgen.refine_nvb (== the reference's
+    refineNVB) on randomly marked L-shape and square meshes."""
+    rng = np.random.default_rng(5)
+    for start in (meshgen.l_shape, meshgen.criss_square):
+        c, e, b = start()
+        ct = torch.from_numpy(c).cuda()
+        et = torch.from_numpy(e.astype(np.int32)).cuda()
+        bt = [torch.from_numpy(x.astype(np.int32)).cuda() for x in b]
+        for step in range(9):
+            marked = np.flatnonzero(rng.random(e.shape[0]) < (1.0 if step < 2 else 0.3))
+            c, e, b = meshgen.refine_nvb(c, e, marked, b)
+            ct, et, bt = meshgen.refine_nvb_device(
+                ct, et, torch.from_numpy(marked).cuda(), bt)
+            assert np.array_equal(ct.cpu().numpy(), c)
+            assert np.array_equal(et.cpu().numpy(), e)
+            for x, y in zip(bt, b):
+                assert np.array_equal(x.cpu().numpy(), y)
