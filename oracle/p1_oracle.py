@@ -30,7 +30,7 @@ sort makes the summation order undefined (CSR diagonals).
 from __future__ import annotations
 
 import numpy as np
-from scipy.sparse import coo_matrix, find
+from scipy.sparse import coo_matrix
 
 # --------------------------------------------------------------------------
 # geometry  (reference: p1afempy/mesh.py:10-51)

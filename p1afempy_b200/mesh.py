@@ -2,8 +2,6 @@
 (/root/reference/p1afempy/mesh.py:10-51, 87-161)."""
 from __future__ import annotations
 
-import numpy as np
-
 from .device import DeviceMesh, to_host
 
 __all__ = ['get_area', 'get_directional_vectors', 'provide_geometric_data']

@@ -12,7 +12,7 @@ import numpy as np
 
 import torch
 
-from . import _lib, devarray, options
+from . import devarray, options
 from .cubature import resolve_rule
 from .device import DeviceMesh, to_host
 

@@ -1,6 +1,6 @@
 import sys, os, ctypes as C
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np, torch
+import torch
 from bench import generate_mesh, parse_profile
 from p1afempy_b200 import _lib
 from p1afempy_b200.device import DeviceMesh, context
