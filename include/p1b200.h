@@ -93,6 +93,10 @@ int p1_widen_indices(p1_ctx *ctx, const int32_t *src, int64_t count,
 #define P1_PLAN_KEEP_ELEMENTS 2 /* remember the element of every record: needed */
                             /* to assemble a second operator on the same plan, */
                             /* for load vectors, edge numbering and eta_R      */
+#define P1_PLAN_TOPOLOGY 4  /* p1_plan_create only: 16 bytes per incidence, no     */
+                            /* values and no row pointer -- all that load vectors, */
+                            /* edge numbering and eta_R need.  At most 8 elements  */
+                            /* per node: P1_ERETRY otherwise (use KEEP_ELEMENTS)   */
 int p1_plan_create(p1_ctx *ctx, const int32_t *elements, int64_t n_elements,
                    int64_t n_nodes, int64_t row_begin, int64_t row_end,
                    int flags, void *stream, p1_plan **out);

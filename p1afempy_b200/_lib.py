@@ -25,6 +25,7 @@ P1_ERETRY = -7
 PLAN_DEFAULT = 0
 PLAN_EXACT = 1
 PLAN_KEEP_ELEMENTS = 2
+PLAN_TOPOLOGY = 4
 
 OP_STORED = 0
 OP_STIFFNESS = 1

@@ -299,6 +299,10 @@ extern "C" int p1_assemble_csr(const p1_plan *cplan, int op, const double *coord
   P1_REQUIRE(cplan, "null plan");
   P1_REQUIRE(data || cplan->nnz == 0, "null data");
   p1_plan *plan = const_cast<p1_plan *>(cplan);
+  if (plan->topo) {
+    set_error("p1_assemble_csr: a P1_PLAN_TOPOLOGY plan has no records to assemble");
+    return P1_EINVAL;
+  }
   p1_ctx *ctx = plan->ctx;
   DeviceGuard guard(ctx->device);
   cudaStream_t s = (cudaStream_t)stream;

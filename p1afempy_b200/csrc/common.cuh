@@ -42,6 +42,7 @@ enum : int {
   FLAG_NONMANIFOLD = 2,    // directed edge appears twice
   FLAG_BOUNDARY_MISS = 4,  // boundary edge not found among element edges
   FLAG_UNCOVERED = 8,      // boundary half-edge not listed in any boundary
+  FLAG_OVERFLOW = 32,      // topology-only plan: a node has more than 8 incident elements
   FLAG_RETRY = 16,         // a row contradicted the closed-fan shortcut: re-plan exactly
 };
 

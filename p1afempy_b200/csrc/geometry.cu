@@ -26,22 +26,34 @@ twin_kernel(int n_nodes, Rows rows, int *__restrict__ twin, int *__restrict__ fl
   if (a >= n_nodes) return;
   const int deg = rows.deg(a);
   if (deg == 0) return;
-  const Rec *rec = rows.ptr(a, deg);
-  const int *code = rows.elem(a, deg);
   int open_edges = 0;
   bool nonmanifold = false;
+  const Rec *rec = rows.topo ? nullptr : rows.ptr(a, deg);
+  const int *code = rows.topo ? nullptr : rows.elem(a, deg);
   if (deg <= GROUP) {
     // the row's records and element codes in registers, all pairs unrolled
     int nx[GROUP], pv[GROUP], cd[GROUP];
-    const int4 c0 = __ldg(reinterpret_cast<const int4 *>(code));
-    const int4 c1 = __ldg(reinterpret_cast<const int4 *>(code) + 1);
-    const int cc[GROUP] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+    if (rows.topo) {
+      const int4 *slot = rows.topo + (int64_t)a * GROUP;
 #pragma unroll
-    for (int i = 0; i < GROUP; ++i) {
-      nx[i] = -1 - i; pv[i] = -20 - i; cd[i] = cc[i];
-      if (i < deg) {
-        const Rec r = load_rec(rec + i);
-        nx[i] = r.nx; pv[i] = rec_prev(r);
+      for (int i = 0; i < GROUP; ++i) {
+        nx[i] = -1 - i; pv[i] = -20 - i; cd[i] = 0;
+        if (i < deg) {
+          const int4 t = __ldg(slot + i);
+          nx[i] = t.x; pv[i] = t.y & NODE_MASK; cd[i] = t.z;
+        }
+      }
+    } else {
+      const int4 c0 = __ldg(reinterpret_cast<const int4 *>(code));
+      const int4 c1 = __ldg(reinterpret_cast<const int4 *>(code) + 1);
+      const int cc[GROUP] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+#pragma unroll
+      for (int i = 0; i < GROUP; ++i) {
+        nx[i] = -1 - i; pv[i] = -20 - i; cd[i] = cc[i];
+        if (i < deg) {
+          const Rec r = load_rec(rec + i);
+          nx[i] = r.nx; pv[i] = rec_prev(r);
+        }
       }
     }
 #pragma unroll
@@ -155,6 +167,12 @@ element_edges_kernel(const int *__restrict__ elements, int64_t M,
 __device__ __forceinline__ int64_t locate_halfedge(int b0, int b1,
                                                    const Rows &rows) {
   const int end = rows.deg(b0);
+  if (rows.topo) {
+    const int4 *slot = rows.topo + (int64_t)b0 * GROUP;
+    for (int i = 0; i < end && i < GROUP; ++i)
+      if (slot[i].x == b1) return (int64_t)halfedge_of(slot[i].z);
+    return -1;
+  }
   const Rec *rec = rows.ptr(b0, end);
   const int *rec_elem = rows.elem(b0, end);
   for (int i = 0; i < end; ++i)

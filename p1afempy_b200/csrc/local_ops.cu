@@ -335,11 +335,19 @@ gather_nodes_kernel(int n_own, Rows rows, const double *__restrict__ L,
   const int deg = rows.deg(a);
   double sum = 0.;
   if (deg == 0) { b[a] = sum; return; }
-  const int *code = rows.elem(a, deg);
+  const int *code = rows.topo ? nullptr : rows.elem(a, deg);
   if (deg <= GROUP) {
-    const int4 c0 = __ldg(reinterpret_cast<const int4 *>(code));
-    const int4 c1 = __ldg(reinterpret_cast<const int4 *>(code) + 1);
-    const int cc[GROUP] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+    int cc[GROUP];
+    if (rows.topo) {
+      const int4 *slot = rows.topo + (int64_t)a * GROUP;
+#pragma unroll
+      for (int i = 0; i < GROUP; ++i) cc[i] = i < deg ? __ldg(slot + i).z : 0;
+    } else {
+      const int4 c0 = __ldg(reinterpret_cast<const int4 *>(code));
+      const int4 c1 = __ldg(reinterpret_cast<const int4 *>(code) + 1);
+      cc[0] = c0.x; cc[1] = c0.y; cc[2] = c0.z; cc[3] = c0.w;
+      cc[4] = c1.x; cc[5] = c1.y; cc[6] = c1.z; cc[7] = c1.w;
+    }
     unsigned key[GROUP];
 #pragma unroll
     for (int i = 0; i < GROUP; ++i)

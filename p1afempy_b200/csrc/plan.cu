@@ -40,14 +40,30 @@ constexpr int SC_THREADS = P1_SCATTER_THREADS;  // scatter block size
 //                      whose length is not 1 + #records (open fans = boundary
 //                      nodes).  Verified row by row when the matrix is filled.
 //   OVERFLOW == true : only rows with more than 8 records; compact storage.
-template <class V, bool OVERFLOW>
+// TOPO: topology-only plan -- one 16-byte slot {next, prev|k, element code, 0}
+// instead of the 32-byte record (and no separate element array)
+template <bool TOPO>
+__device__ __forceinline__ void store_slot(Rec *rec, int *rec_elem, int64_t pos, int nx,
+                                           int pvk, const double (&v)[3], int code) {
+  if constexpr (TOPO) {
+    reinterpret_cast<int4 *>(rec)[pos] = make_int4(nx, pvk, code, 0);
+  } else {
+    Rec r;
+    r.nx = nx; r.pvk = pvk;
+    r.vd = v[0]; r.vn = v[1]; r.vp = v[2];
+    store_rec(rec + pos, r);
+    if (rec_elem) rec_elem[pos] = code;
+  }
+}
+
+template <class V, bool OVERFLOW, bool TOPO>
 __device__ __forceinline__ void scatter_element(int64_t t, const int (&e)[3], int N,
                                                 const Own &own,
                                                 unsigned long long *__restrict__ acc,
                                                 Rec *__restrict__ rec,
                                                 int *__restrict__ rec_elem,
                                                 int *__restrict__ cursor, const V &values,
-                                                int &mx, bool &bad) {
+                                                int &mx, bool &bad, int *flags) {
   if ((unsigned)e[0] >= (unsigned)N || (unsigned)e[1] >= (unsigned)N ||
       (unsigned)e[2] >= (unsigned)N) {
     bad = true;
@@ -82,15 +98,14 @@ __device__ __forceinline__ void scatter_element(int64_t t, const int (&e)[3], in
         const unsigned d = mix32((unsigned)nx) - mix32((unsigned)pv);
         const unsigned slot =
             (unsigned)atomicAdd(acc + a, ((unsigned long long)d << 32) + 1ull);
-        if (slot >= (unsigned)GROUP) continue;
+        if (slot >= (unsigned)GROUP) {
+          if (TOPO) atomicOr(flags, FLAG_OVERFLOW);
+          continue;
+        }
         pos = (int64_t)a * GROUP + slot;
       }
-      Rec r;
-      r.nx = nx;
-      r.pvk = pv | (k << NODE_BITS);
-      r.vd = v[k][0]; r.vn = v[k][1]; r.vp = v[k][2];
-      store_rec(rec + pos, r);
-      if (rec_elem) rec_elem[pos] = (int)((t << 2) | k);
+      store_slot<TOPO>(rec, rec_elem, pos, nx, pv | (k << NODE_BITS), v[k],
+                       (int)((t << 2) | k));
     }
 }
 
@@ -98,13 +113,13 @@ __device__ __forceinline__ void scatter_element(int64_t t, const int (&e)[3], in
 // vertices, so the 6 vertex references are grouped in registers -- one atomic
 // per DISTINCT node (typically 4 instead of 6).  The kernel is bound by LSU
 // operations per lane; the 15 comparisons are free.
-template <class V>
+template <class V, bool TOPO>
 __device__ __forceinline__ void scatter_pair(int64_t t, const int (&id)[6], int N,
                                              const Own &own,
                                              unsigned long long *__restrict__ acc,
                                              Rec *__restrict__ rec,
                                              int *__restrict__ rec_elem, const V &values,
-                                             int &mx, bool &bad) {
+                                             int &mx, bool &bad, int *flags) {
   bool valid[2], touched[2], mine[6];
   int row[6];
 #pragma unroll
@@ -169,14 +184,14 @@ __device__ __forceinline__ void scatter_pair(int64_t t, const int (&id)[6], int 
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
       const int i = 3 * j + k;
-      if (slot[i] >= (unsigned)GROUP) continue;
+      if (slot[i] >= (unsigned)GROUP) {
+        if (TOPO && mine[i]) atomicOr(flags, FLAG_OVERFLOW);
+        continue;
+      }
       const int64_t pos = (int64_t)row[i] * GROUP + slot[i];
-      Rec rc;
-      rc.nx = e[k == 2 ? 0 : k + 1];
-      rc.pvk = e[k == 0 ? 2 : k - 1] | (k << NODE_BITS);
-      rc.vd = v[k][0]; rc.vn = v[k][1]; rc.vp = v[k][2];
-      store_rec(rec + pos, rc);
-      if (rec_elem) rec_elem[pos] = (int)(((t + j) << 2) | k);
+      store_slot<TOPO>(rec, rec_elem, pos, e[k == 2 ? 0 : k + 1],
+                       e[k == 0 ? 2 : k - 1] | (k << NODE_BITS), v[k],
+                       (int)(((t + j) << 2) | k));
     }
   }
 }
@@ -192,7 +207,7 @@ __device__ __forceinline__ void scatter_pair(int64_t t, const int (&id)[6], int 
 // (register allocation of the PAIRS form, measured at 64M: 80 registers 2.20 ms --
 // what ptxas picks without a min-blocks hint --, 99 registers 2.74 ms, 64 with
 // spills 2.35 ms, 48 with spills 2.82 ms)
-template <class V, bool OVERFLOW, bool PAIRS>
+template <class V, bool OVERFLOW, bool PAIRS, bool TOPO>
 __global__ void __launch_bounds__(SC_THREADS)
 scatter_kernel(const int *__restrict__ elements, int64_t M, int N, Own own, int vec,
                unsigned long long *__restrict__ acc, Rec *__restrict__ rec,
@@ -208,21 +223,21 @@ scatter_kernel(const int *__restrict__ elements, int64_t M, int N, Own own, int 
     const int4 p = __ldg(e4 + 3 * g), q = __ldg(e4 + 3 * g + 1), r = __ldg(e4 + 3 * g + 2);
     if constexpr (!OVERFLOW && PAIRS) {
       const int ab[6] = {p.x, p.y, p.z, p.w, q.x, q.y}, cd[6] = {q.z, q.w, r.x, r.y, r.z, r.w};
-      scatter_pair<V>(4 * g, ab, N, own, acc, rec, rec_elem, values, mx, bad);
-      scatter_pair<V>(4 * g + 2, cd, N, own, acc, rec, rec_elem, values, mx, bad);
+      scatter_pair<V, TOPO>(4 * g, ab, N, own, acc, rec, rec_elem, values, mx, bad, flags);
+      scatter_pair<V, TOPO>(4 * g + 2, cd, N, own, acc, rec, rec_elem, values, mx, bad, flags);
       continue;
     }
     const int ea[3] = {p.x, p.y, p.z}, eb[3] = {p.w, q.x, q.y}, ec[3] = {q.z, q.w, r.x},
               ed[3] = {r.y, r.z, r.w};
-    scatter_element<V, OVERFLOW>(4 * g, ea, N, own, acc, rec, rec_elem, cursor, values, mx, bad);
-    scatter_element<V, OVERFLOW>(4 * g + 1, eb, N, own, acc, rec, rec_elem, cursor, values, mx, bad);
-    scatter_element<V, OVERFLOW>(4 * g + 2, ec, N, own, acc, rec, rec_elem, cursor, values, mx, bad);
-    scatter_element<V, OVERFLOW>(4 * g + 3, ed, N, own, acc, rec, rec_elem, cursor, values, mx, bad);
+    scatter_element<V, OVERFLOW, TOPO>(4 * g, ea, N, own, acc, rec, rec_elem, cursor, values, mx, bad, flags);
+    scatter_element<V, OVERFLOW, TOPO>(4 * g + 1, eb, N, own, acc, rec, rec_elem, cursor, values, mx, bad, flags);
+    scatter_element<V, OVERFLOW, TOPO>(4 * g + 2, ec, N, own, acc, rec, rec_elem, cursor, values, mx, bad, flags);
+    scatter_element<V, OVERFLOW, TOPO>(4 * g + 3, ed, N, own, acc, rec, rec_elem, cursor, values, mx, bad, flags);
   }
   for (int64_t t = 4 * quads + tid; t < M; t += stride) {
     const int e[3] = {__ldg(elements + 3 * t), __ldg(elements + 3 * t + 1),
                       __ldg(elements + 3 * t + 2)};
-    scatter_element<V, OVERFLOW>(t, e, N, own, acc, rec, rec_elem, cursor, values, mx, bad);
+    scatter_element<V, OVERFLOW, TOPO>(t, e, N, own, acc, rec, rec_elem, cursor, values, mx, bad, flags);
   }
   if (!OVERFLOW) {
     mx = __reduce_max_sync(0xffffffffu, mx);
@@ -236,11 +251,24 @@ static void launch_one(bool pairs, unsigned grid, cudaStream_t s, const int *ele
                        int N, Own own, int vec, unsigned long long *acc, Rec *rec,
                        int *rec_elem, int *cursor, V values, int *fl) {
   if (pairs && !OVERFLOW)
-    scatter_kernel<V, OVERFLOW, true><<<grid, SC_THREADS, 0, s>>>(
+    scatter_kernel<V, OVERFLOW, true, false><<<grid, SC_THREADS, 0, s>>>(
         elements, M, N, own, vec, acc, rec, rec_elem, cursor, values, fl);
   else
-    scatter_kernel<V, OVERFLOW, false><<<grid, SC_THREADS, 0, s>>>(
+    scatter_kernel<V, OVERFLOW, false, false><<<grid, SC_THREADS, 0, s>>>(
         elements, M, N, own, vec, acc, rec, rec_elem, cursor, values, fl);
+}
+
+static void launch_scatter_topo(p1_ctx *ctx, unsigned grid, cudaStream_t s, const int *elements,
+                                int64_t M, int N, Own own, unsigned long long *acc, int4 *topo) {
+  const int vec = ((uintptr_t)elements & 15) == 0;
+  const bool pairs = own.world == 1 && own.re - own.rb == N;
+  Rec *slots = reinterpret_cast<Rec *>(topo);
+  if (pairs)
+    scatter_kernel<NoValues, false, true, true><<<grid, SC_THREADS, 0, s>>>(
+        elements, M, N, own, vec, acc, slots, nullptr, nullptr, NoValues{}, ctx->d_flags);
+  else
+    scatter_kernel<NoValues, false, false, true><<<grid, SC_THREADS, 0, s>>>(
+        elements, M, N, own, vec, acc, slots, nullptr, nullptr, NoValues{}, ctx->d_flags);
 }
 
 template <bool OVERFLOW>
@@ -431,8 +459,8 @@ rowlen_big_kernel(const int *__restrict__ big_rows, Own own, Rows rows,
 }
 
 int require_elements(const p1_plan *p, const char *who) {
-  if (p->rec_elem) return P1_OK;
-  set_error("%s needs a plan created with P1_PLAN_KEEP_ELEMENTS", who);
+  if (p->rec_elem || p->topo) return P1_OK;
+  set_error("%s needs a plan created with P1_PLAN_KEEP_ELEMENTS or P1_PLAN_TOPOLOGY", who);
   return P1_EINVAL;
 }
 
@@ -577,6 +605,33 @@ static int plan_build(p1_ctx *ctx, const int32_t *elements, int64_t n_elements,
       cudaMemsetAsync(ctx->d_flags + 1, 0xff, sizeof(int), s) != cudaSuccess)
     return cuda_fail("memset");
   if ((rc = pool_alloc(ctx, &p->acc, (size_t)n_own + 1, s))) return fail(rc);
+  if (flags & P1_PLAN_TOPOLOGY) {
+    // edge numbering / eta_R / load vectors: one 16-byte slot per incidence, no values,
+    // no row pointer, one synchronisation
+    P1_REQUIRE(op == 0, "a topology-only plan carries no operator");
+    if ((rc = pool_alloc(ctx, &p->topo, (size_t)n_own * GROUP, s))) return fail(rc);
+    cudaMemsetAsync(p->acc, 0, ((size_t)n_own + 1) * sizeof(unsigned long long), s);
+    const unsigned tg = min(grid_for(M, THREADS), (unsigned)(ctx->sm_count * 32));
+    prof_begin(ctx, "scatter", s);
+    launch_scatter_topo(ctx, tg, s, elements, M, N, own, p->acc, p->topo);
+    prof_end(ctx, s);
+    cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, 8 * sizeof(int), cudaMemcpyDeviceToHost, s);
+    if (cudaStreamSynchronize(s) != cudaSuccess || cudaGetLastError() != cudaSuccess)
+      return cuda_fail("scatter");
+    if (ctx->h_flags[0] & FLAG_INDEX_RANGE) {
+      set_error("p1_plan_create: element index out of range [0, %lld)", (long long)n_nodes);
+      return fail(P1_EINDEX);
+    }
+    if (ctx->h_flags[0] & FLAG_OVERFLOW) {
+      set_error("p1_plan_create: P1_PLAN_TOPOLOGY holds at most 8 elements per node; "
+                "use P1_PLAN_KEEP_ELEMENTS for this mesh");
+      return fail(P1_ERETRY);
+    }
+    p->max_index = ctx->h_flags[1];
+    p->nnz = 0;
+    *out = p;
+    return P1_OK;
+  }
   if ((rc = pool_alloc(ctx, &p->rec, (size_t)n_own * GROUP, s))) return fail(rc);
   if (keep && (rc = pool_alloc(ctx, &p->rec_elem, (size_t)n_own * GROUP, s))) return fail(rc);
   if ((rc = pool_alloc(ctx, &p->indptr, (size_t)n_own + 1, s))) return fail(rc);
@@ -739,7 +794,7 @@ extern "C" int64_t p1_plan_rows(const p1_plan *p) { return p ? p->n_own : -1; }
 extern "C" int p1_plan_destroy(p1_plan *p) {
   if (!p) return P1_OK;
   DeviceGuard guard(p->ctx->device);
-  void *blocks[] = {p->acc, p->rec, p->rec_elem, p->ovf_off, p->ovf_rec, p->ovf_elem,
+  void *blocks[] = {p->acc, p->rec, p->rec_elem, p->topo, p->ovf_off, p->ovf_rec, p->ovf_elem,
                     p->indptr, p->slow_rows, p->big_rows, p->big_first, p->twin};
   for (void *b : blocks) pool_free(p->ctx, b, p->stream);
   delete p;

@@ -74,6 +74,9 @@ struct p1_plan {
   p1::Rec *rec;        // 8 * n_own
   int *rec_elem;       // 8 * n_own: (element << 2) | k of the record
                        // (P1_PLAN_KEEP_ELEMENTS) or null
+  int4 *topo;          // P1_PLAN_TOPOLOGY: 8 * n_own slots {next, prev | k<<29, (element<<2)|k, 0}
+                       // INSTEAD of rec / rec_elem / indptr (edge numbering, eta_R, load
+                       // vectors need no values and no row pointer)
   int *ovf_off;        // n_own+1 (only when some row overflows) or null
   p1::Rec *ovf_rec;    // n_ovf
   int *ovf_elem;       // n_ovf or null
@@ -119,6 +122,7 @@ struct Rows {
   const int *ovf_off;
   Rec *ovf_rec;
   int *ovf_elem;
+  const int4 *topo;  // topology-only plans: everything in one 16-byte slot
   __device__ __forceinline__ int deg(int a) const { return (int)(unsigned)acc[a]; }
   __device__ __forceinline__ Rec *ptr(int a, int deg) const {
     return deg <= 8 ? rec + (int64_t)a * 8 : ovf_rec + ovf_off[a];
@@ -128,7 +132,7 @@ struct Rows {
   }
 };
 inline Rows rows_of(const p1_plan *p) {
-  return Rows{p->acc, p->rec, p->rec_elem, p->ovf_off, p->ovf_rec, p->ovf_elem};
+  return Rows{p->acc, p->rec, p->rec_elem, p->ovf_off, p->ovf_rec, p->ovf_elem, p->topo};
 }
 
 // sm_100a has 256-bit global loads/stores (LDG.E.256 / STG.E.256)

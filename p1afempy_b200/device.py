@@ -162,6 +162,8 @@ class DeviceMesh:
         self.reuse = bool(reuse)
         self._plan = None
         self._plan_keeps_elements = False
+        self._plan_topology = False
+        self._topology_fits = True      # until a node with > 8 elements shows up
         self._exact = False
         self.nnz = None
         self.max_index = None
@@ -189,9 +191,10 @@ class DeviceMesh:
         return ((_lib.PLAN_EXACT if self._exact else 0)
                 | (_lib.PLAN_KEEP_ELEMENTS if keep else 0))
 
-    def _adopt(self, handle, keep):
+    def _adopt(self, handle, keep, topology=False):
         self._plan = handle
         self._plan_keeps_elements = keep
+        self._plan_topology = topology
         self.n_rows = int(self._lib.p1_plan_rows(handle))
         nnz, mx = C.c_int64(), C.c_int64()
         _lib.check(self._lib.p1_plan_info(handle, C.byref(nnz), C.byref(mx), None, None))
@@ -222,8 +225,22 @@ class DeviceMesh:
     def plan(self):
         """Symbolic plan that remembers the element of every record (what load
         vectors, edge numbering and eta_R need)."""
-        if self._plan is not None and not self._plan_keeps_elements:
+        if self._plan is not None and not (self._plan_keeps_elements or self._plan_topology):
             self.close()
+        if self._plan is None and not self.reuse and self._topology_fits \
+                and self.interleave is None:
+            # no matrix will be refreshed from this plan: 16 bytes per incidence
+            # instead of 36, no row pointer (P1_PLAN_TOPOLOGY)
+            handle = C.c_void_p()
+            rc = self._lib.p1_plan_create(
+                self.ctx, _ptr(self.elements), self.n_elements, self.n_nodes,
+                self.rows[0], self.rows[1], _lib.PLAN_TOPOLOGY, _stream(self.device),
+                C.byref(handle))
+            if rc == _lib.P1_ERETRY:
+                self._topology_fits = False     # a node with more than 8 elements
+            else:
+                _lib.check(rc)
+                self._adopt(handle, False, True)
         if self._plan is None:
             self._create(True, 0, None)
         return self._plan

@@ -492,6 +492,54 @@ def test_device_resident_api_and_plan_reuse():
         assert np.array_equal(b.cpu().numpy(), orc.load_vector_midpoint(pts, e, H.f_load))
 
 
+def test_topology_plan_matches_element_keeping_plan():
+    """P1_PLAN_TOPOLOGY (16-byte slots, no values, no row pointer) serves load
+    vectors, edge numbering and eta_R with the same bits as the element-keeping
+    plan; a mesh with a node of more than 8 elements falls back to that plan;
+    asking such a plan for a matrix is an error at the C ABI."""
+    import ctypes as C
+    import torch
+    from p1afempy_b200 import _lib
+    from p1afempy_b200.device import DeviceMesh
+    pts, e, bnd = H.perturbed_square(4)
+    bnds = [np.asarray(b, dtype=np.int64) for b in bnd]
+    ct, et = torch.from_numpy(pts).cuda(), torch.from_numpy(e.astype(np.int32)).cuda()
+    bt = [torch.from_numpy(b.astype(np.int32)).cuda() for b in bnds]
+    out = {}
+    for reuse in (False, True):
+        with DeviceMesh(ct, et, reuse=reuse) as mesh:
+            fc = torch.from_numpy(H.f_load(mesh.centroids().cpu().numpy())).cuda()
+            b = mesh.load_vector_midpoint(fc)
+            assert mesh._plan_topology == (not reuse)
+            gd = mesh.geometric_data(bt)
+            out[reuse] = [b.cpu().numpy()] + [np.asarray(x.cpu().numpy()) for x in gd[:2]] + \
+                         [x.cpu().numpy() for x in gd[2]]
+            if not reuse:
+                topo = mesh._plan
+                rc = mesh._lib.p1_assemble_csr(topo, _lib.OP_STIFFNESS, None, None, None, None,
+                                               None, None)
+                assert rc == _lib.P1_EINVAL
+                mesh.stiffness_csr()            # replaces the plan, still works
+                assert not mesh._plan_topology
+    for a, b in zip(out[False], out[True]):
+        assert np.array_equal(a, b)
+    assert np.array_equal(out[False][0], orc.load_vector_midpoint(pts, e, H.f_load))
+    o2e, o2n, ob2e = orc.geometric_data(e, bnds)
+    assert np.array_equal(out[False][1], o2e) and np.array_equal(out[False][2], o2n)
+    for got, want in zip(out[False][3:], ob2e):
+        assert np.array_equal(got, want)
+    # fan with 12 elements around the centre: no room in 8 slots
+    n = 12
+    ang = 2 * np.pi * np.arange(n) / n
+    fp = np.vstack([[0., 0.], np.c_[np.cos(ang), np.sin(ang)]])
+    fe = np.array([[0, 1 + i, 1 + (i + 1) % n] for i in range(n)], dtype=np.int64)
+    with DeviceMesh(torch.from_numpy(fp).cuda(), torch.from_numpy(fe.astype(np.int32)).cuda()) as mesh:
+        fc = torch.from_numpy(H.f_load(mesh.centroids().cpu().numpy())).cuda()
+        b = mesh.load_vector_midpoint(fc)
+        assert not mesh._plan_topology and not mesh._topology_fits
+        assert np.array_equal(b.cpu().numpy(), orc.load_vector_midpoint(fp, fe, H.f_load))
+
+
 def test_empty_and_tiny_inputs(api):
     """Empty element arrays (the reference: scipy cannot infer a shape ->
     ValueError; explicit-shape builders return empty matrices) and a single
