@@ -242,6 +242,23 @@ int p1_integrate_quadrature(p1_ctx *ctx, const double *coords, const int32_t *el
 int p1_load_vector_midpoint(const p1_plan *plan, const double *coords,
                             const double *f_centroid, double *b, void *stream);
 
+/* Cold load vectors without a plan (nothing is cached between calls, like the
+ * reference's stateless get_right_hand_side*, solvers.py:380-426, 540-598): the
+ * quadrature sum / the midpoint share of every element is computed by the thread
+ * that scans the element and delivered to the element's three nodes as (element
+ * code, value); each node then adds its values in the reference's bincount order.
+ * Bit-identical to p1_load_vector / p1_load_vector_midpoint.  fq: [n_qp x M]
+ * values of f at the quadrature points (p1_quadrature_points).  P1_ERETRY when a
+ * node has more than 8 elements: use a plan and the functions above. */
+int p1_load_vector_direct(p1_ctx *ctx, const int32_t *elements, int64_t n_elements,
+                          int64_t n_nodes, const double *coords, const double *fq,
+                          const double *weights_host, const double *points_host,
+                          int n_qp, double *b, void *stream);
+int p1_load_vector_midpoint_direct(p1_ctx *ctx, const int32_t *elements,
+                                   int64_t n_elements, int64_t n_nodes,
+                                   const double *coords, const double *f_centroid,
+                                   double *b, void *stream);
+
 /* mesh.py:87-161 provide_geometric_data.  boundary_nodes: concatenated
  * (K x 2) int32 rows of all boundaries; boundary_offsets_host: n_boundaries+1
  * row offsets (host).  Outputs: element2edges (M x 3), edge2nodes (E x 2,

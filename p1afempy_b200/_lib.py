@@ -84,6 +84,8 @@ PROTOTYPES = {
                                 _vp],
     'p1_load_vector': [_vp, _vp, _vp, _vp, _vp, _int, _vp, _vp],
     'p1_load_vector_midpoint': [_vp, _vp, _vp, _vp, _vp],
+    'p1_load_vector_direct': [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _int, _vp, _vp],
+    'p1_load_vector_midpoint_direct': [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp],
     'p1_geometric_data': [_vp, _vp, _vp, _int, _vp, _vp, _vp, C.POINTER(_i64),
                           _vp],
     'p1_eta_r': [_vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp],

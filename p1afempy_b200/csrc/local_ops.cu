@@ -13,6 +13,16 @@
 namespace p1 {
 
 constexpr int THREADS = 256;
+// quadrature points fetched together by the streaming kernels: a thread keeps QB
+// loads of the [n_qp x M] arrays in flight (local loads at 64M: 2.70 ms with 1, 2.37 with 4,
+// 3.14 with 8)
+#ifndef P1_QB
+#define P1_QB 4
+#endif
+constexpr int QB = P1_QB;
+#ifndef P1_INTEGRATE_BLOCKS
+#define P1_INTEGRATE_BLOCKS 8192
+#endif
 
 struct Verts {
   int e0, e1, e2;
@@ -165,13 +175,26 @@ local_general_kernel(const double2 *__restrict__ coords, const int *__restrict__
     const double alpha = dz2y, beta = -dz2x, gamma = -dz1y, delta = dz1x;
     const double areas = 0.5 * (dz1x * dz2y - dz1y * dz2x);
     double a = 0., b = 0., c = 0., d = 0.;
-    for (int q = 0; q < n_qp; ++q) {
-      const double w = weights[q];
-      const int64_t i = (int64_t)q * M + t;
-      a += w * __ldg(a11q + i);
-      b += w * __ldg(a12q + i);
-      c += w * __ldg(a21q + i);
-      d += w * __ldg(a22q + i);
+    for (int q0 = 0; q0 < n_qp; q0 += 4) {  // 16 loads in flight
+      double v11[4], v12[4], v21[4], v22[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int64_t i = (int64_t)(q0 + u) * M + t;
+        const bool in = q0 + u < n_qp;
+        v11[u] = in ? __ldg(a11q + i) : 0.;
+        v12[u] = in ? __ldg(a12q + i) : 0.;
+        v21[u] = in ? __ldg(a21q + i) : 0.;
+        v22[u] = in ? __ldg(a22q + i) : 0.;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (q0 + u < n_qp) {
+          const double w = weights[q0 + u];
+          a += w * v11[u];
+          b += w * v12[u];
+          c += w * v21[u];
+          d += w * v22[u];
+        }
     }
     const double pre = -1. / (2. * areas);
     const double b11 = pre * (a * alpha * alpha + b * beta * alpha +
@@ -210,14 +233,22 @@ local_wmass_kernel(const double2 *__restrict__ coords, const int *__restrict__ e
     double m[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) m[k] = 0.;
-    for (int q = 0; q < n_qp; ++q) {
-      const double eta = points[q].x, xi = points[q].y;
-      const double h[3] = {1 - eta - xi, eta, xi};
-      const double base = 2 * areas * weights[q] * __ldg(phiq + (int64_t)q * M + t);
+    for (int q0 = 0; q0 < n_qp; q0 += QB) {
+      double fv[QB];
 #pragma unroll
-      for (int k = 0; k < 3; ++k)
+      for (int u = 0; u < QB; ++u)
+        fv[u] = q0 + u < n_qp ? __ldg(phiq + (int64_t)(q0 + u) * M + t) : 0.;
 #pragma unroll
-        for (int l = 0; l < 3; ++l) m[3 * k + l] += base * h[k] * h[l];
+      for (int u = 0; u < QB; ++u)
+        if (q0 + u < n_qp) {
+          const double eta = points[q0 + u].x, xi = points[q0 + u].y;
+          const double h[3] = {1 - eta - xi, eta, xi};
+          const double base = 2 * areas * weights[q0 + u] * fv[u];
+#pragma unroll
+          for (int k = 0; k < 3; ++k)
+#pragma unroll
+            for (int l = 0; l < 3; ++l) m[3 * k + l] += base * h[k] * h[l];
+        }
     }
     double *out = local + 9 * t;
 #pragma unroll
@@ -238,13 +269,21 @@ local_load_kernel(const double2 *__restrict__ coords, const int *__restrict__ el
     const double qx = v.z2.x - v.z0.x, qy = v.z2.y - v.z0.y;
     const double area = 0.5 * (px * qy - py * qx);
     double l0 = 0., l1 = 0., l2 = 0.;
-    for (int q = 0; q < n_qp; ++q) {
-      const double eta = points[q].x, xi = points[q].y;
-      const double f = __ldg(fq + (int64_t)q * M + t);
-      const double s = 2. * weights[q] * area;
-      l0 += s * (1. - eta - xi) * f;
-      l1 += s * eta * f;
-      l2 += s * xi * f;
+    // QB points at a time in flight; the sums stay in the reference's order
+    for (int q0 = 0; q0 < n_qp; q0 += QB) {
+      double fv[QB];
+#pragma unroll
+      for (int u = 0; u < QB; ++u)
+        fv[u] = q0 + u < n_qp ? __ldg(fq + (int64_t)(q0 + u) * M + t) : 0.;
+#pragma unroll
+      for (int u = 0; u < QB; ++u)
+        if (q0 + u < n_qp) {
+          const double eta = points[q0 + u].x, xi = points[q0 + u].y;
+          const double s = 2. * weights[q0 + u] * area;
+          l0 += s * (1. - eta - xi) * fv[u];
+          l1 += s * eta * fv[u];
+          l2 += s * xi * fv[u];
+        }
     }
     L[3 * t] = l0; L[3 * t + 1] = l1; L[3 * t + 2] = l2;
   }
@@ -287,8 +326,15 @@ integrate_kernel(const double2 *__restrict__ coords, const int *__restrict__ ele
     const double qx = v.z2.x - v.z0.x, qy = v.z2.y - v.z0.y;
     const double area = 0.5 * (px * qy - py * qx);
     double l = 0.;
-    for (int q = 0; q < n_qp; ++q)
-      l += weights[q] * __ldg(fq + (int64_t)q * M + t) * 2. * area;
+    for (int q0 = 0; q0 < n_qp; q0 += QB) {
+      double fv[QB];
+#pragma unroll
+      for (int u = 0; u < QB; ++u)
+        fv[u] = q0 + u < n_qp ? __ldg(fq + (int64_t)(q0 + u) * M + t) : 0.;
+#pragma unroll
+      for (int u = 0; u < QB; ++u)
+        if (q0 + u < n_qp) l += weights[q0 + u] * fv[u] * 2. * area;
+    }
     acc += l;
   }
   red[threadIdx.x] = acc;
@@ -603,8 +649,9 @@ extern "C" int p1_local_general_stiffness(p1_ctx *ctx, const double *coords,
   cudaStream_t s = (cudaStream_t)stream;
   double *w = nullptr;
   P1_TRY(upload_small(ctx, &w, weights_host, (size_t)n_qp, s));
-  local_general_kernel<<<egrid(ctx, M), THREADS, 0, s>>>(
-      (const double2 *)coords, elements, M, a11q, a12q, a21q, a22q, w, n_qp, local);
+  P1_TIMED(ctx, "local_general", s,
+           (local_general_kernel<<<egrid(ctx, M), THREADS, 0, s>>>(
+               (const double2 *)coords, elements, M, a11q, a12q, a21q, a22q, w, n_qp, local)));
   pool_free(ctx, w, s);
   P1_CUDA(cudaGetLastError());
   return P1_OK;
@@ -623,8 +670,9 @@ extern "C" int p1_local_weighted_mass(p1_ctx *ctx, const double *coords,
   double *w = nullptr, *pts = nullptr;
   P1_TRY(upload_small(ctx, &w, weights_host, (size_t)n_qp, s));
   P1_TRY(upload_small(ctx, &pts, points_host, (size_t)2 * n_qp, s));
-  local_wmass_kernel<<<egrid(ctx, M), THREADS, 0, s>>>(
-      (const double2 *)coords, elements, M, phiq, w, (const double2 *)pts, n_qp, local);
+  P1_TIMED(ctx, "local_wmass", s,
+           (local_wmass_kernel<<<egrid(ctx, M), THREADS, 0, s>>>(
+               (const double2 *)coords, elements, M, phiq, w, (const double2 *)pts, n_qp, local)));
   pool_free(ctx, w, s);
   pool_free(ctx, pts, s);
   P1_CUDA(cudaGetLastError());
@@ -641,12 +689,15 @@ extern "C" int p1_integrate_quadrature(p1_ctx *ctx, const double *coords,
   *result_host = 0.;
   if (M == 0) return P1_OK;
   cudaStream_t s = (cudaStream_t)stream;
-  const int blocks = 1024;  // fixed: the summation tree must not depend on the device
+  // fixed: the summation tree must not depend on the device (8192 slices: the last wave
+  // of blocks is short on any SM count; 1024 left a third of the B200 idle for half the time)
+  const int blocks = P1_INTEGRATE_BLOCKS;
   double *w = nullptr, *partial = nullptr;
   P1_TRY(upload_small(ctx, &w, weights_host, (size_t)n_qp, s));
   P1_TRY(pool_alloc(ctx, &partial, (size_t)blocks + 1, s));
-  integrate_kernel<<<blocks, THREADS, 0, s>>>((const double2 *)coords, elements, M, fq, w,
-                                             n_qp, partial);
+  P1_TIMED(ctx, "integrate", s,
+           (integrate_kernel<<<blocks, THREADS, 0, s>>>((const double2 *)coords, elements, M, fq,
+                                                       w, n_qp, partial)));
   sum_partials_kernel<<<1, THREADS, 0, s>>>(partial, blocks, partial + blocks);
   P1_CUDA(cudaMemcpyAsync(result_host, partial + blocks, sizeof(double),
                           cudaMemcpyDeviceToHost, s));

@@ -40,13 +40,18 @@ constexpr int SC_THREADS = P1_SCATTER_THREADS;  // scatter block size
 //                      whose length is not 1 + #records (open fans = boundary
 //                      nodes).  Verified row by row when the matrix is filled.
 //   OVERFLOW == true : only rows with more than 8 records; compact storage.
-// TOPO: topology-only plan -- one 16-byte slot {next, prev|k, element code, 0}
-// instead of the 32-byte record (and no separate element array)
-template <bool TOPO>
+// TOPO 0: the 32-byte record (+ the optional element code array)
+//      1: topology-only plan -- one 16-byte slot {next, prev|k, element code, 0}
+//      2: vector payload -- one 16-byte slot {element code, 0, v[0] as two words}:
+//         what a load vector needs of an incidence, no topology at all
+template <int TOPO>
 __device__ __forceinline__ void store_slot(Rec *rec, int *rec_elem, int64_t pos, int nx,
                                            int pvk, const double (&v)[3], int code) {
-  if constexpr (TOPO) {
+  if constexpr (TOPO == 1) {
     reinterpret_cast<int4 *>(rec)[pos] = make_int4(nx, pvk, code, 0);
+  } else if constexpr (TOPO == 2) {
+    reinterpret_cast<int4 *>(rec)[pos] =
+        make_int4(code, 0, __double2loint(v[0]), __double2hiint(v[0]));
   } else {
     Rec r;
     r.nx = nx; r.pvk = pvk;
@@ -56,7 +61,7 @@ __device__ __forceinline__ void store_slot(Rec *rec, int *rec_elem, int64_t pos,
   }
 }
 
-template <class V, bool OVERFLOW, bool TOPO>
+template <class V, bool OVERFLOW, int TOPO>
 __device__ __forceinline__ void scatter_element(int64_t t, const int (&e)[3], int N,
                                                 const Own &own,
                                                 unsigned long long *__restrict__ acc,
@@ -99,7 +104,7 @@ __device__ __forceinline__ void scatter_element(int64_t t, const int (&e)[3], in
         const unsigned slot =
             (unsigned)atomicAdd(acc + a, ((unsigned long long)d << 32) + 1ull);
         if (slot >= (unsigned)GROUP) {
-          if (TOPO) atomicOr(flags, FLAG_OVERFLOW);
+          if (TOPO != 0) atomicOr(flags, FLAG_OVERFLOW);
           continue;
         }
         pos = (int64_t)a * GROUP + slot;
@@ -113,7 +118,7 @@ __device__ __forceinline__ void scatter_element(int64_t t, const int (&e)[3], in
 // vertices, so the 6 vertex references are grouped in registers -- one atomic
 // per DISTINCT node (typically 4 instead of 6).  The kernel is bound by LSU
 // operations per lane; the 15 comparisons are free.
-template <class V, bool TOPO>
+template <class V, int TOPO>
 __device__ __forceinline__ void scatter_pair(int64_t t, const int (&id)[6], int N,
                                              const Own &own,
                                              unsigned long long *__restrict__ acc,
@@ -185,7 +190,7 @@ __device__ __forceinline__ void scatter_pair(int64_t t, const int (&id)[6], int 
     for (int k = 0; k < 3; ++k) {
       const int i = 3 * j + k;
       if (slot[i] >= (unsigned)GROUP) {
-        if (TOPO && mine[i]) atomicOr(flags, FLAG_OVERFLOW);
+        if (TOPO != 0 && mine[i]) atomicOr(flags, FLAG_OVERFLOW);
         continue;
       }
       const int64_t pos = (int64_t)row[i] * GROUP + slot[i];
@@ -207,7 +212,7 @@ __device__ __forceinline__ void scatter_pair(int64_t t, const int (&id)[6], int 
 // (register allocation of the PAIRS form, measured at 64M: 80 registers 2.20 ms --
 // what ptxas picks without a min-blocks hint --, 99 registers 2.74 ms, 64 with
 // spills 2.35 ms, 48 with spills 2.82 ms)
-template <class V, bool OVERFLOW, bool PAIRS, bool TOPO>
+template <class V, bool OVERFLOW, bool PAIRS, int TOPO>
 __global__ void __launch_bounds__(SC_THREADS)
 scatter_kernel(const int *__restrict__ elements, int64_t M, int N, Own own, int vec,
                unsigned long long *__restrict__ acc, Rec *__restrict__ rec,
@@ -251,24 +256,28 @@ static void launch_one(bool pairs, unsigned grid, cudaStream_t s, const int *ele
                        int N, Own own, int vec, unsigned long long *acc, Rec *rec,
                        int *rec_elem, int *cursor, V values, int *fl) {
   if (pairs && !OVERFLOW)
-    scatter_kernel<V, OVERFLOW, true, false><<<grid, SC_THREADS, 0, s>>>(
+    scatter_kernel<V, OVERFLOW, true, 0><<<grid, SC_THREADS, 0, s>>>(
         elements, M, N, own, vec, acc, rec, rec_elem, cursor, values, fl);
   else
-    scatter_kernel<V, OVERFLOW, false, false><<<grid, SC_THREADS, 0, s>>>(
+    scatter_kernel<V, OVERFLOW, false, 0><<<grid, SC_THREADS, 0, s>>>(
         elements, M, N, own, vec, acc, rec, rec_elem, cursor, values, fl);
 }
 
-static void launch_scatter_topo(p1_ctx *ctx, unsigned grid, cudaStream_t s, const int *elements,
-                                int64_t M, int N, Own own, unsigned long long *acc, int4 *topo) {
+// 16-byte slots instead of records (MODE 1: topology, 2: vector payload)
+template <int MODE, class V>
+static void launch_scatter_slots(p1_ctx *ctx, unsigned grid, cudaStream_t s, const int *elements,
+                                 int64_t M, int N, Own own, unsigned long long *acc, int4 *slots_,
+                                 V values, bool allow_pairs) {
   const int vec = ((uintptr_t)elements & 15) == 0;
-  const bool pairs = own.world == 1 && own.re - own.rb == N;
-  Rec *slots = reinterpret_cast<Rec *>(topo);
+  bool pairs = allow_pairs && own.world == 1 && own.re - own.rb == N;
+  if (const char *force = getenv("P1_SLOT_PAIRS")) pairs = force[0] == '1';  // experiments
+  Rec *slots = reinterpret_cast<Rec *>(slots_);
   if (pairs)
-    scatter_kernel<NoValues, false, true, true><<<grid, SC_THREADS, 0, s>>>(
-        elements, M, N, own, vec, acc, slots, nullptr, nullptr, NoValues{}, ctx->d_flags);
+    scatter_kernel<V, false, true, MODE><<<grid, SC_THREADS, 0, s>>>(
+        elements, M, N, own, vec, acc, slots, nullptr, nullptr, values, ctx->d_flags);
   else
-    scatter_kernel<NoValues, false, false, true><<<grid, SC_THREADS, 0, s>>>(
-        elements, M, N, own, vec, acc, slots, nullptr, nullptr, NoValues{}, ctx->d_flags);
+    scatter_kernel<V, false, false, MODE><<<grid, SC_THREADS, 0, s>>>(
+        elements, M, N, own, vec, acc, slots, nullptr, nullptr, values, ctx->d_flags);
 }
 
 template <bool OVERFLOW>
@@ -458,6 +467,293 @@ rowlen_big_kernel(const int *__restrict__ big_rows, Own own, Rows rows,
   if (threadIdx.x == 0) rowlen[a] = total;
 }
 
+
+// ------------------------------------------------ load vectors without a plan
+// b = bincount(elements, weights = local loads) in the reference's summation
+// order needs, per node, only (element code, value) of every incidence: the
+// scatter writes exactly that into the node's 8 slots and one thread per node
+// sorts the codes in registers and adds.  No topology, no row pointer, and no
+// random gather of the local loads (at 64M that gather read 13 GB for 1.6 GB of
+// values: the three vertices of a triangle live in rows that are far apart).
+struct LoadQuadValues {  // solvers.py:564-591, the arithmetic of local_load_kernel
+  static constexpr bool needs_xy = true;
+  const double2 *__restrict__ coords;
+  const double *__restrict__ fq;       // [n_qp x M]
+  const double *__restrict__ weights;  // device, n_qp
+  const double2 *__restrict__ points;  // device, n_qp (eta, xi)
+  int n_qp;
+  int64_t M;
+  __device__ __forceinline__ void rows(int64_t t, const int *, double2 z0, double2 z1,
+                                       double2 z2, double (*v)[3]) const {
+    const double px = z1.x - z0.x, py = z1.y - z0.y;
+    const double qx = z2.x - z0.x, qy = z2.y - z0.y;
+    const double area = 0.5 * (px * qy - py * qx);
+    double l0 = 0., l1 = 0., l2 = 0.;
+    for (int q = 0; q < n_qp; ++q) {
+      const double2 pt = __ldg(points + q);
+      const double f = __ldg(fq + (int64_t)q * M + t);
+      const double s = 2. * __ldg(weights + q) * area;
+      l0 += s * (1. - pt.x - pt.y) * f;
+      l1 += s * pt.x * f;
+      l2 += s * pt.y * f;
+    }
+    v[0][0] = l0; v[1][0] = l1; v[2][0] = l2;
+  }
+};
+struct LoadMidpointValues {  // solvers.py:415-424: share = area4*fsT/12. for all three
+  static constexpr bool needs_xy = true;
+  const double2 *__restrict__ coords;
+  const double *__restrict__ f_centroid;
+  __device__ __forceinline__ void rows(int64_t t, const int *, double2 z0, double2 z1,
+                                       double2 z2, double (*v)[3]) const {
+    const double px = z1.x - z0.x, py = z1.y - z0.y;
+    const double qx = z2.x - z0.x, qy = z2.y - z0.y;
+    const double area4 = 4. * (0.5 * (px * qy - py * qx));
+    const double share = area4 * __ldg(f_centroid + t) / 12.;
+    v[0][0] = v[1][0] = v[2][0] = share;
+  }
+};
+
+// The local loads of FOUR consecutive triangles in registers (the [n_qp x M]
+// values of f are read as one 32-byte load per thread and point: 1 KB per warp
+// instruction), handed to scatter_pair two triangles at a time.
+struct PairLoads {
+  static constexpr bool needs_xy = false;
+  double l0[3], l1[3];  // the even and the odd triangle of the pair
+  __device__ __forceinline__ void rows(int64_t t, const int *, double2, double2, double2,
+                                       double (*v)[3]) const {
+    const bool odd = (t & 1) != 0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      v[k][0] = odd ? l1[k] : l0[k];
+      v[k][1] = v[k][2] = 0.;
+    }
+  }
+};
+
+template <bool MIDPOINT>
+__global__ void __launch_bounds__(SC_THREADS)
+load_scatter_kernel(const int *__restrict__ elements, int64_t M, int N, Own own,
+                    const double2 *__restrict__ coords, const double *__restrict__ f,
+                    const double *__restrict__ weights, const double2 *__restrict__ points,
+                    int n_qp, int wide, unsigned long long *__restrict__ acc,
+                    Rec *__restrict__ slots, int *__restrict__ flags) {
+  int mx = -1;
+  bool bad = false;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t quads = M / 4;
+  const int4 *e4 = reinterpret_cast<const int4 *>(elements);
+  for (int64_t g = tid; g < quads; g += stride) {
+    const int4 p = __ldg(e4 + 3 * g), q = __ldg(e4 + 3 * g + 1), r = __ldg(e4 + 3 * g + 2);
+    const int id[12] = {p.x, p.y, p.z, p.w, q.x, q.y, q.z, q.w, r.x, r.y, r.z, r.w};
+    double area[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      area[j] = 0.;
+      if ((unsigned)id[3 * j] < (unsigned)N && (unsigned)id[3 * j + 1] < (unsigned)N &&
+          (unsigned)id[3 * j + 2] < (unsigned)N) {
+        const double2 z0 = __ldg(coords + id[3 * j]), z1 = __ldg(coords + id[3 * j + 1]),
+                      z2 = __ldg(coords + id[3 * j + 2]);
+        const double px = z1.x - z0.x, py = z1.y - z0.y;
+        const double qx = z2.x - z0.x, qy = z2.y - z0.y;
+        area[j] = 0.5 * (px * qy - py * qx);
+      }
+    }
+    double l[4][3];
+    if (MIDPOINT) {
+      double fv[4];
+      if (wide) {
+        const double4 w4 = *reinterpret_cast<const double4 *>(f + 4 * g);
+        fv[0] = w4.x; fv[1] = w4.y; fv[2] = w4.z; fv[3] = w4.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) fv[j] = __ldg(f + 4 * g + j);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const double area4 = 4. * area[j];
+        l[j][0] = l[j][1] = l[j][2] = area4 * fv[j] / 12.;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) l[j][0] = l[j][1] = l[j][2] = 0.;
+      // four points at a time: 128 bytes per thread in flight (the sums themselves
+      // stay in the reference's order, point after point)
+      for (int qp0 = 0; qp0 < n_qp; qp0 += 4) {
+        double fv[4][4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const double *fp = f + (int64_t)(qp0 + u) * M + 4 * g;
+          fv[u][0] = fv[u][1] = fv[u][2] = fv[u][3] = 0.;
+          if (qp0 + u < n_qp) {
+            if (wide) {
+              const double4 w4 = *reinterpret_cast<const double4 *>(fp);
+              fv[u][0] = w4.x; fv[u][1] = w4.y; fv[u][2] = w4.z; fv[u][3] = w4.w;
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) fv[u][j] = __ldg(fp + j);
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (qp0 + u < n_qp) {
+            const double2 pt = __ldg(points + qp0 + u);
+            const double w = __ldg(weights + qp0 + u);
+            const double h0 = 1. - pt.x - pt.y;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const double s = 2. * w * area[j];
+              l[j][0] += s * h0 * fv[u][j];
+              l[j][1] += s * pt.x * fv[u][j];
+              l[j][2] += s * pt.y * fv[u][j];
+            }
+          }
+        }
+      }
+    }
+    const int ab[6] = {id[0], id[1], id[2], id[3], id[4], id[5]},
+              cd[6] = {id[6], id[7], id[8], id[9], id[10], id[11]};
+    const PairLoads v01{{l[0][0], l[0][1], l[0][2]}, {l[1][0], l[1][1], l[1][2]}};
+    const PairLoads v23{{l[2][0], l[2][1], l[2][2]}, {l[3][0], l[3][1], l[3][2]}};
+    scatter_pair<PairLoads, 2>(4 * g, ab, N, own, acc, slots, nullptr, v01, mx, bad, flags);
+    scatter_pair<PairLoads, 2>(4 * g + 2, cd, N, own, acc, slots, nullptr, v23, mx, bad, flags);
+  }
+  for (int64_t t = 4 * quads + tid; t < M; t += stride) {  // the last M % 4 triangles
+    const int e[3] = {__ldg(elements + 3 * t), __ldg(elements + 3 * t + 1),
+                      __ldg(elements + 3 * t + 2)};
+    if (MIDPOINT)
+      scatter_element<LoadMidpointValues, false, 2>(t, e, N, own, acc, slots, nullptr, nullptr,
+                                                    LoadMidpointValues{coords, f}, mx, bad, flags);
+    else
+      scatter_element<LoadQuadValues, false, 2>(t, e, N, own, acc, slots, nullptr, nullptr,
+                                                LoadQuadValues{coords, f, weights, points, n_qp, M},
+                                                mx, bad, flags);
+  }
+  mx = __reduce_max_sync(0xffffffffu, mx);
+  if ((threadIdx.x & 31) == 0 && mx >= 0) atomicMax(flags + 1, mx);
+  if (bad) atomicOr(flags, FLAG_INDEX_RANGE);
+}
+
+// ascending (element, vertex) for the cubature rule (bincount over
+// elements.flatten(), solvers.py:593-596), ascending (vertex, element) for the
+// legacy rule (elements.flatten('F'), solvers.py:422-425)
+template <bool VERTEX_MAJOR>
+__global__ void __launch_bounds__(THREADS)
+sum_slots_kernel(int n, const unsigned long long *__restrict__ acc,
+                 const int4 *__restrict__ slots, double *__restrict__ b) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= n) return;
+  const int deg = (int)(unsigned)acc[a];
+  double sum = 0.;
+  if (deg >= 1 && deg <= GROUP) {  // (more than 8: flagged by the scatter, b is discarded)
+    const int4 *row = slots + (int64_t)a * GROUP;
+    unsigned key[GROUP];
+    double val[GROUP];
+#pragma unroll
+    for (int i = 0; i < GROUP; ++i) {
+      key[i] = 0xffffffffu;
+      val[i] = 0.;
+      if (i < deg) {
+        const int4 s = __ldg(row + i);
+        const unsigned c = (unsigned)s.x;
+        key[i] = VERTEX_MAJOR ? ((c & 3u) << 29) | (c >> 2) : c;
+        val[i] = __hiloint2double(s.w, s.z);
+      }
+    }
+    int rank[GROUP];
+#pragma unroll
+    for (int i = 0; i < GROUP; ++i) {
+      rank[i] = 0;
+#pragma unroll
+      for (int j = 0; j < GROUP; ++j) rank[i] += key[j] < key[i];
+    }
+    for (int q = 0; q < deg; ++q) {
+#pragma unroll
+      for (int i = 0; i < GROUP; ++i)
+        if (rank[i] == q) sum += val[i];
+    }
+  }
+  b[a] = sum;
+}
+
+// f as 32-byte loads: the rows of the [n_qp x M] array must stay 32-byte aligned
+static void launch_load_scatter(unsigned grid, cudaStream_t s, const int *elements, int64_t M,
+                                int N, Own own, const LoadQuadValues &v, unsigned long long *acc,
+                                int4 *slots, int *flags) {
+  const int wide = ((uintptr_t)v.fq & 31) == 0 && (M & 3) == 0;
+  load_scatter_kernel<false><<<grid, SC_THREADS, 0, s>>>(
+      elements, M, N, own, v.coords, v.fq, v.weights, v.points, v.n_qp, wide, acc,
+      reinterpret_cast<Rec *>(slots), flags);
+}
+static void launch_load_scatter(unsigned grid, cudaStream_t s, const int *elements, int64_t M,
+                                int N, Own own, const LoadMidpointValues &v,
+                                unsigned long long *acc, int4 *slots, int *flags) {
+  const int wide = ((uintptr_t)v.f_centroid & 31) == 0;
+  load_scatter_kernel<true><<<grid, SC_THREADS, 0, s>>>(
+      elements, M, N, own, v.coords, v.f_centroid, nullptr, nullptr, 0, wide, acc,
+      reinterpret_cast<Rec *>(slots), flags);
+}
+
+template <class V>
+static int load_vector_direct(p1_ctx *ctx, const int32_t *elements, int64_t M, int64_t n_nodes,
+                              V values, bool vertex_major, bool allow_pairs, double *b,
+                              cudaStream_t s, const char *who) {
+  const int N = (int)n_nodes;
+  const Own own{0, N, 0, 1, 0, 0};
+  unsigned long long *acc = nullptr;
+  int4 *slots = nullptr;
+  int rc;
+  if ((rc = pool_alloc(ctx, &acc, (size_t)N + 1, s))) return rc;
+  if ((rc = pool_alloc(ctx, &slots, (size_t)N * GROUP, s))) {
+    pool_free(ctx, acc, s);
+    return rc;
+  }
+  cudaMemsetAsync(ctx->d_flags, 0, 8 * sizeof(int), s);
+  cudaMemsetAsync(acc, 0, ((size_t)N + 1) * sizeof(unsigned long long), s);
+  const unsigned grid = min(grid_for(M, THREADS), (unsigned)(ctx->sm_count * 32));
+  if (M > 0) {
+    prof_begin(ctx, "load_scatter", s);
+    static const bool quad_kernel = []() {
+      const char *e = getenv("P1_LOAD_QUADS");
+      return !(e && e[0] == '0');
+    }();
+    if (quad_kernel && ((uintptr_t)elements & 15) == 0)
+      launch_load_scatter(grid, s, elements, M, N, own, values, acc, slots, ctx->d_flags);
+    else
+      launch_scatter_slots<2>(ctx, grid, s, elements, M, N, own, acc, slots, values, allow_pairs);
+    prof_end(ctx, s);
+  }
+  if (N > 0) {
+    prof_begin(ctx, "load_sum", s);
+    if (vertex_major)
+      sum_slots_kernel<true><<<grid_for(N, THREADS), THREADS, 0, s>>>(N, acc, slots, b);
+    else
+      sum_slots_kernel<false><<<grid_for(N, THREADS), THREADS, 0, s>>>(N, acc, slots, b);
+    prof_end(ctx, s);
+  }
+  cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, 8 * sizeof(int), cudaMemcpyDeviceToHost, s);
+  cudaError_t e = cudaStreamSynchronize(s);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  pool_free(ctx, acc, s);
+  pool_free(ctx, slots, s);
+  if (e != cudaSuccess) {
+    set_error("%s: %s", who, cudaGetErrorString(e));
+    return P1_ECUDA;
+  }
+  if (ctx->h_flags[0] & FLAG_INDEX_RANGE) {
+    set_error("%s: element index out of range [0, %lld)", who, (long long)n_nodes);
+    return P1_EINDEX;
+  }
+  if (ctx->h_flags[0] & FLAG_OVERFLOW) {
+    set_error("%s: a node has more than 8 elements; use a plan "
+              "(P1_PLAN_KEEP_ELEMENTS) and p1_load_vector", who);
+    return P1_ERETRY;
+  }
+  return P1_OK;
+}
+
 int require_elements(const p1_plan *p, const char *who) {
   if (p->rec_elem || p->topo) return P1_OK;
   set_error("%s needs a plan created with P1_PLAN_KEEP_ELEMENTS or P1_PLAN_TOPOLOGY", who);
@@ -613,7 +909,7 @@ static int plan_build(p1_ctx *ctx, const int32_t *elements, int64_t n_elements,
     cudaMemsetAsync(p->acc, 0, ((size_t)n_own + 1) * sizeof(unsigned long long), s);
     const unsigned tg = min(grid_for(M, THREADS), (unsigned)(ctx->sm_count * 32));
     prof_begin(ctx, "scatter", s);
-    launch_scatter_topo(ctx, tg, s, elements, M, N, own, p->acc, p->topo);
+    launch_scatter_slots<1>(ctx, tg, s, elements, M, N, own, p->acc, p->topo, NoValues{}, true);
     prof_end(ctx, s);
     cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, 8 * sizeof(int), cudaMemcpyDeviceToHost, s);
     if (cudaStreamSynchronize(s) != cudaSuccess || cudaGetLastError() != cudaSuccess)
@@ -787,6 +1083,44 @@ extern "C" int p1_plan_create_interleaved(p1_ctx *ctx, const int32_t *elements,
              "interleaved plans take P1_OP_LOCAL for these operators");
   return plan_build(ctx, elements, n_elements, n_nodes, 0, n_nodes, chunk_log2, world, rank,
                     flags, op, coords, local, nullptr, stream, out);
+}
+
+extern "C" int p1_load_vector_direct(p1_ctx *ctx, const int32_t *elements, int64_t n_elements,
+                                     int64_t n_nodes, const double *coords, const double *fq,
+                                     const double *weights_host, const double *points_host,
+                                     int n_qp, double *b, void *stream) {
+  P1_REQUIRE(ctx && b, "null ctx/b");
+  P1_REQUIRE(n_elements >= 0 && n_nodes >= 0 && n_nodes <= (int64_t)NODE_MASK &&
+                 n_elements < (1LL << 29), "bad size");
+  P1_REQUIRE(n_elements == 0 || (elements && coords && fq), "null input");
+  P1_REQUIRE(n_qp > 0 && weights_host && points_host, "bad rule");
+  DeviceGuard guard(ctx->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  double *rule = nullptr;  // points (16-byte aligned pairs), then weights
+  P1_TRY(pool_alloc(ctx, &rule, (size_t)3 * n_qp, s));
+  cudaMemcpyAsync(rule, points_host, 2 * n_qp * sizeof(double), cudaMemcpyHostToDevice, s);
+  cudaMemcpyAsync(rule + 2 * n_qp, weights_host, n_qp * sizeof(double), cudaMemcpyHostToDevice,
+                  s);
+  const LoadQuadValues values{(const double2 *)coords, fq, rule + 2 * n_qp,
+                              (const double2 *)rule, n_qp, n_elements};
+  const int rc = load_vector_direct(ctx, elements, n_elements, n_nodes, values, false, false, b, s,
+                                    "p1_load_vector_direct");
+  pool_free(ctx, rule, s);
+  return rc;
+}
+
+extern "C" int p1_load_vector_midpoint_direct(p1_ctx *ctx, const int32_t *elements,
+                                              int64_t n_elements, int64_t n_nodes,
+                                              const double *coords, const double *f_centroid,
+                                              double *b, void *stream) {
+  P1_REQUIRE(ctx && b, "null ctx/b");
+  P1_REQUIRE(n_elements >= 0 && n_nodes >= 0 && n_nodes <= (int64_t)NODE_MASK &&
+                 n_elements < (1LL << 29), "bad size");
+  P1_REQUIRE(n_elements == 0 || (elements && coords && f_centroid), "null input");
+  DeviceGuard guard(ctx->device);
+  const LoadMidpointValues values{(const double2 *)coords, f_centroid};
+  return load_vector_direct(ctx, elements, n_elements, n_nodes, values, true, true, b,
+                            (cudaStream_t)stream, "p1_load_vector_midpoint_direct");
 }
 
 extern "C" int64_t p1_plan_rows(const p1_plan *p) { return p ? p->n_own : -1; }

@@ -356,14 +356,22 @@ struct WeightedValues {
     double m[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) m[k] = 0.;
-    for (int q = 0; q < n_qp; ++q) {
-      const double2 pt = __ldg(points + q);
-      const double h[3] = {1 - pt.x - pt.y, pt.x, pt.y};
-      const double base = 2 * areas * __ldg(weights + q) * __ldg(phiq + (int64_t)q * M + t);
+    for (int q0 = 0; q0 < n_qp; q0 += 4) {  // four loads in flight, sums in order
+      double fv[4];
 #pragma unroll
-      for (int k = 0; k < 3; ++k)
+      for (int u = 0; u < 4; ++u)
+        fv[u] = q0 + u < n_qp ? __ldg(phiq + (int64_t)(q0 + u) * M + t) : 0.;
 #pragma unroll
-        for (int l = 0; l < 3; ++l) m[3 * k + l] += base * h[k] * h[l];
+      for (int u = 0; u < 4; ++u)
+        if (q0 + u < n_qp) {
+          const double2 pt = __ldg(points + q0 + u);
+          const double h[3] = {1 - pt.x - pt.y, pt.x, pt.y};
+          const double base = 2 * areas * __ldg(weights + q0 + u) * fv[u];
+#pragma unroll
+          for (int k = 0; k < 3; ++k)
+#pragma unroll
+            for (int l = 0; l < 3; ++l) m[3 * k + l] += base * h[k] * h[l];
+        }
     }
 #pragma unroll
     for (int k = 0; k < 3; ++k) {

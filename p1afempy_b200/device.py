@@ -432,9 +432,25 @@ class DeviceMesh:
         return length, mid
 
     # ---------------------------------------------------------- load vectors
+    def _direct_vectors(self):
+        """No plan to reuse and none wanted: load vectors go through the plan-free
+        entry points (p1_load_vector*_direct)."""
+        return (self._plan is None and not self.reuse and self._topology_fits
+                and self.interleave is None and self.rows == (0, self.n_nodes))
+
     def load_vector(self, fq, weights, points):
         w, p = _host_f64(weights), _host_f64(points)
         fq = to_device_f64(fq, self.device, (w.shape[0], self.n_elements))
+        if self._direct_vectors():
+            b = self._empty(self.n_nodes)
+            rc = self._lib.p1_load_vector_direct(
+                self.ctx, _ptr(self.elements), self.n_elements, self.n_nodes, _ptr(self.coords),
+                _ptr(fq), w.ctypes.data_as(C.c_void_p), p.ctypes.data_as(C.c_void_p),
+                w.shape[0], _ptr(b), _stream(self.device))
+            if rc != _lib.P1_ERETRY:
+                _lib.check(rc)
+                return b
+            self._topology_fits = False         # a node with more than 8 elements
         self.plan  # noqa: B018  (fixes n_rows)
         b = self._empty(self.n_rows)
         _lib.check(self._lib.p1_load_vector(
@@ -454,6 +470,15 @@ class DeviceMesh:
 
     def load_vector_midpoint(self, f_centroid):
         fc = to_device_f64(f_centroid, self.device, (self.n_elements,))
+        if self._direct_vectors():
+            b = self._empty(self.n_nodes)
+            rc = self._lib.p1_load_vector_midpoint_direct(
+                self.ctx, _ptr(self.elements), self.n_elements, self.n_nodes, _ptr(self.coords),
+                _ptr(fc), _ptr(b), _stream(self.device))
+            if rc != _lib.P1_ERETRY:
+                _lib.check(rc)
+                return b
+            self._topology_fits = False
         self.plan  # noqa: B018
         b = self._empty(self.n_rows)
         _lib.check(self._lib.p1_load_vector_midpoint(

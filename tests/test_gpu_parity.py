@@ -509,9 +509,9 @@ def test_topology_plan_matches_element_keeping_plan():
     for reuse in (False, True):
         with DeviceMesh(ct, et, reuse=reuse) as mesh:
             fc = torch.from_numpy(H.f_load(mesh.centroids().cpu().numpy())).cuda()
-            b = mesh.load_vector_midpoint(fc)
-            assert mesh._plan_topology == (not reuse)
             gd = mesh.geometric_data(bt)
+            assert mesh._plan_topology == (not reuse)
+            b = mesh.load_vector_midpoint(fc)       # gathers through the existing plan
             out[reuse] = [b.cpu().numpy()] + [np.asarray(x.cpu().numpy()) for x in gd[:2]] + \
                          [x.cpu().numpy() for x in gd[2]]
             if not reuse:
@@ -528,6 +528,22 @@ def test_topology_plan_matches_element_keeping_plan():
     assert np.array_equal(out[False][1], o2e) and np.array_equal(out[False][2], o2n)
     for got, want in zip(out[False][3:], ob2e):
         assert np.array_equal(got, want)
+    # no plan at all: the plan-free load vectors (element code + value per slot)
+    w, p = cubature.resolve_rule(cubature.CubatureRuleEnum.DAYTAYLOR)
+    with DeviceMesh(ct, et) as mesh:
+        fc = torch.from_numpy(H.f_load(mesh.centroids().cpu().numpy())).cuda()
+        b = mesh.load_vector_midpoint(fc)
+        assert mesh._plan is None
+        assert np.array_equal(b.cpu().numpy(), out[False][0])
+        xq = mesh.quadrature_points(p)
+        fq = torch.from_numpy(np.stack([H.f_load(xq[q].cpu().numpy())
+                                        for q in range(len(w))])).cuda()
+        bq = mesh.load_vector(fq, w, p)
+        assert mesh._plan is None
+        assert np.array_equal(bq.cpu().numpy(), orc.load_vector_cubature(pts, e, H.f_load, w, p))
+    with DeviceMesh(ct, et, reuse=True) as mesh:
+        assert np.array_equal(mesh.load_vector(fq, w, p).cpu().numpy(), bq.cpu().numpy())
+        assert mesh._plan is not None
     # fan with 12 elements around the centre: no room in 8 slots
     n = 12
     ang = 2 * np.pi * np.arange(n) / n

@@ -27,3 +27,17 @@ def lv(): mesh.close(); return mesh.load_vector(fq, w, p)
 def gd(): mesh.close(); return mesh.geometric_data([b])
 def er(): mesh.close(); return mesh.eta_r(u, b, none, None, fc)
 run('load vector cold', lv); run('geometric data cold', gd); run('eta_r cold', er)
+fcen = torch.sin(mesh.centroids()[:, 0])
+def lm(): mesh.close(); return mesh.load_vector_midpoint(fcen)
+run('midpoint load vector cold', lm)
+q2, q3, q4 = fq + 1., fq * 2., fq - 1.
+def gs(): return mesh.general_stiffness_csr(fq, q2, q3, q4, w)
+def wm(): return mesh.weighted_mass_csr(fq, w, p)
+def it(): return mesh.integrate(fq, w)
+run('general stiffness cold', gs); run('weighted mass cold', wm); run('integrate', it)
+def ms(): return mesh.mass_csr()
+run('mass cold', ms)
+rm = DeviceMesh(c, e, reuse=True)
+def lvr(): return rm.load_vector(fq, w, p)
+def lmr(): return rm.load_vector_midpoint(fcen)
+run('load vector, plan reused', lvr); run('midpoint load vector, plan reused', lmr)
