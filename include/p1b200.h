@@ -97,6 +97,11 @@ int p1_widen_indices(p1_ctx *ctx, const int32_t *src, int64_t count,
                             /* values and no row pointer -- all that load vectors, */
                             /* edge numbering and eta_R need.  At most 8 elements  */
                             /* per node: P1_ERETRY otherwise (use KEEP_ELEMENTS)   */
+#define P1_PLAN_SLOT_INDEX 8 /* with P1_PLAN_TOPOLOGY: also record the slot of every   */
+                             /* half-edge, so that p1_eta_r gets ALL half-edge twins  */
+                             /* by a gather instead of scattered stores (+0.2 ms on   */
+                             /* the plan, -1.5 ms on the twins at 64M); not worth it  */
+                             /* for p1_geometric_data alone, which reads half of them */
 int p1_plan_create(p1_ctx *ctx, const int32_t *elements, int64_t n_elements,
                    int64_t n_nodes, int64_t row_begin, int64_t row_end,
                    int flags, void *stream, p1_plan **out);

@@ -26,6 +26,7 @@ PLAN_DEFAULT = 0
 PLAN_EXACT = 1
 PLAN_KEEP_ELEMENTS = 2
 PLAN_TOPOLOGY = 4
+PLAN_SLOT_INDEX = 8
 
 OP_STORED = 0
 OP_STIFFNESS = 1

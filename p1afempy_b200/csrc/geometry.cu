@@ -20,6 +20,12 @@ constexpr int THREADS = 256;
 // half-edge id 3*T + k from a record's element code (T << 2) | k
 __device__ __forceinline__ int halfedge_of(int code) { return 3 * (code >> 2) + (code & 3); }
 
+// BACKWARD_ONLY: store only the twins of half-edges a -> x with x < a -- all the
+// edge numbering reads.  The 4-byte stores land in other rows' sectors (the
+// elements around a node are far apart in the element order): every store that
+// misses L2 costs a sector fill and a sector write-back, 11.8 GB of DRAM traffic at
+// 64M for 0.8 GB of twins; half the stores, half of that.
+template <bool BACKWARD_ONLY>
 __global__ void __launch_bounds__(THREADS)
 twin_kernel(int n_nodes, Rows rows, int *__restrict__ twin, int *__restrict__ flags) {
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
@@ -66,12 +72,13 @@ twin_kernel(int n_nodes, Rows rows, int *__restrict__ twin, int *__restrict__ fl
       }
       if (i < deg) {
         const int he = halfedge_of(cd[i]);
+        const bool keep = !BACKWARD_ONLY || nx[i] < a;
         if (hits == 0) {
-          twin[he] = -1;
+          if (keep) twin[he] = -1;
           ++open_edges;
         } else {
           // the twin (target -> a) is edge prev(k_s) of the matching element
-          twin[he] = 3 * (found >> 2) + prev_local(found & 3);
+          if (keep) twin[he] = 3 * (found >> 2) + prev_local(found & 3);
           nonmanifold = nonmanifold || hits > 1;
         }
       }
@@ -83,11 +90,12 @@ twin_kernel(int n_nodes, Rows rows, int *__restrict__ twin, int *__restrict__ fl
       for (int s = 0; s < deg; ++s)
         if (rec_prev(rec[s]) == target) { found = code[s]; ++hits; }
       const int he = halfedge_of(code[i]);
+      const bool keep = !BACKWARD_ONLY || target < a;
       if (hits == 0) {
-        twin[he] = -1;
+        if (keep) twin[he] = -1;
         ++open_edges;
       } else {
-        twin[he] = 3 * (found >> 2) + prev_local(found & 3);
+        if (keep) twin[he] = 3 * (found >> 2) + prev_local(found & 3);
         nonmanifold = nonmanifold || hits > 1;
       }
       for (int s = i + 1; s < deg; ++s)
@@ -96,6 +104,61 @@ twin_kernel(int n_nodes, Rows rows, int *__restrict__ twin, int *__restrict__ fl
   }
   if (open_edges) atomicAdd(flags + 1, open_edges);
   if (nonmanifold) atomicOr(flags, FLAG_NONMANIFOLD);
+}
+
+// Topology-only plans that know the slot of every half-edge (p1_plan::slot_of):
+// the row thread keeps its results in its own 32 bytes (tw[8a + i], coalesced) and
+// an element-major pass gathers twin[h] = tw[slot_of[h]].  A gather that misses L2
+// costs one sector read; the scattered store it replaces costs a fill and a
+// write-back (full twins at 64M: 3.0 ms with scattered stores).
+__global__ void __launch_bounds__(THREADS)
+twin_rows_kernel(int n_nodes, const unsigned long long *__restrict__ acc,
+                 const int4 *__restrict__ topo, int *__restrict__ tw,
+                 int *__restrict__ flags) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= n_nodes) return;
+  const int deg = (int)(unsigned)acc[a];
+  if (deg == 0) return;  // (more than 8: the plan does not exist)
+  int open_edges = 0;
+  bool nonmanifold = false;
+  int nx[GROUP], pv[GROUP], cd[GROUP], out[GROUP];
+  const int4 *slot = topo + (int64_t)a * GROUP;
+#pragma unroll
+  for (int i = 0; i < GROUP; ++i) {
+    nx[i] = -1 - i; pv[i] = -20 - i; cd[i] = 0;
+    if (i < deg) {
+      const int4 t = __ldg(slot + i);
+      nx[i] = t.x; pv[i] = t.y & NODE_MASK; cd[i] = t.z;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < GROUP; ++i) {
+    int found = -1, hits = 0;
+#pragma unroll
+    for (int s = 0; s < GROUP; ++s) {
+      if (pv[s] == nx[i]) { found = cd[s]; ++hits; }
+      if (s > i && nx[s] == nx[i]) nonmanifold = true;  // same directed edge twice
+    }
+    out[i] = -1;
+    if (i < deg) {
+      if (hits == 0) ++open_edges;
+      else out[i] = 3 * (found >> 2) + prev_local(found & 3);
+      nonmanifold = nonmanifold || hits > 1;
+    }
+  }
+  int4 *dst = reinterpret_cast<int4 *>(tw + (int64_t)a * GROUP);
+  dst[0] = make_int4(out[0], out[1], out[2], out[3]);
+  if (deg > 4) dst[1] = make_int4(out[4], out[5], out[6], out[7]);
+  if (open_edges) atomicAdd(flags + 1, open_edges);
+  if (nonmanifold) atomicOr(flags, FLAG_NONMANIFOLD);
+}
+
+__global__ void __launch_bounds__(THREADS)
+twin_gather_kernel(int64_t n_halfedges, const int *__restrict__ slot_of,
+                   const int *__restrict__ tw, int *__restrict__ twin) {
+  for (int64_t h = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; h < n_halfedges;
+       h += (int64_t)gridDim.x * blockDim.x)
+    twin[h] = __ldg(tw + __ldg(slot_of + h));
 }
 
 // position p of the reference's concatenated half-edge list:
@@ -382,16 +445,35 @@ static int full_plan_required(const p1_plan *p, const char *who) {
   return P1_OK;
 }
 
-int ensure_twins(p1_plan *p, cudaStream_t s) {
-  if (p->twin) return P1_OK;
+// backward_only: the caller reads twin[h] only for half-edges I -> J with J < I
+// (edge numbering); a later caller that needs all of them rebuilds
+int ensure_twins(p1_plan *p, cudaStream_t s, bool backward_only) {
+  if (p->twin && (!p->twin_partial || backward_only)) return P1_OK;
   p1_ctx *ctx = p->ctx;
   P1_TRY(full_plan_required(p, "half-edge twins"));
   P1_TRY(require_elements(p, "half-edge twins (edge numbering, eta_R)"));
-  P1_TRY(pool_alloc(ctx, &p->twin, (size_t)(3 * p->M), s));
+  if (!p->twin) P1_TRY(pool_alloc(ctx, &p->twin, (size_t)(3 * p->M), s));
+  p->twin_partial = backward_only;
   P1_CUDA(cudaMemsetAsync(p->ctx->d_flags, 0, 8 * sizeof(int), s));
-  if (p->N > 0)
-    P1_TIMED(ctx, "twin", s, twin_kernel<<<grid_for(p->N, THREADS), THREADS, 0, s>>>(
-        (int)p->N, rows_of(p), p->twin, p->ctx->d_flags));
+  if (p->N > 0 && p->topo && p->slot_of) {
+    int *tw = nullptr;
+    P1_TRY(pool_alloc(ctx, &tw, (size_t)p->N * GROUP, s));
+    p->twin_partial = false;
+    P1_TIMED(ctx, "twin", s, {
+      twin_rows_kernel<<<grid_for(p->N, THREADS), THREADS, 0, s>>>((int)p->N, p->acc, p->topo, tw,
+                                                                  p->ctx->d_flags);
+      twin_gather_kernel<<<min(grid_for(3 * p->M, THREADS), (unsigned)(ctx->sm_count * 32)),
+                           THREADS, 0, s>>>(3 * p->M, p->slot_of, tw, p->twin);
+    });
+    pool_free(ctx, tw, s);
+  } else if (p->N > 0) {
+    if (backward_only)
+      P1_TIMED(ctx, "twin", s, twin_kernel<true><<<grid_for(p->N, THREADS), THREADS, 0, s>>>(
+          (int)p->N, rows_of(p), p->twin, p->ctx->d_flags));
+    else
+      P1_TIMED(ctx, "twin", s, twin_kernel<false><<<grid_for(p->N, THREADS), THREADS, 0, s>>>(
+          (int)p->N, rows_of(p), p->twin, p->ctx->d_flags));
+  }
   P1_CUDA(cudaGetLastError());
   P1_TRY(read_flags(p->ctx, s));
   if (p->ctx->h_flags[0] & FLAG_NONMANIFOLD) {
@@ -425,7 +507,8 @@ extern "C" int p1_geometric_data(const p1_plan *cplan, const int32_t *boundary_n
   P1_REQUIRE(K == 0 || boundary_nodes, "null boundary_nodes");
   P1_REQUIRE(M == 0 || (element2edges && edge2nodes), "null output");
   if (3 * M + K > 0x7fffffffLL) { set_error("too many half-edges"); return P1_ERANGE; }
-  P1_TRY(ensure_twins(p, s));
+  // a one-shot (topology-only) plan: build only the twins the numbering reads
+  P1_TRY(ensure_twins(p, s, p->topo != nullptr));
   const int64_t total = 3 * M + K;
   int *num = nullptr, *tile_sums = nullptr;
   unsigned char *fwd = nullptr;

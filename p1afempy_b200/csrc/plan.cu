@@ -49,6 +49,9 @@ __device__ __forceinline__ void store_slot(Rec *rec, int *rec_elem, int64_t pos,
                                            int pvk, const double (&v)[3], int code) {
   if constexpr (TOPO == 1) {
     reinterpret_cast<int4 *>(rec)[pos] = make_int4(nx, pvk, code, 0);
+    // where the half-edge 3T+k sits: element-major consumers gather per-slot
+    // results through it (geometry.cu: twins)
+    if (rec_elem) rec_elem[3 * (code >> 2) + (code & 3)] = (int)pos;
   } else if constexpr (TOPO == 2) {
     reinterpret_cast<int4 *>(rec)[pos] =
         make_int4(code, 0, __double2loint(v[0]), __double2hiint(v[0]));
@@ -124,7 +127,11 @@ __device__ __forceinline__ void scatter_pair(int64_t t, const int (&id)[6], int 
                                              unsigned long long *__restrict__ acc,
                                              Rec *__restrict__ rec,
                                              int *__restrict__ rec_elem, const V &values,
-                                             int &mx, bool &bad, int *flags) {
+                                             int &mx, bool &bad, int *flags, int (&where)[6]) {
+  // where[i]: slot index of reference i (TOPO 1: the caller stores them, 48 bytes
+  // per thread at once -- 4-byte stores per record cost 1.2 ms at 64M)
+#pragma unroll
+  for (int i = 0; i < 6; ++i) where[i] = -1;
   bool valid[2], touched[2], mine[6];
   int row[6];
 #pragma unroll
@@ -194,7 +201,8 @@ __device__ __forceinline__ void scatter_pair(int64_t t, const int (&id)[6], int 
         continue;
       }
       const int64_t pos = (int64_t)row[i] * GROUP + slot[i];
-      store_slot<TOPO>(rec, rec_elem, pos, e[k == 2 ? 0 : k + 1],
+      where[i] = (int)pos;
+      store_slot<TOPO>(rec, TOPO == 1 ? nullptr : rec_elem, pos, e[k == 2 ? 0 : k + 1],
                        e[k == 0 ? 2 : k - 1] | (k << NODE_BITS), v[k],
                        (int)(((t + j) << 2) | k));
     }
@@ -228,8 +236,15 @@ scatter_kernel(const int *__restrict__ elements, int64_t M, int N, Own own, int 
     const int4 p = __ldg(e4 + 3 * g), q = __ldg(e4 + 3 * g + 1), r = __ldg(e4 + 3 * g + 2);
     if constexpr (!OVERFLOW && PAIRS) {
       const int ab[6] = {p.x, p.y, p.z, p.w, q.x, q.y}, cd[6] = {q.z, q.w, r.x, r.y, r.z, r.w};
-      scatter_pair<V, TOPO>(4 * g, ab, N, own, acc, rec, rec_elem, values, mx, bad, flags);
-      scatter_pair<V, TOPO>(4 * g + 2, cd, N, own, acc, rec, rec_elem, values, mx, bad, flags);
+      int w0[6], w1[6];
+      scatter_pair<V, TOPO>(4 * g, ab, N, own, acc, rec, rec_elem, values, mx, bad, flags, w0);
+      scatter_pair<V, TOPO>(4 * g + 2, cd, N, own, acc, rec, rec_elem, values, mx, bad, flags, w1);
+      if (TOPO == 1 && rec_elem) {  // slot of the 12 half-edges: 3 x 16 bytes, aligned
+        int4 *dst = reinterpret_cast<int4 *>(rec_elem + 12 * g);
+        dst[0] = make_int4(w0[0], w0[1], w0[2], w0[3]);
+        dst[1] = make_int4(w0[4], w0[5], w1[0], w1[1]);
+        dst[2] = make_int4(w1[2], w1[3], w1[4], w1[5]);
+      }
       continue;
     }
     const int ea[3] = {p.x, p.y, p.z}, eb[3] = {p.w, q.x, q.y}, ec[3] = {q.z, q.w, r.x},
@@ -267,17 +282,17 @@ static void launch_one(bool pairs, unsigned grid, cudaStream_t s, const int *ele
 template <int MODE, class V>
 static void launch_scatter_slots(p1_ctx *ctx, unsigned grid, cudaStream_t s, const int *elements,
                                  int64_t M, int N, Own own, unsigned long long *acc, int4 *slots_,
-                                 V values, bool allow_pairs) {
+                                 V values, bool allow_pairs, int *slot_of = nullptr) {
   const int vec = ((uintptr_t)elements & 15) == 0;
   bool pairs = allow_pairs && own.world == 1 && own.re - own.rb == N;
   if (const char *force = getenv("P1_SLOT_PAIRS")) pairs = force[0] == '1';  // experiments
   Rec *slots = reinterpret_cast<Rec *>(slots_);
   if (pairs)
     scatter_kernel<V, false, true, MODE><<<grid, SC_THREADS, 0, s>>>(
-        elements, M, N, own, vec, acc, slots, nullptr, nullptr, values, ctx->d_flags);
+        elements, M, N, own, vec, acc, slots, slot_of, nullptr, values, ctx->d_flags);
   else
     scatter_kernel<V, false, false, MODE><<<grid, SC_THREADS, 0, s>>>(
-        elements, M, N, own, vec, acc, slots, nullptr, nullptr, values, ctx->d_flags);
+        elements, M, N, own, vec, acc, slots, slot_of, nullptr, values, ctx->d_flags);
 }
 
 template <bool OVERFLOW>
@@ -617,8 +632,10 @@ load_scatter_kernel(const int *__restrict__ elements, int64_t M, int N, Own own,
               cd[6] = {id[6], id[7], id[8], id[9], id[10], id[11]};
     const PairLoads v01{{l[0][0], l[0][1], l[0][2]}, {l[1][0], l[1][1], l[1][2]}};
     const PairLoads v23{{l[2][0], l[2][1], l[2][2]}, {l[3][0], l[3][1], l[3][2]}};
-    scatter_pair<PairLoads, 2>(4 * g, ab, N, own, acc, slots, nullptr, v01, mx, bad, flags);
-    scatter_pair<PairLoads, 2>(4 * g + 2, cd, N, own, acc, slots, nullptr, v23, mx, bad, flags);
+    int unused[6];
+    scatter_pair<PairLoads, 2>(4 * g, ab, N, own, acc, slots, nullptr, v01, mx, bad, flags, unused);
+    scatter_pair<PairLoads, 2>(4 * g + 2, cd, N, own, acc, slots, nullptr, v23, mx, bad, flags,
+                               unused);
   }
   for (int64_t t = 4 * quads + tid; t < M; t += stride) {  // the last M % 4 triangles
     const int e[3] = {__ldg(elements + 3 * t), __ldg(elements + 3 * t + 1),
@@ -906,10 +923,16 @@ static int plan_build(p1_ctx *ctx, const int32_t *elements, int64_t n_elements,
     // no row pointer, one synchronisation
     P1_REQUIRE(op == 0, "a topology-only plan carries no operator");
     if ((rc = pool_alloc(ctx, &p->topo, (size_t)n_own * GROUP, s))) return fail(rc);
+    // slot of every half-edge (all rows owned, slot numbers fit an int)
+    if ((flags & P1_PLAN_SLOT_INDEX) && own.world == 1 && own.re - own.rb == N &&
+        (int64_t)n_own * GROUP <= 0x7fffffffLL &&
+        (rc = pool_alloc(ctx, &p->slot_of, (size_t)(3 * M) + 1, s)))
+      return fail(rc);
     cudaMemsetAsync(p->acc, 0, ((size_t)n_own + 1) * sizeof(unsigned long long), s);
     const unsigned tg = min(grid_for(M, THREADS), (unsigned)(ctx->sm_count * 32));
     prof_begin(ctx, "scatter", s);
-    launch_scatter_slots<1>(ctx, tg, s, elements, M, N, own, p->acc, p->topo, NoValues{}, true);
+    launch_scatter_slots<1>(ctx, tg, s, elements, M, N, own, p->acc, p->topo, NoValues{}, true,
+                            p->slot_of);
     prof_end(ctx, s);
     cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, 8 * sizeof(int), cudaMemcpyDeviceToHost, s);
     if (cudaStreamSynchronize(s) != cudaSuccess || cudaGetLastError() != cudaSuccess)
@@ -1128,7 +1151,7 @@ extern "C" int64_t p1_plan_rows(const p1_plan *p) { return p ? p->n_own : -1; }
 extern "C" int p1_plan_destroy(p1_plan *p) {
   if (!p) return P1_OK;
   DeviceGuard guard(p->ctx->device);
-  void *blocks[] = {p->acc, p->rec, p->rec_elem, p->topo, p->ovf_off, p->ovf_rec, p->ovf_elem,
+  void *blocks[] = {p->acc, p->rec, p->rec_elem, p->topo, p->slot_of, p->ovf_off, p->ovf_rec, p->ovf_elem,
                     p->indptr, p->slow_rows, p->big_rows, p->big_first, p->twin};
   for (void *b : blocks) pool_free(p->ctx, b, p->stream);
   delete p;

@@ -77,6 +77,7 @@ struct p1_plan {
   int4 *topo;          // P1_PLAN_TOPOLOGY: 8 * n_own slots {next, prev | k<<29, (element<<2)|k, 0}
                        // INSTEAD of rec / rec_elem / indptr (edge numbering, eta_R, load
                        // vectors need no values and no row pointer)
+  int *slot_of;        // with topo: 3M, slot index 8a+i of half-edge 3T+k (or null)
   int *ovf_off;        // n_own+1 (only when some row overflows) or null
   p1::Rec *ovf_rec;    // n_ovf
   int *ovf_elem;       // n_ovf or null
@@ -91,6 +92,7 @@ struct p1_plan {
   int n_big;
   unsigned char *big_first;  // scratch flags for big rows (2*n_ovf+n_own) or null
   int *twin;           // lazily built: 3M, twin half-edge id T'*3+k' or -1
+  bool twin_partial;   // only the entries of half-edges I -> J with J < I are valid
   int64_t n_open;      // half-edges without twin (valid once twin is built)
 };
 
@@ -237,7 +239,7 @@ __device__ __forceinline__ RowLane analyse_row(int self, const Rec *row, int deg
   return o;
 }
 
-int ensure_twins(p1_plan *plan, cudaStream_t s);
+int ensure_twins(p1_plan *plan, cudaStream_t s, bool backward_only = false);
 // error unless the plan was created with P1_PLAN_KEEP_ELEMENTS
 int require_elements(const p1_plan *plan, const char *who);
 

@@ -225,6 +225,12 @@ class DeviceMesh:
     def plan(self):
         """Symbolic plan that remembers the element of every record (what load
         vectors, edge numbering and eta_R need)."""
+        return self._element_plan(False)
+
+    def _element_plan(self, all_twins):
+        """all_twins: the caller (eta_R) needs the twin of EVERY half-edge; a fresh
+        topology-only plan then also records the slot of every half-edge
+        (P1_PLAN_SLOT_INDEX)."""
         if self._plan is not None and not (self._plan_keeps_elements or self._plan_topology):
             self.close()
         if self._plan is None and not self.reuse and self._topology_fits \
@@ -234,8 +240,9 @@ class DeviceMesh:
             handle = C.c_void_p()
             rc = self._lib.p1_plan_create(
                 self.ctx, _ptr(self.elements), self.n_elements, self.n_nodes,
-                self.rows[0], self.rows[1], _lib.PLAN_TOPOLOGY, _stream(self.device),
-                C.byref(handle))
+                self.rows[0], self.rows[1],
+                _lib.PLAN_TOPOLOGY | (_lib.PLAN_SLOT_INDEX if all_twins else 0),
+                _stream(self.device), C.byref(handle))
             if rc == _lib.P1_ERETRY:
                 self._topology_fits = False     # a node with more than 8 elements
             else:
@@ -519,7 +526,7 @@ class DeviceMesh:
               if neumann.shape[0] else None)
         eta = self._empty(self.n_elements)
         _lib.check(self._lib.p1_eta_r(
-            self.plan, _ptr(self.coords), _ptr(x),
+            self._element_plan(True), _ptr(self.coords), _ptr(x),
             _ptr(dirichlet) if dirichlet.shape[0] else None, int(dirichlet.shape[0]),
             _ptr(neumann) if neumann.shape[0] else None, int(neumann.shape[0]),
             _ptr(nt), _ptr(fc), _ptr(eta), _stream(self.device)))

@@ -523,6 +523,24 @@ def test_topology_plan_matches_element_keeping_plan():
                 assert not mesh._plan_topology
     for a, b in zip(out[False], out[True]):
         assert np.array_equal(a, b)
+    # edge numbering on a one-shot plan builds only the twins it reads (half-edges
+    # I -> J with J < I); an estimator call on the same plan completes them
+    x = torch.from_numpy(H.u_nodal(pts)).cuda()
+    dirichlet = torch.cat(bt)
+    none = torch.zeros((0, 2), dtype=torch.int32, device='cuda')
+    with DeviceMesh(ct, et) as mesh:
+        fc = torch.from_numpy(H.f_load(mesh.centroids().cpu().numpy())).cuda()
+        eta_first = mesh.eta_r(x, dirichlet, none, None, fc).cpu().numpy()
+        gd = mesh.geometric_data(bt)            # twins by gather (P1_PLAN_SLOT_INDEX), all valid
+        assert np.array_equal(gd[0].cpu().numpy(), out[True][1])
+    with DeviceMesh(ct, et) as mesh:
+        gd = mesh.geometric_data(bt)
+        assert np.array_equal(gd[0].cpu().numpy(), out[True][1])
+        assert np.array_equal(mesh.eta_r(x, dirichlet, none, None, fc).cpu().numpy(), eta_first)
+        gd = mesh.geometric_data(bt)            # and the full twins serve the numbering
+        assert np.array_equal(gd[0].cpu().numpy(), out[True][1])
+    assert np.array_equal(eta_first, orc.eta_r(H.u_nodal(pts), pts, e, np.vstack(bnds),
+                                               np.zeros((0, 2), dtype=int), H.f_load, H.g_neu))
     assert np.array_equal(out[False][0], orc.load_vector_midpoint(pts, e, H.f_load))
     o2e, o2n, ob2e = orc.geometric_data(e, bnds)
     assert np.array_equal(out[False][1], o2e) and np.array_equal(out[False][2], o2n)
