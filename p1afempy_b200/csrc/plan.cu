@@ -40,6 +40,35 @@ constexpr int SC_THREADS = P1_SCATTER_THREADS;  // scatter block size
 //                      whose length is not 1 + #records (open fans = boundary
 //                      nodes).  Verified row by row when the matrix is filled.
 //   OVERFLOW == true : only rows with more than 8 records; compact storage.
+// Records that do not fit the 8 slots of their row (a node with more than 8
+// elements: coarse-mesh vertices of an adaptive mesh, a few per cent of the nodes
+// of a Delaunay mesh) go to a spill list; plan_build then gathers every such
+// row's records into compact storage.  Only when the list overflows are the
+// elements scanned a second time.  The descriptor lives in device memory and is
+// read only by the rare thread that spills.
+struct SpillDesc {
+  Rec *rec;
+  int *row, *elem;  // owning row; element code (null unless the plan keeps elements)
+  int cap;
+};
+// (called from a cold block behind ONE branch per triangle / pair: inside the store
+// loop it cost 0.14 ms at 64M without ever running)
+__device__ __forceinline__ void spill_record(const SpillDesc *sp, int *flags, int a, int nx,
+                                             int pvk, double v0, double v1, double v2, int code) {
+#ifdef P1_NO_SPILL
+  return;
+#endif
+  const SpillDesc d = *sp;
+  const int idx = atomicAdd(flags + 5, 1);  // counts every spilled record, kept or not
+  if (idx >= d.cap) return;
+  Rec r;
+  r.nx = nx; r.pvk = pvk;
+  r.vd = v0; r.vn = v1; r.vp = v2;
+  store_rec(d.rec + idx, r);
+  d.row[idx] = a;
+  if (d.elem) d.elem[idx] = code;
+}
+
 // TOPO 0: the 32-byte record (+ the optional element code array)
 //      1: topology-only plan -- one 16-byte slot {next, prev|k, element code, 0}
 //      2: vector payload -- one 16-byte slot {element code, 0, v[0] as two words}:
@@ -94,6 +123,7 @@ __device__ __forceinline__ void scatter_element(int64_t t, const int (&e)[3], in
     z2 = __ldg(values.coords + e[2]);
   }
   values.rows(t, e, z0, z1, z2, v);
+  unsigned over = 0;  // vertices whose row had no free slot
 #pragma unroll
   for (int k = 0; k < 3; ++k)
     if (mine[k]) {
@@ -107,7 +137,7 @@ __device__ __forceinline__ void scatter_element(int64_t t, const int (&e)[3], in
         const unsigned slot =
             (unsigned)atomicAdd(acc + a, ((unsigned long long)d << 32) + 1ull);
         if (slot >= (unsigned)GROUP) {
-          if (TOPO != 0) atomicOr(flags, FLAG_OVERFLOW);
+          over |= 1u << k;
           continue;
         }
         pos = (int64_t)a * GROUP + slot;
@@ -115,6 +145,18 @@ __device__ __forceinline__ void scatter_element(int64_t t, const int (&e)[3], in
       store_slot<TOPO>(rec, rec_elem, pos, nx, pv | (k << NODE_BITS), v[k],
                        (int)((t << 2) | k));
     }
+  if (over) {  // cold: a node with more than 8 elements
+    if (TOPO != 0) {
+      atomicOr(flags, FLAG_OVERFLOW);
+    } else if (cursor) {  // (not the overflow pass: `cursor` is the spill descriptor)
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+        if ((over >> k) & 1u)
+          spill_record(reinterpret_cast<const SpillDesc *>(cursor), flags, row[k],
+                       e[k == 2 ? 0 : k + 1], e[k == 0 ? 2 : k - 1] | (k << NODE_BITS), v[k][0],
+                       v[k][1], v[k][2], (int)((t << 2) | k));
+    }
+  }
 }
 
 // Two consecutive triangles at once: NVB siblings share two of their three
@@ -127,7 +169,8 @@ __device__ __forceinline__ void scatter_pair(int64_t t, const int (&id)[6], int 
                                              unsigned long long *__restrict__ acc,
                                              Rec *__restrict__ rec,
                                              int *__restrict__ rec_elem, const V &values,
-                                             int &mx, bool &bad, int *flags, int (&where)[6]) {
+                                             int &mx, bool &bad, int *flags, int (&where)[6],
+                                             const SpillDesc *spill = nullptr) {
   // where[i]: slot index of reference i (TOPO 1: the caller stores them, 48 bytes
   // per thread at once -- 4-byte stores per record cost 1.2 ms at 64M)
 #pragma unroll
@@ -187,6 +230,7 @@ __device__ __forceinline__ void scatter_pair(int64_t t, const int (&id)[6], int 
     }
     slot[i] = mine[i] ? base[i] + rank : 0xffu;
   }
+  bool over = false;  // some owned reference found its row full
 #pragma unroll
   for (int j = 0; j < 2; ++j) {
     if (!touched[j]) continue;
@@ -197,7 +241,7 @@ __device__ __forceinline__ void scatter_pair(int64_t t, const int (&id)[6], int 
     for (int k = 0; k < 3; ++k) {
       const int i = 3 * j + k;
       if (slot[i] >= (unsigned)GROUP) {
-        if (TOPO != 0 && mine[i]) atomicOr(flags, FLAG_OVERFLOW);
+        if (mine[i]) over = true;
         continue;
       }
       const int64_t pos = (int64_t)row[i] * GROUP + slot[i];
@@ -205,6 +249,32 @@ __device__ __forceinline__ void scatter_pair(int64_t t, const int (&id)[6], int 
       store_slot<TOPO>(rec, TOPO == 1 ? nullptr : rec_elem, pos, e[k == 2 ? 0 : k + 1],
                        e[k == 0 ? 2 : k - 1] | (k << NODE_BITS), v[k],
                        (int)(((t + j) << 2) | k));
+    }
+  }
+  if (over) {  // cold: a node with more than 8 elements; the values are computed again
+    if (TOPO != 0) {
+      atomicOr(flags, FLAG_OVERFLOW);
+    } else if (spill) {
+      for (int j = 0; j < 2; ++j) {
+        if (!touched[j]) continue;
+        const int e[3] = {id[3 * j], id[3 * j + 1], id[3 * j + 2]};
+        double v[3][3];
+        double2 y0 = make_double2(0., 0.), y1 = y0, y2 = y0;
+        if constexpr (V::needs_xy) {  // gathered again: keeping z[] alive costs 18 registers
+          y0 = __ldg(values.coords + e[0]);
+          y1 = __ldg(values.coords + e[1]);
+          y2 = __ldg(values.coords + e[2]);
+        }
+        values.rows(t + j, e, y0, y1, y2, v);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const int i = 3 * j + k;
+          if (mine[i] && slot[i] >= (unsigned)GROUP)
+            spill_record(spill, flags, row[i], e[k == 2 ? 0 : k + 1],
+                         e[k == 0 ? 2 : k - 1] | (k << NODE_BITS), v[k][0], v[k][1], v[k][2],
+                         (int)(((t + j) << 2) | k));
+        }
+      }
     }
   }
 }
@@ -237,8 +307,10 @@ scatter_kernel(const int *__restrict__ elements, int64_t M, int N, Own own, int 
     if constexpr (!OVERFLOW && PAIRS) {
       const int ab[6] = {p.x, p.y, p.z, p.w, q.x, q.y}, cd[6] = {q.z, q.w, r.x, r.y, r.z, r.w};
       int w0[6], w1[6];
-      scatter_pair<V, TOPO>(4 * g, ab, N, own, acc, rec, rec_elem, values, mx, bad, flags, w0);
-      scatter_pair<V, TOPO>(4 * g + 2, cd, N, own, acc, rec, rec_elem, values, mx, bad, flags, w1);
+      const SpillDesc *sp = reinterpret_cast<const SpillDesc *>(cursor);
+      scatter_pair<V, TOPO>(4 * g, ab, N, own, acc, rec, rec_elem, values, mx, bad, flags, w0, sp);
+      scatter_pair<V, TOPO>(4 * g + 2, cd, N, own, acc, rec, rec_elem, values, mx, bad, flags, w1,
+                            sp);
       if (TOPO == 1 && rec_elem) {  // slot of the 12 half-edges: 3 x 16 bytes, aligned
         int4 *dst = reinterpret_cast<int4 *>(rec_elem + 12 * g);
         dst[0] = make_int4(w0[0], w0[1], w0[2], w0[3]);
@@ -387,6 +459,34 @@ overflow_count_kernel(int n_own, const unsigned long long *__restrict__ acc,
   if (a >= n_own) return;
   const int deg = (int)(unsigned)acc[a];
   cnt[a] = deg > GROUP ? deg : 0;
+}
+
+// rows with more than 8 records: their 8 slot records move to the head of the
+// row's compact storage (cursor[a] then points behind them) ...
+__global__ void __launch_bounds__(THREADS)
+overflow_heads_kernel(int n_own, const unsigned long long *__restrict__ acc,
+                      const Rec *__restrict__ rec, const int *__restrict__ rec_elem,
+                      const int *__restrict__ ovf_off, Rec *__restrict__ ovf_rec,
+                      int *__restrict__ ovf_elem, int *__restrict__ cursor) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= n_own) return;
+  if ((int)(unsigned)acc[a] <= GROUP) return;
+  const int off = ovf_off[a];
+  for (int i = 0; i < GROUP; ++i) {
+    ovf_rec[off + i] = rec[(int64_t)a * GROUP + i];
+    if (ovf_elem) ovf_elem[off + i] = rec_elem[(int64_t)a * GROUP + i];
+  }
+  cursor[a] = off + GROUP;
+}
+// ... and the spilled ones follow in arrival order
+__global__ void __launch_bounds__(THREADS)
+overflow_place_kernel(int n_spill, SpillDesc sp, int *__restrict__ cursor,
+                      Rec *__restrict__ ovf_rec, int *__restrict__ ovf_elem) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_spill) return;
+  const int pos = atomicAdd(cursor + sp.row[i], 1);
+  ovf_rec[pos] = sp.rec[i];
+  if (ovf_elem) ovf_elem[pos] = sp.elem[i];
 }
 
 // distinct values of {self} U {next_i} U {prev_i}, any number of records;
@@ -900,7 +1000,16 @@ static int plan_build(p1_ctx *ctx, const int32_t *elements, int64_t n_elements,
   int rc = P1_OK;
   int *rowlen = nullptr, *cnt = nullptr;
   double *d_weights = nullptr, *d_points = nullptr;
+  SpillDesc spill{nullptr, nullptr, nullptr, 0};  // records of rows with more than 8
+  SpillDesc *d_spill = nullptr;
+  auto free_spill = [&]() {
+    pool_free(ctx, spill.rec, s); pool_free(ctx, spill.row, s); pool_free(ctx, spill.elem, s);
+    pool_free(ctx, d_spill, s);
+    spill = SpillDesc{nullptr, nullptr, nullptr, 0};
+    d_spill = nullptr;
+  };
   auto fail = [&](int code) {
+    free_spill();
     pool_free(ctx, rowlen, s);
     pool_free(ctx, cnt, s);
     pool_free(ctx, d_weights, s);
@@ -978,9 +1087,23 @@ static int plan_build(p1_ctx *ctx, const int32_t *elements, int64_t n_elements,
     pool_free(ctx, d_points, s);
     d_weights = d_points = nullptr;
   };
+  {  // spill list (see SpillDesc)
+    int64_t cap = (3 * M) / 64;
+    cap = cap < 4096 ? 4096 : (cap > (1 << 22) ? (1 << 22) : cap);
+    if (const char *e = getenv("P1_SPILL_CAP")) cap = atoi(e) > 0 ? atoi(e) : 1;  // tests
+    spill.cap = (int)cap;
+    if ((rc = pool_alloc(ctx, &spill.rec, (size_t)cap, s)) ||
+        (rc = pool_alloc(ctx, &spill.row, (size_t)cap, s)) ||
+        (keep && (rc = pool_alloc(ctx, &spill.elem, (size_t)cap, s))) ||
+        (rc = pool_alloc(ctx, &d_spill, (size_t)1, s)))
+      return fail(rc);
+    // (pageable host source: the copy is staged before the call returns)
+    cudaMemcpyAsync(d_spill, &spill, sizeof(spill), cudaMemcpyHostToDevice, s);
+  }
   prof_begin(ctx, "scatter", s);
   launch_scatter<false>(ctx, eg, s, op, elements, M, N, own, p->acc, p->rec,
-                        p->rec_elem, nullptr, coords, local, qa, d_weights, d_points);
+                        p->rec_elem, reinterpret_cast<int *>(d_spill), coords, local, qa,
+                        d_weights, d_points);
   prof_end(ctx, s);
   p->val_op = op;
   const Rows rows0 = rows_of(p);
@@ -1035,10 +1158,23 @@ static int plan_build(p1_ctx *ctx, const int32_t *elements, int64_t n_elements,
     if ((rc = pool_alloc(ctx, &p->ovf_rec, (size_t)p->n_ovf, s))) return fail(rc);
     if (keep && (rc = pool_alloc(ctx, &p->ovf_elem, (size_t)p->n_ovf, s))) return fail(rc);
     cudaMemcpyAsync(cnt, p->ovf_off, (size_t)n_own * sizeof(int), cudaMemcpyDeviceToDevice, s);
-    prof_begin(ctx, "scatter_overflow", s);
-    launch_scatter<true>(ctx, eg, s, op, elements, M, N, own, p->acc, p->ovf_rec,
-                         p->ovf_elem, cnt, coords, local, qa, d_weights, d_points);
-    prof_end(ctx, s);
+    const int n_spill = ctx->h_flags[5];
+    if (n_spill <= spill.cap) {
+      // the common case: a few rows; their records are already here
+      prof_begin(ctx, "overflow_collect", s);
+      overflow_heads_kernel<<<grid_for(n_own, THREADS), THREADS, 0, s>>>(
+          n_own, p->acc, p->rec, p->rec_elem, p->ovf_off, p->ovf_rec, p->ovf_elem, cnt);
+      if (n_spill > 0)
+        overflow_place_kernel<<<grid_for(n_spill, THREADS), THREADS, 0, s>>>(
+            n_spill, spill, cnt, p->ovf_rec, p->ovf_elem);
+      prof_end(ctx, s);
+    } else {
+      // the spill list was too small: scan the elements again for those rows
+      prof_begin(ctx, "scatter_overflow", s);
+      launch_scatter<true>(ctx, eg, s, op, elements, M, N, own, p->acc, p->ovf_rec,
+                           p->ovf_elem, cnt, coords, local, qa, d_weights, d_points);
+      prof_end(ctx, s);
+    }
     pool_free(ctx, cnt, s);
     cnt = nullptr;
     const Rows rows = rows_of(p);
@@ -1063,6 +1199,7 @@ static int plan_build(p1_ctx *ctx, const int32_t *elements, int64_t n_elements,
   pool_free(ctx, rowlen, s);
   rowlen = nullptr;
   free_rule();
+  free_spill();
   p->nnz = h_nnz;
   *out = p;
   return P1_OK;

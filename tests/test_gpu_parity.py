@@ -574,6 +574,36 @@ def test_topology_plan_matches_element_keeping_plan():
         assert np.array_equal(b.cpu().numpy(), orc.load_vector_midpoint(fp, fe, H.f_load))
 
 
+def test_spill_list_and_second_pass_agree(api, monkeypatch):
+    """Rows with more than 8 records: their extra records travel through a spill
+    list; when the list is too small the elements are scanned a second time.  Both
+    routes give the same matrix (Delaunay mesh, valence up to 10+; and a fan)."""
+    from scipy.spatial import Delaunay
+    rng = np.random.default_rng(5)
+    pts = np.vstack([rng.random((4000, 2)), [[0., 0.], [1., 0.], [1., 1.], [0., 1.]]])
+    e = Delaunay(pts).simplices.astype(np.int64)
+    d1, d2 = pts[e[:, 1]] - pts[e[:, 0]], pts[e[:, 2]] - pts[e[:, 0]]
+    flip = (d1[:, 0] * d2[:, 1] - d1[:, 1] * d2[:, 0]) < 0
+    e[flip] = e[flip][:, [0, 2, 1]]
+    assert np.bincount(e.reshape(-1)).max() > 8
+    ref = orc.stiffness_coo(pts, e).tocsr()
+    got = {}
+    for cap in (None, '3'):
+        if cap is None:
+            monkeypatch.delenv('P1_SPILL_CAP', raising=False)
+        else:
+            monkeypatch.setenv('P1_SPILL_CAP', cap)
+        a = api[0].get_stiffness_matrix(pts, e)
+        assert np.array_equal(a.indptr, ref.indptr) and np.array_equal(a.indices, ref.indices)
+        H.csr_values_close(a, ref, RTOL)
+        m = api[0].get_mass_matrix(pts, e)
+        H.csr_values_close(m, orc.mass_coo(pts, e).tocsr(), RTOL)
+        got[cap] = a.data.copy()
+    # off-diagonals identical; diagonals of high-valence rows may differ in the last
+    # bits (their summation order is the arrival order of the records)
+    assert np.abs(got[None] - got['3']).max() <= 1e-13 * np.abs(ref.data).max()
+
+
 def test_empty_and_tiny_inputs(api):
     """Empty element arrays (the reference: scipy cannot infer a shape ->
     ValueError; explicit-shape builders return empty matrices) and a single

@@ -88,10 +88,34 @@ def cold():
     return mesh.eta_r(x, dirichlet, none, None, ones)
 
 
+def kernels(fn, reps=3):
+    """per-kernel CUDA-event times of one call (library profiler)"""
+    import ctypes as C
+    from bench import parse_profile
+    from p1afempy_b200 import _lib
+    from p1afempy_b200.device import context
+    ctx, _ = context(0)
+    lib = _lib.load()
+    fn()
+    torch.cuda.synchronize()
+    lib.p1_profile_reset(ctx)
+    lib.p1_profile_enable(ctx, 1)
+    for _ in range(reps):
+        fn()
+    torch.cuda.synchronize()
+    buf = C.create_string_buffer(1 << 14)
+    lib.p1_profile_report(ctx, buf, len(buf))
+    lib.p1_profile_enable(ctx, 0)
+    return {k: round(v[0] / reps, 3) for k, v in parse_profile(buf.value.decode()).items()}
+
+
 t_cold = timed(cold)
 t_warm = timed(lambda: mesh.eta_r(x, dirichlet, none, None, ones))
 eta = mesh.eta_r(x, dirichlet, none, None, ones)
 t_asm = timed(lambda: mesh.stiffness_csr())
+k_cold = kernels(cold)
+k_asm = kernels(lambda: mesh.stiffness_csr())
+deg = torch.bincount(et.reshape(-1).long(), minlength=n)
 out = {
     'config': 'compute_eta_r on an adaptively refined L-shape (Doerfler 0.5 from 6.3M uniform)',
     'M': m, 'N': n, 'boundary_edges': int(dirichlet.shape[0]),
@@ -103,5 +127,7 @@ out = {
     'eta_r_reused_algorithmic_GBs': 40.0 * m / t_warm / 1e6,
     'stiffness_to_csr_ms': t_asm, 'stiffness_Gelem_s': m / t_asm / 1e6,
     'eta_sum': float(eta.sum()), 'eta_finite': bool(torch.isfinite(eta).all()),
+    'eta_r_cold_kernels_ms': k_cold, 'stiffness_kernels_ms': k_asm,
+    'max_elements_per_node': int(deg.max()), 'nodes_with_more_than_8': int((deg > 8).sum()),
 }
 print(json.dumps(out, indent=1))
