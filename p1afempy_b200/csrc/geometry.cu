@@ -32,6 +32,7 @@ twin_kernel(int n_nodes, Rows rows, int *__restrict__ twin, int *__restrict__ fl
   if (a >= n_nodes) return;
   const int deg = rows.deg(a);
   if (deg == 0) return;
+  if (rows.topo && deg > GROUP) return;  // twin_overflow_kernel
   int open_edges = 0;
   bool nonmanifold = false;
   const Rec *rec = rows.topo ? nullptr : rows.ptr(a, deg);
@@ -118,7 +119,7 @@ twin_rows_kernel(int n_nodes, const unsigned long long *__restrict__ acc,
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= n_nodes) return;
   const int deg = (int)(unsigned)acc[a];
-  if (deg == 0) return;  // (more than 8: the plan does not exist)
+  if (deg == 0 || deg > GROUP) return;  // (more than 8: twin_overflow_kernel)
   int open_edges = 0;
   bool nonmanifold = false;
   int nx[GROUP], pv[GROUP], cd[GROUP], out[GROUP];
@@ -159,6 +160,37 @@ twin_gather_kernel(int64_t n_halfedges, const int *__restrict__ slot_of,
   for (int64_t h = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; h < n_halfedges;
        h += (int64_t)gridDim.x * blockDim.x)
     twin[h] = __ldg(tw + __ldg(slot_of + h));
+}
+
+// Rows of a topology-only plan with more than 8 records (few: TSPILL_CAP): the
+// thread of the FIRST spilled record of a row matches all of the row's records.
+// tw != null: results go to tw[where] (gathered later through slot_of), else
+// straight to twin[half-edge] (backward_only: only for half-edges a -> x, x < a).
+__global__ void __launch_bounds__(THREADS)
+twin_overflow_kernel(Rows rows, int n_rows, int *__restrict__ tw, int *__restrict__ twin,
+                     int backward_only, int *__restrict__ flags) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= rows.n_tspill) return;
+  const int a = rows.tspill[s].w;
+  for (int j = 0; j < s; ++j)
+    if (rows.tspill[j].w == a) return;  // not the first of its row
+  int open_edges = 0;
+  bool nonmanifold = false;
+  topo_row_records(rows, a, n_rows, [&](int where, int4 r) {
+    const int target = r.x;
+    int found = -1, hits = 0, same = 0;
+    topo_row_records(rows, a, n_rows, [&](int, int4 q) {
+      if ((q.y & NODE_MASK) == target) { found = q.z; ++hits; }
+      same += q.x == target;
+    });
+    nonmanifold = nonmanifold || hits > 1 || same > 1;
+    const int result = hits == 0 ? -1 : 3 * (found >> 2) + prev_local(found & 3);
+    open_edges += hits == 0;
+    if (tw) tw[where] = result;
+    else if (!backward_only || target < a) twin[halfedge_of(r.z)] = result;
+  });
+  if (open_edges) atomicAdd(flags + 1, open_edges);
+  if (nonmanifold) atomicOr(flags, FLAG_NONMANIFOLD);
 }
 
 // position p of the reference's concatenated half-edge list:
@@ -303,6 +335,11 @@ __device__ __forceinline__ int64_t locate_halfedge(int b0, int b1,
     const int4 *slot = rows.topo + (int64_t)b0 * GROUP;
     for (int i = 0; i < end && i < GROUP; ++i)
       if (slot[i].x == b1) return (int64_t)halfedge_of(slot[i].z);
+    if (end > GROUP)
+      for (int j = 0; j < rows.n_tspill; ++j) {
+        const int4 r = rows.tspill[j];
+        if (r.w == b0 && r.x == b1) return (int64_t)halfedge_of(r.z);
+      }
     return -1;
   }
   const Rec *rec = rows.ptr(b0, end);
@@ -457,11 +494,14 @@ int ensure_twins(p1_plan *p, cudaStream_t s, bool backward_only) {
   P1_CUDA(cudaMemsetAsync(p->ctx->d_flags, 0, 8 * sizeof(int), s));
   if (p->N > 0 && p->topo && p->slot_of) {
     int *tw = nullptr;
-    P1_TRY(pool_alloc(ctx, &tw, (size_t)p->N * GROUP, s));
+    P1_TRY(pool_alloc(ctx, &tw, (size_t)p->N * GROUP + TSPILL_CAP, s));
     p->twin_partial = false;
     P1_TIMED(ctx, "twin", s, {
       twin_rows_kernel<<<grid_for(p->N, THREADS), THREADS, 0, s>>>((int)p->N, p->acc, p->topo, tw,
                                                                   p->ctx->d_flags);
+      if (p->n_tspill > 0)
+        twin_overflow_kernel<<<grid_for(p->n_tspill, THREADS), THREADS, 0, s>>>(
+            rows_of(p), (int)p->N, tw, nullptr, 0, p->ctx->d_flags);
       twin_gather_kernel<<<min(grid_for(3 * p->M, THREADS), (unsigned)(ctx->sm_count * 32)),
                            THREADS, 0, s>>>(3 * p->M, p->slot_of, tw, p->twin);
     });
@@ -473,6 +513,9 @@ int ensure_twins(p1_plan *p, cudaStream_t s, bool backward_only) {
     else
       P1_TIMED(ctx, "twin", s, twin_kernel<false><<<grid_for(p->N, THREADS), THREADS, 0, s>>>(
           (int)p->N, rows_of(p), p->twin, p->ctx->d_flags));
+    if (p->topo && p->n_tspill > 0)
+      twin_overflow_kernel<<<grid_for(p->n_tspill, THREADS), THREADS, 0, s>>>(
+          rows_of(p), (int)p->n_own, nullptr, p->twin, backward_only ? 1 : 0, p->ctx->d_flags);
   }
   P1_CUDA(cudaGetLastError());
   P1_TRY(read_flags(p->ctx, s));

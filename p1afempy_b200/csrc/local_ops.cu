@@ -427,9 +427,16 @@ gather_nodes_kernel(int n_own, Rows rows, const double *__restrict__ L,
     for (int q = 0; q < deg; ++q) {
       unsigned best = 0xffffffffu;
       int pick = 0;
-      for (int i = 0; i < deg; ++i) {
-        const unsigned key = gather_key(code[i], VERTEX_MAJOR);
-        if ((first || key > last) && key < best) { best = key; pick = code[i]; }
+      if (rows.topo) {
+        topo_row_records(rows, a, n_own, [&](int, int4 r) {
+          const unsigned key = gather_key(r.z, VERTEX_MAJOR);
+          if ((first || key > last) && key < best) { best = key; pick = r.z; }
+        });
+      } else {
+        for (int i = 0; i < deg; ++i) {
+          const unsigned key = gather_key(code[i], VERTEX_MAJOR);
+          if ((first || key > last) && key < best) { best = key; pick = code[i]; }
+        }
       }
       const int t = pick >> 2, k = pick & 3;
       sum += __ldg(L + (STRIDE == 3 ? 3 * (int64_t)t + k : (int64_t)t));

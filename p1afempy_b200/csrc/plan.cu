@@ -146,7 +146,29 @@ __device__ __forceinline__ void scatter_element(int64_t t, const int (&e)[3], in
                        (int)((t << 2) | k));
     }
   if (over) {  // cold: a node with more than 8 elements
-    if (TOPO != 0) {
+    if (TOPO == 1 && cursor) {  // `cursor` is the topology spill list
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+        if ((over >> k) & 1u) {
+          const int idx = atomicAdd(flags + 5, 1);
+          if (idx < TSPILL_CAP) {
+            reinterpret_cast<int4 *>(cursor)[idx] =
+                make_int4(e[k == 2 ? 0 : k + 1], e[k == 0 ? 2 : k - 1] | (k << NODE_BITS),
+                          (int)((t << 2) | k), row[k]);
+            if (rec_elem) rec_elem[3 * t + k] = N * GROUP + idx;
+          }
+        }
+    } else if (TOPO == 2 && cursor) {  // payload spill list: {code, row, value}
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+        if ((over >> k) & 1u) {
+          const int idx = atomicAdd(flags + 5, 1);
+          if (idx < TSPILL_CAP)
+            reinterpret_cast<int4 *>(cursor)[idx] =
+                make_int4((int)((t << 2) | k), row[k], __double2loint(v[k][0]),
+                          __double2hiint(v[k][0]));
+        }
+    } else if (TOPO != 0) {
       atomicOr(flags, FLAG_OVERFLOW);
     } else if (cursor) {  // (not the overflow pass: `cursor` is the spill descriptor)
 #pragma unroll
@@ -252,7 +274,44 @@ __device__ __forceinline__ void scatter_pair(int64_t t, const int (&id)[6], int 
     }
   }
   if (over) {  // cold: a node with more than 8 elements; the values are computed again
-    if (TOPO != 0) {
+    if (TOPO == 1 && spill) {  // `spill` is the topology spill list
+#pragma unroll
+      for (int i = 0; i < 6; ++i)
+        if (mine[i] && slot[i] >= (unsigned)GROUP) {
+          const int j = i / 3, k = i - 3 * j;
+          const int idx = atomicAdd(flags + 5, 1);
+          if (idx < TSPILL_CAP) {
+            reinterpret_cast<int4 *>(const_cast<SpillDesc *>(spill))[idx] =
+                make_int4(id[3 * j + (k == 2 ? 0 : k + 1)],
+                          id[3 * j + (k == 0 ? 2 : k - 1)] | (k << NODE_BITS),
+                          (int)(((t + j) << 2) | k), row[i]);
+            where[i] = N * GROUP + idx;
+          }
+        }
+    } else if (TOPO == 2 && spill) {  // payload spill list: {code, row, value}
+      for (int j = 0; j < 2; ++j) {
+        if (!touched[j]) continue;
+        const int e[3] = {id[3 * j], id[3 * j + 1], id[3 * j + 2]};
+        double v[3][3];
+        double2 y0 = make_double2(0., 0.), y1 = y0, y2 = y0;
+        if constexpr (V::needs_xy) {
+          y0 = __ldg(values.coords + e[0]);
+          y1 = __ldg(values.coords + e[1]);
+          y2 = __ldg(values.coords + e[2]);
+        }
+        values.rows(t + j, e, y0, y1, y2, v);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const int i = 3 * j + k;
+          if (!(mine[i] && slot[i] >= (unsigned)GROUP)) continue;
+          const int idx = atomicAdd(flags + 5, 1);
+          if (idx < TSPILL_CAP)
+            reinterpret_cast<int4 *>(const_cast<SpillDesc *>(spill))[idx] =
+                make_int4((int)(((t + j) << 2) | k), row[i], __double2loint(v[k][0]),
+                          __double2hiint(v[k][0]));
+        }
+      }
+    } else if (TOPO != 0) {
       atomicOr(flags, FLAG_OVERFLOW);
     } else if (spill) {
       for (int j = 0; j < 2; ++j) {
@@ -354,17 +413,20 @@ static void launch_one(bool pairs, unsigned grid, cudaStream_t s, const int *ele
 template <int MODE, class V>
 static void launch_scatter_slots(p1_ctx *ctx, unsigned grid, cudaStream_t s, const int *elements,
                                  int64_t M, int N, Own own, unsigned long long *acc, int4 *slots_,
-                                 V values, bool allow_pairs, int *slot_of = nullptr) {
+                                 V values, bool allow_pairs, int *slot_of = nullptr,
+                                 int4 *tspill = nullptr) {
   const int vec = ((uintptr_t)elements & 15) == 0;
   bool pairs = allow_pairs && own.world == 1 && own.re - own.rb == N;
   if (const char *force = getenv("P1_SLOT_PAIRS")) pairs = force[0] == '1';  // experiments
   Rec *slots = reinterpret_cast<Rec *>(slots_);
   if (pairs)
     scatter_kernel<V, false, true, MODE><<<grid, SC_THREADS, 0, s>>>(
-        elements, M, N, own, vec, acc, slots, slot_of, nullptr, values, ctx->d_flags);
+        elements, M, N, own, vec, acc, slots, slot_of, reinterpret_cast<int *>(tspill), values,
+        ctx->d_flags);
   else
     scatter_kernel<V, false, false, MODE><<<grid, SC_THREADS, 0, s>>>(
-        elements, M, N, own, vec, acc, slots, slot_of, nullptr, values, ctx->d_flags);
+        elements, M, N, own, vec, acc, slots, slot_of, reinterpret_cast<int *>(tspill), values,
+        ctx->d_flags);
 }
 
 template <bool OVERFLOW>
@@ -652,7 +714,8 @@ load_scatter_kernel(const int *__restrict__ elements, int64_t M, int N, Own own,
                     const double2 *__restrict__ coords, const double *__restrict__ f,
                     const double *__restrict__ weights, const double2 *__restrict__ points,
                     int n_qp, int wide, unsigned long long *__restrict__ acc,
-                    Rec *__restrict__ slots, int *__restrict__ flags) {
+                    Rec *__restrict__ slots, int4 *__restrict__ spill_list,
+                    int *__restrict__ flags) {
   int mx = -1;
   bool bad = false;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -733,18 +796,22 @@ load_scatter_kernel(const int *__restrict__ elements, int64_t M, int N, Own own,
     const PairLoads v01{{l[0][0], l[0][1], l[0][2]}, {l[1][0], l[1][1], l[1][2]}};
     const PairLoads v23{{l[2][0], l[2][1], l[2][2]}, {l[3][0], l[3][1], l[3][2]}};
     int unused[6];
-    scatter_pair<PairLoads, 2>(4 * g, ab, N, own, acc, slots, nullptr, v01, mx, bad, flags, unused);
+    const SpillDesc *sp = reinterpret_cast<const SpillDesc *>(spill_list);
+    scatter_pair<PairLoads, 2>(4 * g, ab, N, own, acc, slots, nullptr, v01, mx, bad, flags, unused,
+                               sp);
     scatter_pair<PairLoads, 2>(4 * g + 2, cd, N, own, acc, slots, nullptr, v23, mx, bad, flags,
-                               unused);
+                               unused, sp);
   }
   for (int64_t t = 4 * quads + tid; t < M; t += stride) {  // the last M % 4 triangles
     const int e[3] = {__ldg(elements + 3 * t), __ldg(elements + 3 * t + 1),
                       __ldg(elements + 3 * t + 2)};
     if (MIDPOINT)
-      scatter_element<LoadMidpointValues, false, 2>(t, e, N, own, acc, slots, nullptr, nullptr,
+      scatter_element<LoadMidpointValues, false, 2>(t, e, N, own, acc, slots, nullptr,
+                                                    reinterpret_cast<int *>(spill_list),
                                                     LoadMidpointValues{coords, f}, mx, bad, flags);
     else
-      scatter_element<LoadQuadValues, false, 2>(t, e, N, own, acc, slots, nullptr, nullptr,
+      scatter_element<LoadQuadValues, false, 2>(t, e, N, own, acc, slots, nullptr,
+                                                reinterpret_cast<int *>(spill_list),
                                                 LoadQuadValues{coords, f, weights, points, n_qp, M},
                                                 mx, bad, flags);
   }
@@ -795,22 +862,63 @@ sum_slots_kernel(int n, const unsigned long long *__restrict__ acc,
   b[a] = sum;
 }
 
+// nodes with more than 8 incidences: the thread of the FIRST spilled entry of a node
+// adds all of the node's values (8 slots + its spilled entries) in key order
+__global__ void __launch_bounds__(THREADS)
+sum_spilled_kernel(const unsigned long long *__restrict__ acc, const int4 *__restrict__ slots,
+                   const int4 *__restrict__ spill_list, const int *__restrict__ n_spilled,
+                   int vertex_major, double *__restrict__ b) {
+  const int n = min(*n_spilled, TSPILL_CAP);
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  const int a = spill_list[s].y;
+  for (int j = 0; j < s; ++j)
+    if (spill_list[j].y == a) return;
+  const int deg = (int)(unsigned)acc[a];
+  auto key_of = [&](int code) {
+    const unsigned c = (unsigned)code;
+    return vertex_major ? ((c & 3u) << 29) | (c >> 2) : c;
+  };
+  double sum = 0.;
+  unsigned last = 0;
+  for (int q = 0; q < deg; ++q) {
+    unsigned best = 0xffffffffu;
+    double val = 0.;
+    for (int i = 0; i < GROUP; ++i) {
+      const int4 r = slots[(int64_t)a * GROUP + i];
+      const unsigned key = key_of(r.x);
+      if ((q == 0 || key > last) && key < best) { best = key; val = __hiloint2double(r.w, r.z); }
+    }
+    for (int j = 0; j < n; ++j) {
+      const int4 r = spill_list[j];
+      if (r.y != a) continue;
+      const unsigned key = key_of(r.x);
+      if ((q == 0 || key > last) && key < best) { best = key; val = __hiloint2double(r.w, r.z); }
+    }
+    if (best == 0xffffffffu) break;  // (entries beyond the list's capacity: call refused)
+    sum += val;
+    last = best;
+  }
+  b[a] = sum;
+}
+
 // f as 32-byte loads: the rows of the [n_qp x M] array must stay 32-byte aligned
 static void launch_load_scatter(unsigned grid, cudaStream_t s, const int *elements, int64_t M,
                                 int N, Own own, const LoadQuadValues &v, unsigned long long *acc,
-                                int4 *slots, int *flags) {
+                                int4 *slots, int4 *spill_list, int *flags) {
   const int wide = ((uintptr_t)v.fq & 31) == 0 && (M & 3) == 0;
   load_scatter_kernel<false><<<grid, SC_THREADS, 0, s>>>(
       elements, M, N, own, v.coords, v.fq, v.weights, v.points, v.n_qp, wide, acc,
-      reinterpret_cast<Rec *>(slots), flags);
+      reinterpret_cast<Rec *>(slots), spill_list, flags);
 }
 static void launch_load_scatter(unsigned grid, cudaStream_t s, const int *elements, int64_t M,
                                 int N, Own own, const LoadMidpointValues &v,
-                                unsigned long long *acc, int4 *slots, int *flags) {
+                                unsigned long long *acc, int4 *slots, int4 *spill_list,
+                                int *flags) {
   const int wide = ((uintptr_t)v.f_centroid & 31) == 0;
   load_scatter_kernel<true><<<grid, SC_THREADS, 0, s>>>(
       elements, M, N, own, v.coords, v.f_centroid, nullptr, nullptr, 0, wide, acc,
-      reinterpret_cast<Rec *>(slots), flags);
+      reinterpret_cast<Rec *>(slots), spill_list, flags);
 }
 
 template <class V>
@@ -823,8 +931,11 @@ static int load_vector_direct(p1_ctx *ctx, const int32_t *elements, int64_t M, i
   int4 *slots = nullptr;
   int rc;
   if ((rc = pool_alloc(ctx, &acc, (size_t)N + 1, s))) return rc;
-  if ((rc = pool_alloc(ctx, &slots, (size_t)N * GROUP, s))) {
+  int4 *spill_list = nullptr;  // {code, row, value} of the records beyond 8 per node
+  if ((rc = pool_alloc(ctx, &slots, (size_t)N * GROUP, s)) ||
+      (rc = pool_alloc(ctx, &spill_list, (size_t)TSPILL_CAP, s))) {
     pool_free(ctx, acc, s);
+    pool_free(ctx, slots, s);
     return rc;
   }
   cudaMemsetAsync(ctx->d_flags, 0, 8 * sizeof(int), s);
@@ -837,9 +948,11 @@ static int load_vector_direct(p1_ctx *ctx, const int32_t *elements, int64_t M, i
       return !(e && e[0] == '0');
     }();
     if (quad_kernel && ((uintptr_t)elements & 15) == 0)
-      launch_load_scatter(grid, s, elements, M, N, own, values, acc, slots, ctx->d_flags);
+      launch_load_scatter(grid, s, elements, M, N, own, values, acc, slots, spill_list,
+                          ctx->d_flags);
     else
-      launch_scatter_slots<2>(ctx, grid, s, elements, M, N, own, acc, slots, values, allow_pairs);
+      launch_scatter_slots<2>(ctx, grid, s, elements, M, N, own, acc, slots, values, allow_pairs,
+                              nullptr, spill_list);
     prof_end(ctx, s);
   }
   if (N > 0) {
@@ -848,6 +961,9 @@ static int load_vector_direct(p1_ctx *ctx, const int32_t *elements, int64_t M, i
       sum_slots_kernel<true><<<grid_for(N, THREADS), THREADS, 0, s>>>(N, acc, slots, b);
     else
       sum_slots_kernel<false><<<grid_for(N, THREADS), THREADS, 0, s>>>(N, acc, slots, b);
+    // nodes with more than 8 elements (the count of spilled records is read on the device)
+    sum_spilled_kernel<<<grid_for(TSPILL_CAP, THREADS), THREADS, 0, s>>>(
+        acc, slots, spill_list, ctx->d_flags + 5, vertex_major ? 1 : 0, b);
     prof_end(ctx, s);
   }
   cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, 8 * sizeof(int), cudaMemcpyDeviceToHost, s);
@@ -855,6 +971,7 @@ static int load_vector_direct(p1_ctx *ctx, const int32_t *elements, int64_t M, i
   if (e == cudaSuccess) e = cudaGetLastError();
   pool_free(ctx, acc, s);
   pool_free(ctx, slots, s);
+  pool_free(ctx, spill_list, s);
   if (e != cudaSuccess) {
     set_error("%s: %s", who, cudaGetErrorString(e));
     return P1_ECUDA;
@@ -863,9 +980,9 @@ static int load_vector_direct(p1_ctx *ctx, const int32_t *elements, int64_t M, i
     set_error("%s: element index out of range [0, %lld)", who, (long long)n_nodes);
     return P1_EINDEX;
   }
-  if (ctx->h_flags[0] & FLAG_OVERFLOW) {
-    set_error("%s: a node has more than 8 elements; use a plan "
-              "(P1_PLAN_KEEP_ELEMENTS) and p1_load_vector", who);
+  if ((ctx->h_flags[0] & FLAG_OVERFLOW) || ctx->h_flags[5] > TSPILL_CAP) {
+    set_error("%s: more than %d incidences beyond 8 per node; use a plan "
+              "(P1_PLAN_KEEP_ELEMENTS) and p1_load_vector", who, TSPILL_CAP);
     return P1_ERETRY;
   }
   return P1_OK;
@@ -1033,15 +1150,16 @@ static int plan_build(p1_ctx *ctx, const int32_t *elements, int64_t n_elements,
     P1_REQUIRE(op == 0, "a topology-only plan carries no operator");
     if ((rc = pool_alloc(ctx, &p->topo, (size_t)n_own * GROUP, s))) return fail(rc);
     // slot of every half-edge (all rows owned, slot numbers fit an int)
+    if ((rc = pool_alloc(ctx, &p->tspill, (size_t)TSPILL_CAP, s))) return fail(rc);
     if ((flags & P1_PLAN_SLOT_INDEX) && own.world == 1 && own.re - own.rb == N &&
-        (int64_t)n_own * GROUP <= 0x7fffffffLL &&
+        (int64_t)n_own * GROUP + TSPILL_CAP <= 0x7fffffffLL &&
         (rc = pool_alloc(ctx, &p->slot_of, (size_t)(3 * M) + 1, s)))
       return fail(rc);
     cudaMemsetAsync(p->acc, 0, ((size_t)n_own + 1) * sizeof(unsigned long long), s);
     const unsigned tg = min(grid_for(M, THREADS), (unsigned)(ctx->sm_count * 32));
     prof_begin(ctx, "scatter", s);
     launch_scatter_slots<1>(ctx, tg, s, elements, M, N, own, p->acc, p->topo, NoValues{}, true,
-                            p->slot_of);
+                            p->slot_of, p->tspill);
     prof_end(ctx, s);
     cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, 8 * sizeof(int), cudaMemcpyDeviceToHost, s);
     if (cudaStreamSynchronize(s) != cudaSuccess || cudaGetLastError() != cudaSuccess)
@@ -1050,11 +1168,12 @@ static int plan_build(p1_ctx *ctx, const int32_t *elements, int64_t n_elements,
       set_error("p1_plan_create: element index out of range [0, %lld)", (long long)n_nodes);
       return fail(P1_EINDEX);
     }
-    if (ctx->h_flags[0] & FLAG_OVERFLOW) {
-      set_error("p1_plan_create: P1_PLAN_TOPOLOGY holds at most 8 elements per node; "
-                "use P1_PLAN_KEEP_ELEMENTS for this mesh");
+    if ((ctx->h_flags[0] & FLAG_OVERFLOW) || ctx->h_flags[5] > TSPILL_CAP) {
+      set_error("p1_plan_create: P1_PLAN_TOPOLOGY holds 8 elements per node plus %d in "
+                "total beyond that; use P1_PLAN_KEEP_ELEMENTS for this mesh", TSPILL_CAP);
       return fail(P1_ERETRY);
     }
+    p->n_tspill = ctx->h_flags[5];
     p->max_index = ctx->h_flags[1];
     p->nnz = 0;
     *out = p;
@@ -1288,7 +1407,7 @@ extern "C" int64_t p1_plan_rows(const p1_plan *p) { return p ? p->n_own : -1; }
 extern "C" int p1_plan_destroy(p1_plan *p) {
   if (!p) return P1_OK;
   DeviceGuard guard(p->ctx->device);
-  void *blocks[] = {p->acc, p->rec, p->rec_elem, p->topo, p->slot_of, p->ovf_off, p->ovf_rec, p->ovf_elem,
+  void *blocks[] = {p->acc, p->rec, p->rec_elem, p->topo, p->slot_of, p->tspill, p->ovf_off, p->ovf_rec, p->ovf_elem,
                     p->indptr, p->slow_rows, p->big_rows, p->big_first, p->twin};
   for (void *b : blocks) pool_free(p->ctx, b, p->stream);
   delete p;

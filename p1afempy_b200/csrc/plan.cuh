@@ -78,6 +78,9 @@ struct p1_plan {
                        // INSTEAD of rec / rec_elem / indptr (edge numbering, eta_R, load
                        // vectors need no values and no row pointer)
   int *slot_of;        // with topo: 3M, slot index 8a+i of half-edge 3T+k (or null)
+  int4 *tspill;        // with topo: the records that found their row full, {next, prev|k,
+  int n_tspill;        // element code, ROW}; at most TSPILL_CAP, else the plan is refused.
+                       // Their slot index (slot_of) is 8*N + position in this list.
   int *ovf_off;        // n_own+1 (only when some row overflows) or null
   p1::Rec *ovf_rec;    // n_ovf
   int *ovf_elem;       // n_ovf or null
@@ -105,6 +108,7 @@ __host__ __device__ __forceinline__ unsigned mix32(unsigned x) {
 }
 
 constexpr int GROUP = 8;      // lanes per row in the fast kernels = max records
+constexpr int TSPILL_CAP = 1024;  // topology-only plans: records beyond 8 per row, in total
 constexpr int DEG_BIG = 40;   // rows with more records take the block-per-row path
 // node ids must leave the top 3 bits of an int free (k is packed into pvk)
 constexpr int NODE_BITS = 29;
@@ -125,6 +129,8 @@ struct Rows {
   Rec *ovf_rec;
   int *ovf_elem;
   const int4 *topo;  // topology-only plans: everything in one 16-byte slot
+  const int4 *tspill;  // ... and the few records beyond 8 per row (.w = row)
+  int n_tspill;
   __device__ __forceinline__ int deg(int a) const { return (int)(unsigned)acc[a]; }
   __device__ __forceinline__ Rec *ptr(int a, int deg) const {
     return deg <= 8 ? rec + (int64_t)a * 8 : ovf_rec + ovf_off[a];
@@ -134,7 +140,8 @@ struct Rows {
   }
 };
 inline Rows rows_of(const p1_plan *p) {
-  return Rows{p->acc, p->rec, p->rec_elem, p->ovf_off, p->ovf_rec, p->ovf_elem, p->topo};
+  return Rows{p->acc, p->rec, p->rec_elem, p->ovf_off, p->ovf_rec, p->ovf_elem, p->topo, p->tspill,
+              p->n_tspill};
 }
 
 // sm_100a has 256-bit global loads/stores (LDG.E.256 / STG.E.256)
@@ -237,6 +244,21 @@ __device__ __forceinline__ RowLane analyse_row(int self, const Rec *row, int deg
   }
   o.len = 1 + deg + __popc(emask);
   return o;
+}
+
+// All records of row a of a topology-only plan: f(where, slot) with where = 8a+i for
+// the slots, 8*n_rows + j for spilled record j.  (Rows with more than 8 records are
+// few -- TSPILL_CAP bounds the list -- so scanning it is fine.)
+template <class F>
+__device__ __forceinline__ void topo_row_records(const Rows &rows, int a, int n_rows, F f) {
+  const int deg = rows.deg(a);
+  const int4 *slot = rows.topo + (int64_t)a * GROUP;
+  for (int i = 0; i < deg && i < GROUP; ++i) f(a * GROUP + i, slot[i]);
+  if (deg > GROUP)
+    for (int j = 0; j < rows.n_tspill; ++j) {
+      const int4 r = rows.tspill[j];
+      if (r.w == a) f(n_rows * GROUP + j, r);
+    }
 }
 
 int ensure_twins(p1_plan *plan, cudaStream_t s, bool backward_only = false);

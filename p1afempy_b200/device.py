@@ -163,7 +163,8 @@ class DeviceMesh:
         self._plan = None
         self._plan_keeps_elements = False
         self._plan_topology = False
-        self._topology_fits = True      # until a node with > 8 elements shows up
+        self._topology_fits = True      # until the topology-only plan is refused
+        self._direct_fits = True        # ... or the plan-free load vectors are
         self._exact = False
         self.nnz = None
         self.max_index = None
@@ -442,7 +443,7 @@ class DeviceMesh:
     def _direct_vectors(self):
         """No plan to reuse and none wanted: load vectors go through the plan-free
         entry points (p1_load_vector*_direct)."""
-        return (self._plan is None and not self.reuse and self._topology_fits
+        return (self._plan is None and not self.reuse and self._direct_fits
                 and self.interleave is None and self.rows == (0, self.n_nodes))
 
     def load_vector(self, fq, weights, points):
@@ -457,7 +458,7 @@ class DeviceMesh:
             if rc != _lib.P1_ERETRY:
                 _lib.check(rc)
                 return b
-            self._topology_fits = False         # a node with more than 8 elements
+            self._direct_fits = False           # too many nodes with more than 8 elements
         self.plan  # noqa: B018  (fixes n_rows)
         b = self._empty(self.n_rows)
         _lib.check(self._lib.p1_load_vector(
@@ -485,7 +486,7 @@ class DeviceMesh:
             if rc != _lib.P1_ERETRY:
                 _lib.check(rc)
                 return b
-            self._topology_fits = False
+            self._direct_fits = False
         self.plan  # noqa: B018
         b = self._empty(self.n_rows)
         _lib.check(self._lib.p1_load_vector_midpoint(

@@ -562,16 +562,47 @@ def test_topology_plan_matches_element_keeping_plan():
     with DeviceMesh(ct, et, reuse=True) as mesh:
         assert np.array_equal(mesh.load_vector(fq, w, p).cpu().numpy(), bq.cpu().numpy())
         assert mesh._plan is not None
-    # fan with 12 elements around the centre: no room in 8 slots
-    n = 12
-    ang = 2 * np.pi * np.arange(n) / n
-    fp = np.vstack([[0., 0.], np.c_[np.cos(ang), np.sin(ang)]])
-    fe = np.array([[0, 1 + i, 1 + (i + 1) % n] for i in range(n)], dtype=np.int64)
-    with DeviceMesh(torch.from_numpy(fp).cuda(), torch.from_numpy(fe.astype(np.int32)).cuda()) as mesh:
-        fc = torch.from_numpy(H.f_load(mesh.centroids().cpu().numpy())).cuda()
-        b = mesh.load_vector_midpoint(fc)
-        assert not mesh._plan_topology and not mesh._topology_fits
-        assert np.array_equal(b.cpu().numpy(), orc.load_vector_midpoint(fp, fe, H.f_load))
+    # fans around one node: 12 elements -- 4 records beyond the 8 slots travel through
+    # the spill lists of the plan-free load vectors and of the topology-only plan;
+    # 1100 elements -- more than the lists hold: both are refused (P1_ERETRY) and the
+    # element-keeping plan takes over
+    for n, fits in ((12, True), (1100, False)):
+        ang = 2 * np.pi * np.arange(n) / n
+        fp = np.vstack([[0., 0.], np.c_[np.cos(ang), np.sin(ang)]])
+        fe = np.array([[0, 1 + i, 1 + (i + 1) % n] for i in range(n)], dtype=np.int64)
+        fb = np.array([[1 + i, 1 + (i + 1) % n] for i in range(n)], dtype=np.int64)
+        xt = torch.from_numpy(H.u_nodal(fp)).cuda()
+        bt12 = torch.from_numpy(fb.astype(np.int32)).cuda()
+        o2e, o2n, ob2e = orc.geometric_data(fe, [fb])
+        w1, p1 = cubature.resolve_rule(cubature.CubatureRuleEnum.SMPLX1)
+        with DeviceMesh(torch.from_numpy(fp).cuda(),
+                        torch.from_numpy(fe.astype(np.int32)).cuda()) as mesh:
+            fc = torch.from_numpy(H.f_load(mesh.centroids().cpu().numpy())).cuda()
+            b = mesh.load_vector_midpoint(fc)
+            assert mesh._direct_fits == fits and (mesh._plan is None) == fits
+            assert np.array_equal(b.cpu().numpy(), orc.load_vector_midpoint(fp, fe, H.f_load))
+            xq = mesh.quadrature_points(p1)
+            fq1 = torch.from_numpy(np.stack([H.f_load(xq[q].cpu().numpy())
+                                             for q in range(len(w1))])).cuda()
+            assert np.array_equal(mesh.load_vector(fq1, w1, p1).cpu().numpy(),
+                                  orc.load_vector_cubature(fp, fe, H.f_load, w1, p1))
+            mesh.close()
+            eta = mesh.eta_r(xt, bt12, none, None, fc).cpu().numpy()
+            assert mesh._plan_topology == fits and mesh._topology_fits == fits
+            assert np.array_equal(eta, orc.eta_r(H.u_nodal(fp), fp, fe, fb,
+                                                 np.zeros((0, 2), dtype=int), H.f_load, H.g_neu))
+            gd = mesh.geometric_data([bt12])
+            assert np.array_equal(gd[0].cpu().numpy(), o2e)
+            assert np.array_equal(gd[1].cpu().numpy(), o2n)
+            assert np.array_equal(gd[2][0].cpu().numpy(), ob2e[0])
+            # load vectors through the plan that is there now (gather route)
+            assert np.array_equal(mesh.load_vector_midpoint(fc).cpu().numpy(), b.cpu().numpy())
+        with DeviceMesh(torch.from_numpy(fp).cuda(),
+                        torch.from_numpy(fe.astype(np.int32)).cuda()) as mesh:
+            gd = mesh.geometric_data([bt12])     # one-shot plan, backward twins only
+            assert mesh._plan_topology == fits
+            assert np.array_equal(gd[0].cpu().numpy(), o2e)
+            assert np.array_equal(gd[2][0].cpu().numpy(), ob2e[0])
 
 
 def test_spill_list_and_second_pass_agree(api, monkeypatch):
