@@ -339,13 +339,26 @@ struct GeneralValues {
     const double alpha = dz2y, beta = -dz2x, gamma = -dz1y, delta = dz1x;
     const double areas = 0.5 * (dz1x * dz2y - dz1y * dz2x);
     double a = 0., b = 0., c = 0., d = 0.;
-    for (int q = 0; q < n_qp; ++q) {
-      const double w = __ldg(weights + q);
-      const int64_t i = (int64_t)q * M + t;
-      a += w * __ldg(a11q + i);
-      b += w * __ldg(a12q + i);
-      c += w * __ldg(a21q + i);
-      d += w * __ldg(a22q + i);
+    for (int q0 = 0; q0 < n_qp; q0 += 4) {  // 16 loads in flight, sums in order
+      double v11[4], v12[4], v21[4], v22[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int64_t i = (int64_t)(q0 + u) * M + t;
+        const bool in = q0 + u < n_qp;
+        v11[u] = in ? __ldg(a11q + i) : 0.;
+        v12[u] = in ? __ldg(a12q + i) : 0.;
+        v21[u] = in ? __ldg(a21q + i) : 0.;
+        v22[u] = in ? __ldg(a22q + i) : 0.;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (q0 + u < n_qp) {
+          const double w = __ldg(weights + q0 + u);
+          a += w * v11[u];
+          b += w * v12[u];
+          c += w * v21[u];
+          d += w * v22[u];
+        }
     }
     const double pre = -1. / (2. * areas);
     const double b11 = pre * (a * alpha * alpha + b * beta * alpha +

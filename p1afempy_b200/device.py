@@ -351,15 +351,18 @@ class DeviceMesh:
         return self.assemble(_lib.OP_MASS, pattern=pattern)
 
     def general_stiffness_csr(self, a11q, a12q, a21q, a22q, weights, pattern=True,
-                              fused=False):
+                              fused=True):
         """a_ij_q: (n_qp, M) CUDA float64 values of the coefficients at the
-        quadrature points (see ``quadrature_points``)."""
+        quadrature points (see ``quadrature_points``).  fused: cold calls evaluate
+        the quadrature sums and the local matrix inside the scatter
+        (p1_plan_create_quad) instead of writing an [M x 9] array first."""
         w = _host_f64(weights)
         qs = [to_device_f64(a, self.device, (w.shape[0], self.n_elements))
               for a in (a11q, a12q, a21q, a22q)]
         if fused and not self.reuse and self.interleave is None:
-            # measured slower than the two-step route at 64M (12.5 vs 12.1 ms): four
-            # streamed arrays per triangle do not mix well with the scatter's atomics
+            # 64M triangles, 16 points: 10.6 ms, against 12.4 ms through
+            # p1_local_general_stiffness + P1_OP_LOCAL (since the scatter keeps four
+            # points of the four arrays in flight; before that the two-step route won)
             args = _lib.QuadArgs(qs[0].data_ptr(), qs[1].data_ptr(), qs[2].data_ptr(),
                                  qs[3].data_ptr(), None, w.ctypes.data, None, w.shape[0])
             return self._assemble_quad(_lib.OP_GENERAL, args, (qs, w), pattern)

@@ -31,10 +31,11 @@ fcen = torch.sin(mesh.centroids()[:, 0])
 def lm(): mesh.close(); return mesh.load_vector_midpoint(fcen)
 run('midpoint load vector cold', lm)
 q2, q3, q4 = fq + 1., fq * 2., fq - 1.
-def gs(): return mesh.general_stiffness_csr(fq, q2, q3, q4, w)
+def gs(): return mesh.general_stiffness_csr(fq, q2, q3, q4, w, fused=False)
 def wm(): return mesh.weighted_mass_csr(fq, w, p)
 def it(): return mesh.integrate(fq, w)
-run('general stiffness cold', gs); run('weighted mass cold', wm); run('integrate', it)
+def gsf(): return mesh.general_stiffness_csr(fq, q2, q3, q4, w, fused=True)
+run('general stiffness cold two-step', gs); run('general stiffness cold fused', gsf); run('weighted mass cold', wm); run('integrate', it)
 def ms(): return mesh.mass_csr()
 run('mass cold', ms)
 rm = DeviceMesh(c, e, reuse=True)
