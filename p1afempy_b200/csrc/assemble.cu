@@ -4,9 +4,8 @@
 // reference's arithmetic, plan.cuh: *Values) in a fixed order and writes the
 // finished row (sorted unique columns, explicit zeros kept).
 //
-// Fast path: 8 lanes per row, one 32-byte record per lane (one coalesced
-// 256-bit load), all-pairs comparison through shared memory (plan.cuh:
-// analyse_row).  HBM traffic per triangle: 96 B records + 42 B CSR output.
+// Fast path: one thread per row, its <= 8 records in registers (fill_rows_kernel).
+// HBM traffic per triangle: 96 B records + 42 B CSR output.
 #include "plan.cuh"
 
 namespace p1 {

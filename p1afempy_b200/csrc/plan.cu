@@ -55,9 +55,6 @@ struct SpillDesc {
 // loop it cost 0.14 ms at 64M without ever running)
 __device__ __forceinline__ void spill_record(const SpillDesc *sp, int *flags, int a, int nx,
                                              int pvk, double v0, double v1, double v2, int code) {
-#ifdef P1_NO_SPILL
-  return;
-#endif
   const SpillDesc d = *sp;
   const int idx = atomicAdd(flags + 5, 1);  // counts every spilled record, kept or not
   if (idx >= d.cap) return;
@@ -417,7 +414,6 @@ static void launch_scatter_slots(p1_ctx *ctx, unsigned grid, cudaStream_t s, con
                                  int4 *tspill = nullptr) {
   const int vec = ((uintptr_t)elements & 15) == 0;
   bool pairs = allow_pairs && own.world == 1 && own.re - own.rb == N;
-  if (const char *force = getenv("P1_SLOT_PAIRS")) pairs = force[0] == '1';  // experiments
   Rec *slots = reinterpret_cast<Rec *>(slots_);
   if (pairs)
     scatter_kernel<V, false, true, MODE><<<grid, SC_THREADS, 0, s>>>(
@@ -442,8 +438,7 @@ static void launch_scatter(p1_ctx *ctx, unsigned grid, cudaStream_t s, int op,
   // which wants consecutive lanes on consecutive triangles (measured at 64M: 24.5 ms
   // with, 12.5 ms without; the unfused route through p1_local_general_stiffness is
   // 12.1 ms, so the drop-in layer uses that one)
-  int vec = ((uintptr_t)elements & 15) == 0 && op != P1_OP_GENERAL;
-  if (const char *force = getenv("P1_SCATTER_VEC")) vec = vec && force[0] == '1';  // experiments
+  const int vec = ((uintptr_t)elements & 15) == 0 && op != P1_OP_GENERAL;
   // all rows owned (the weighted mass gains too since its values are prefetched: 5.8 -> 5.3 ms)
   bool pairs = own.world == 1 && own.re - own.rb == N && op != P1_OP_GENERAL;
   if (const char *force = getenv("P1_SCATTER_PAIRS")) pairs = force[0] == '1';  // experiments
@@ -943,11 +938,7 @@ static int load_vector_direct(p1_ctx *ctx, const int32_t *elements, int64_t M, i
   const unsigned grid = min(grid_for(M, THREADS), (unsigned)(ctx->sm_count * 32));
   if (M > 0) {
     prof_begin(ctx, "load_scatter", s);
-    static const bool quad_kernel = []() {
-      const char *e = getenv("P1_LOAD_QUADS");
-      return !(e && e[0] == '0');
-    }();
-    if (quad_kernel && ((uintptr_t)elements & 15) == 0)
+    if (((uintptr_t)elements & 15) == 0)
       launch_load_scatter(grid, s, elements, M, N, own, values, acc, slots, spill_list,
                           ctx->d_flags);
     else

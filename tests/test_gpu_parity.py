@@ -635,6 +635,43 @@ def test_spill_list_and_second_pass_agree(api, monkeypatch):
     assert np.abs(got[None] - got['3']).max() <= 1e-13 * np.abs(ref.data).max()
 
 
+def test_unaligned_element_array():
+    """The element array as a view at a 4-byte offset (no 128-bit loads possible):
+    every kernel takes its scalar path and the results do not change."""
+    import torch
+    from p1afempy_b200.device import DeviceMesh
+    pts, e, bnd = H.perturbed_square(4)
+    m = e.shape[0]
+    assert m % 4 == 0
+    e = e[:m - 3]                      # and a tail that is not a multiple of 4 triangles
+    keep = np.unique(e)
+    assert keep.size == pts.shape[0]   # (all nodes still used)
+    ct = torch.from_numpy(pts).cuda()
+    aligned = torch.from_numpy(e.astype(np.int32)).cuda()
+    buf = torch.empty(3 * e.shape[0] + 1, dtype=torch.int32, device='cuda')
+    buf[1:] = aligned.reshape(-1)
+    shifted = buf[1:].view(-1, 3)
+    assert shifted.data_ptr() % 16 != 0 and shifted.is_contiguous()
+    w, p = cubature.resolve_rule(cubature.CubatureRuleEnum.DAYTAYLOR)
+    out = []
+    for et in (aligned, shifted):
+        with DeviceMesh(ct, et) as mesh:
+            ip, ix, a = mesh.stiffness_csr()
+            fc = torch.from_numpy(H.f_load(mesh.centroids().cpu().numpy())).cuda()
+            xq = mesh.quadrature_points(p)
+            fq = torch.from_numpy(np.stack([H.f_load(xq[q].cpu().numpy())
+                                            for q in range(len(w))])).cuda()
+            out.append([t.cpu().numpy() for t in
+                        (ip, ix, a, mesh.load_vector_midpoint(fc), mesh.load_vector(fq, w, p),
+                         mesh.mass_csr()[2], mesh.weighted_mass_csr(fq, w, p)[2],
+                         mesh.general_stiffness_csr(fq, fq + 1., fq * 2., fq - 1., w)[2])])
+    for x, y in zip(*out):
+        assert np.array_equal(x, y)
+    ref = orc.stiffness_coo(pts, e).tocsr()
+    assert np.array_equal(out[1][1], ref.indices)
+    assert np.array_equal(out[1][3], orc.load_vector_midpoint(pts, e, H.f_load))
+
+
 def test_empty_and_tiny_inputs(api):
     """Empty element arrays (the reference: scipy cannot infer a shape ->
     ValueError; explicit-shape builders return empty matrices) and a single
