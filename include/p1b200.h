@@ -95,8 +95,9 @@ int p1_widen_indices(p1_ctx *ctx, const int32_t *src, int64_t count,
                             /* for load vectors, edge numbering and eta_R      */
 #define P1_PLAN_TOPOLOGY 4  /* p1_plan_create only: 16 bytes per incidence, no     */
                             /* values and no row pointer -- all that load vectors, */
-                            /* edge numbering and eta_R need.  At most 8 elements  */
-                            /* per node: P1_ERETRY otherwise (use KEEP_ELEMENTS)   */
+                            /* edge numbering and eta_R need.  8 elements per node */
+                            /* plus 1024 in total beyond that; P1_ERETRY otherwise */
+                            /* (use P1_PLAN_KEEP_ELEMENTS for such a mesh)         */
 #define P1_PLAN_SLOT_INDEX 8 /* with P1_PLAN_TOPOLOGY: also record the slot of every   */
                              /* half-edge, so that p1_eta_r gets ALL half-edge twins  */
                              /* by a gather instead of scattered stores (+0.2 ms on   */
@@ -253,8 +254,9 @@ int p1_load_vector_midpoint(const p1_plan *plan, const double *coords,
  * that scans the element and delivered to the element's three nodes as (element
  * code, value); each node then adds its values in the reference's bincount order.
  * Bit-identical to p1_load_vector / p1_load_vector_midpoint.  fq: [n_qp x M]
- * values of f at the quadrature points (p1_quadrature_points).  P1_ERETRY when a
- * node has more than 8 elements: use a plan and the functions above. */
+ * values of f at the quadrature points (p1_quadrature_points).  P1_ERETRY when
+ * the nodes with more than 8 elements hold more than 1024 incidences beyond 8:
+ * use a plan (P1_PLAN_KEEP_ELEMENTS) and the functions above. */
 int p1_load_vector_direct(p1_ctx *ctx, const int32_t *elements, int64_t n_elements,
                           int64_t n_nodes, const double *coords, const double *fq,
                           const double *weights_host, const double *points_host,
