@@ -129,6 +129,146 @@ fill_rows_kernel(int n_own, Own own, int exact,
   }
 }
 
+// ------------------------------------- fast path of slim plans: gather and compute
+// (multi-GPU stiffness / mass, plan.cu: plan_build).  The slots hold only
+// (next, prev|k): 64 bytes per row instead of 256.  The thread gathers the
+// coordinates of its node and of the `next` of every record (the `prev` of a
+// record is the `next` of the record before it in a closed fan; both indices come
+// out of the all-pairs comparison and address per-thread columns in shared
+// memory), and recomputes entry (k,k), (k,k+1), (k,k+2) of each incident element
+// with the arithmetic of the scatter (plan.cuh: slim_values).  1830 instructions
+// per row against ~900 of fill_rows_kernel: issue-bound, not HBM-bound.
+#ifndef P1_GATHER_MIN_BLOCKS
+#define P1_GATHER_MIN_BLOCKS 20
+#endif
+template <class V>
+__global__ void __launch_bounds__(FR, P1_GATHER_MIN_BLOCKS)
+fill_gather_kernel(int n_own, Own own, const unsigned long long *__restrict__ acc,
+                   const int2 *__restrict__ slim, V values,
+                   const int *__restrict__ indptr, int *__restrict__ indices,
+                   double *__restrict__ data, int *__restrict__ flags) {
+  __shared__ int cols_s[CAP_OUT];
+  __shared__ double vals_s[CAP_OUT];
+  // per-thread columns ([record][thread]: conflict-free for any record index):
+  // the coordinates of every `next`, and the (k,k+2) entry of every record
+  __shared__ double2 zs[(GROUP + 1) * FR];  // column GROUP: the row's own node
+  __shared__ double vps[GROUP * FR];
+  __shared__ unsigned char src_s[GROUP * FR];  // record whose `next` is my `prev`
+  const int tid = threadIdx.x;
+  const int row0 = blockIdx.x * FR;
+  const int nrows = min(FR, n_own - row0);
+  const int obeg = __ldg(indptr + row0), oend = __ldg(indptr + row0 + nrows);
+  const int span = oend - obeg;
+  const bool out_staged = span <= CAP_OUT;  // block-uniform
+  int deg = 0, ob = 0;
+  unsigned hash = 0;
+  if (tid < nrows) {
+    const unsigned long long v = __ldg(acc + row0 + tid);
+    deg = (int)(unsigned)v;
+    hash = (unsigned)(v >> 32);
+    ob = __ldg(indptr + row0 + tid);
+  }
+  const bool process = deg >= 1 && deg <= GROUP && hash == 0u;
+  const int self = own.global(row0 + tid);
+  if (process) {
+    const int4 *row4 = reinterpret_cast<const int4 *>(slim + (int64_t)(row0 + tid) * GROUP);
+    int4 q[4];
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      q[h] = make_int4(0, 0, 0, 0);
+      if (2 * h < deg) q[h] = __ldg(row4 + h);
+    }
+    zs[GROUP * FR + tid] = __ldg(values.coords + self);
+    int nx[GROUP], pv[GROUP], kk[GROUP];
+#pragma unroll
+    for (int i = 0; i < GROUP; ++i) {
+      const int sx = (i & 1) ? q[i >> 1].z : q[i >> 1].x;
+      const int sy = (i & 1) ? q[i >> 1].w : q[i >> 1].y;
+      nx[i] = 0x7fffffff - i;  // never below a valid column, never equal to one
+      pv[i] = -2 - i;
+      kk[i] = 0;
+      if (i < deg) {
+        nx[i] = sx; pv[i] = sy & NODE_MASK; kk[i] = (int)((unsigned)sy >> NODE_BITS);
+        zs[i * FR + tid] = __ldg(values.coords + sx);
+      }
+    }
+    int *cs = out_staged ? cols_s + (ob - obeg) : indices + ob;
+    double *vs = out_staged ? vals_s + (ob - obeg) : data + ob;
+    const bool put_cols = out_staged || indices != nullptr;
+    bool ok = true;
+    int slot_self = 0;
+    unsigned ranks = 0, sourced = 0;
+    int meta[GROUP];  // slot | mate << 4
+    double vn[GROUP];
+    // all pairs: the rank of every column and the record AFTER each record (its
+    // `prev` is my `next`: its (k,k+2) entry shares my column).  The record BEFORE
+    // (its `next` is my `prev`: my third vertex) is the inverse permutation.
+#pragma unroll
+    for (int i = 0; i < GROUP; ++i) {
+      int below = 0, mate = -1;
+#pragma unroll
+      for (int j = 0; j < GROUP; ++j) {
+        below += nx[j] < nx[i];
+        if (pv[j] == nx[i]) mate = j;
+      }
+      const bool live = i < deg;
+      // closed, repeat-free fan: every next has a mate, the mates are all different
+      // (so every prev has a source), nothing equals the row; distinct ranks <=>
+      // distinct nexts
+      ok = ok && (!live || (mate >= 0 && nx[i] != self && pv[i] != self));
+      if (live) {
+        ranks |= 1u << below;
+        sourced |= 1u << max(mate, 0);
+        src_s[max(mate, 0) * FR + tid] = (unsigned char)i;
+      }
+      slot_self += live && nx[i] < self;
+      meta[i] = (below + (self < nx[i])) | (max(mate, 0) << 4);
+    }
+    ok = ok && ranks == (1u << deg) - 1u && sourced == (1u << deg) - 1u;
+    if (ok) {
+#pragma unroll
+      for (int i = 0; i < GROUP; ++i) {
+        vn[i] = 0.;
+        if (i < deg) {
+          // vertex c of the element is column (c - k) mod 3 of {self, next, prev}
+          const int k = kk[i], src = src_s[i * FR + tid];
+          const int c0 = k == 0 ? GROUP : (k == 1 ? src : i);
+          const int c1 = k == 0 ? i : (k == 1 ? GROUP : src);
+          const int c2 = k == 0 ? src : (k == 1 ? i : GROUP);
+          double v[3][3];
+          values.rows(0, nullptr, zs[c0 * FR + tid], zs[c1 * FR + tid], zs[c2 * FR + tid], v);
+          const double vd = k == 0 ? v[0][0] : (k == 1 ? v[1][0] : v[2][0]);
+          vn[i] = k == 0 ? v[0][1] : (k == 1 ? v[1][1] : v[2][1]);
+          vps[i * FR + tid] = k == 0 ? v[0][2] : (k == 1 ? v[1][2] : v[2][2]);
+          const int slot = meta[i] & 15;
+          vs[slot] = vd;  // parked: the diagonal is summed in ascending column order
+          if (put_cols) cs[slot] = nx[i];
+        }
+      }
+    }
+    if (!ok) {
+      // (whatever was written is overwritten by the rebuilt exact plan)
+      atomicOr(flags, FLAG_RETRY);
+    } else {
+      double diag = 0.;
+      for (int c = 0; c <= deg; ++c)
+        if (c != slot_self) diag += vs[c];
+#pragma unroll
+      for (int i = 0; i < GROUP; ++i)
+        if (i < deg) vs[meta[i] & 15] = vn[i] + vps[(meta[i] >> 4) * FR + tid];
+      if (put_cols) cs[slot_self] = self;
+      vs[slot_self] = diag;
+    }
+  }
+  __syncthreads();
+  if (out_staged) {
+    for (int i = tid; i < span; i += FR) {
+      if (indices) indices[(int64_t)obeg + i] = cols_s[i];
+      data[(int64_t)obeg + i] = vals_s[i];
+    }
+  }
+}
+
 // -------------------------------------------- slow path: one thread per row
 // open fans (boundary nodes), more than 8 records, repeated neighbours
 // (non-manifold / degenerate elements): sorted unique columns by insertion into
@@ -154,8 +294,10 @@ __device__ __forceinline__ int insert_unique(int *cols, int n, int c) {
   return n + 1;
 }
 
+// (slim plans: V recomputes the <= 8 records of the row into local memory)
+template <class V>
 __global__ void __launch_bounds__(SLOW_THREADS)
-fill_slow_kernel(const int *__restrict__ slow_rows, int n_slow, Own own, Rows rows,
+fill_slow_kernel(const int *__restrict__ slow_rows, int n_slow, Own own, Rows rows, V values,
                  const int *__restrict__ indptr, int *__restrict__ indices,
                  double *__restrict__ data) {
   __shared__ int cols_s[SLOW_THREADS * SLOW_COLS];
@@ -164,7 +306,21 @@ fill_slow_kernel(const int *__restrict__ slow_rows, int n_slow, Own own, Rows ro
   const int a = slow_rows[idx];
   const int deg = rows.deg(a);
   const int self = own.global(a);
-  const Rec *nb = rows.ptr(a, deg);
+  const Rec *nb;
+  Rec made[GROUP];
+  if constexpr (V::needs_xy) {
+    const double2 za = __ldg(values.coords + self);
+    for (int i = 0; i < deg && i < GROUP; ++i) {
+      const int2 e = rows.slim[(int64_t)a * GROUP + i];
+      made[i].nx = e.x;
+      made[i].pvk = e.y;
+      slim_values(values, (int)((unsigned)e.y >> NODE_BITS), za, __ldg(values.coords + e.x),
+                  __ldg(values.coords + (e.y & NODE_MASK)), made[i].vd, made[i].vn, made[i].vp);
+    }
+    nb = made;
+  } else {
+    nb = rows.ptr(a, deg);
+  }
   int *cs = cols_s + threadIdx.x * SLOW_COLS;
   int n = insert_unique(cs, 0, self);
   for (int i = 0; i < deg; ++i) {
@@ -292,12 +448,64 @@ static void launch_refresh(p1_plan *plan, V values, cudaStream_t s) {
 
 using namespace p1;
 
+// Slim plans (multi-GPU stiffness / mass, no row with more than 8 records): the
+// values are computed while filling, from the plan's coordinates or the ones
+// passed here.
+template <class V>
+static void launch_slim(p1_plan *plan, V values, int *indices, double *data, cudaStream_t s) {
+  p1_ctx *ctx = plan->ctx;
+  const int n_own = (int)plan->n_own;
+  if (n_own > 0)
+    P1_TIMED(ctx, "fill_rows", s,
+             (fill_gather_kernel<<<grid_for(n_own, FR), FR, 0, s>>>(
+                 n_own, plan->own, plan->acc, plan->slim, values, plan->indptr, indices, data,
+                 ctx->d_flags)));
+  if (plan->n_slow > 0)
+    P1_TIMED(ctx, "fill_slow", s,
+             (fill_slow_kernel<<<grid_for(plan->n_slow, SLOW_THREADS), SLOW_THREADS, 0, s>>>(
+                 plan->slow_rows, plan->n_slow, plan->own, rows_of(plan), values, plan->indptr,
+                 indices, data)));
+}
+
+static int assemble_slim(p1_plan *plan, int op, const double *coords, int32_t *indptr,
+                         int32_t *indices, double *data, void *stream) {
+  p1_ctx *ctx = plan->ctx;
+  DeviceGuard guard(ctx->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (op == P1_OP_STORED) op = plan->val_op;
+  else if (coords) plan->coords = (const double2 *)coords;
+  if (op != P1_OP_STIFFNESS && op != P1_OP_MASS) {
+    set_error("p1_assemble_csr: this plan assembles P1_OP_STIFFNESS or P1_OP_MASS only "
+              "(create it with P1_PLAN_KEEP_ELEMENTS for other operators)");
+    return P1_EINVAL;
+  }
+  P1_REQUIRE(plan->coords || plan->M == 0, "stiffness/mass need coords");
+  plan->val_op = op;
+  if (indptr)
+    P1_CUDA(cudaMemcpyAsync(indptr, plan->indptr, ((size_t)plan->n_own + 1) * sizeof(int),
+                            cudaMemcpyDeviceToDevice, s));
+  P1_CUDA(cudaMemsetAsync(ctx->d_flags, 0, sizeof(int), s));
+  if (op == P1_OP_STIFFNESS) launch_slim(plan, StiffnessValues{plan->coords}, indices, data, s);
+  else launch_slim(plan, MassValues{plan->coords}, indices, data, s);
+  P1_CUDA(cudaGetLastError());
+  P1_CUDA(cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, sizeof(int), cudaMemcpyDeviceToHost, s));
+  P1_CUDA(cudaStreamSynchronize(s));
+  if (ctx->h_flags[0] & FLAG_RETRY) {
+    set_error("p1_assemble_csr: the mesh contradicts the plan's closed-fan shortcut "
+              "(non-manifold vertex or degenerate element); rebuild the plan with "
+              "P1_PLAN_EXACT");
+    return P1_ERETRY;
+  }
+  return P1_OK;
+}
+
 extern "C" int p1_assemble_csr(const p1_plan *cplan, int op, const double *coords,
                                const double *local, int32_t *indptr,
                                int32_t *indices, double *data, void *stream) {
   P1_REQUIRE(cplan, "null plan");
   P1_REQUIRE(data || cplan->nnz == 0, "null data");
   p1_plan *plan = const_cast<p1_plan *>(cplan);
+  if (plan->slim) return assemble_slim(plan, op, coords, indptr, indices, data, stream);
   if (plan->topo) {
     set_error("p1_assemble_csr: a P1_PLAN_TOPOLOGY plan has no records to assemble");
     return P1_EINVAL;
@@ -349,8 +557,8 @@ extern "C" int p1_assemble_csr(const p1_plan *cplan, int op, const double *coord
   if (plan->n_slow > 0)
     P1_TIMED(ctx, "fill_slow", s,
              (fill_slow_kernel<<<grid_for(plan->n_slow, SLOW_THREADS), SLOW_THREADS, 0, s>>>(
-                 plan->slow_rows, plan->n_slow, own, rows_of(plan), plan->indptr, indices,
-                 data)));
+                 plan->slow_rows, plan->n_slow, own, rows_of(plan), NoValues{}, plan->indptr,
+                 indices, data)));
   if (plan->n_big > 0)
     fill_big_kernel<<<plan->n_big, THREADS, 0, s>>>(
         plan->big_rows, own, rows_of(plan), plan->big_first, plan->indptr, indices, data);

@@ -70,6 +70,7 @@ __device__ __forceinline__ void spill_record(const SpillDesc *sp, int *flags, in
 //      1: topology-only plan -- one 16-byte slot {next, prev|k, element code, 0}
 //      2: vector payload -- one 16-byte slot {element code, 0, v[0] as two words}:
 //         what a load vector needs of an incidence, no topology at all
+//      3: slim plan -- one 8-byte slot {next, prev|k}; the fill recomputes the values
 template <int TOPO>
 __device__ __forceinline__ void store_slot(Rec *rec, int *rec_elem, int64_t pos, int nx,
                                            int pvk, const double (&v)[3], int code) {
@@ -81,6 +82,8 @@ __device__ __forceinline__ void store_slot(Rec *rec, int *rec_elem, int64_t pos,
   } else if constexpr (TOPO == 2) {
     reinterpret_cast<int4 *>(rec)[pos] =
         make_int4(code, 0, __double2loint(v[0]), __double2hiint(v[0]));
+  } else if constexpr (TOPO == 3) {
+    reinterpret_cast<int2 *>(rec)[pos] = make_int2(nx, pvk);
   } else {
     Rec r;
     r.nx = nx; r.pvk = pvk;
@@ -409,7 +412,7 @@ static void launch_one(bool pairs, unsigned grid, cudaStream_t s, const int *ele
 // 16-byte slots instead of records (MODE 1: topology, 2: vector payload)
 template <int MODE, class V>
 static void launch_scatter_slots(p1_ctx *ctx, unsigned grid, cudaStream_t s, const int *elements,
-                                 int64_t M, int N, Own own, unsigned long long *acc, int4 *slots_,
+                                 int64_t M, int N, Own own, unsigned long long *acc, void *slots_,
                                  V values, bool allow_pairs, int *slot_of = nullptr,
                                  int4 *tspill = nullptr) {
   const int vec = ((uintptr_t)elements & 15) == 0;
@@ -559,13 +562,14 @@ rowlen_slow_kernel(const int *__restrict__ slow_rows, const int *__restrict__ n_
   const int deg = rows.deg(a);
   if (deg > GROUP && !rows.ovf_rec) continue;  // redone after the overflow pass
   const int self = own.global(a);
-  const Rec *nb = rows.ptr(a, deg);
   int n = 1;
   for (int i = 0; i < deg; ++i) {
-    const int x = rec_next(nb[i]), y = rec_prev(nb[i]);
+    const int2 ei = rows.edge(a, deg, i);
+    const int x = ei.x, y = ei.y & NODE_MASK;
     bool fx = x != self, fy = y != self && y != x;
     for (int j = 0; j < deg; ++j) {
-      const int qx = rec_next(nb[j]), qy = rec_prev(nb[j]);
+      const int2 ej = rows.edge(a, deg, j);
+      const int qx = ej.x, qy = ej.y & NODE_MASK;
       fx = fx && !(j < i && qx == x);             // an earlier next equals it
       fy = fy && qx != y && !(j < i && qy == y);  // any next / an earlier prev
     }
@@ -1055,6 +1059,8 @@ extern "C" int p1_partition_rows(p1_ctx *ctx, const int32_t *elements,
   return P1_OK;
 }
 
+constexpr int PLAN_NO_SLIM = 1 << 16;  // internal: second attempt after an overflow
+
 static int plan_build(p1_ctx *ctx, const int32_t *elements, int64_t n_elements,
                       int64_t n_nodes, int64_t row_begin, int64_t row_end, int chunk_log2,
                       int world, int rank, int flags,
@@ -1170,7 +1176,23 @@ static int plan_build(p1_ctx *ctx, const int32_t *elements, int64_t n_elements,
     *out = p;
     return P1_OK;
   }
-  if ((rc = pool_alloc(ctx, &p->rec, (size_t)n_own * GROUP, s))) return fail(rc);
+  // Multi-GPU stiffness / mass: 8-byte slots, values recomputed by the fill from
+  // gathered coordinates.  On one GPU that loses (every element's local row is then
+  // computed three times: fill 1.9 -> 3.0 ms, step 4.55 -> 4.98 ms), but a rank that
+  // owns 1/G of the rows meets most of its elements only once anyway, and its
+  // scatter no longer gathers three coordinates for every element that touches one
+  // of its rows (1 - (1 - 1/G)^3 of them).  P1_SLIM=0/1 overrides.
+  bool slim = (own.world > 1 || n_own < N) && !p->exact && !keep && !(flags & PLAN_NO_SLIM) &&
+              (op == P1_OP_STIFFNESS || op == P1_OP_MASS);
+  if (const char *e = getenv("P1_SLIM"))
+    slim = e[0] == '1' && !p->exact && !keep && !(flags & PLAN_NO_SLIM) &&
+           (op == P1_OP_STIFFNESS || op == P1_OP_MASS);
+  if (slim) {
+    if ((rc = pool_alloc(ctx, &p->slim, (size_t)n_own * GROUP, s))) return fail(rc);
+    p->coords = (const double2 *)coords;
+  } else if ((rc = pool_alloc(ctx, &p->rec, (size_t)n_own * GROUP, s))) {
+    return fail(rc);
+  }
   if (keep && (rc = pool_alloc(ctx, &p->rec_elem, (size_t)n_own * GROUP, s))) return fail(rc);
   if ((rc = pool_alloc(ctx, &p->indptr, (size_t)n_own + 1, s))) return fail(rc);
   if ((rc = pool_alloc(ctx, &rowlen, (size_t)n_own + 1, s))) return fail(rc);
@@ -1211,9 +1233,12 @@ static int plan_build(p1_ctx *ctx, const int32_t *elements, int64_t n_elements,
     cudaMemcpyAsync(d_spill, &spill, sizeof(spill), cudaMemcpyHostToDevice, s);
   }
   prof_begin(ctx, "scatter", s);
-  launch_scatter<false>(ctx, eg, s, op, elements, M, N, own, p->acc, p->rec,
-                        p->rec_elem, reinterpret_cast<int *>(d_spill), coords, local, qa,
-                        d_weights, d_points);
+  if (slim)
+    launch_scatter_slots<3>(ctx, eg, s, elements, M, N, own, p->acc, p->slim, NoValues{}, true);
+  else
+    launch_scatter<false>(ctx, eg, s, op, elements, M, N, own, p->acc, p->rec,
+                          p->rec_elem, reinterpret_cast<int *>(d_spill), coords, local, qa,
+                          d_weights, d_points);
   prof_end(ctx, s);
   p->val_op = op;
   const Rows rows0 = rows_of(p);
@@ -1254,6 +1279,12 @@ static int plan_build(p1_ctx *ctx, const int32_t *elements, int64_t n_elements,
   p->max_index = ctx->h_flags[1];
   p->n_big = ctx->h_flags[2];
   p->n_slow = ctx->h_flags[3];
+  if (ctx->h_flags[4] > 0 && slim) {
+    // a node with more than 8 elements: this mesh takes the record path
+    fail(P1_OK);
+    return plan_build(ctx, elements, n_elements, n_nodes, row_begin, row_end, chunk_log2, world,
+                      rank, flags | PLAN_NO_SLIM, op, coords, local, qa, stream, out);
+  }
   if (ctx->h_flags[4] > 0) {
     // some rows have more than 8 records: give them compact storage and redo
     // their incidences (a second pass over the elements; never on an NVB mesh)
@@ -1398,7 +1429,7 @@ extern "C" int64_t p1_plan_rows(const p1_plan *p) { return p ? p->n_own : -1; }
 extern "C" int p1_plan_destroy(p1_plan *p) {
   if (!p) return P1_OK;
   DeviceGuard guard(p->ctx->device);
-  void *blocks[] = {p->acc, p->rec, p->rec_elem, p->topo, p->slot_of, p->tspill, p->ovf_off, p->ovf_rec, p->ovf_elem,
+  void *blocks[] = {p->acc, p->rec, p->rec_elem, p->topo, p->slot_of, p->tspill, p->slim, p->ovf_off, p->ovf_rec, p->ovf_elem,
                     p->indptr, p->slow_rows, p->big_rows, p->big_first, p->twin};
   for (void *b : blocks) pool_free(p->ctx, b, p->stream);
   delete p;

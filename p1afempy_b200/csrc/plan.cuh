@@ -77,6 +77,10 @@ struct p1_plan {
   int4 *topo;          // P1_PLAN_TOPOLOGY: 8 * n_own slots {next, prev | k<<29, (element<<2)|k, 0}
                        // INSTEAD of rec / rec_elem / indptr (edge numbering, eta_R, load
                        // vectors need no values and no row pointer)
+  int2 *slim;          // multi-GPU stiffness / mass plans: 8 * n_own slots {next, prev | k<<29}
+                       // INSTEAD of rec; the fill gathers the coordinates and recomputes
+                       // the entries (plan_build explains when that pays)
+  const double2 *coords;  // borrowed with a slim plan (must outlive it)
   int *slot_of;        // with topo: 3M, slot index 8a+i of half-edge 3T+k (or null)
   int4 *tspill;        // with topo: the records that found their row full, {next, prev|k,
   int n_tspill;        // element code, ROW}; at most TSPILL_CAP, else the plan is refused.
@@ -131,7 +135,14 @@ struct Rows {
   const int4 *topo;  // topology-only plans: everything in one 16-byte slot
   const int4 *tspill;  // ... and the few records beyond 8 per row (.w = row)
   int n_tspill;
+  const int2 *slim;  // slim plans: {next, prev | k << 29}, values recomputed by the fill
   __device__ __forceinline__ int deg(int a) const { return (int)(unsigned)acc[a]; }
+  // (next, prev | k << 29) of record i of row a, whatever the storage
+  __device__ __forceinline__ int2 edge(int a, int deg, int i) const {
+    if (slim) return slim[(int64_t)a * 8 + i];
+    const Rec *r = ptr(a, deg) + i;
+    return make_int2(r->nx, r->pvk);
+  }
   __device__ __forceinline__ Rec *ptr(int a, int deg) const {
     return deg <= 8 ? rec + (int64_t)a * 8 : ovf_rec + ovf_off[a];
   }
@@ -141,7 +152,7 @@ struct Rows {
 };
 inline Rows rows_of(const p1_plan *p) {
   return Rows{p->acc, p->rec, p->rec_elem, p->ovf_off, p->ovf_rec, p->ovf_elem, p->topo, p->tspill,
-              p->n_tspill};
+              p->n_tspill, p->slim};
 }
 
 // sm_100a has 256-bit global loads/stores (LDG.E.256 / STG.E.256)
@@ -320,6 +331,22 @@ struct LocalValues {  // 3x3 local matrix given per element, row-major
     }
   }
 };
+
+// A slim slot turned back into record values: vertex k of the element is the
+// row's node, k+1 its next, k+2 its prev -- rotate the three coordinates back
+// into element order so that the arithmetic is the scatter's, bit for bit.
+template <class V>
+__device__ __forceinline__ void slim_values(const V &values, int k, double2 za, double2 zn,
+                                            double2 zp, double &vd, double &vn, double &vp) {
+  const double2 z0 = k == 0 ? za : (k == 1 ? zp : zn);
+  const double2 z1 = k == 0 ? zn : (k == 1 ? za : zp);
+  const double2 z2 = k == 0 ? zp : (k == 1 ? zn : za);
+  double v[3][3];
+  values.rows(0, nullptr, z0, z1, z2, v);
+  vd = k == 0 ? v[0][0] : (k == 1 ? v[1][0] : v[2][0]);
+  vn = k == 0 ? v[0][1] : (k == 1 ? v[1][1] : v[2][1]);
+  vp = k == 0 ? v[0][2] : (k == 1 ? v[1][2] : v[2][2]);
+}
 
 // solvers.py:306-366 evaluated inside the scatter: the quadrature sums of the
 // four coefficients ([n_qp x M] arrays) and the local matrix never touch HBM

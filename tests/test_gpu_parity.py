@@ -672,6 +672,25 @@ def test_unaligned_element_array():
     assert np.array_equal(out[1][3], orc.load_vector_midpoint(pts, e, H.f_load))
 
 
+def test_slim_plans_match_record_plans(api, mesh_case, monkeypatch):
+    """Multi-GPU plans for stiffness / mass keep 8-byte slots and recompute the
+    entries while filling (P1_SLIM=1 forces that on one GPU): same pattern, same
+    off-diagonals bit for bit, diagonals within the usual rounding."""
+    c, e, _ = mesh_case
+    monkeypatch.setenv('P1_SLIM', '0')
+    a0 = api[0].get_stiffness_matrix(c, e)
+    m0 = api[0].get_mass_matrix(c, e)
+    monkeypatch.setenv('P1_SLIM', '1')
+    a1 = api[0].get_stiffness_matrix(c, e)
+    m1 = api[0].get_mass_matrix(c, e)
+    for x, y in ((a0, a1), (m0, m1)):
+        assert np.array_equal(x.indptr, y.indptr) and np.array_equal(x.indices, y.indices)
+        off = x.indices != np.repeat(np.arange(x.shape[0]), np.diff(x.indptr))
+        assert np.array_equal(x.data[off], y.data[off])
+        H.csr_values_close(y, x, RTOL)
+    H.csr_values_close(a1, orc.stiffness_coo(c, e).tocsr(), RTOL)
+
+
 def test_empty_and_tiny_inputs(api):
     """Empty element arrays (the reference: scipy cannot infer a shape ->
     ValueError; explicit-shape builders return empty matrices) and a single
