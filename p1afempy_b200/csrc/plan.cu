@@ -707,9 +707,18 @@ struct PairLoads {
   }
 };
 
+// points in flight per thread and resident blocks of the cubature kernel, measured at
+// 64M / 16 points: (4, unhinted = 126 registers) 3.35 ms, (2, unhinted) 3.64, (8, unhinted)
+// 5.01, (4, 3 blocks) 3.29, (2, 3 blocks) 3.20.  The midpoint kernel keeps the compiler's
+// own choice (66 registers; a min-blocks hint of 1 made it 2.19 instead of 1.85 ms).
+#ifndef P1_LOAD_MIN_BLOCKS
+#define P1_LOAD_MIN_BLOCKS 3
+#endif
+#ifndef P1_LOAD_PF
+#define P1_LOAD_PF 2
+#endif
 template <bool MIDPOINT>
-__global__ void __launch_bounds__(SC_THREADS)
-load_scatter_kernel(const int *__restrict__ elements, int64_t M, int N, Own own,
+__device__ __forceinline__ void load_scatter_body(const int *__restrict__ elements, int64_t M, int N, Own own,
                     const double2 *__restrict__ coords, const double *__restrict__ f,
                     const double *__restrict__ weights, const double2 *__restrict__ points,
                     int n_qp, int wide, unsigned long long *__restrict__ acc,
@@ -757,10 +766,10 @@ load_scatter_kernel(const int *__restrict__ elements, int64_t M, int N, Own own,
       for (int j = 0; j < 4; ++j) l[j][0] = l[j][1] = l[j][2] = 0.;
       // four points at a time: 128 bytes per thread in flight (the sums themselves
       // stay in the reference's order, point after point)
-      for (int qp0 = 0; qp0 < n_qp; qp0 += 4) {
-        double fv[4][4];
+      for (int qp0 = 0; qp0 < n_qp; qp0 += P1_LOAD_PF) {
+        double fv[P1_LOAD_PF][4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < P1_LOAD_PF; ++u) {
           const double *fp = f + (int64_t)(qp0 + u) * M + 4 * g;
           fv[u][0] = fv[u][1] = fv[u][2] = fv[u][3] = 0.;
           if (qp0 + u < n_qp) {
@@ -774,7 +783,7 @@ load_scatter_kernel(const int *__restrict__ elements, int64_t M, int N, Own own,
           }
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < P1_LOAD_PF; ++u) {
           if (qp0 + u < n_qp) {
             const double2 pt = __ldg(points + qp0 + u);
             const double w = __ldg(weights + qp0 + u);
@@ -817,6 +826,26 @@ load_scatter_kernel(const int *__restrict__ elements, int64_t M, int N, Own own,
   mx = __reduce_max_sync(0xffffffffu, mx);
   if ((threadIdx.x & 31) == 0 && mx >= 0) atomicMax(flags + 1, mx);
   if (bad) atomicOr(flags, FLAG_INDEX_RANGE);
+}
+
+__global__ void __launch_bounds__(SC_THREADS, P1_LOAD_MIN_BLOCKS)
+load_scatter_cubature_kernel(const int *__restrict__ elements, int64_t M, int N, Own own,
+                             const double2 *__restrict__ coords, const double *__restrict__ f,
+                             const double *__restrict__ weights,
+                             const double2 *__restrict__ points, int n_qp, int wide,
+                             unsigned long long *__restrict__ acc, Rec *__restrict__ slots,
+                             int4 *__restrict__ spill_list, int *__restrict__ flags) {
+  load_scatter_body<false>(elements, M, N, own, coords, f, weights, points, n_qp, wide, acc, slots,
+                           spill_list, flags);
+}
+__global__ void __launch_bounds__(SC_THREADS)
+load_scatter_midpoint_kernel(const int *__restrict__ elements, int64_t M, int N, Own own,
+                             const double2 *__restrict__ coords, const double *__restrict__ f,
+                             int wide, unsigned long long *__restrict__ acc,
+                             Rec *__restrict__ slots, int4 *__restrict__ spill_list,
+                             int *__restrict__ flags) {
+  load_scatter_body<true>(elements, M, N, own, coords, f, nullptr, nullptr, 0, wide, acc, slots,
+                          spill_list, flags);
 }
 
 // ascending (element, vertex) for the cubature rule (bincount over
@@ -906,7 +935,7 @@ static void launch_load_scatter(unsigned grid, cudaStream_t s, const int *elemen
                                 int N, Own own, const LoadQuadValues &v, unsigned long long *acc,
                                 int4 *slots, int4 *spill_list, int *flags) {
   const int wide = ((uintptr_t)v.fq & 31) == 0 && (M & 3) == 0;
-  load_scatter_kernel<false><<<grid, SC_THREADS, 0, s>>>(
+  load_scatter_cubature_kernel<<<grid, SC_THREADS, 0, s>>>(
       elements, M, N, own, v.coords, v.fq, v.weights, v.points, v.n_qp, wide, acc,
       reinterpret_cast<Rec *>(slots), spill_list, flags);
 }
@@ -915,9 +944,9 @@ static void launch_load_scatter(unsigned grid, cudaStream_t s, const int *elemen
                                 unsigned long long *acc, int4 *slots, int4 *spill_list,
                                 int *flags) {
   const int wide = ((uintptr_t)v.f_centroid & 31) == 0;
-  load_scatter_kernel<true><<<grid, SC_THREADS, 0, s>>>(
-      elements, M, N, own, v.coords, v.f_centroid, nullptr, nullptr, 0, wide, acc,
-      reinterpret_cast<Rec *>(slots), spill_list, flags);
+  load_scatter_midpoint_kernel<<<grid, SC_THREADS, 0, s>>>(
+      elements, M, N, own, v.coords, v.f_centroid, wide, acc, reinterpret_cast<Rec *>(slots),
+      spill_list, flags);
 }
 
 template <class V>
