@@ -7,7 +7,10 @@ minutes at this size, so it is only used on a window of rows:
     in the kernel, energy of a P1-exact function = |grad|^2 * area;
   * mass: entries sum to the area of the domain;
   * a window of rows equals the oracle restricted to those rows bit for bit in
-    the indices and to 1e-12 in the values.
+    the indices and to 1e-12 in the values;
+  * load vectors of f = 1 add up to the area; eta_R of a P1-exact function equals
+    |T|^2 exactly; the edge numbering satisfies Euler's relation, uses every id,
+    interior edges twice and boundary edges once.
 """
 import numpy as np
 import pytest
@@ -23,8 +26,9 @@ LEVEL = 12
 @pytest.fixture(scope='module')
 def big():
     from p1afempy_b200.device import DeviceMesh
-    c, e, _ = meshgen.unit_square(LEVEL)
+    c, e, boundaries = meshgen.unit_square(LEVEL)
     mesh = DeviceMesh(c, e, reuse=True)
+    mesh.test_boundaries = boundaries
     yield c, e, mesh
     mesh.close()
 
@@ -71,3 +75,44 @@ def test_stiffness_and_mass_at_64m(big):
     _, _, m = mesh.mass_csr(pattern=False)                            # re-assembly: values only
     assert abs(float(m.sum()) - 1.0) < 1e-12
     assert float(m.min()) > 0.
+
+
+def test_vectors_edges_and_estimator_at_64m(big):
+    """The cold routes of the non-matrix operators at full size: plan-free load
+    vectors (payload slots), topology-only plan with the slot of every half-edge,
+    twins by gather, edge numbering -- checked by exact invariants."""
+    from p1afempy_b200 import cubature
+    from p1afempy_b200.device import DeviceMesh
+    c, e, kept = big
+    kept.close()                                        # make room: 64M-sized scratch below
+    n = 2 ** LEVEL
+    m_el, n_nodes = e.shape[0], c.shape[0]
+    with DeviceMesh(kept.coords, kept.elements, check=False) as mesh:
+        ones = torch.ones(m_el, dtype=torch.float64, device='cuda')
+        # load vectors of f = 1: the entries add up to the area of the domain
+        b = mesh.load_vector_midpoint(ones)
+        assert mesh._plan is None and abs(float(b.sum()) - 1.0) < 1e-12 and float(b.min()) > 0.
+        w, p = cubature.resolve_rule(cubature.CubatureRuleEnum.SMPLX1)
+        fq = torch.ones((len(w), m_el), dtype=torch.float64, device='cuda')
+        bq = mesh.load_vector(fq, w, p)
+        assert mesh._plan is None and abs(float(bq.sum()) - 1.0) < 1e-12
+        del fq, bq
+        # the estimator of a P1-exact function with f = 1: all jumps vanish exactly on
+        # the dyadic mesh, eta_T = (0.5 * 2|T| * 1)^2 = |T|^2 with |T| = 1/M
+        x = 3. * mesh.coords[:, 0] - 2. * mesh.coords[:, 1]
+        bd = torch.from_numpy(np.vstack(kept.test_boundaries).astype(np.int32)).cuda()
+        none = torch.zeros((0, 2), dtype=torch.int32, device='cuda')
+        eta = mesh.eta_r(x, bd, none, None, ones)
+        assert mesh._plan_topology
+        area2 = (1.0 / m_el) ** 2
+        assert bool((eta == area2).all())
+        del eta
+        # edge numbering: Euler's relation, every id used, interior edges twice
+        e2e, e2n, b2e = mesh.geometric_data([bd])
+        n_edges = e2n.shape[0]
+        assert n_edges == n_nodes + m_el - 1
+        counts = torch.bincount(e2e.reshape(-1), minlength=n_edges)
+        assert int(counts.min()) == 1 and int(counts.max()) == 2
+        assert int((counts == 1).sum()) == bd.shape[0] == 4 * n
+        assert bool((e2n[:, 0] < e2n[:, 1]).all())
+        assert bool((counts[b2e[0]] == 1).all())
