@@ -521,17 +521,24 @@ overflow_count_kernel(int n_own, const unsigned long long *__restrict__ acc,
   cnt[a] = deg > GROUP ? deg : 0;
 }
 
-// rows with more than 8 records: their 8 slot records move to the head of the
-// row's compact storage (cursor[a] then points behind them) ...
+// rows with more than 8 records (they are all in the slow / big row lists): the
+// row takes the next free range of the compact storage (the order of the ranges
+// does not matter), its 8 slot records move to the head of it (cursor[a] then
+// points behind them) ...
 __global__ void __launch_bounds__(THREADS)
-overflow_heads_kernel(int n_own, const unsigned long long *__restrict__ acc,
+overflow_heads_kernel(const int *__restrict__ list, int n_list,
+                      const unsigned long long *__restrict__ acc,
                       const Rec *__restrict__ rec, const int *__restrict__ rec_elem,
-                      const int *__restrict__ ovf_off, Rec *__restrict__ ovf_rec,
-                      int *__restrict__ ovf_elem, int *__restrict__ cursor) {
-  const int a = blockIdx.x * blockDim.x + threadIdx.x;
-  if (a >= n_own) return;
-  if ((int)(unsigned)acc[a] <= GROUP) return;
-  const int off = ovf_off[a];
+                      int *__restrict__ ovf_off, Rec *__restrict__ ovf_rec,
+                      int *__restrict__ ovf_elem, int *__restrict__ cursor,
+                      int *__restrict__ next_free) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_list) return;
+  const int a = list[idx];
+  const int deg = (int)(unsigned)acc[a];
+  if (deg <= GROUP) return;
+  const int off = atomicAdd(next_free, deg);
+  ovf_off[a] = off;
   for (int i = 0; i < GROUP; ++i) {
     ovf_rec[off + i] = rec[(int64_t)a * GROUP + i];
     if (ovf_elem) ovf_elem[off + i] = rec_elem[(int64_t)a * GROUP + i];
@@ -1319,27 +1326,39 @@ static int plan_build(p1_ctx *ctx, const int32_t *elements, int64_t n_elements,
     // their incidences (a second pass over the elements; never on an NVB mesh)
     if ((rc = pool_alloc(ctx, &cnt, (size_t)n_own + 1, s))) return fail(rc);
     if ((rc = pool_alloc(ctx, &p->ovf_off, (size_t)n_own + 1, s))) return fail(rc);
-    overflow_count_kernel<<<grid_for(n_own, THREADS), THREADS, 0, s>>>(n_own, p->acc, cnt);
-    if ((rc = exclusive_scan_i32(ctx, cnt, p->ovf_off, n_own, true, s))) return fail(rc);
-    int h = 0;
-    cudaMemcpyAsync(&h, p->ovf_off + n_own, sizeof(int), cudaMemcpyDeviceToHost, s);
-    if (cudaStreamSynchronize(s) != cudaSuccess) return cuda_fail("overflow scan");
-    p->n_ovf = h;
-    if ((rc = pool_alloc(ctx, &p->ovf_rec, (size_t)p->n_ovf, s))) return fail(rc);
-    if (keep && (rc = pool_alloc(ctx, &p->ovf_elem, (size_t)p->n_ovf, s))) return fail(rc);
-    cudaMemcpyAsync(cnt, p->ovf_off, (size_t)n_own * sizeof(int), cudaMemcpyDeviceToDevice, s);
     const int n_spill = ctx->h_flags[5];
     if (n_spill <= spill.cap) {
-      // the common case: a few rows; their records are already here
+      // the common case: a few rows, their records are already here.  Every such row
+      // has exactly 8 records in its slots and the rest in the spill list, so the size
+      // of the compact storage is known without counting; ovf_off / the cursors are
+      // valid for those rows only.
+      p->n_ovf = (int64_t)GROUP * ctx->h_flags[4] + n_spill;
+      if ((rc = pool_alloc(ctx, &p->ovf_rec, (size_t)p->n_ovf, s))) return fail(rc);
+      if (keep && (rc = pool_alloc(ctx, &p->ovf_elem, (size_t)p->n_ovf, s))) return fail(rc);
       prof_begin(ctx, "overflow_collect", s);
-      overflow_heads_kernel<<<grid_for(n_own, THREADS), THREADS, 0, s>>>(
-          n_own, p->acc, p->rec, p->rec_elem, p->ovf_off, p->ovf_rec, p->ovf_elem, cnt);
+      if (p->n_slow > 0)
+        overflow_heads_kernel<<<grid_for(p->n_slow, THREADS), THREADS, 0, s>>>(
+            p->slow_rows, p->n_slow, p->acc, p->rec, p->rec_elem, p->ovf_off, p->ovf_rec,
+            p->ovf_elem, cnt, ctx->d_flags + 6);
+      if (p->n_big > 0)
+        overflow_heads_kernel<<<grid_for(p->n_big, THREADS), THREADS, 0, s>>>(
+            p->big_rows, p->n_big, p->acc, p->rec, p->rec_elem, p->ovf_off, p->ovf_rec,
+            p->ovf_elem, cnt, ctx->d_flags + 6);
       if (n_spill > 0)
         overflow_place_kernel<<<grid_for(n_spill, THREADS), THREADS, 0, s>>>(
             n_spill, spill, cnt, p->ovf_rec, p->ovf_elem);
       prof_end(ctx, s);
     } else {
-      // the spill list was too small: scan the elements again for those rows
+      // the spill list was too small: count, and scan the elements again for those rows
+      overflow_count_kernel<<<grid_for(n_own, THREADS), THREADS, 0, s>>>(n_own, p->acc, cnt);
+      if ((rc = exclusive_scan_i32(ctx, cnt, p->ovf_off, n_own, true, s))) return fail(rc);
+      int h = 0;
+      cudaMemcpyAsync(&h, p->ovf_off + n_own, sizeof(int), cudaMemcpyDeviceToHost, s);
+      if (cudaStreamSynchronize(s) != cudaSuccess) return cuda_fail("overflow scan");
+      p->n_ovf = h;
+      if ((rc = pool_alloc(ctx, &p->ovf_rec, (size_t)p->n_ovf, s))) return fail(rc);
+      if (keep && (rc = pool_alloc(ctx, &p->ovf_elem, (size_t)p->n_ovf, s))) return fail(rc);
+      cudaMemcpyAsync(cnt, p->ovf_off, (size_t)n_own * sizeof(int), cudaMemcpyDeviceToDevice, s);
       prof_begin(ctx, "scatter_overflow", s);
       launch_scatter<true>(ctx, eg, s, op, elements, M, N, own, p->acc, p->ovf_rec,
                            p->ovf_elem, cnt, coords, local, qa, d_weights, d_points);
