@@ -14,6 +14,11 @@
 // per incidence: ONE 64-bit atomic (slot number + closed-fan hash; row a owns
 // the fixed slots rec[8a..8a+7], so there is no counting pass, no offset scan)
 // and ONE 256-bit store.
+//
+// Contents: the scatter (four slot kinds: records, topology, payload, slim),
+// the spill lists for rows with more than 8 records, split / row lengths, the
+// plan-free load vectors (p1_load_vector*_direct), row partitioning for
+// multi-GPU, plan_build and the p1_plan_* entry points.
 #include "plan.cuh"
 #include <stdlib.h>
 #include <vector>
@@ -32,14 +37,15 @@ constexpr int SC_THREADS = P1_SCATTER_THREADS;  // scatter block size
 // -------------------------------------------------------------- scatter
 // The thread that owns element t computes the element's local matrix ONCE
 // (value source V) and stores, for every owned vertex, one 32-byte record.
-//   OVERFLOW == false: slot = old value of the row's counter; slots >= 8 are
-//                      dropped here (their row is redone by the overflow pass).
+//   OVERFLOW == false: slot = old value of the row's counter; records that find
+//                      slots >= 8 go to a spill list (cold block, SpillDesc).
 //                      The atomic also accumulates hash(next) - hash(prev): the
 //                      nexts and prevs of a closed fan are the same set, so an
 //                      interior node ends at 0; a non-zero word marks the rows
 //                      whose length is not 1 + #records (open fans = boundary
 //                      nodes).  Verified row by row when the matrix is filled.
-//   OVERFLOW == true : only rows with more than 8 records; compact storage.
+//   OVERFLOW == true : second pass, only when the spill list was too small: the
+//                      rows with more than 8 records, into compact storage.
 // Records that do not fit the 8 slots of their row (a node with more than 8
 // elements: coarse-mesh vertices of an adaptive mesh, a few per cent of the nodes
 // of a Delaunay mesh) go to a spill list; plan_build then gathers every such
