@@ -30,6 +30,33 @@ def test_library_exports_every_declared_symbol():
     assert set(names) == set(_lib.PROTOTYPES), set(names) ^ set(_lib.PROTOTYPES)
 
 
+def test_ctypes_prototypes_match_the_header():
+    """Same number of arguments, and pointer / 64-bit / 32-bit in the same places:
+    a mismatch here would not fail loudly at call time."""
+    text = open(os.path.join(REPO, 'include', 'p1b200.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    text = re.sub(r'^\s*#.*$', '', text, flags=re.M)
+    decls = re.findall(r'\b(?:int|int64_t|const char \*)\s*(p1_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;', text, flags=re.S)
+    seen = {}
+    for name, args in decls:
+        args = ' '.join(args.split())
+        params = [] if args in ('', 'void') else [a.strip() for a in args.split(',')]
+        seen[name] = params
+    assert set(seen) == set(_lib.PROTOTYPES), set(seen) ^ set(_lib.PROTOTYPES)
+    for name, params in seen.items():
+        proto = _lib.PROTOTYPES[name]
+        assert len(proto) == len(params), (name, params, proto)
+        for c_decl, ct in zip(params, proto):
+            is_ptr = '*' in c_decl
+            if is_ptr:
+                assert ct is ctypes.c_void_p or isinstance(ct, type(ctypes.POINTER(ctypes.c_int))) \
+                    or ct is ctypes.c_char_p, (name, c_decl, ct)
+            elif c_decl.startswith('int64_t'):
+                assert ct is ctypes.c_int64, (name, c_decl, ct)
+            elif c_decl.startswith('int '):
+                assert ct is ctypes.c_int, (name, c_decl, ct)
+
+
 def test_no_compute_without_gpu_is_loud():
     import torch
     if torch.cuda.is_available():
