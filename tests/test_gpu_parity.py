@@ -691,6 +691,27 @@ def test_slim_plans_match_record_plans(api, mesh_case, monkeypatch):
     H.csr_values_close(a1, orc.stiffness_coo(c, e).tocsr(), RTOL)
 
 
+def test_integration_md_stub_is_real(api):
+    """The ctypes stub printed in INTEGRATION.md (what a maintainer would paste into
+    the reference's solvers.py) runs as written and returns reference(...).tocsr()."""
+    import re
+    from p1afempy_b200 import _lib
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(repo, 'INTEGRATION.md')).read()
+    blocks = re.findall(r"```python\n(.*?)```", text, flags=re.S)
+    stub = [b for b in blocks if 'def get_stiffness_matrix' in b]
+    assert len(stub) == 1
+    code = stub[0].replace('C.CDLL("libp1b200.so")', 'C.CDLL(%r)' % _lib.LIB_PATH)
+    ns = {}
+    exec(compile(code, 'INTEGRATION.md', 'exec'), ns)
+    for c, e, _ in (H.perturbed_square(3), meshgen.l_shape()):
+        a = ns['get_stiffness_matrix'](c, e)
+        ref = orc.stiffness_coo(c, e).tocsr()
+        assert a.shape == ref.shape
+        assert np.array_equal(a.indptr, ref.indptr) and np.array_equal(a.indices, ref.indices)
+        H.csr_values_close(a, ref, RTOL)
+
+
 def test_empty_and_tiny_inputs(api):
     """Empty element arrays (the reference: scipy cannot infer a shape ->
     ValueError; explicit-shape builders return empty matrices) and a single
