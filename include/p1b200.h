@@ -103,13 +103,28 @@ int p1_widen_indices(p1_ctx *ctx, const int32_t *src, int64_t count,
                              /* by a gather instead of scattered stores (+0.2 ms on   */
                              /* the plan, -1.5 ms on the twins at 64M); not worth it  */
                              /* for p1_geometric_data alone, which reads half of them */
+/* Diagnostic flags (tests and measurements choose a storage the library would not
+ * pick by itself; results are the same): */
+#define P1_PLAN_FORCE_RECORDS 16 /* one GPU: 32-byte records through HBM for every  */
+                                 /* incidence instead of the tiled path             */
+#define P1_PLAN_FORCE_SLIM 32    /* one GPU: the 8-byte slots of multi-GPU plans     */
+#define P1_PLAN_TINY_SPILL 64    /* spill list of one record: rows with more than 8  */
+                                 /* records take the second pass over the elements   */
+#define P1_PLAN_TILED 128        /* one GPU, all rows, p1_plan_create_for/_quad: the  */
+                                 /* tiled path (see below; measured: 5 GB instead of  */
+                                 /* 18 GB of DRAM traffic per 64M-triangle step, but  */
+                                 /* instruction-bound and slower: DESIGN.md)          */
 int p1_plan_create(p1_ctx *ctx, const int32_t *elements, int64_t n_elements,
                    int64_t n_nodes, int64_t row_begin, int64_t row_end,
                    int flags, void *stream, p1_plan **out);
-/* The cold path of one matrix: the scatter that groups the incidences also
- * computes the local matrix of every element (once) and stores its rows in the
- * records; assemble with P1_OP_STORED afterwards.  op/coords/local as for
- * p1_assemble_csr. */
+/* The cold path of one matrix; assemble with P1_OP_STORED afterwards.  op/coords/
+ * local as for p1_assemble_csr; they are borrowed until the plan is destroyed.
+ * The scatter that groups the incidences also computes the local matrix of every
+ * element (once) and stores its rows in the records.  With P1_PLAN_TILED (one GPU,
+ * all rows, no P1_PLAN_KEEP_ELEMENTS): a count pass fixes the row pointer, then
+ * blocks of 1024 consecutive elements finish in shared memory every row whose
+ * elements all lie in the block and write it straight into the CSR arrays; only the
+ * other rows' incidences travel through HBM as 32-byte records. */
 int p1_plan_create_for(p1_ctx *ctx, const int32_t *elements, int64_t n_elements,
                        int64_t n_nodes, int64_t row_begin, int64_t row_end,
                        int flags, int op, const double *coords, const double *local,
@@ -167,7 +182,10 @@ int p1_plan_info(const p1_plan *plan, int64_t *nnz, int64_t *max_index,
 /* Assemble to CSR over the owned rows.
  *   indptr  : (row_end-row_begin+1) int32, local offsets starting at 0
  *   indices : nnz int32, sorted and unique per row, explicit zeros kept
- *   data    : nnz float64; duplicates summed in increasing (element, vertex)
+ *   data    : nnz float64; an off-diagonal entry is the sum of its (at most two)
+ *             contributions, a diagonal entry the sum of the (k,k) entries of
+ *             the incident elements taken in ascending order of their `next`
+ *             vertex (= ascending column): a fixed order, whatever the path
  * indptr and/or indices may be NULL (re-assembly on an unchanged mesh writes
  * values only).  `coords` (n_nodes x 2) is used by P1_OP_STIFFNESS/MASS,
  * `local` (n_elements x 9) by P1_OP_LOCAL; any op other than P1_OP_STORED

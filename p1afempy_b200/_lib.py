@@ -27,6 +27,10 @@ PLAN_EXACT = 1
 PLAN_KEEP_ELEMENTS = 2
 PLAN_TOPOLOGY = 4
 PLAN_SLOT_INDEX = 8
+PLAN_FORCE_RECORDS = 16
+PLAN_FORCE_SLIM = 32
+PLAN_TINY_SPILL = 64
+PLAN_TILED = 128
 
 OP_STORED = 0
 OP_STIFFNESS = 1

@@ -30,6 +30,64 @@ constexpr int THREADS = 256;
 constexpr int FR = P1_FILL_ROWS;  // rows per block = threads per block
 constexpr int CAP_OUT = FR * 10;  // CSR entries staged per block (9 per regular row + slack)
 
+// One row from its <= 8 records: cs / vs point at the row's place (the block's
+// staged image or the output itself; cs may be null).  False when the fan is not
+// closed and repeat-free.
+__device__ __forceinline__ bool row_from_records(int self, int deg, const Rec *row, int *cs,
+                                                 double *vs) {
+  int nx[GROUP], pv[GROUP], slot[GROUP];
+  double vd[GROUP], vn[GROUP], vp[GROUP], mvp[GROUP];
+  int slot_self = 0;
+#pragma unroll
+  for (int i = 0; i < GROUP; ++i) {
+    nx[i] = 0x7fffffff - i;  // never below a valid column, never equal to one
+    pv[i] = -2 - i;
+    vd[i] = vn[i] = vp[i] = 0.;
+    if (i < deg) {
+      const Rec r = load_rec(row + i);
+      nx[i] = r.nx; pv[i] = rec_prev(r);
+      vd[i] = r.vd; vn[i] = r.vn; vp[i] = r.vp;
+    }
+  }
+  // all pairs, in registers
+  bool ok = true;
+#pragma unroll
+  for (int i = 0; i < GROUP; ++i) {
+    int below = 0;
+    bool mated = false;
+    mvp[i] = 0.;
+#pragma unroll
+    for (int j = 0; j < GROUP; ++j) {
+      below += nx[j] < nx[i];
+      if (pv[j] == nx[i]) { mvp[i] = vp[j]; mated = true; }
+      if (j > i) ok = ok && nx[j] != nx[i] && pv[j] != pv[i];
+    }
+    const bool live = i < deg;
+    // closed, repeat-free fan: every next has a mate, nothing equals the row
+    ok = ok && (!live || (mated && nx[i] != self && pv[i] != self));
+    slot[i] = below + (self < nx[i]);
+    slot_self += live && nx[i] < self;
+  }
+  if (!ok) return false;
+  // diagonal in a fixed order: park the (k,k) entries at their columns and
+  // add them up in ascending column order
+#pragma unroll
+  for (int i = 0; i < GROUP; ++i)
+    if (i < deg) vs[slot[i]] = vd[i];
+  double diag = 0.;
+  for (int q = 0; q <= deg; ++q)
+    if (q != slot_self) diag += vs[q];
+#pragma unroll
+  for (int i = 0; i < GROUP; ++i)
+    if (i < deg) {
+      if (cs) cs[slot[i]] = nx[i];
+      vs[slot[i]] = vn[i] + mvp[i];
+    }
+  if (cs) cs[slot_self] = self;
+  vs[slot_self] = diag;
+  return true;
+}
+
 __global__ void __launch_bounds__(FR, P1_FILL_MIN_BLOCKS)
 fill_rows_kernel(int n_own, Own own, int exact,
                  const unsigned long long *__restrict__ acc, const Rec *__restrict__ rec,
@@ -52,71 +110,16 @@ fill_rows_kernel(int n_own, Own own, int exact,
     ob = __ldg(indptr + row0 + tid);
   }
   const Rec *row = rec + (int64_t)(row0 + tid) * GROUP;  // the row's 8 slots
-  bool process = deg >= 1 && deg <= GROUP && (exact || hash == 0u);
-  const int self = own.global(row0 + tid);
-  int nx[GROUP], pv[GROUP], slot[GROUP];
-  double vd[GROUP], vn[GROUP], vp[GROUP], mvp[GROUP];
-  int slot_self = 0;
-  if (process) {
-#pragma unroll
-    for (int i = 0; i < GROUP; ++i) {
-      nx[i] = 0x7fffffff - i;  // never below a valid column, never equal to one
-      pv[i] = -2 - i;
-      vd[i] = vn[i] = vp[i] = 0.;
-      if (i < deg) {
-        const Rec r = load_rec(row + i);
-        nx[i] = r.nx; pv[i] = rec_prev(r);
-        vd[i] = r.vd; vn[i] = r.vn; vp[i] = r.vp;
-      }
-    }
-    // all pairs, in registers
-    bool ok = true;
-#pragma unroll
-    for (int i = 0; i < GROUP; ++i) {
-      int below = 0;
-      bool mated = false;
-      mvp[i] = 0.;
-#pragma unroll
-      for (int j = 0; j < GROUP; ++j) {
-        below += nx[j] < nx[i];
-        if (pv[j] == nx[i]) { mvp[i] = vp[j]; mated = true; }
-        if (j > i) ok = ok && nx[j] != nx[i] && pv[j] != pv[i];
-      }
-      const bool live = i < deg;
-      // closed, repeat-free fan: every next has a mate, nothing equals the row
-      ok = ok && (!live || (mated && nx[i] != self && pv[i] != self));
-      slot[i] = below + (self < nx[i]);
-      slot_self += live && nx[i] < self;
-    }
-    if (!ok) {
-      // exact plan: the row is in slow_rows.  Hash plan: the shortcut
-      // "closed fan => 1 + #records columns" does not hold for this row.
-      if (!exact) atomicOr(flags, FLAG_RETRY);
-      process = false;
-    }
-  }
+  const bool process = deg >= 1 && deg <= GROUP && (exact || hash == 0u);
   if (process) {
     // staged: the row is built in the block's image; otherwise (irregular rows
     // inside the block made the span oversize) directly in the output
-    int *cs = out_staged ? cols_s + (ob - obeg) : indices + ob;
+    int *cs = out_staged ? cols_s + (ob - obeg) : (indices ? indices + ob : nullptr);
     double *vs = out_staged ? vals_s + (ob - obeg) : data + ob;
-    const bool put_cols = out_staged || indices != nullptr;
-    // diagonal in a fixed order: park the (k,k) entries at their columns and
-    // add them up in ascending column order
-#pragma unroll
-    for (int i = 0; i < GROUP; ++i)
-      if (i < deg) vs[slot[i]] = vd[i];
-    double diag = 0.;
-    for (int q = 0; q <= deg; ++q)
-      if (q != slot_self) diag += vs[q];
-#pragma unroll
-    for (int i = 0; i < GROUP; ++i)
-      if (i < deg) {
-        if (put_cols) cs[slot[i]] = nx[i];
-        vs[slot[i]] = vn[i] + mvp[i];
-      }
-    if (put_cols) cs[slot_self] = self;
-    vs[slot_self] = diag;
+    // exact plan: a row that fails is in slow_rows.  Hash plan: the shortcut
+    // "closed fan => 1 + #records columns" does not hold for this row.
+    if (!row_from_records(own.global(row0 + tid), deg, row, cs, vs) && !exact)
+      atomicOr(flags, FLAG_RETRY);
   }
   __syncthreads();
   if (out_staged) {
@@ -126,6 +129,25 @@ fill_rows_kernel(int n_own, Own own, int exact,
       if (indices) indices[(int64_t)obeg + i] = cols_s[i];
       data[(int64_t)obeg + i] = vals_s[i];
     }
+  }
+}
+
+// Tiled plans: the regular rows the tiles did not complete (their fan crosses a tile
+// boundary), listed in no particular order; the row is built in its place in the
+// output.  The list's length is read on the device.
+__global__ void __launch_bounds__(128)
+fill_list_kernel(const int *__restrict__ list, const int *__restrict__ n_list,
+                 const unsigned long long *__restrict__ acc, const Rec *__restrict__ rec,
+                 const int *__restrict__ indptr, int *__restrict__ indices,
+                 double *__restrict__ data, int *__restrict__ flags) {
+  const int n = *n_list;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
+    const int a = list[idx];
+    const int deg = (int)(unsigned)__ldg(acc + a);
+    const int ob = __ldg(indptr + a);
+    if (!row_from_records(a, deg, rec + (int64_t)a * GROUP, indices ? indices + ob : nullptr,
+                          data + ob))
+      atomicOr(flags, FLAG_RETRY);
   }
 }
 
@@ -299,7 +321,7 @@ template <class V>
 __global__ void __launch_bounds__(SLOW_THREADS)
 fill_slow_kernel(const int *__restrict__ slow_rows, int n_slow, Own own, Rows rows, V values,
                  const int *__restrict__ indptr, int *__restrict__ indices,
-                 double *__restrict__ data) {
+                 double *__restrict__ data, int *__restrict__ verify = nullptr) {
   __shared__ int cols_s[SLOW_THREADS * SLOW_COLS];
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n_slow) return;
@@ -328,6 +350,12 @@ fill_slow_kernel(const int *__restrict__ slow_rows, int n_slow, Own own, Rows ro
     n = insert_unique(cs, n, rec_prev(nb[i]));
   }
   const int64_t base = indptr[a];
+  if (verify && n != indptr[a + 1] - indptr[a]) {
+    // tiled plans take the row length from the record count (closed fan: 1 + deg,
+    // else 2 + deg) without looking at the records: this row is not that simple
+    atomicOr(verify, FLAG_RETRY);
+    return;
+  }
   double *vs = data + base;
   for (int j = 0; j < n; ++j) {
     if (indices) indices[base + j] = cs[j];
@@ -448,6 +476,19 @@ static void launch_refresh(p1_plan *plan, V values, cudaStream_t s) {
 
 using namespace p1;
 
+void p1::launch_fill_fallback(p1_plan *plan, int *indices, double *data, cudaStream_t s) {
+  p1_ctx *ctx = plan->ctx;
+  P1_TIMED(ctx, "fill_list", s,
+           (fill_list_kernel<<<ctx->sm_count * 8, 128, 0, s>>>(
+               plan->fb_rows, plan->tctr, plan->acc, plan->rec, plan->indptr, indices, data,
+               ctx->d_flags)));
+  if (plan->n_slow > 0)
+    P1_TIMED(ctx, "fill_slow", s,
+             (fill_slow_kernel<<<grid_for(plan->n_slow, SLOW_THREADS), SLOW_THREADS, 0, s>>>(
+                 plan->slow_rows, plan->n_slow, plan->own, rows_of(plan), NoValues{},
+                 plan->indptr, indices, data, ctx->d_flags)));
+}
+
 // Slim plans (multi-GPU stiffness / mass, no row with more than 8 records): the
 // values are computed while filling, from the plan's coordinates or the ones
 // passed here.
@@ -505,6 +546,7 @@ extern "C" int p1_assemble_csr(const p1_plan *cplan, int op, const double *coord
   P1_REQUIRE(cplan, "null plan");
   P1_REQUIRE(data || cplan->nnz == 0, "null data");
   p1_plan *plan = const_cast<p1_plan *>(cplan);
+  if (plan->tiled) return assemble_tiled(plan, op, indptr, indices, data, stream);
   if (plan->slim) return assemble_slim(plan, op, coords, indptr, indices, data, stream);
   if (plan->topo) {
     set_error("p1_assemble_csr: a P1_PLAN_TOPOLOGY plan has no records to assemble");

@@ -52,26 +52,6 @@ constexpr int SC_THREADS = P1_SCATTER_THREADS;  // scatter block size
 // row's records into compact storage.  Only when the list overflows are the
 // elements scanned a second time.  The descriptor lives in device memory and is
 // read only by the rare thread that spills.
-struct SpillDesc {
-  Rec *rec;
-  int *row, *elem;  // owning row; element code (null unless the plan keeps elements)
-  int cap;
-};
-// (called from a cold block behind ONE branch per triangle / pair: inside the store
-// loop it cost 0.14 ms at 64M without ever running)
-__device__ __forceinline__ void spill_record(const SpillDesc *sp, int *flags, int a, int nx,
-                                             int pvk, double v0, double v1, double v2, int code) {
-  const SpillDesc d = *sp;
-  const int idx = atomicAdd(flags + 5, 1);  // counts every spilled record, kept or not
-  if (idx >= d.cap) return;
-  Rec r;
-  r.nx = nx; r.pvk = pvk;
-  r.vd = v0; r.vn = v1; r.vp = v2;
-  store_rec(d.rec + idx, r);
-  d.row[idx] = a;
-  if (d.elem) d.elem[idx] = code;
-}
-
 // TOPO 0: the 32-byte record (+ the optional element code array)
 //      1: topology-only plan -- one 16-byte slot {next, prev|k, element code, 0}
 //      2: vector payload -- one 16-byte slot {element code, 0, v[0] as two words}:
@@ -449,8 +429,7 @@ static void launch_scatter(p1_ctx *ctx, unsigned grid, cudaStream_t s, int op,
   // 12.1 ms, so the drop-in layer uses that one)
   const int vec = ((uintptr_t)elements & 15) == 0 && op != P1_OP_GENERAL;
   // all rows owned (the weighted mass gains too since its values are prefetched: 5.8 -> 5.3 ms)
-  bool pairs = own.world == 1 && own.re - own.rb == N && op != P1_OP_GENERAL;
-  if (const char *force = getenv("P1_SCATTER_PAIRS")) pairs = force[0] == '1';  // experiments
+  const bool pairs = own.world == 1 && own.re - own.rb == N && op != P1_OP_GENERAL;
   if (op == P1_OP_GENERAL)
     launch_one<GeneralValues, OVERFLOW>(pairs, grid, s, elements, M, N, own, vec, acc, rec, rec_elem,
             cursor, GeneralValues{xy, qa->a11q, qa->a12q, qa->a21q, qa->a22q, d_weights, qa->n_qp, M}, fl);
@@ -1101,7 +1080,25 @@ extern "C" int p1_partition_rows(p1_ctx *ctx, const int32_t *elements,
   return P1_OK;
 }
 
-constexpr int PLAN_NO_SLIM = 1 << 16;  // internal: second attempt after an overflow
+constexpr int PLAN_NO_SLIM = 1 << 16;   // internal: second attempt after an overflow
+constexpr int PLAN_NO_TILED = 1 << 17;  // internal: the tiled plan declined this mesh
+
+void p1::overflow_collect(p1_plan *p, int *cursor, int *next_free, cudaStream_t s) {
+  p1_ctx *ctx = p->ctx;
+  prof_begin(ctx, "overflow_collect", s);
+  if (p->n_slow > 0)
+    overflow_heads_kernel<<<grid_for(p->n_slow, THREADS), THREADS, 0, s>>>(
+        p->slow_rows, p->n_slow, p->acc, p->rec, p->rec_elem, p->ovf_off, p->ovf_rec,
+        p->ovf_elem, cursor, next_free);
+  if (p->n_big > 0)
+    overflow_heads_kernel<<<grid_for(p->n_big, THREADS), THREADS, 0, s>>>(
+        p->big_rows, p->n_big, p->acc, p->rec, p->rec_elem, p->ovf_off, p->ovf_rec,
+        p->ovf_elem, cursor, next_free);
+  if (p->n_spill > 0)
+    overflow_place_kernel<<<grid_for(p->n_spill, THREADS), THREADS, 0, s>>>(
+        p->n_spill, p->spill, cursor, p->ovf_rec, p->ovf_elem);
+  prof_end(ctx, s);
+}
 
 static int plan_build(p1_ctx *ctx, const int32_t *elements, int64_t n_elements,
                       int64_t n_nodes, int64_t row_begin, int64_t row_end, int chunk_log2,
@@ -1136,6 +1133,16 @@ static int plan_build(p1_ctx *ctx, const int32_t *elements, int64_t n_elements,
              "P1_OP_LOCAL needs the local matrices");
   DeviceGuard guard(ctx->device);
   cudaStream_t s = (cudaStream_t)stream;
+  // One GPU, all rows, one operator, nothing to keep: the tiled path on request (tiled.cu).
+  if ((flags & P1_PLAN_TILED) && op != 0 && world == 1 && row_begin == 0 &&
+      row_end == n_nodes &&
+      !(flags & (P1_PLAN_EXACT | P1_PLAN_KEEP_ELEMENTS | P1_PLAN_TOPOLOGY | P1_PLAN_FORCE_SLIM |
+                 P1_PLAN_FORCE_RECORDS | P1_PLAN_TINY_SPILL | PLAN_NO_SLIM | PLAN_NO_TILED)) &&
+      ((uintptr_t)elements & 15) == 0 && out) {
+    const int rc = plan_build_tiled(ctx, elements, n_elements, n_nodes, op, coords, local, qa, s,
+                                    out);
+    if (rc != P1_ERETRY) return rc;  // (P1_ERETRY: a fan of more than 40 elements)
+  }
   int wshift = -1;
   for (int b = 0; b < 31; ++b)
     if ((1 << b) == world) wshift = b;
@@ -1223,12 +1230,10 @@ static int plan_build(p1_ctx *ctx, const int32_t *elements, int64_t n_elements,
   // computed three times: fill 1.9 -> 3.0 ms, step 4.55 -> 4.98 ms), but a rank that
   // owns 1/G of the rows meets most of its elements only once anyway, and its
   // scatter no longer gathers three coordinates for every element that touches one
-  // of its rows (1 - (1 - 1/G)^3 of them).  P1_SLIM=0/1 overrides.
-  bool slim = (own.world > 1 || n_own < N) && !p->exact && !keep && !(flags & PLAN_NO_SLIM) &&
-              (op == P1_OP_STIFFNESS || op == P1_OP_MASS);
-  if (const char *e = getenv("P1_SLIM"))
-    slim = e[0] == '1' && !p->exact && !keep && !(flags & PLAN_NO_SLIM) &&
-           (op == P1_OP_STIFFNESS || op == P1_OP_MASS);
+  // of its rows (1 - (1 - 1/G)^3 of them).  (P1_PLAN_FORCE_SLIM: one-GPU measurements.)
+  const bool slim = (own.world > 1 || n_own < N || (flags & P1_PLAN_FORCE_SLIM)) && !p->exact &&
+                    !keep && !(flags & PLAN_NO_SLIM) &&
+                    (op == P1_OP_STIFFNESS || op == P1_OP_MASS);
   if (slim) {
     if ((rc = pool_alloc(ctx, &p->slim, (size_t)n_own * GROUP, s))) return fail(rc);
     p->coords = (const double2 *)coords;
@@ -1264,7 +1269,7 @@ static int plan_build(p1_ctx *ctx, const int32_t *elements, int64_t n_elements,
   {  // spill list (see SpillDesc)
     int64_t cap = (3 * M) / 64;
     cap = cap < 4096 ? 4096 : (cap > (1 << 22) ? (1 << 22) : cap);
-    if (const char *e = getenv("P1_SPILL_CAP")) cap = atoi(e) > 0 ? atoi(e) : 1;  // tests
+    if (flags & P1_PLAN_TINY_SPILL) cap = 1;  // tests: force the second pass over the elements
     spill.cap = (int)cap;
     if ((rc = pool_alloc(ctx, &spill.rec, (size_t)cap, s)) ||
         (rc = pool_alloc(ctx, &spill.row, (size_t)cap, s)) ||
@@ -1341,19 +1346,10 @@ static int plan_build(p1_ctx *ctx, const int32_t *elements, int64_t n_elements,
       p->n_ovf = (int64_t)GROUP * ctx->h_flags[4] + n_spill;
       if ((rc = pool_alloc(ctx, &p->ovf_rec, (size_t)p->n_ovf, s))) return fail(rc);
       if (keep && (rc = pool_alloc(ctx, &p->ovf_elem, (size_t)p->n_ovf, s))) return fail(rc);
-      prof_begin(ctx, "overflow_collect", s);
-      if (p->n_slow > 0)
-        overflow_heads_kernel<<<grid_for(p->n_slow, THREADS), THREADS, 0, s>>>(
-            p->slow_rows, p->n_slow, p->acc, p->rec, p->rec_elem, p->ovf_off, p->ovf_rec,
-            p->ovf_elem, cnt, ctx->d_flags + 6);
-      if (p->n_big > 0)
-        overflow_heads_kernel<<<grid_for(p->n_big, THREADS), THREADS, 0, s>>>(
-            p->big_rows, p->n_big, p->acc, p->rec, p->rec_elem, p->ovf_off, p->ovf_rec,
-            p->ovf_elem, cnt, ctx->d_flags + 6);
-      if (n_spill > 0)
-        overflow_place_kernel<<<grid_for(n_spill, THREADS), THREADS, 0, s>>>(
-            n_spill, spill, cnt, p->ovf_rec, p->ovf_elem);
-      prof_end(ctx, s);
+      p->spill = spill;
+      p->n_spill = n_spill;
+      overflow_collect(p, cnt, ctx->d_flags + 6, s);
+      p->spill = SpillDesc{nullptr, nullptr, nullptr, 0};  // (freed with the builder's scratch)
     } else {
       // the spill list was too small: count, and scan the elements again for those rows
       overflow_count_kernel<<<grid_for(n_own, THREADS), THREADS, 0, s>>>(n_own, p->acc, cnt);
@@ -1483,8 +1479,11 @@ extern "C" int64_t p1_plan_rows(const p1_plan *p) { return p ? p->n_own : -1; }
 extern "C" int p1_plan_destroy(p1_plan *p) {
   if (!p) return P1_OK;
   DeviceGuard guard(p->ctx->device);
-  void *blocks[] = {p->acc, p->rec, p->rec_elem, p->topo, p->slot_of, p->tspill, p->slim, p->ovf_off, p->ovf_rec, p->ovf_elem,
-                    p->indptr, p->slow_rows, p->big_rows, p->big_first, p->twin};
+  void *blocks[] = {p->acc, p->rec, p->rec_elem, p->topo, p->slot_of, p->tspill, p->slim,
+                    p->ovf_off, p->ovf_rec, p->ovf_elem, p->indptr, p->slow_rows, p->big_rows,
+                    p->big_first, p->twin, p->slotcode, p->fb_rows, p->tctr, p->ovf_cursor,
+                    p->spill.rec, p->spill.row, p->spill.elem, p->d_spill, p->d_weights,
+                    p->d_points};
   for (void *b : blocks) pool_free(p->ctx, b, p->stream);
   delete p;
   return P1_OK;

@@ -14,6 +14,13 @@ struct __align__(32) Rec {
   double vd, vn, vp;
 };
 
+// Spill list for the records of rows with more than 8 records (see spill_record).
+struct SpillDesc {
+  Rec *rec;
+  int *row, *elem;  // owning row; element code (null unless the plan keeps elements)
+  int cap;
+};
+
 // Which rows a plan owns, and the local <-> global row numbering.
 //   contiguous : rows [rb, re)                                   (world == 1)
 //   interleaved: of the chunks of 2^cshift rows inside [rb, re), those with
@@ -101,6 +108,20 @@ struct p1_plan {
   int *twin;           // lazily built: 3M, twin half-edge id T'*3+k' or -1
   bool twin_partial;   // only the entries of half-edges I -> J with J < I are valid
   int64_t n_open;      // half-edges without twin (valid once twin is built)
+  // Tiled plans (tiled.cu): the count pass stored the slot of every incidence, the
+  // tile kernel of p1_assemble_csr completes tile-interior rows in shared memory and
+  // only the incidences of the other rows travel through `rec`.
+  bool tiled;
+  unsigned short *slotcode;  // M: slot of vertex k in bits 4k..4k+3 (15 = beyond 8)
+  int *fb_rows;        // rows the tiles left to the record path (filled per assemble)
+  int *tctr;           // 8 device counters: [0] #fb_rows, [1] next free overflow range
+  int *ovf_cursor;     // n_own (only when some row has more than 8 records)
+  int n_gt8, n_spill;  // rows with more than 8 records / their records beyond 8
+  p1::SpillDesc spill; // spill list (capacity n_spill) and its device copy
+  p1::SpillDesc *d_spill;
+  const double *v_coords, *v_local;  // borrowed value sources of the stored operator
+  p1_quad_args v_qa;                 // (device arrays borrowed)
+  double *d_weights, *d_points;      // the rule on the device (quadrature operators)
 };
 
 namespace p1 {
@@ -181,6 +202,25 @@ __device__ __forceinline__ Rec load_rec(const Rec *p) {
   r.vp = __longlong_as_double(d);
   return r;
 }
+
+// Records that do not fit the 8 slots of their row (a node with more than 8
+// elements) go to a spill list; the descriptor lives in device memory and is read
+// only by the rare thread that spills (plan.cu: scatter, tiled.cu: tile kernel).
+// (called from a cold block behind ONE branch per triangle / pair: inside the store
+// loop it cost 0.14 ms at 64M without ever running)
+__device__ __forceinline__ void spill_record(const SpillDesc *sp, int *flags, int a, int nx,
+                                             int pvk, double v0, double v1, double v2, int code) {
+  const SpillDesc d = *sp;
+  const int idx = atomicAdd(flags + 5, 1);  // counts every spilled record, kept or not
+  if (idx >= d.cap) return;
+  Rec r;
+  r.nx = nx; r.pvk = pvk;
+  r.vd = v0; r.vn = v1; r.vp = v2;
+  store_rec(d.rec + idx, r);
+  d.row[idx] = a;
+  if (d.elem) d.elem[idx] = code;
+}
+
 
 // What one lane of an 8-lane group knows about "its" record and its row after
 // the all-pairs comparison.  A row is `simple` when it has at most 8 records,
@@ -273,6 +313,19 @@ __device__ __forceinline__ void topo_row_records(const Rows &rows, int a, int n_
 }
 
 int ensure_twins(p1_plan *plan, cudaStream_t s, bool backward_only = false);
+// tiled.cu: the one-GPU cold path (count pass, tile kernel); P1_ERETRY from the
+// plan builder means "use the record plan for this mesh"
+int plan_build_tiled(p1_ctx *ctx, const int32_t *elements, int64_t M, int64_t n_nodes, int op,
+                     const double *coords, const double *local, const p1_quad_args *qa,
+                     cudaStream_t s, p1_plan **out);
+int assemble_tiled(p1_plan *plan, int op, int32_t *indptr, int32_t *indices, double *data,
+                   void *stream);
+// plan.cu: rows with more than 8 records move to compact storage (8 slot records +
+// the spilled ones); cursor: n_own scratch ints, next_free: a zeroed device counter
+void overflow_collect(p1_plan *plan, int *cursor, int *next_free, cudaStream_t s);
+// assemble.cu: the rows a tiled plan left to the record path (plan->fb_rows, counted on
+// the device in plan->tctr[0]) and the slow rows
+void launch_fill_fallback(p1_plan *plan, int *indices, double *data, cudaStream_t s);
 // error unless the plan was created with P1_PLAN_KEEP_ELEMENTS
 int require_elements(const p1_plan *plan, const char *who);
 
@@ -280,8 +333,29 @@ int require_elements(const p1_plan *plan, const char *who);
 // rows(t, e, z0, z1, z2, v): v[k][0..2] = entries (k,k), (k,k+1), (k,k+2) of
 // element t; z0..z2 are the vertex coordinates (supplied by the caller, who can
 // share them between neighbouring triangles) when needs_xy
+// Tiled assembly (tiled.cu) parks what an element contributes in shared memory:
+// NV doubles per element, written by pack() (strided by `ld`), from which
+// unpack() rebuilds the entries (k,k), (k,k+1), (k,k+2) of vertex k with the
+// expressions of rows(), bit for bit.  Sources without a compact form park all
+// nine entries.
+#define P1_GENERIC_PACK                                                               \
+  static constexpr int NV = 9;                                                        \
+  static constexpr bool lane_major = true;                                            \
+  __device__ __forceinline__ void pack(int64_t t, const int *e, double2 z0, double2 z1, \
+                                       double2 z2, double *out, int ld) const {       \
+    double v[3][3];                                                                   \
+    rows(t, e, z0, z1, z2, v);                                                        \
+    _Pragma("unroll") for (int k = 0; k < 3; ++k)                                     \
+      _Pragma("unroll") for (int c = 0; c < 3; ++c) out[(3 * k + c) * ld] = v[k][c]; \
+  }                                                                                   \
+  __device__ static __forceinline__ void unpack(int k, const double *in, int ld,      \
+                                                double &vd, double &vn, double &vp) { \
+    vd = in[(3 * k) * ld]; vn = in[(3 * k + 1) * ld]; vp = in[(3 * k + 2) * ld];      \
+  }
+
 struct NoValues {
   static constexpr bool needs_xy = false;
+  P1_GENERIC_PACK
   __device__ __forceinline__ void rows(int64_t, const int *, double2, double2, double2,
                                        double (*v)[3]) const {
 #pragma unroll
@@ -303,6 +377,25 @@ struct StiffnessValues {  // solvers.py:31-45
     v[1][0] = b;               v[1][1] = -a;    v[1][2] = a - b;
     v[2][0] = c;               v[2][1] = a - c; v[2][2] = -a;
   }
+  // compact form: a, b, c
+  static constexpr int NV = 3;
+  static constexpr bool lane_major = false;
+  __device__ __forceinline__ void pack(int64_t, const int *, double2 z0, double2 z1,
+                                       double2 z2, double *out, int ld) const {
+    const double d21x = z1.x - z0.x, d21y = z1.y - z0.y;
+    const double d31x = z2.x - z0.x, d31y = z2.y - z0.y;
+    const double area4 = 4. * (0.5 * (d21x * d31y - d21y * d31x));
+    out[0] = (d21x * d31x + d21y * d31y) / area4;
+    out[ld] = (d31x * d31x + d31y * d31y) / area4;
+    out[2 * ld] = (d21x * d21x + d21y * d21y) / area4;
+  }
+  __device__ static __forceinline__ void unpack(int k, const double *in, int ld, double &vd,
+                                                double &vn, double &vp) {
+    const double a = in[0], b = in[ld], c = in[2 * ld];
+    if (k == 0) { vd = -2. * a + b + c; vn = a - b; vp = a - c; }
+    else if (k == 1) { vd = b; vn = -a; vp = a - b; }
+    else { vd = c; vn = a - c; vp = -a; }
+  }
 };
 struct MassValues {  // solvers.py:176-181
   static constexpr bool needs_xy = true;
@@ -316,9 +409,25 @@ struct MassValues {  // solvers.py:176-181
 #pragma unroll
     for (int k = 0; k < 3; ++k) { v[k][0] = on; v[k][1] = off; v[k][2] = off; }
   }
+  // compact form: area/6, area/12
+  static constexpr int NV = 2;
+  static constexpr bool lane_major = false;
+  __device__ __forceinline__ void pack(int64_t, const int *, double2 z0, double2 z1,
+                                       double2 z2, double *out, int ld) const {
+    const double d21x = z1.x - z0.x, d21y = z1.y - z0.y;
+    const double d31x = z2.x - z0.x, d31y = z2.y - z0.y;
+    const double area = 0.5 * (d21x * d31y - d21y * d31x);
+    out[0] = area / 6.;
+    out[ld] = area / 12.;
+  }
+  __device__ static __forceinline__ void unpack(int, const double *in, int ld, double &vd,
+                                                double &vn, double &vp) {
+    vd = in[0]; vn = vp = in[ld];
+  }
 };
 struct LocalValues {  // 3x3 local matrix given per element, row-major
   static constexpr bool needs_xy = false;
+  P1_GENERIC_PACK
   const double *__restrict__ local;
   __device__ __forceinline__ void rows(int64_t t, const int *, double2, double2, double2,
                                        double (*v)[3]) const {
@@ -353,6 +462,7 @@ __device__ __forceinline__ void slim_values(const V &values, int k, double2 za, 
 // as an [M x 9] array.
 struct GeneralValues {
   static constexpr bool needs_xy = true;
+  P1_GENERIC_PACK
   const double2 *__restrict__ coords;
   const double *__restrict__ a11q, *__restrict__ a12q, *__restrict__ a21q,
       *__restrict__ a22q;
@@ -406,6 +516,7 @@ struct GeneralValues {
 // solvers.py:86-129 evaluated inside the scatter
 struct WeightedValues {
   static constexpr bool needs_xy = true;
+  P1_GENERIC_PACK
   const double2 *__restrict__ coords;
   const double *__restrict__ phiq;     // [n_qp x M]
   const double *__restrict__ weights;  // device, n_qp

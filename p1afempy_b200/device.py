@@ -14,7 +14,7 @@ import threading
 import numpy as np
 import torch
 
-from . import _lib
+from . import _lib, options
 
 _contexts = {}
 _ctx_lock = threading.Lock()
@@ -190,7 +190,8 @@ class DeviceMesh:
     # ------------------------------------------------------------------ plan
     def _flags(self, keep):
         return ((_lib.PLAN_EXACT if self._exact else 0)
-                | (_lib.PLAN_KEEP_ELEMENTS if keep else 0))
+                | (_lib.PLAN_KEEP_ELEMENTS if keep else 0)
+                | int(options.plan_flags))
 
     def _adopt(self, handle, keep, topology=False):
         self._plan = handle

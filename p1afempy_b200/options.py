@@ -11,7 +11,13 @@ callbacks = 'device' callbacks are first tried on a device-resident ndarray
                      of bit for bit.  Callbacks the stand-in cannot express
                      fall back to the host one by one.
 Set with ``p1afempy_b200.options.callbacks = 'device'`` or P1_CALLBACKS=device.
+
+plan_flags           diagnostic P1_PLAN_FORCE_* / P1_PLAN_TINY_SPILL bits (include/
+                     p1b200.h) OR-ed into every plan the drop-in layer creates:
+                     tests and measurements use them to choose a storage the
+                     library would not pick by itself.  Results do not change.
 """
 import os
 
 callbacks = os.environ.get('P1_CALLBACKS', 'host')
+plan_flags = 0

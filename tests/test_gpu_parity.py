@@ -607,8 +607,10 @@ def test_topology_plan_matches_element_keeping_plan():
 
 def test_spill_list_and_second_pass_agree(api, monkeypatch):
     """Rows with more than 8 records: their extra records travel through a spill
-    list; when the list is too small the elements are scanned a second time.  Both
-    routes give the same matrix (Delaunay mesh, valence up to 10+; and a fan)."""
+    list (tiled path and record path); when the list is too small the record path
+    scans the elements a second time.  All routes give the same matrix (Delaunay
+    mesh, valence up to 10+)."""
+    from p1afempy_b200 import _lib, options
     from scipy.spatial import Delaunay
     rng = np.random.default_rng(5)
     pts = np.vstack([rng.random((4000, 2)), [[0., 0.], [1., 0.], [1., 1.], [0., 1.]]])
@@ -619,11 +621,8 @@ def test_spill_list_and_second_pass_agree(api, monkeypatch):
     assert np.bincount(e.reshape(-1)).max() > 8
     ref = orc.stiffness_coo(pts, e).tocsr()
     got = {}
-    for cap in (None, '3'):
-        if cap is None:
-            monkeypatch.delenv('P1_SPILL_CAP', raising=False)
-        else:
-            monkeypatch.setenv('P1_SPILL_CAP', cap)
+    for cap, flags in ((None, 0), ('rec', _lib.PLAN_TILED), ('3', _lib.PLAN_TINY_SPILL)):
+        monkeypatch.setattr(options, 'plan_flags', flags)
         a = api[0].get_stiffness_matrix(pts, e)
         assert np.array_equal(a.indptr, ref.indptr) and np.array_equal(a.indices, ref.indices)
         H.csr_values_close(a, ref, RTOL)
@@ -633,6 +632,7 @@ def test_spill_list_and_second_pass_agree(api, monkeypatch):
     # off-diagonals identical; diagonals of high-valence rows may differ in the last
     # bits (their summation order is the arrival order of the records)
     assert np.abs(got[None] - got['3']).max() <= 1e-13 * np.abs(ref.data).max()
+    assert np.abs(got['rec'] - got['3']).max() <= 1e-13 * np.abs(ref.data).max()
 
 
 def test_unaligned_element_array():
@@ -674,13 +674,14 @@ def test_unaligned_element_array():
 
 def test_slim_plans_match_record_plans(api, mesh_case, monkeypatch):
     """Multi-GPU plans for stiffness / mass keep 8-byte slots and recompute the
-    entries while filling (P1_SLIM=1 forces that on one GPU): same pattern, same
+    entries while filling (P1_PLAN_FORCE_SLIM forces that on one GPU): same pattern, same
     off-diagonals bit for bit, diagonals within the usual rounding."""
+    from p1afempy_b200 import _lib, options
     c, e, _ = mesh_case
-    monkeypatch.setenv('P1_SLIM', '0')
+    monkeypatch.setattr(options, 'plan_flags', 0)
     a0 = api[0].get_stiffness_matrix(c, e)
     m0 = api[0].get_mass_matrix(c, e)
-    monkeypatch.setenv('P1_SLIM', '1')
+    monkeypatch.setattr(options, 'plan_flags', _lib.PLAN_FORCE_SLIM)
     a1 = api[0].get_stiffness_matrix(c, e)
     m1 = api[0].get_mass_matrix(c, e)
     for x, y in ((a0, a1), (m0, m1)):
@@ -689,6 +690,54 @@ def test_slim_plans_match_record_plans(api, mesh_case, monkeypatch):
         assert np.array_equal(x.data[off], y.data[off])
         H.csr_values_close(y, x, RTOL)
     H.csr_values_close(a1, orc.stiffness_coo(c, e).tocsr(), RTOL)
+
+
+@pytest.mark.parametrize('rule', ['MIDPOINT', 'DAYTAYLOR'])
+def test_tiled_plans_match_record_plans(api, mesh_case, rule, monkeypatch):
+    """P1_PLAN_TILED (tile-interior rows finished in shared memory, the others
+    through records): every matrix is bit for bit the record path's -- both build
+    a row in the same arithmetic order."""
+    from p1afempy_b200 import _lib, options
+    c, e, _ = mesh_case
+    r = cubature.CubatureRuleEnum[rule]
+    u = H.u_nodal(c)
+    out = []
+    for flags in (0, _lib.PLAN_TILED):
+        monkeypatch.setattr(options, 'plan_flags', flags)
+        out.append([api[0].get_stiffness_matrix(c, e), api[0].get_mass_matrix(c, e),
+                    api[0].get_general_stiffness_matrix(c, e, H.a11, H.a12, H.a21, H.a22, r),
+                    api[0].get_weighted_mass_matrix(c, e, u, H.phi, r)])
+    for x, y in zip(*out):
+        assert x.shape == y.shape
+        assert np.array_equal(x.indptr, y.indptr) and np.array_equal(x.indices, y.indices)
+        assert np.array_equal(x.data, y.data)
+    H.csr_values_close(out[1][0], orc.stiffness_coo(c, e).tocsr(), RTOL)
+
+
+def test_tiled_plan_irregular_meshes(api, monkeypatch):
+    """The tiled path on meshes that defeat its shortcuts: random element order (no
+    row completes inside a tile), a non-manifold vertex (closed-fan shortcut
+    contradicted -> exact plan), an unused node, 7 triangles (a partial quad)."""
+    from p1afempy_b200 import _lib, options
+    monkeypatch.setattr(options, 'plan_flags', _lib.PLAN_TILED)
+    c, e, _ = H.perturbed_square(5)
+    perm = np.random.default_rng(3).permutation(e.shape[0])
+    for ee in (e[perm], e[:e.shape[0] - 1], e[perm][:4099]):
+        cc = c
+        a = api[0].get_stiffness_matrix(cc, ee)
+        ref = orc.stiffness_coo(cc, ee).tocsr()
+        assert a.shape == ref.shape
+        assert np.array_equal(a.indptr, ref.indptr) and np.array_equal(a.indices, ref.indices)
+        H.csr_values_close(a, ref, RTOL)
+    # bow tie: two closed fans that share one vertex
+    c2 = np.vstack([c, c + [2., 0.]])
+    e2 = np.vstack([e, e + c.shape[0]])
+    centre = int(np.argmin(np.abs(c - 0.5).sum(axis=1)))
+    e2[e2 == centre + c.shape[0]] = centre
+    a = api[0].get_stiffness_matrix(c2, e2)
+    ref = orc.stiffness_coo(c2, e2).tocsr()
+    assert np.array_equal(a.indptr, ref.indptr) and np.array_equal(a.indices, ref.indices)
+    H.csr_values_close(a, ref, RTOL)
 
 
 def test_integration_md_stub_is_real(api):
