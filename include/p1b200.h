@@ -53,6 +53,9 @@ int p1_ctx_destroy(p1_ctx *ctx);
 /* Scratch memory is cached in the context between calls (same sizes recur on
  * the same mesh); p1_ctx_trim returns the unused blocks to the driver. */
 int p1_ctx_trim(p1_ctx *ctx);
+/* Idle scratch beyond `bytes` is returned as soon as a block is released (largest
+ * first); default 48 GB.  0 = cache nothing. */
+int p1_ctx_set_cache_limit(p1_ctx *ctx, int64_t bytes);
 
 /* numpy hands elements over as int64 (refinement.py:641) or uint32
  * (io_helpers.py:91); the device works on int32.  Values outside
@@ -195,6 +198,29 @@ int p1_assemble_csr(const p1_plan *plan, int op, const double *coords,
                     const double *local, int32_t *indptr, int32_t *indices,
                     double *data, void *stream);
 
+/* The whole cold assembly (plan + fill of p1_plan_create_for / _quad / _interleaved and
+ * p1_assemble_csr(P1_OP_STORED)) WITHOUT a host synchronisation: nothing the host
+ * would have to wait for is needed to launch the next kernel.  The outputs have a
+ * CAPACITY instead of an exact size (indices / data: `capacity` entries; any mesh
+ * whose boundary nodes have one open fan each satisfies nnz <= 2 * rows + incidences
+ * of the owned rows), indptr has rows + 1 entries and indptr[rows] = nnz.
+ * status: 8 device ints, valid once the stream has passed the call:
+ *   [0] P1_STATUS_* bits, [1] largest node index in `elements`, [6] nnz.
+ * When a status bit is set NOTHING was written to indices / data; the caller takes
+ * the plan route (P1_STATUS_SLOWPATH: a node with more than 8 elements, or nnz above
+ * the capacity; P1_STATUS_RETRY: as P1_ERETRY) or reports the error (INDEX).
+ * world / rank / chunk_log2 as for p1_plan_create_interleaved (1, 0, 0: all rows).
+ * qa: P1_OP_GENERAL / P1_OP_WEIGHTED only, else NULL.  Scratch memory returns to the
+ * context's arena in stream order. */
+#define P1_STATUS_INDEX 1
+#define P1_STATUS_RETRY 16
+#define P1_STATUS_SLOWPATH 64
+int p1_assemble_cold(p1_ctx *ctx, const int32_t *elements, int64_t n_elements,
+                     int64_t n_nodes, int chunk_log2, int world, int rank, int op,
+                     const double *coords, const double *local, const p1_quad_args *qa,
+                     int64_t capacity, int32_t *indptr, int32_t *indices, double *data,
+                     int32_t *status, void *stream);
+
 /* solvers.py:156-182 get_mass_matrix_elements: the 9M triplets in the
  * reference's order (element-major, entry k: row = vertex k%3, col = k/3). */
 int p1_mass_triplets(p1_ctx *ctx, const double *coords,
@@ -286,8 +312,9 @@ int p1_load_vector_midpoint_direct(p1_ctx *ctx, const int32_t *elements,
 
 /* mesh.py:87-161 provide_geometric_data.  boundary_nodes: concatenated
  * (K x 2) int32 rows of all boundaries; boundary_offsets_host: n_boundaries+1
- * row offsets (host).  Outputs: element2edges (M x 3), edge2nodes (E x 2,
- * capacity 3M+K rows... exactly (3M+K)/2 are written), boundary2edges (K);
+ * row offsets (host).  Outputs: element2edges (M x 3), edge2nodes (E x 2: the
+ * caller provides (3M+K+1)/2 rows, E = (3M+K)/2 are written; on the error path
+ * below nothing is written past that capacity), boundary2edges (K);
  * *n_edges_host receives E.  SYNCHRONISES the stream. */
 int p1_geometric_data(const p1_plan *plan, const int32_t *boundary_nodes,
                       const int64_t *boundary_offsets_host, int n_boundaries,

@@ -22,6 +22,10 @@ P1_ERANGE = -5
 P1_ECOMM = -6
 P1_ERETRY = -7
 
+STATUS_INDEX = 1
+STATUS_RETRY = 16
+STATUS_SLOWPATH = 64
+
 PLAN_DEFAULT = 0
 PLAN_EXACT = 1
 PLAN_KEEP_ELEMENTS = 2
@@ -56,6 +60,7 @@ PROTOTYPES = {
     'p1_ctx_create': [_int, C.POINTER(_vp)],
     'p1_ctx_destroy': [_vp],
     'p1_ctx_trim': [_vp],
+    'p1_ctx_set_cache_limit': [_vp, _i64],
     'p1_profile_enable': [_vp, _int],
     'p1_profile_reset': [_vp],
     'p1_profile_report': [_vp, C.c_char_p, _i64],
@@ -75,6 +80,8 @@ PROTOTYPES = {
     'p1_plan_info': [_vp, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64),
                      C.POINTER(_i64)],
     'p1_assemble_csr': [_vp, _int, _vp, _vp, _vp, _vp, _vp, _vp],
+    'p1_assemble_cold': [_vp, _vp, _i64, _i64, _int, _int, _int, _int, _vp, _vp,
+                         C.POINTER(QuadArgs), _i64, _vp, _vp, _vp, _vp, _vp],
     'p1_mass_triplets': [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp],
     'p1_stiffness_triplets': [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp],
     'p1_geometry': [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp],

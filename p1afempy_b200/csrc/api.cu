@@ -49,6 +49,9 @@ struct p1_arena {
   struct Block { void *ptr; size_t bytes; bool used; cudaStream_t last; };
   std::vector<Block> blocks;
   std::mutex lock;
+  // unused blocks beyond this many bytes go back to the driver (largest first): torch's
+  // allocator cannot reclaim what sits here (p1_ctx_set_cache_limit)
+  size_t limit = (size_t)48 << 30;
 };
 
 namespace p1 {
@@ -103,7 +106,20 @@ void arena_free(p1_ctx *ctx, void *ptr, cudaStream_t s) {
   p1_arena *ar = ctx->arena;
   std::lock_guard<std::mutex> g(ar->lock);
   for (auto &b : ar->blocks)
-    if (b.ptr == ptr) { b.used = false; b.last = s; return; }
+    if (b.ptr == ptr) { b.used = false; b.last = s; break; }
+  size_t idle = 0;
+  for (auto &b : ar->blocks)
+    if (!b.used) idle += b.bytes;
+  while (idle > ar->limit) {
+    int big = -1;
+    for (int i = 0; i < (int)ar->blocks.size(); ++i)
+      if (!ar->blocks[i].used && (big < 0 || ar->blocks[i].bytes > ar->blocks[big].bytes)) big = i;
+    if (big < 0) break;
+    cudaStreamSynchronize(ar->blocks[big].last);  // queued work may still use it
+    cudaFree(ar->blocks[big].ptr);
+    idle -= ar->blocks[big].bytes;
+    ar->blocks.erase(ar->blocks.begin() + big);
+  }
 }
 
 void prof_begin(p1_ctx *ctx, const char *name, cudaStream_t s) {
@@ -122,7 +138,7 @@ using namespace p1;
 
 extern "C" int p1_profile_enable(p1_ctx *ctx, int on) {
   P1_REQUIRE(ctx, "null ctx");
-  DeviceGuard guard(ctx->device);
+  DeviceGuard guard(ctx);
   if (!ctx->prof) ctx->prof = new p1_prof();
   ctx->prof->drain();
   ctx->prof->on = on != 0;
@@ -131,7 +147,7 @@ extern "C" int p1_profile_enable(p1_ctx *ctx, int on) {
 
 extern "C" int p1_profile_reset(p1_ctx *ctx) {
   P1_REQUIRE(ctx, "null ctx");
-  DeviceGuard guard(ctx->device);
+  DeviceGuard guard(ctx);
   if (ctx->prof) { ctx->prof->drain(); ctx->prof->totals.clear(); }
   return P1_OK;
 }
@@ -139,7 +155,7 @@ extern "C" int p1_profile_reset(p1_ctx *ctx) {
 // text: one line per timed span, "name total_ms launches\n"
 extern "C" int p1_profile_report(p1_ctx *ctx, char *buf, int64_t cap) {
   P1_REQUIRE(ctx && buf && cap > 0, "bad buffer");
-  DeviceGuard guard(ctx->device);
+  DeviceGuard guard(ctx);
   buf[0] = 0;
   if (!ctx->prof) return P1_OK;
   ctx->prof->drain();
@@ -156,7 +172,7 @@ extern "C" int p1_profile_report(p1_ctx *ctx, char *buf, int64_t cap) {
 // returns every cached, unused scratch block to the driver
 extern "C" int p1_ctx_trim(p1_ctx *ctx) {
   P1_REQUIRE(ctx, "null ctx");
-  DeviceGuard guard(ctx->device);
+  DeviceGuard guard(ctx);
   std::lock_guard<std::mutex> g(ctx->arena->lock);
   cudaDeviceSynchronize();
   auto &bl = ctx->arena->blocks;
@@ -165,7 +181,14 @@ extern "C" int p1_ctx_trim(p1_ctx *ctx) {
   return P1_OK;
 }
 
-extern "C" int p1_version(void) { return 100; }  // 0.1.0
+extern "C" int p1_ctx_set_cache_limit(p1_ctx *ctx, int64_t bytes) {
+  P1_REQUIRE(ctx && bytes >= 0, "bad argument");
+  std::lock_guard<std::mutex> g(ctx->arena->lock);
+  ctx->arena->limit = (size_t)bytes;
+  return P1_OK;
+}
+
+extern "C" int p1_version(void) { return 200; }  // 0.2.0
 
 extern "C" const char *p1_last_error(void) { return g_error; }
 
@@ -206,7 +229,7 @@ extern "C" int p1_ctx_create(int device, p1_ctx **out) {
 
 extern "C" int p1_ctx_destroy(p1_ctx *ctx) {
   if (!ctx) return P1_OK;
-  DeviceGuard guard(ctx->device);
+  DeviceGuard guard(ctx->device);  // (not the locking form: the lock dies with the context)
   if (ctx->d_flags) cudaFree(ctx->d_flags);
   if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
   if (ctx->prof) { ctx->prof->drain(); delete ctx->prof; }

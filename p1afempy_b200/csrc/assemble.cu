@@ -95,6 +95,8 @@ fill_rows_kernel(int n_own, Own own, int exact,
                  double *__restrict__ data, int *__restrict__ flags) {
   __shared__ int cols_s[CAP_OUT];
   __shared__ double vals_s[CAP_OUT];
+  // (p1_assemble_cold: the output may be too small, or the mesh needs the plan route)
+  if (*(volatile const int *)flags & (FLAG_SLOWPATH | FLAG_INDEX_RANGE)) return;
   const int tid = threadIdx.x;
   const int row0 = blockIdx.x * FR;
   const int nrows = min(FR, n_own - row0);
@@ -176,6 +178,7 @@ fill_gather_kernel(int n_own, Own own, const unsigned long long *__restrict__ ac
   __shared__ double2 zs[(GROUP + 1) * FR];  // column GROUP: the row's own node
   __shared__ double vps[GROUP * FR];
   __shared__ unsigned char src_s[GROUP * FR];  // record whose `next` is my `prev`
+  if (*(volatile const int *)flags & (FLAG_SLOWPATH | FLAG_INDEX_RANGE)) return;
   const int tid = threadIdx.x;
   const int row0 = blockIdx.x * FR;
   const int nrows = min(FR, n_own - row0);
@@ -321,10 +324,15 @@ template <class V>
 __global__ void __launch_bounds__(SLOW_THREADS)
 fill_slow_kernel(const int *__restrict__ slow_rows, int n_slow, Own own, Rows rows, V values,
                  const int *__restrict__ indptr, int *__restrict__ indices,
-                 double *__restrict__ data, int *__restrict__ verify = nullptr) {
+                 double *__restrict__ data, int *__restrict__ verify = nullptr,
+                 const int *__restrict__ n_slow_dev = nullptr,
+                 const int *__restrict__ status = nullptr) {
   __shared__ int cols_s[SLOW_THREADS * SLOW_COLS];
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n_slow) return;
+  // n_slow_dev: the list's length is read on the device and the grid strides over it
+  if (status && (*(volatile const int *)status & (FLAG_SLOWPATH | FLAG_INDEX_RANGE))) return;
+  if (n_slow_dev) n_slow = *n_slow_dev;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_slow;
+       idx += gridDim.x * blockDim.x) {
   const int a = slow_rows[idx];
   const int deg = rows.deg(a);
   const int self = own.global(a);
@@ -354,7 +362,7 @@ fill_slow_kernel(const int *__restrict__ slow_rows, int n_slow, Own own, Rows ro
     // tiled plans take the row length from the record count (closed fan: 1 + deg,
     // else 2 + deg) without looking at the records: this row is not that simple
     atomicOr(verify, FLAG_RETRY);
-    return;
+    continue;
   }
   double *vs = data + base;
   for (int j = 0; j < n; ++j) {
@@ -384,6 +392,7 @@ fill_slow_kernel(const int *__restrict__ slow_rows, int n_slow, Own own, Rows ro
       }
       last_pv = pick_pv;
     }
+  }
   }
 }
 
@@ -489,6 +498,38 @@ void p1::launch_fill_fallback(p1_plan *plan, int *indices, double *data, cudaStr
                  plan->indptr, indices, data, ctx->d_flags)));
 }
 
+void p1::launch_fill_cold(p1_ctx *ctx, const Own &own, int n_own, const Rows &rows, int slim_op,
+                          const double2 *coords, const int *indptr, const int *slow_rows,
+                          const int *n_slow_dev, int *indices, double *data, int *status,
+                          cudaStream_t s) {
+  if (n_own <= 0) return;
+  const unsigned sg = (unsigned)(ctx->sm_count * 2);
+  prof_begin(ctx, "fill_rows", s);
+  if (slim_op == P1_OP_STIFFNESS)
+    fill_gather_kernel<<<grid_for(n_own, FR), FR, 0, s>>>(n_own, own, rows.acc, rows.slim,
+                                                         StiffnessValues{coords}, indptr, indices,
+                                                         data, status);
+  else if (slim_op == P1_OP_MASS)
+    fill_gather_kernel<<<grid_for(n_own, FR), FR, 0, s>>>(n_own, own, rows.acc, rows.slim,
+                                                         MassValues{coords}, indptr, indices, data,
+                                                         status);
+  else
+    fill_rows_kernel<<<grid_for(n_own, FR), FR, 0, s>>>(n_own, own, 0, rows.acc, rows.rec, indptr,
+                                                       indices, data, status);
+  prof_end(ctx, s);
+  prof_begin(ctx, "fill_slow", s);
+  if (slim_op == P1_OP_STIFFNESS)
+    fill_slow_kernel<<<sg, SLOW_THREADS, 0, s>>>(slow_rows, 0, own, rows, StiffnessValues{coords},
+                                                 indptr, indices, data, nullptr, n_slow_dev, status);
+  else if (slim_op == P1_OP_MASS)
+    fill_slow_kernel<<<sg, SLOW_THREADS, 0, s>>>(slow_rows, 0, own, rows, MassValues{coords},
+                                                 indptr, indices, data, nullptr, n_slow_dev, status);
+  else
+    fill_slow_kernel<<<sg, SLOW_THREADS, 0, s>>>(slow_rows, 0, own, rows, NoValues{}, indptr,
+                                                 indices, data, nullptr, n_slow_dev, status);
+  prof_end(ctx, s);
+}
+
 // Slim plans (multi-GPU stiffness / mass, no row with more than 8 records): the
 // values are computed while filling, from the plan's coordinates or the ones
 // passed here.
@@ -511,7 +552,7 @@ static void launch_slim(p1_plan *plan, V values, int *indices, double *data, cud
 static int assemble_slim(p1_plan *plan, int op, const double *coords, int32_t *indptr,
                          int32_t *indices, double *data, void *stream) {
   p1_ctx *ctx = plan->ctx;
-  DeviceGuard guard(ctx->device);
+  DeviceGuard guard(ctx);
   cudaStream_t s = (cudaStream_t)stream;
   if (op == P1_OP_STORED) op = plan->val_op;
   else if (coords) plan->coords = (const double2 *)coords;
@@ -553,7 +594,7 @@ extern "C" int p1_assemble_csr(const p1_plan *cplan, int op, const double *coord
     return P1_EINVAL;
   }
   p1_ctx *ctx = plan->ctx;
-  DeviceGuard guard(ctx->device);
+  DeviceGuard guard(ctx);
   cudaStream_t s = (cudaStream_t)stream;
   const int n_own = (int)plan->n_own;
   const Own own = plan->own;

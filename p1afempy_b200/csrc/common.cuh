@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <stdarg.h>
 #include <string.h>
+#include <mutex>
 
 #include "../../include/p1b200.h"
 
@@ -44,6 +45,7 @@ enum : int {
   FLAG_UNCOVERED = 8,      // boundary half-edge not listed in any boundary
   FLAG_OVERFLOW = 32,      // topology-only plan: a node has more than 8 incident elements
   FLAG_RETRY = 16,         // a row contradicted the closed-fan shortcut: re-plan exactly
+  FLAG_SLOWPATH = 64,      // p1_assemble_cold: the mesh needs the plan route (nothing written)
 };
 
 }  // namespace p1
@@ -53,10 +55,16 @@ struct p1_arena;
 struct p1_ctx {
   int device;
   int sm_count;
-  int *d_flags;        // 4 ints: [0] status bits, [1] max node index, [2..3] spare
+  int *d_flags;        // 8 ints: [0] status bits, [1] max node index, [2..7] list lengths
   int *h_flags;        // pinned mirror
   p1_prof *prof;       // per-kernel CUDA-event timing, off unless enabled
   p1_arena *arena;     // cached scratch blocks
+  // The status words, their mirror and the profiler are one per context: every entry
+  // point holds this lock from start to return (DeviceGuard), so calls on one context
+  // from several host threads serialise instead of clearing each other's flags.
+  // (p1_assemble_cold keeps its status in caller memory and only needs the lock for
+  // the profiler.)
+  std::recursive_mutex lock;
 };
 
 namespace p1 {
@@ -81,11 +89,21 @@ inline void pool_free(p1_ctx *ctx, void *ptr, cudaStream_t s) {
 
 struct DeviceGuard {
   int prev;
+  std::recursive_mutex *lock = nullptr;
   explicit DeviceGuard(int dev) {
     cudaGetDevice(&prev);
     if (prev != dev) cudaSetDevice(dev);
   }
-  ~DeviceGuard() { cudaSetDevice(prev); }
+  // entry points: select the context's device AND serialise on the context
+  explicit DeviceGuard(p1_ctx *ctx) : lock(&ctx->lock) {
+    lock->lock();
+    cudaGetDevice(&prev);
+    if (prev != ctx->device) cudaSetDevice(ctx->device);
+  }
+  ~DeviceGuard() {
+    cudaSetDevice(prev);
+    if (lock) lock->unlock();
+  }
 };
 
 inline unsigned grid_for(int64_t n, int block, int per_thread = 1) {

@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(THREADS)
 element_edges_kernel(const int *__restrict__ elements, int64_t M,
                      const int *__restrict__ num, const int *__restrict__ twin,
                      long long *__restrict__ element2edges,
-                     long long *__restrict__ edge2nodes) {
+                     long long *__restrict__ edge2nodes, int64_t cap_edges) {
   for (int64_t h = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; h < 3 * M;
        h += (int64_t)gridDim.x * blockDim.x) {
     const int64_t m = h / 3;
@@ -327,8 +327,13 @@ element_edges_kernel(const int *__restrict__ elements, int64_t M,
     if (I < J) {
       const int id = num[p];
       element2edges[h] = id;
-      edge2nodes[2 * (int64_t)id] = I;
-      edge2nodes[2 * (int64_t)id + 1] = J;
+      // (more forward than backward half-edges -- boundary edges missing or listed
+      // the wrong way round -- is reported by the caller; do not write past the
+      // (3M + K + 1) / 2 rows a consistent mesh needs)
+      if (id < cap_edges) {
+        edge2nodes[2 * (int64_t)id] = I;
+        edge2nodes[2 * (int64_t)id + 1] = J;
+      }
     } else {
       const int t = twin[h];
       if (t >= 0) {
@@ -370,7 +375,8 @@ boundary_numbers_kernel(const int *__restrict__ bnd, int64_t K, int64_t M, int n
                         Rows rows, const int *__restrict__ num,
                         long long *__restrict__ element2edges,
                         long long *__restrict__ edge2nodes,
-                        long long *__restrict__ boundary2edges, int *__restrict__ flags) {
+                        long long *__restrict__ boundary2edges, int *__restrict__ flags,
+                        int64_t cap_edges) {
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= K) return;
   const int b0 = bnd[2 * r], b1 = bnd[2 * r + 1];
@@ -393,8 +399,10 @@ boundary_numbers_kernel(const int *__restrict__ bnd, int64_t K, int64_t M, int n
     // the appended (reversed) entry is forward and owns the number
     const int id = num[3 * M + r];
     boundary2edges[r] = id;
-    edge2nodes[2 * (int64_t)id] = b1;
-    edge2nodes[2 * (int64_t)id + 1] = b0;
+    if (id < cap_edges) {
+      edge2nodes[2 * (int64_t)id] = b1;
+      edge2nodes[2 * (int64_t)id + 1] = b0;
+    }
     element2edges[h] = id;
   }
 }
@@ -558,7 +566,7 @@ extern "C" int p1_geometric_data(const p1_plan *cplan, const int32_t *boundary_n
              "bad boundary list");
   p1_plan *p = const_cast<p1_plan *>(cplan);
   p1_ctx *ctx = p->ctx;
-  DeviceGuard guard(ctx->device);
+  DeviceGuard guard(ctx);
   cudaStream_t s = (cudaStream_t)stream;
   const int64_t M = p->M;
   const int64_t K = n_boundaries ? boundary_offsets_host[n_boundaries] : 0;
@@ -602,12 +610,12 @@ extern "C" int p1_geometric_data(const p1_plan *cplan, const int32_t *boundary_n
     P1_TIMED(ctx, "edge_numbers", s,
              element_edges_kernel<<<egrid(ctx, 3 * M), THREADS, 0, s>>>(
                  p->elements, M, num, p->twin, (long long *)element2edges,
-                 (long long *)edge2nodes));
+                 (long long *)edge2nodes, (total + 1) / 2));
   if (K > 0)
     boundary_numbers_kernel<<<grid_for(K, THREADS), THREADS, 0, s>>>(
         boundary_nodes, K, M, (int)p->N, rows_of(p), num,
         (long long *)element2edges, (long long *)edge2nodes, (long long *)boundary2edges,
-        ctx->d_flags);
+        ctx->d_flags, (total + 1) / 2);
   release();
   P1_CUDA(cudaGetLastError());
   P1_TRY(read_flags(ctx, s));
@@ -640,7 +648,7 @@ extern "C" int p1_eta_r(const p1_plan *cplan, const double *coords, const double
   P1_REQUIRE(n_dirichlet >= 0 && n_neumann >= 0, "negative boundary size");
   P1_REQUIRE(n_dirichlet == 0 || dirichlet, "null dirichlet");
   P1_REQUIRE(n_neumann == 0 || (neumann && neumann_term), "null neumann");
-  DeviceGuard guard(ctx->device);
+  DeviceGuard guard(ctx);
   cudaStream_t s = (cudaStream_t)stream;
   P1_TRY(ensure_twins(p, s));
   if (p->n_open != n_dirichlet + n_neumann) {

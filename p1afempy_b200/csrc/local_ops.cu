@@ -497,7 +497,7 @@ using namespace p1;
 extern "C" int p1_narrow_indices(p1_ctx *ctx, const void *src, int src_kind,
                                  int64_t count, int32_t *dst, void *stream) {
   P1_REQUIRE(ctx && (count == 0 || (src && dst)), "null argument");
-  DeviceGuard guard(ctx->device);
+  DeviceGuard guard(ctx);
   cudaStream_t s = (cudaStream_t)stream;
   if (count == 0) return P1_OK;
   if (src_kind == 0)
@@ -516,7 +516,7 @@ extern "C" int p1_check_indices(p1_ctx *ctx, const int32_t *indices, int64_t cou
                                 int64_t n_nodes, void *stream) {
   P1_REQUIRE(ctx && (count == 0 || indices), "null argument");
   P1_REQUIRE(n_nodes >= 0 && n_nodes <= 0x7fffffffLL, "bad n_nodes");
-  DeviceGuard guard(ctx->device);
+  DeviceGuard guard(ctx);
   if (count == 0) return P1_OK;
   cudaStream_t s = (cudaStream_t)stream;
   P1_CUDA(cudaMemsetAsync(ctx->d_flags, 0, sizeof(int), s));
@@ -534,7 +534,7 @@ extern "C" int p1_check_indices(p1_ctx *ctx, const int32_t *indices, int64_t cou
 extern "C" int p1_widen_indices(p1_ctx *ctx, const int32_t *src, int64_t count,
                                 int64_t *dst, void *stream) {
   P1_REQUIRE(ctx && (count == 0 || (src && dst)), "null argument");
-  DeviceGuard guard(ctx->device);
+  DeviceGuard guard(ctx);
   if (count == 0) return P1_OK;
   widen_kernel<<<egrid(ctx, count), THREADS, 0, (cudaStream_t)stream>>>(
       src, count, (long long *)dst);
@@ -546,7 +546,7 @@ extern "C" int p1_geometry(p1_ctx *ctx, const double *coords, const int32_t *ele
                            int64_t M, double *area, double *d21, double *d31,
                            void *stream) {
   P1_REQUIRE(ctx && (M == 0 || (coords && elements)), "null argument");
-  DeviceGuard guard(ctx->device);
+  DeviceGuard guard(ctx);
   if (M == 0) return P1_OK;
   geometry_kernel<<<egrid(ctx, M), THREADS, 0, (cudaStream_t)stream>>>(
       (const double2 *)coords, elements, M, area, (double2 *)d21, (double2 *)d31);
@@ -559,7 +559,7 @@ static int triplets(p1_ctx *ctx, bool stiffness, const double *coords,
                     double *vals, void *stream) {
   P1_REQUIRE(ctx && (M == 0 || (coords && elements && rows && cols && vals)),
              "null argument");
-  DeviceGuard guard(ctx->device);
+  DeviceGuard guard(ctx);
   if (M == 0) return P1_OK;
   cudaStream_t s = (cudaStream_t)stream;
   if (stiffness)
@@ -589,7 +589,7 @@ extern "C" int p1_quadrature_points(p1_ctx *ctx, const double *coords,
                                     void *stream) {
   P1_REQUIRE(ctx && points_host && n_qp > 0, "bad rule");
   P1_REQUIRE(M == 0 || (coords && elements && xq), "null argument");
-  DeviceGuard guard(ctx->device);
+  DeviceGuard guard(ctx);
   if (M == 0) return P1_OK;
   cudaStream_t s = (cudaStream_t)stream;
   double *pts = nullptr;
@@ -607,7 +607,7 @@ extern "C" int p1_nodal_at_quadrature(p1_ctx *ctx, const double *u,
                                       void *stream) {
   P1_REQUIRE(ctx && points_host && n_qp > 0, "bad rule");
   P1_REQUIRE(M == 0 || (u && elements && uq), "null argument");
-  DeviceGuard guard(ctx->device);
+  DeviceGuard guard(ctx);
   if (M == 0) return P1_OK;
   cudaStream_t s = (cudaStream_t)stream;
   double *pts = nullptr;
@@ -622,7 +622,7 @@ extern "C" int p1_nodal_at_quadrature(p1_ctx *ctx, const double *u,
 extern "C" int p1_centroids(p1_ctx *ctx, const double *coords, const int32_t *elements,
                             int64_t M, double *centroids, void *stream) {
   P1_REQUIRE(ctx && (M == 0 || (coords && elements && centroids)), "null argument");
-  DeviceGuard guard(ctx->device);
+  DeviceGuard guard(ctx);
   if (M == 0) return P1_OK;
   centroids_kernel<<<egrid(ctx, M), THREADS, 0, (cudaStream_t)stream>>>(
       (const double2 *)coords, elements, M, (double2 *)centroids);
@@ -634,7 +634,7 @@ extern "C" int p1_boundary_edges(p1_ctx *ctx, const double *coords, const int32_
                                  int64_t K, double *length, double *midpoint,
                                  void *stream) {
   P1_REQUIRE(ctx && (K == 0 || (coords && edges)), "null argument");
-  DeviceGuard guard(ctx->device);
+  DeviceGuard guard(ctx);
   if (K == 0) return P1_OK;
   boundary_edges_kernel<<<egrid(ctx, K), THREADS, 0, (cudaStream_t)stream>>>(
       (const double2 *)coords, edges, K, length, (double2 *)midpoint);
@@ -651,7 +651,7 @@ extern "C" int p1_local_general_stiffness(p1_ctx *ctx, const double *coords,
   P1_REQUIRE(ctx && weights_host && n_qp > 0, "bad rule");
   P1_REQUIRE(M == 0 || (coords && elements && a11q && a12q && a21q && a22q && local),
              "null argument");
-  DeviceGuard guard(ctx->device);
+  DeviceGuard guard(ctx);
   if (M == 0) return P1_OK;
   cudaStream_t s = (cudaStream_t)stream;
   double *w = nullptr;
@@ -671,7 +671,7 @@ extern "C" int p1_local_weighted_mass(p1_ctx *ctx, const double *coords,
                                       double *local, void *stream) {
   P1_REQUIRE(ctx && weights_host && points_host && n_qp > 0, "bad rule");
   P1_REQUIRE(M == 0 || (coords && elements && phiq && local), "null argument");
-  DeviceGuard guard(ctx->device);
+  DeviceGuard guard(ctx);
   if (M == 0) return P1_OK;
   cudaStream_t s = (cudaStream_t)stream;
   double *w = nullptr, *pts = nullptr;
@@ -692,7 +692,7 @@ extern "C" int p1_integrate_quadrature(p1_ctx *ctx, const double *coords,
                                        int n_qp, double *result_host, void *stream) {
   P1_REQUIRE(ctx && weights_host && n_qp > 0 && result_host, "bad argument");
   P1_REQUIRE(M == 0 || (coords && elements && fq), "null argument");
-  DeviceGuard guard(ctx->device);
+  DeviceGuard guard(ctx);
   *result_host = 0.;
   if (M == 0) return P1_OK;
   cudaStream_t s = (cudaStream_t)stream;
@@ -725,7 +725,7 @@ extern "C" int p1_load_vector(const p1_plan *plan, const double *coords,
   P1_REQUIRE(n_own == 0 || b, "null b");
   P1_REQUIRE(M == 0 || (coords && fq), "null argument");
   p1_ctx *ctx = plan->ctx;
-  DeviceGuard guard(ctx->device);
+  DeviceGuard guard(ctx);
   cudaStream_t s = (cudaStream_t)stream;
   P1_TRY(require_elements(plan, "p1_load_vector"));
   double *w = nullptr, *pts = nullptr, *L = nullptr;
@@ -757,7 +757,7 @@ extern "C" int p1_load_vector_midpoint(const p1_plan *plan, const double *coords
   P1_REQUIRE(n_own == 0 || b, "null b");
   P1_REQUIRE(M == 0 || (coords && f_centroid), "null argument");
   p1_ctx *ctx = plan->ctx;
-  DeviceGuard guard(ctx->device);
+  DeviceGuard guard(ctx);
   cudaStream_t s = (cudaStream_t)stream;
   P1_TRY(require_elements(plan, "p1_load_vector_midpoint"));
   double *share = nullptr;

@@ -400,18 +400,19 @@ template <int MODE, class V>
 static void launch_scatter_slots(p1_ctx *ctx, unsigned grid, cudaStream_t s, const int *elements,
                                  int64_t M, int N, Own own, unsigned long long *acc, void *slots_,
                                  V values, bool allow_pairs, int *slot_of = nullptr,
-                                 int4 *tspill = nullptr) {
+                                 int4 *tspill = nullptr, int *fl = nullptr) {
   const int vec = ((uintptr_t)elements & 15) == 0;
   bool pairs = allow_pairs && own.world == 1 && own.re - own.rb == N;
   Rec *slots = reinterpret_cast<Rec *>(slots_);
+  if (!fl) fl = ctx->d_flags;
   if (pairs)
     scatter_kernel<V, false, true, MODE><<<grid, SC_THREADS, 0, s>>>(
         elements, M, N, own, vec, acc, slots, slot_of, reinterpret_cast<int *>(tspill), values,
-        ctx->d_flags);
+        fl);
   else
     scatter_kernel<V, false, false, MODE><<<grid, SC_THREADS, 0, s>>>(
         elements, M, N, own, vec, acc, slots, slot_of, reinterpret_cast<int *>(tspill), values,
-        ctx->d_flags);
+        fl);
 }
 
 template <bool OVERFLOW>
@@ -420,9 +421,9 @@ static void launch_scatter(p1_ctx *ctx, unsigned grid, cudaStream_t s, int op,
                            unsigned long long *acc, Rec *rec, int *rec_elem, int *cursor,
                            const double *coords, const double *local,
                            const p1_quad_args *qa, const double *d_weights,
-                           const double *d_points) {
+                           const double *d_points, int *fl = nullptr) {
   const double2 *xy = (const double2 *)coords;
-  int *fl = ctx->d_flags;
+  if (!fl) fl = ctx->d_flags;
   // 4 triangles per thread; not for the source that streams four [n_qp x M] arrays,
   // which wants consecutive lanes on consecutive triangles (measured at 64M: 24.5 ms
   // with, 12.5 ms without; the unfused route through p1_local_general_stiffness is
@@ -1041,7 +1042,7 @@ extern "C" int p1_partition_rows(p1_ctx *ctx, const int32_t *elements,
                                  int64_t *boundaries_host, void *stream) {
   P1_REQUIRE(ctx && boundaries_host && world >= 1, "bad argument");
   P1_REQUIRE(n_elements >= 0 && n_nodes >= 0 && n_nodes <= 0x7fffffffLL, "bad size");
-  DeviceGuard guard(ctx->device);
+  DeviceGuard guard(ctx);
   cudaStream_t s = (cudaStream_t)stream;
   const int buckets = 8192;
   const int stride = n_elements > (1 << 22) ? 16 : 1;
@@ -1131,7 +1132,7 @@ static int plan_build(p1_ctx *ctx, const int32_t *elements, int64_t n_elements,
              "null phiq/points");
   P1_REQUIRE(op != P1_OP_LOCAL || local || n_elements == 0,
              "P1_OP_LOCAL needs the local matrices");
-  DeviceGuard guard(ctx->device);
+  DeviceGuard guard(ctx);
   cudaStream_t s = (cudaStream_t)stream;
   // One GPU, all rows, one operator, nothing to keep: the tiled path on request (tiled.cu).
   if ((flags & P1_PLAN_TILED) && op != 0 && world == 1 && row_begin == 0 &&
@@ -1323,6 +1324,11 @@ static int plan_build(p1_ctx *ctx, const int32_t *elements, int64_t n_elements,
     set_error("p1_plan_create: element index out of range [0, %lld)", (long long)n_nodes);
     return fail(P1_EINDEX);
   }
+  if (h_nnz < 0) {
+    set_error("p1_plan_create: more than 2^31 - 1 stored entries in these rows; split the rows "
+              "(row_begin / row_end) so that every piece fits an int32 row pointer");
+    return fail(P1_ERANGE);
+  }
   p->max_index = ctx->h_flags[1];
   p->n_big = ctx->h_flags[2];
   p->n_slow = ctx->h_flags[3];
@@ -1445,7 +1451,7 @@ extern "C" int p1_load_vector_direct(p1_ctx *ctx, const int32_t *elements, int64
                  n_elements < (1LL << 29), "bad size");
   P1_REQUIRE(n_elements == 0 || (elements && coords && fq), "null input");
   P1_REQUIRE(n_qp > 0 && weights_host && points_host, "bad rule");
-  DeviceGuard guard(ctx->device);
+  DeviceGuard guard(ctx);
   cudaStream_t s = (cudaStream_t)stream;
   double *rule = nullptr;  // points (16-byte aligned pairs), then weights
   P1_TRY(pool_alloc(ctx, &rule, (size_t)3 * n_qp, s));
@@ -1468,17 +1474,139 @@ extern "C" int p1_load_vector_midpoint_direct(p1_ctx *ctx, const int32_t *elemen
   P1_REQUIRE(n_elements >= 0 && n_nodes >= 0 && n_nodes <= (int64_t)NODE_MASK &&
                  n_elements < (1LL << 29), "bad size");
   P1_REQUIRE(n_elements == 0 || (elements && coords && f_centroid), "null input");
-  DeviceGuard guard(ctx->device);
+  DeviceGuard guard(ctx);
   const LoadMidpointValues values{(const double2 *)coords, f_centroid};
   return load_vector_direct(ctx, elements, n_elements, n_nodes, values, true, true, b,
                             (cudaStream_t)stream, "p1_load_vector_midpoint_direct");
+}
+
+// ------------------------------------------------------- cold assembly, no host sync
+// Everything the host used to wait for stays on the device: the status words are
+// the caller's (flags, max index, list lengths, nnz), the outputs have a capacity
+// instead of an exact size, the boundary-row list is walked with its length read on
+// the device.  Meshes that need more than the common case (a node with more than 8
+// elements, nnz above the capacity) are reported in the status word
+// (P1_STATUS_SLOWPATH) and nothing is written; the caller then takes the plan route.
+namespace p1 {
+__global__ void cold_finalize_kernel(int *__restrict__ status, const int *__restrict__ indptr,
+                                     int n_own, int64_t cap) {
+  const int nnz = indptr[n_own];
+  status[6] = nnz;
+  if (status[4] > 0 || status[2] > 0 || nnz < 0 || (int64_t)nnz > cap)
+    atomicOr(status, FLAG_SLOWPATH);
+}
+}  // namespace p1
+
+extern "C" int p1_assemble_cold(p1_ctx *ctx, const int32_t *elements, int64_t n_elements,
+                                int64_t n_nodes, int chunk_log2, int world, int rank, int op,
+                                const double *coords, const double *local,
+                                const p1_quad_args *qa, int64_t capacity, int32_t *indptr,
+                                int32_t *indices, double *data, int32_t *status, void *stream) {
+  P1_REQUIRE(ctx && indptr && status, "null ctx/indptr/status");
+  P1_REQUIRE(n_elements >= 0 && n_nodes >= 0 && capacity >= 0, "negative size");
+  P1_REQUIRE(data || capacity == 0, "null data");
+  P1_REQUIRE(world >= 1 && rank >= 0 && rank < world && chunk_log2 >= 0 && chunk_log2 < 31,
+             "bad interleave");
+  if (n_nodes > (int64_t)NODE_MASK || n_elements >= (1LL << 29) ||
+      3 * n_elements + n_nodes > 0x7fffffffLL) {
+    set_error("p1_assemble_cold: mesh too large for int32 device indices");
+    return P1_ERANGE;
+  }
+  P1_REQUIRE(elements || n_elements == 0, "null elements");
+  const bool quad = op == P1_OP_GENERAL || op == P1_OP_WEIGHTED;
+  P1_REQUIRE(op == P1_OP_STIFFNESS || op == P1_OP_MASS || op == P1_OP_LOCAL || quad, "unknown op");
+  P1_REQUIRE(op == P1_OP_LOCAL || coords || n_elements == 0, "this operator needs coords");
+  P1_REQUIRE(op != P1_OP_LOCAL || local || n_elements == 0, "P1_OP_LOCAL needs the local matrices");
+  P1_REQUIRE(!quad || (qa && qa->n_qp > 0 && qa->weights_host), "bad p1_quad_args");
+  P1_REQUIRE(op != P1_OP_GENERAL || n_elements == 0 ||
+                 (qa->a11q && qa->a12q && qa->a21q && qa->a22q), "null coefficient array");
+  P1_REQUIRE(op != P1_OP_WEIGHTED || (qa->points_host && (n_elements == 0 || qa->phiq)),
+             "null phiq/points");
+  DeviceGuard guard(ctx);
+  cudaStream_t s = (cudaStream_t)stream;
+  int wshift = -1;
+  for (int b = 0; b < 31; ++b)
+    if ((1 << b) == world) wshift = b;
+  const Own own{0, (int)n_nodes, chunk_log2, world, rank, wshift};
+  const int n_own = (int)own.count();
+  const int N = (int)n_nodes;
+  const int64_t M = n_elements;
+  const bool slim = world > 1 && (op == P1_OP_STIFFNESS || op == P1_OP_MASS);
+
+  unsigned long long *acc = nullptr;
+  Rec *rec = nullptr;
+  int2 *slots = nullptr;
+  int *rowlen = nullptr, *slow_rows = nullptr, *big_rows = nullptr;
+  SpillDesc *d_spill = nullptr;
+  double *d_weights = nullptr, *d_points = nullptr;
+  auto release = [&]() {
+    for (void *b : {(void *)acc, (void *)rec, (void *)slots, (void *)rowlen, (void *)slow_rows,
+                    (void *)big_rows, (void *)d_spill, (void *)d_weights, (void *)d_points})
+      pool_free(ctx, b, s);
+  };
+  int rc = P1_OK;
+  if ((rc = pool_alloc(ctx, &acc, (size_t)n_own + 1, s)) ||
+      (slim ? (rc = pool_alloc(ctx, &slots, (size_t)n_own * GROUP, s))
+            : (rc = pool_alloc(ctx, &rec, (size_t)n_own * GROUP, s))) ||
+      (rc = pool_alloc(ctx, &rowlen, (size_t)n_own + 1, s)) ||
+      (rc = pool_alloc(ctx, &slow_rows, (size_t)n_own + 1, s)) ||
+      (rc = pool_alloc(ctx, &big_rows, (size_t)((3 * M) / (DEG_BIG + 1)) + 1, s)) ||
+      (rc = pool_alloc(ctx, &d_spill, (size_t)1, s)) ||
+      (quad && ((rc = pool_alloc(ctx, &d_weights, (size_t)qa->n_qp, s)) ||
+                (rc = pool_alloc(ctx, &d_points, (size_t)2 * qa->n_qp, s))))) {
+    release();
+    return rc;
+  }
+  cudaMemsetAsync(status, 0, 8 * sizeof(int), s);
+  cudaMemsetAsync(status + 1, 0xff, sizeof(int), s);
+  cudaMemsetAsync(acc, 0, ((size_t)n_own + 1) * sizeof(unsigned long long), s);
+  cudaMemsetAsync(d_spill, 0, sizeof(SpillDesc), s);  // capacity 0: spilled records are dropped
+  if (quad) {
+    cudaMemcpyAsync(d_weights, qa->weights_host, qa->n_qp * sizeof(double),
+                    cudaMemcpyHostToDevice, s);
+    if (qa->points_host)
+      cudaMemcpyAsync(d_points, qa->points_host, 2 * qa->n_qp * sizeof(double),
+                      cudaMemcpyHostToDevice, s);
+  }
+  const unsigned eg = min(grid_for(M, THREADS), (unsigned)(ctx->sm_count * 32));
+  prof_begin(ctx, "scatter", s);
+  if (slim)
+    launch_scatter_slots<3>(ctx, eg, s, elements, M, N, own, acc, slots, NoValues{}, true, nullptr,
+                            nullptr, status);
+  else
+    launch_scatter<false>(ctx, eg, s, op, elements, M, N, own, acc, rec, nullptr,
+                          reinterpret_cast<int *>(d_spill), coords, local, qa, d_weights,
+                          d_points, status);
+  prof_end(ctx, s);
+  const Rows rows{acc, rec, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, slots};
+  if (n_own > 0) {
+    P1_TIMED(ctx, "split", s,
+             split_kernel<<<grid_for(n_own, THREADS), THREADS, 0, s>>>(
+                 n_own, acc, rowlen, slow_rows, big_rows, status + 2));
+    rowlen_slow_kernel<<<(unsigned)(ctx->sm_count * 4), THREADS, 0, s>>>(slow_rows, status + 3,
+                                                                         own, rows, rowlen);
+  } else {
+    cudaMemsetAsync(rowlen, 0, sizeof(int), s);
+  }
+  rc = exclusive_scan_i32(ctx, rowlen, indptr, n_own, true, s);
+  if (rc == P1_OK) {
+    cold_finalize_kernel<<<1, 1, 0, s>>>(status, indptr, n_own, capacity);
+    launch_fill_cold(ctx, own, n_own, rows, slim ? op : 0, (const double2 *)coords, indptr,
+                     slow_rows, status + 3, indices, data, status, s);
+    if (cudaGetLastError() != cudaSuccess) {
+      set_error("p1_assemble_cold: %s", cudaGetErrorString(cudaGetLastError()));
+      rc = P1_ECUDA;
+    }
+  }
+  release();
+  return rc;
 }
 
 extern "C" int64_t p1_plan_rows(const p1_plan *p) { return p ? p->n_own : -1; }
 
 extern "C" int p1_plan_destroy(p1_plan *p) {
   if (!p) return P1_OK;
-  DeviceGuard guard(p->ctx->device);
+  DeviceGuard guard(p->ctx);
   void *blocks[] = {p->acc, p->rec, p->rec_elem, p->topo, p->slot_of, p->tspill, p->slim,
                     p->ovf_off, p->ovf_rec, p->ovf_elem, p->indptr, p->slow_rows, p->big_rows,
                     p->big_first, p->twin, p->slotcode, p->fb_rows, p->tctr, p->ovf_cursor,

@@ -59,16 +59,18 @@ scan_reduce_kernel(const int *__restrict__ in, int64_t n,
 
 __global__ void __launch_bounds__(1024)
 scan_sums_kernel(int *__restrict__ block_sums, int nb) {
-  int carry = 0;
+  // the grand total is tracked in 64 bits: a sum beyond INT32_MAX (a row pointer that
+  // int32 cannot hold) is reported as -1 instead of wrapping silently
+  long long carry = 0;
   for (int start = 0; start < nb; start += 1024) {
     int idx = start + threadIdx.x;
     int v = idx < nb ? block_sums[idx] : 0;
     int total;
     int ex = block_exclusive<1024>(v, &total);
-    if (idx < nb) block_sums[idx] = carry + ex;
+    if (idx < nb) block_sums[idx] = (int)carry + ex;
     carry += total;
   }
-  if (threadIdx.x == 0) block_sums[nb] = carry;
+  if (threadIdx.x == 0) block_sums[nb] = carry > 0x7fffffffLL ? -1 : (int)carry;
 }
 
 __global__ void __launch_bounds__(SCAN_THREADS)

@@ -708,6 +708,10 @@ int p1::plan_build_tiled(p1_ctx *ctx, const int32_t *elements, int64_t M, int64_
     set_error("p1_plan_create: element index out of range [0, %lld)", (long long)n_nodes);
     return fail(P1_EINDEX);
   }
+  if (h_nnz < 0) {
+    set_error("p1_plan_create: more than 2^31 - 1 stored entries");
+    return fail(P1_ERANGE);
+  }
   p->max_index = ctx->h_flags[1];
   p->n_big = ctx->h_flags[2];
   p->n_slow = ctx->h_flags[3];
@@ -737,7 +741,7 @@ int p1::plan_build_tiled(p1_ctx *ctx, const int32_t *elements, int64_t M, int64_
 int p1::assemble_tiled(p1_plan *plan, int op, int32_t *indptr, int32_t *indices, double *data,
                        void *stream) {
   p1_ctx *ctx = plan->ctx;
-  DeviceGuard guard(ctx->device);
+  DeviceGuard guard(ctx);
   cudaStream_t s = (cudaStream_t)stream;
   if (op != P1_OP_STORED && op != plan->val_op) {
     set_error("p1_assemble_csr: this plan was created for one operator (p1_plan_create_for); "

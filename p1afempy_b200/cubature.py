@@ -14,16 +14,23 @@ offline, so this module
   pair;
 * ships MIDPOINT (one point (1/3,1/3), weight 1/2 -- the only table the
   reference's tests pin numerically, test_solver.py:88-129), the vertex rule
-  and the edge-midpoint rule, and a degree-6 STAND-IN under the name DAYTAYLOR:
-  the 4x4 Gauss-Legendre rule on the unit square collapsed onto the triangle
-  by (s, t) -> (s, t(1-s)) with weight factor (1-s) (16 points, positive
-  weights, sum 1/2).  Its numeric values are NOT those of Day & Taylor's
-  11-point rule ("parity unpinned"); every test feeds
-  the oracle and the CUDA path the same arrays, so parity is unaffected.
+  LAUFFER_LINEAR, and two rules under their own names: EDGE_MIDPOINTS (degree
+  2) and CONICAL_GAUSS_4X4 (degree 6: the 4x4 Gauss-Legendre rule on the unit
+  square collapsed onto the triangle by (s, t) -> (s, t(1-s)) with weight
+  factor (1-s); 16 points, positive weights, sum 1/2);
+* resolves the names DAYTAYLOR and SMPLX1 through the real ``triangle_cubature``
+  package when it is importable; when it is not, they fall back to
+  CONICAL_GAUSS_4X4 / EDGE_MIDPOINTS and say so once with a
+  ``StandInRuleWarning``: same degree of exactness, but NOT the numeric table
+  the reference would use ("parity unpinned"), so
+  results for non-polynomial integrands differ from the reference's in the
+  quadrature error.  Every parity test feeds the oracle and the CUDA path the
+  same arrays, so parity is unaffected.
 """
 from __future__ import annotations
 
 import enum
+import warnings
 from dataclasses import dataclass
 
 import numpy as np
@@ -34,6 +41,18 @@ class CubatureRuleEnum(enum.Enum):
     LAUFFER_LINEAR = 2
     SMPLX1 = 3
     DAYTAYLOR = 4
+    EDGE_MIDPOINTS = 5
+    CONICAL_GAUSS_4X4 = 6
+
+
+class StandInRuleWarning(UserWarning):
+    """A rule name of ``triangle_cubature`` was resolved to this module's stand-in
+    table because that package is not installed."""
+
+
+_STAND_INS = {CubatureRuleEnum.DAYTAYLOR: CubatureRuleEnum.CONICAL_GAUSS_4X4,
+              CubatureRuleEnum.SMPLX1: CubatureRuleEnum.EDGE_MIDPOINTS}
+_warned = set()
 
 
 @dataclass(frozen=True)
@@ -75,20 +94,43 @@ _TABLES = {
             weights=np.array([1. / 6., 1. / 6., 1. / 6.]),
             integration_points=np.array([[0., 0.], [1., 0.], [0., 1.]])),
         degree_of_exactness=1, name='lauffer-linear (vertices)'),
-    CubatureRuleEnum.SMPLX1: CubatureRule(
+    CubatureRuleEnum.EDGE_MIDPOINTS: CubatureRule(
         WeightsAndIntegrationPoints(
             weights=np.array([1. / 6., 1. / 6., 1. / 6.]),
             integration_points=np.array([[.5, 0.], [.5, .5], [0., .5]])),
-        degree_of_exactness=2, name='edge midpoints (stand-in for smplx1)'),
-    CubatureRuleEnum.DAYTAYLOR: CubatureRule(
-        _conical_gauss(4), degree_of_exactness=6,
-        name='4x4 conical Gauss (degree-6 stand-in for Day-Taylor)'),
+        degree_of_exactness=2, name='edge midpoints'),
+    CubatureRuleEnum.CONICAL_GAUSS_4X4: CubatureRule(
+        _conical_gauss(4), degree_of_exactness=6, name='4x4 conical Gauss'),
 }
+
+
+def _real_rule(name):
+    """The table ``triangle_cubature`` ships under `name`, or None offline."""
+    try:
+        from triangle_cubature.cubature_rule import CubatureRuleEnum as Real
+        from triangle_cubature.rule_factory import get_rule as real_get_rule
+        if real_get_rule is get_rule:   # the oracle's import shim re-exports this module
+            return None
+        return real_get_rule(rule=Real[name])
+    except Exception:
+        return None
 
 
 def get_rule(rule: CubatureRuleEnum) -> CubatureRule:
     """Same call shape as ``triangle_cubature.rule_factory.get_rule``."""
-    return _TABLES[CubatureRuleEnum(rule)]
+    rule = CubatureRuleEnum(rule)
+    if rule in _STAND_INS:
+        real = _real_rule(rule.name)
+        if real is not None:
+            return real
+        if rule not in _warned:
+            _warned.add(rule)
+            warnings.warn(
+                'triangle_cubature is not installed: %s resolves to the stand-in rule %s (same '
+                'degree of exactness, different points and weights than the reference uses)'
+                % (rule.name, _STAND_INS[rule].name), StandInRuleWarning, stacklevel=3)
+        rule = _STAND_INS[rule]
+    return _TABLES[rule]
 
 
 def resolve_rule(rule) -> tuple[np.ndarray, np.ndarray]:

@@ -139,6 +139,10 @@ class DeviceArray:
         raise DeviceArrayUnsupported('truth value of an array')
 
     # ---- numpy protocols
+    def __getattr__(self, name):
+        # (only reached for attributes this class does not have)
+        raise DeviceArrayUnsupported('ndarray attribute %r' % name)
+
     def __array_ufunc__(self, ufunc, method, *inputs, **kwargs):
         if method != '__call__' or kwargs.get('out') is not None or ufunc not in _UFUNCS:
             raise DeviceArrayUnsupported('ufunc %s.%s' % (ufunc.__name__, method))
@@ -149,7 +153,10 @@ class DeviceArray:
             args = [a if isinstance(a, torch.Tensor)
                     else torch.as_tensor(a, dtype=torch.float64, device=self.t.device)
                     for a in args]
-        return _wrap(_UFUNCS[ufunc](*args))
+        try:
+            return _wrap(_UFUNCS[ufunc](*args))
+        except (RuntimeError, TypeError) as exc:   # what torch cannot broadcast / promote
+            raise DeviceArrayUnsupported('%s: %s' % (ufunc.__name__, exc)) from None
 
     def __array_function__(self, func, types, args, kwargs):
         t = self.t
@@ -176,7 +183,10 @@ class DeviceArray:
         a, b = (o, self.t) if swap else (self.t, o)
         if not isinstance(a, torch.Tensor):
             a = torch.as_tensor(a, dtype=torch.float64, device=self.t.device)
-        return _wrap(op(a, b))
+        try:
+            return _wrap(op(a, b))
+        except (RuntimeError, TypeError) as exc:   # what torch cannot broadcast / promote
+            raise DeviceArrayUnsupported('%s: %s' % (getattr(op, '__name__', 'op'), exc)) from None
 
     def __add__(self, o): return self._bin(o, torch.add)
     def __radd__(self, o): return self._bin(o, torch.add, True)
@@ -213,9 +223,7 @@ def evaluate(fn, points: torch.Tensor, n: int):
     try:
         out = fn(DeviceArray(points))
     except DeviceArrayUnsupported:
-        return None
-    except (TypeError, ValueError, RuntimeError, AttributeError, IndexError):
-        return None
+        return None     # (any other exception is the callback's own: it propagates)
     dev = points.device
     if isinstance(out, DeviceArray):
         t = out.t.to(torch.float64)

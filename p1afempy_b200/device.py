@@ -44,6 +44,17 @@ def context(device: int | None = None):
         return _contexts[device], device
 
 
+def trim_scratch(device: int | None = None, limit_bytes: int | None = None):
+    """Returns the library's idle scratch blocks (cached between calls, invisible to
+    torch's allocator) to the driver; limit_bytes also sets how much may stay cached
+    from now on (default 48 GB)."""
+    ctx, _ = context(device)
+    lib = _lib.load()
+    if limit_bytes is not None:
+        _lib.check(lib.p1_ctx_set_cache_limit(ctx, int(limit_bytes)))
+    _lib.check(lib.p1_ctx_trim(ctx))
+
+
 def _stream(device):
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
@@ -116,11 +127,50 @@ def to_host(t: torch.Tensor) -> np.ndarray:
     return host.numpy()
 
 
+def interleaved_count(n_rows, world, rank, chunk_log2):
+    """Rows rank `rank` owns when chunks of 2^chunk_log2 rows are dealt round-robin
+    (plan.cuh: Own::count)."""
+    c = 1 << chunk_log2
+    full, tail = divmod(n_rows, c)
+    mine = (full // world) * c + (c if (full % world) > rank else 0)
+    if tail and (full % world) == rank:
+        mine += tail
+    return mine
+
+
 def scipy_index_dtype(n_elements, n_rows, n_cols):
     """Index dtype scipy gives ``coo_matrix(...).tocsr()`` for 9M triplets
     (scipy/sparse/_coo.py:419: maxval = max(nnz, N))."""
     big = max(9 * n_elements, n_rows, n_cols)
     return np.int64 if big > np.iinfo(np.int32).max else np.int32
+
+
+class ColdAssembly:
+    """What ``DeviceMesh.assemble_cold`` returns: the CSR arrays of a cold assembly
+    that is still in flight.  indices / data have a capacity >= nnz, indptr[-1]
+    (device) is nnz; ``wait()`` synchronises, checks the status words and returns
+    exact-size views -- or the plan route's result when the mesh needed it (a node
+    with more than 8 elements, a non-manifold vertex, nnz above the capacity)."""
+
+    def __init__(self, mesh, indptr, indices, data, status, redo):
+        self.mesh, self.indptr, self.indices, self.data = mesh, indptr, indices, data
+        self.status, self._redo, self._done = status, redo, None
+
+    def wait(self):
+        if self._done is None:
+            st = self.status.cpu().numpy()          # synchronises with the producing stream
+            if st[0] & _lib.STATUS_INDEX:
+                raise IndexError('element index out of range [0, %d)' % self.mesh.n_nodes)
+            if st[0] & (_lib.STATUS_SLOWPATH | _lib.STATUS_RETRY):
+                self._done = self._redo()
+            else:
+                nnz = int(st[6])
+                self.mesh.nnz, self.mesh.max_index = nnz, int(st[1])
+                self._done = (self.indptr,
+                              None if self.indices is None else self.indices[:nnz],
+                              self.data[:nnz])
+            self._redo = None
+        return self._done
 
 
 class DeviceMesh:
@@ -344,6 +394,45 @@ class DeviceMesh:
             if not self.reuse:
                 self.close()
             return indptr, indices, data
+
+    def cold_capacity(self):
+        """Entries the outputs of ``assemble_cold`` hold: rows + incidences + one per
+        row for an open fan (all rows owned: a bound; a share of the rows: the
+        expected count plus 30 %)."""
+        if self.interleave is None and self.rows == (0, self.n_nodes):
+            return 2 * self.n_nodes + 3 * self.n_elements
+        world = self.interleave[0] if self.interleave is not None else max(
+            1, self.n_nodes // max(1, self.rows[1] - self.rows[0]))
+        return 2 * self.n_rows + int(1.3 * 3 * self.n_elements / world) + 4096
+
+    def assemble_cold(self, op, local=None, pattern=True, quad=None, keepalive=None):
+        """Cold assembly without a host synchronisation (p1_assemble_cold): returns a
+        ColdAssembly at once; nothing is cached on the mesh.  op: OP_STIFFNESS /
+        OP_MASS / OP_LOCAL (local: (M, 9) CUDA tensor) / OP_GENERAL / OP_WEIGHTED
+        (quad: _lib.QuadArgs)."""
+        if self.interleave is not None:
+            world, rank, chunk_log2 = self.interleave
+        elif self.rows == (0, self.n_nodes):
+            world, rank, chunk_log2 = 1, 0, 0
+        else:
+            raise ValueError('assemble_cold: all rows or interleave=')
+        if self.interleave is not None:
+            self.n_rows = int(interleaved_count(self.n_nodes, world, rank, chunk_log2))
+        cap = self.cold_capacity()
+        indptr = self._empty(self.n_rows + 1, torch.int32)
+        indices = self._empty(cap, torch.int32) if pattern else None
+        data = self._empty(cap)
+        status = self._empty(8, torch.int32)
+        _lib.check(self._lib.p1_assemble_cold(
+            self.ctx, _ptr(self.elements), self.n_elements, self.n_nodes, chunk_log2, world,
+            rank, op, _ptr(self.coords), _ptr(local), C.byref(quad) if quad is not None else None,
+            cap, _ptr(indptr), _ptr(indices), _ptr(data), _ptr(status), _stream(self.device)))
+
+        def redo(keep=(local, quad, keepalive)):
+            if op in (_lib.OP_GENERAL, _lib.OP_WEIGHTED):
+                return self._assemble_quad(op, keep[1], keep[2], pattern)
+            return self.assemble(op, local=keep[0], pattern=pattern)
+        return ColdAssembly(self, indptr, indices, data, status, redo)
 
     def stiffness_csr(self, pattern=True):
         return self.assemble(_lib.OP_STIFFNESS, pattern=pattern)

@@ -51,6 +51,34 @@ def nnz_offsets(local_nnz: int, device=None, group=None):
     return int(starts[rank]), int(every.sum()), [int(x) for x in every]
 
 
+def global_row_pointer(indptr, n_rows, world, rank, chunk_log2, group=None):
+    """Interleaved ownership: where the calling rank's rows start in the GLOBAL CSR.
+
+    indptr: the rank's local row pointer (owned rows + 1, starting at 0, CUDA or
+    CPU tensor).  Every rank contributes the nnz of each of its chunks (one
+    all-gather of n_rows / 2^chunk_log2 / world integers, the only collective of a
+    multi-GPU assembly); an exclusive scan over the chunks in global order gives
+    every chunk its offset.  Returns (global start of every owned row, int64;
+    total nnz as a 0-dim tensor): everything stays on the device, nothing
+    synchronises the host."""
+    dev = indptr.device
+    c = 1 << chunk_log2
+    n_chunks = (n_rows + c - 1) >> chunk_log2
+    per_rank = (n_chunks + world - 1) // world            # padded: same length on every rank
+    n_own = indptr.numel() - 1
+    ip = indptr.to(torch.int64)
+    starts = torch.arange(0, per_rank * c, c, dtype=torch.int64, device=dev).clamp_(max=n_own)
+    ends = (starts + c).clamp_(max=n_own)
+    mine = ip[ends] - ip[starts]                           # nnz of my chunks (0: padding)
+    every = torch.empty(world * per_rank, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(every, mine, group=group)
+    in_order = every.reshape(world, per_rank).t().reshape(-1)   # chunk q * world + r
+    offs = torch.cumsum(in_order, 0) - in_order
+    my_offs = offs.reshape(per_rank, world)[:, rank]
+    q = torch.arange(n_own, dtype=torch.int64, device=dev) >> chunk_log2
+    return my_offs[q] + ip[:-1] - ip[q << chunk_log2], in_order.sum()
+
+
 def _place(g_indptr, g_indices, g_data, rows, indptr, indices, data):
     """Copies one piece (local CSR over the global rows `rows`) into place."""
     lens = (indptr[1:] - indptr[:-1]).to(torch.int64)
@@ -119,11 +147,57 @@ class DistributedMesh:
         self.local = DeviceMesh(coordinates, elements, device=device,
                                 interleave=(self.world, self.rank, chunk_log2))
 
+        self.chunk_log2 = chunk_log2
+
+    # Every method returns the calling rank's rows (local CSR: indptr starting at 0)
+    # or its entries of a nodal vector, in the order of global_rows().  Matrices
+    # take the cold path without a host synchronisation (p1_assemble_cold).
+    def _cold(self, op, **kw):
+        return self.local.assemble_cold(op, **kw).wait()
+
     def stiffness_csr(self):
-        return self.local.stiffness_csr()
+        from . import _lib
+        return self._cold(_lib.OP_STIFFNESS)
 
     def mass_csr(self):
-        return self.local.mass_csr()
+        from . import _lib
+        return self._cold(_lib.OP_MASS)
+
+    def general_stiffness_csr(self, a11q, a12q, a21q, a22q, weights):
+        """a_ij_q: (n_qp, M) values of the coefficients at the quadrature points of
+        ALL elements (replicated like the mesh); the rank evaluates the local matrices
+        of the elements that touch its rows inside the scatter (solvers.py:278-377)."""
+        from . import _lib
+        from .device import _host_f64, to_device_f64
+        w = _host_f64(weights)
+        qs = [to_device_f64(a, self.local.device, (w.shape[0], self.local.n_elements))
+              for a in (a11q, a12q, a21q, a22q)]
+        args = _lib.QuadArgs(qs[0].data_ptr(), qs[1].data_ptr(), qs[2].data_ptr(),
+                             qs[3].data_ptr(), None, w.ctypes.data, None, w.shape[0])
+        return self._cold(_lib.OP_GENERAL, quad=args, keepalive=(qs, w))
+
+    def weighted_mass_csr(self, phiq, weights, points):
+        """phiq: (n_qp, M) values of phi(u_h) at the quadrature points
+        (solvers.py:50-142)."""
+        from . import _lib
+        from .device import _host_f64, to_device_f64
+        w, p = _host_f64(weights), _host_f64(points)
+        phiq = to_device_f64(phiq, self.local.device, (w.shape[0], self.local.n_elements))
+        args = _lib.QuadArgs(None, None, None, None, phiq.data_ptr(), w.ctypes.data,
+                             p.ctypes.data, w.shape[0])
+        return self._cold(_lib.OP_WEIGHTED, quad=args, keepalive=(phiq, w, p))
+
+    def load_vector(self, fq, weights, points):
+        """Entries of the cubature load vector (solvers.py:540-598) at the owned rows."""
+        return self.local.load_vector(fq, weights, points)
+
+    def load_vector_midpoint(self, f_centroid):
+        """Entries of the legacy load vector (solvers.py:414-426) at the owned rows."""
+        return self.local.load_vector_midpoint(f_centroid)
+
+    def global_row_pointer(self, indptr):
+        return global_row_pointer(indptr, self.n_nodes, self.world, self.rank, self.chunk_log2,
+                                  group=self.group)
 
     def global_rows(self):
         return self.local.global_rows()

@@ -116,3 +116,28 @@ def test_scipy_index_dtype_rule():
     assert a.indices.dtype == scipy_index_dtype(1, 3, 3) == np.int32
     assert scipy_index_dtype(67108864, 33562625, 33562625) == np.int32     # 64M mesh
     assert scipy_index_dtype(268435456, 134234113, 134234113) == np.int64  # 256M mesh
+
+
+def test_cubature_stand_ins_are_named_and_announced():
+    """DAYTAYLOR / SMPLX1 are tables of the third-party triangle_cubature package:
+    offline they resolve to the rules this package ships under their own names,
+    and say so (once per rule)."""
+    import warnings
+    from p1afempy_b200 import cubature as cub
+    cub._warned.clear()
+    with warnings.catch_warnings(record=True) as seen:
+        warnings.simplefilter('always')
+        w, p = cub.resolve_rule(cub.CubatureRuleEnum.DAYTAYLOR)
+        cub.resolve_rule(cub.CubatureRuleEnum.DAYTAYLOR)
+        w2, p2 = cub.resolve_rule(cub.CubatureRuleEnum.CONICAL_GAUSS_4X4)
+    assert [x.category for x in seen] == [cub.StandInRuleWarning]
+    assert np.array_equal(w, w2) and np.array_equal(p, p2)
+    assert abs(w.sum() - 0.5) < 1e-15 and w.shape == (16,)
+    # degree 6: x^a y^b, a + b <= 6, integrates to a! b! / (a + b + 2)!
+    from math import factorial as f
+    for a in range(7):
+        for b in range(7 - a):
+            exact = f(a) * f(b) / f(a + b + 2)
+            assert abs((w * p[:, 0] ** a * p[:, 1] ** b).sum() - exact) < 1e-15
+    w1, p1 = cub.resolve_rule(cub.CubatureRuleEnum.MIDPOINT)
+    assert np.array_equal(w1, [0.5]) and np.array_equal(p1, [[1. / 3., 1. / 3.]])

@@ -42,6 +42,11 @@ def _worker(rank, world, port, result_path, layout):
         data = torch.from_numpy(piece.data.copy())
         offset, total, every = pdist.nnz_offsets(data.numel())
         assert total == ref.nnz
+        if layout == 'interleaved':
+            # the global row pointer from the per-chunk nnz of every rank (one all-gather)
+            gptr, gtotal = pdist.global_row_pointer(indptr, n, world, rank, 5)
+            assert int(gtotal) == ref.nnz
+            assert np.array_equal(gptr.numpy(), ref.indptr[rows.numpy()])
         out = pdist.gather_csr(indptr, indices, data, rows, n, root=0)
         if rank == 0:
             gi, gx, gd = (t.numpy() for t in out)

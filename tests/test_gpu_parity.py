@@ -342,6 +342,32 @@ def test_pinched_vertex_falls_back_to_exact_plan(api):
         H.csr_values_close(api[0].get_mass_matrix(c3, e3), ref, RTOL)
 
 
+def test_default_callbacks_run_on_the_device(api):
+    """The package default evaluates callbacks on the device; arithmetic callbacks
+    (no transcendental) then still give the host mode's bits."""
+    import importlib
+    from p1afempy_b200 import options
+    assert importlib.reload(importlib.import_module('p1afempy_b200.options')).callbacks == \
+        os.environ.get('P1_CALLBACKS', 'device')
+    solvers = api[0]
+    c, e, _ = H.perturbed_square(4)
+    rule = cubature.CubatureRuleEnum.DAYTAYLOR
+    poly = lambda r: 2. + r[:, 0] * r[:, 1] - 0.5 * r[:, 1] ** 2 + r[:, 0] / (3. + r[:, 1])   # noqa: E731
+    out = []
+    for mode in ('host', 'device'):
+        options.callbacks = mode
+        out.append((solvers.get_general_stiffness_matrix(c, e, H.a11, H.a12, H.a21, poly, rule),
+                    solvers.get_weighted_mass_matrix(c, e, H.u_nodal(c), H.phi, rule),
+                    solvers.get_right_hand_side(c, e, poly, cubature_rule=rule),
+                    solvers.get_right_hand_side(c, e, poly)))
+    options.callbacks = 'host'
+    for x, y in zip(*out):
+        if hasattr(x, 'data') and hasattr(x, 'indptr'):
+            assert np.array_equal(x.indices, y.indices) and np.array_equal(x.data, y.data)
+        else:
+            assert np.array_equal(x, y)
+
+
 def test_device_callbacks(api):
     """options.callbacks='device': the reference's callbacks run unchanged on a
     device-resident ndarray stand-in; values agree to 1e-12 (CUDA libm instead
@@ -738,6 +764,70 @@ def test_tiled_plan_irregular_meshes(api, monkeypatch):
     ref = orc.stiffness_coo(c2, e2).tocsr()
     assert np.array_equal(a.indptr, ref.indptr) and np.array_equal(a.indices, ref.indices)
     H.csr_values_close(a, ref, RTOL)
+
+
+def test_cold_assembly_without_host_sync(mesh_case):
+    """p1_assemble_cold (no host synchronisation, outputs with a capacity) gives the
+    plan route's CSR bit for bit: all rows, and the shares of 3 emulated ranks."""
+    import torch
+    from p1afempy_b200 import _lib
+    from p1afempy_b200.device import DeviceMesh
+    c, e, _ = mesh_case
+    ct, et = torch.from_numpy(c).cuda(), torch.from_numpy(e.astype(np.int32)).cuda()
+    for op in (_lib.OP_STIFFNESS, _lib.OP_MASS):
+        with DeviceMesh(ct, et) as mesh:
+            ref = [t.cpu().numpy() for t in mesh.assemble(op)]
+            nnz = mesh.nnz
+            cold = mesh.assemble_cold(op)
+            assert cold.data.numel() >= nnz
+            if int(cold.status[0].item()) == 0:     # (else: the plan route, via wait())
+                assert int(cold.indptr[-1].item()) == nnz == int(cold.status[6].item())
+            got = [t.cpu().numpy() for t in cold.wait()]
+            assert mesh.nnz == nnz
+        for x, y in zip(ref, got):
+            assert x.dtype == y.dtype and np.array_equal(x, y)
+        for rank in range(3):
+            with DeviceMesh(ct, et, interleave=(3, rank, 4)) as mesh:
+                ref = [t.cpu().numpy() for t in mesh.assemble(op)]
+                got = [t.cpu().numpy() for t in mesh.assemble_cold(op).wait()]
+            for x, y in zip(ref, got):
+                assert np.array_equal(x, y)
+
+
+def test_cold_assembly_falls_back_to_the_plan_route(api):
+    """Status words instead of return codes: a node with more than 8 elements
+    (P1_STATUS_SLOWPATH), a non-manifold vertex (P1_STATUS_RETRY) and an index out
+    of range are found when the result is waited for."""
+    import torch
+    from scipy.spatial import Delaunay
+    from p1afempy_b200 import _lib
+    from p1afempy_b200.device import DeviceMesh
+    rng = np.random.default_rng(5)
+    pts = np.vstack([rng.random((3000, 2)), [[0., 0.], [1., 0.], [1., 1.], [0., 1.]]])
+    e = Delaunay(pts).simplices.astype(np.int64)
+    d1, d2 = pts[e[:, 1]] - pts[e[:, 0]], pts[e[:, 2]] - pts[e[:, 0]]
+    flip = (d1[:, 0] * d2[:, 1] - d1[:, 1] * d2[:, 0]) < 0
+    e[flip] = e[flip][:, [0, 2, 1]]
+    assert np.bincount(e.reshape(-1)).max() > 8
+    c, e5, _ = H.perturbed_square(4)
+    c2 = np.vstack([c, c + [2., 0.]])
+    e2 = np.vstack([e5, e5 + c.shape[0]])
+    centre = int(np.argmin(np.abs(c - 0.5).sum(axis=1)))
+    e2[e2 == centre + c.shape[0]] = centre           # bow tie
+    for cc, ee, bit in ((pts, e, _lib.STATUS_SLOWPATH), (c2, e2, _lib.STATUS_RETRY)):
+        with DeviceMesh(cc, ee) as mesh:
+            cold = mesh.assemble_cold(_lib.OP_STIFFNESS)
+            assert int(cold.status[0].item()) & bit
+            ip, ix, data = [t.cpu().numpy() for t in cold.wait()]
+        ref = orc.stiffness_coo(cc, ee).tocsr()
+        assert np.array_equal(ip, ref.indptr) and np.array_equal(ix, ref.indices)
+        assert np.abs(data - ref.data).max() <= RTOL * np.abs(ref.data).max()
+    bad = e5.copy()
+    bad[3, 1] = c.shape[0] + 7
+    mesh = DeviceMesh(c, bad, check=False)
+    with pytest.raises(IndexError):
+        mesh.assemble_cold(_lib.OP_STIFFNESS).wait()
+    mesh.close()
 
 
 def test_integration_md_stub_is_real(api):
