@@ -346,11 +346,11 @@ class Workload:
                     'general': _lib.OP_GENERAL, 'weighted': _lib.OP_WEIGHTED}[op]
             cold = mesh.assemble_cold(code, quad=getattr(self, 'args', None))
             self.statuses.append(cold.status)
-            if self.world > 1:   # the global row pointer: one all-gather of per-chunk nnz
+            if self.world > 1:   # where my chunks start in the global CSR: one all-gather
                 from p1afempy_b200 import dist as pdist
-                gptr, total = pdist.global_row_pointer(cold.indptr, self.nn, self.world,
-                                                       self.rank, 12)
-                return cold, gptr, total
+                offs, total = pdist.global_chunk_offsets(cold.indptr, self.nn, self.world,
+                                                         self.rank, 12)
+                return cold, offs, total
             return cold
         if op == 'load':
             return mesh.load_vector(self.fq, self.w, self.p)

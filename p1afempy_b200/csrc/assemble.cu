@@ -30,6 +30,8 @@ constexpr int THREADS = 256;
 constexpr int FR = P1_FILL_ROWS;  // rows per block = threads per block
 constexpr int CAP_OUT = FR * 10;  // CSR entries staged per block (9 per regular row + slack)
 
+__device__ void slow_row_inline(int self, int deg, const Rec *nb, int *cs_out, double *vs_out);
+
 // One row from its <= 8 records: cs / vs point at the row's place (the block's
 // staged image or the output itself; cs may be null).  False when the fan is not
 // closed and repeat-free.
@@ -92,7 +94,7 @@ __global__ void __launch_bounds__(FR, P1_FILL_MIN_BLOCKS)
 fill_rows_kernel(int n_own, Own own, int exact,
                  const unsigned long long *__restrict__ acc, const Rec *__restrict__ rec,
                  const int *__restrict__ indptr, int *__restrict__ indices,
-                 double *__restrict__ data, int *__restrict__ flags) {
+                 double *__restrict__ data, int *__restrict__ flags, int inline_slow = 0) {
   __shared__ int cols_s[CAP_OUT];
   __shared__ double vals_s[CAP_OUT];
   // (p1_assemble_cold: the output may be too small, or the mesh needs the plan route)
@@ -122,6 +124,10 @@ fill_rows_kernel(int n_own, Own own, int exact,
     // "closed fan => 1 + #records columns" does not hold for this row.
     if (!row_from_records(own.global(row0 + tid), deg, row, cs, vs) && !exact)
       atomicOr(flags, FLAG_RETRY);
+  } else if (inline_slow && deg >= 1 && deg <= GROUP) {  // an open fan (p1_assemble_cold)
+    slow_row_inline(own.global(row0 + tid), deg, row,
+                    out_staged ? cols_s + (ob - obeg) : (indices ? indices + ob : nullptr),
+                    out_staged ? vals_s + (ob - obeg) : data + ob);
   }
   __syncthreads();
   if (out_staged) {
@@ -170,7 +176,7 @@ __global__ void __launch_bounds__(FR, P1_GATHER_MIN_BLOCKS)
 fill_gather_kernel(int n_own, Own own, const unsigned long long *__restrict__ acc,
                    const int2 *__restrict__ slim, V values,
                    const int *__restrict__ indptr, int *__restrict__ indices,
-                   double *__restrict__ data, int *__restrict__ flags) {
+                   double *__restrict__ data, int *__restrict__ flags, int inline_slow = 0) {
   __shared__ int cols_s[CAP_OUT];
   __shared__ double vals_s[CAP_OUT];
   // per-thread columns ([record][thread]: conflict-free for any record index):
@@ -284,6 +290,19 @@ fill_gather_kernel(int n_own, Own own, const unsigned long long *__restrict__ ac
       if (put_cols) cs[slot_self] = self;
       vs[slot_self] = diag;
     }
+  } else if (inline_slow && deg >= 1 && deg <= GROUP) {  // an open fan (p1_assemble_cold)
+    Rec made[GROUP];
+    const double2 za = __ldg(values.coords + self);
+    for (int i = 0; i < deg; ++i) {
+      const int2 e = slim[(int64_t)(row0 + tid) * GROUP + i];
+      made[i].nx = e.x;
+      made[i].pvk = e.y;
+      slim_values(values, (int)((unsigned)e.y >> NODE_BITS), za, __ldg(values.coords + e.x),
+                  __ldg(values.coords + (e.y & NODE_MASK)), made[i].vd, made[i].vn, made[i].vp);
+    }
+    slow_row_inline(self, deg, made,
+                    out_staged ? cols_s + (ob - obeg) : (indices ? indices + ob : nullptr),
+                    out_staged ? vals_s + (ob - obeg) : data + ob);
   }
   __syncthreads();
   if (out_staged) {
@@ -319,6 +338,59 @@ __device__ __forceinline__ int insert_unique(int *cols, int n, int c) {
   return n + 1;
 }
 
+// sorted unique columns {self} U {next_i} U {prev_i} by insertion into cs (2 deg + 1 ints)
+__device__ __forceinline__ int slow_row_columns(int self, int deg, const Rec *nb, int *cs) {
+  int n = insert_unique(cs, 0, self);
+  for (int i = 0; i < deg; ++i) {
+    n = insert_unique(cs, n, rec_next(nb[i]));
+    n = insert_unique(cs, n, rec_prev(nb[i]));
+  }
+  return n;
+}
+
+// the values of such a row, accumulated in vs[0 .. n) in a fixed order: ascending
+// `next`, ties by `prev`
+__device__ __forceinline__ void slow_row_values(int self, int deg, const Rec *nb, const int *cs,
+                                                int n, double *vs) {
+  for (int j = 0; j < n; ++j) vs[j] = 0.;
+  const int js = lower_bound(cs, n, self);
+  for (int j = 0; j < n; ++j) {
+    const int c = cs[j];
+    int last_pv = -1;
+    for (;;) {  // records with next == c in ascending prev order
+      int pick = -1, pick_pv = 0x7fffffff;
+      for (int i = 0; i < deg; ++i) {
+        if (rec_next(nb[i]) != c) continue;
+        const int pv = rec_prev(nb[i]);
+        if (pv > last_pv && pv < pick_pv) { pick = i; pick_pv = pv; }
+      }
+      if (pick < 0) break;
+      // every record with this (next, prev) pair (duplicates: identical elements)
+      for (int i = 0; i < deg; ++i) {
+        if (rec_next(nb[i]) != c || rec_prev(nb[i]) != pick_pv) continue;
+        const Rec p = nb[i];
+        vs[js] += p.vd;
+        vs[j] += p.vn;
+        vs[lower_bound(cs, n, pick_pv)] += p.vp;
+      }
+      last_pv = pick_pv;
+    }
+  }
+}
+
+// p1_assemble_cold fills the rare irregular row (an open fan: a mesh-boundary node)
+// from inside the fast kernels, by the thread that owns the row: no row list, no
+// extra launch.  Same routine, same bits as fill_slow_kernel.  (noinline: the hot
+// path keeps its registers)
+__device__ __noinline__ void slow_row_inline(int self, int deg, const Rec *nb, int *cs_out,
+                                             double *vs_out) {
+  int cs[2 * GROUP + 1];
+  const int n = slow_row_columns(self, deg, nb, cs);
+  if (cs_out)
+    for (int j = 0; j < n; ++j) cs_out[j] = cs[j];
+  slow_row_values(self, deg, nb, cs, n, vs_out);
+}
+
 // (slim plans: V recomputes the <= 8 records of the row into local memory)
 template <class V>
 __global__ void __launch_bounds__(SLOW_THREADS)
@@ -352,11 +424,7 @@ fill_slow_kernel(const int *__restrict__ slow_rows, int n_slow, Own own, Rows ro
     nb = rows.ptr(a, deg);
   }
   int *cs = cols_s + threadIdx.x * SLOW_COLS;
-  int n = insert_unique(cs, 0, self);
-  for (int i = 0; i < deg; ++i) {
-    n = insert_unique(cs, n, rec_next(nb[i]));
-    n = insert_unique(cs, n, rec_prev(nb[i]));
-  }
+  const int n = slow_row_columns(self, deg, nb, cs);
   const int64_t base = indptr[a];
   if (verify && n != indptr[a + 1] - indptr[a]) {
     // tiled plans take the row length from the record count (closed fan: 1 + deg,
@@ -364,35 +432,9 @@ fill_slow_kernel(const int *__restrict__ slow_rows, int n_slow, Own own, Rows ro
     atomicOr(verify, FLAG_RETRY);
     continue;
   }
-  double *vs = data + base;
-  for (int j = 0; j < n; ++j) {
-    if (indices) indices[base + j] = cs[j];
-    vs[j] = 0.;
-  }
-  const int js = lower_bound(cs, n, self);
-  // fixed summation order: ascending `next`, ties by `prev`
-  for (int j = 0; j < n; ++j) {
-    const int c = cs[j];
-    int last_pv = -1;
-    for (;;) {  // records with next == c in ascending prev order
-      int pick = -1, pick_pv = 0x7fffffff;
-      for (int i = 0; i < deg; ++i) {
-        if (rec_next(nb[i]) != c) continue;
-        const int pv = rec_prev(nb[i]);
-        if (pv > last_pv && pv < pick_pv) { pick = i; pick_pv = pv; }
-      }
-      if (pick < 0) break;
-      // every record with this (next, prev) pair (duplicates: identical elements)
-      for (int i = 0; i < deg; ++i) {
-        if (rec_next(nb[i]) != c || rec_prev(nb[i]) != pick_pv) continue;
-        const Rec p = nb[i];
-        vs[js] += p.vd;
-        vs[j] += p.vn;
-        vs[lower_bound(cs, n, pick_pv)] += p.vp;
-      }
-      last_pv = pick_pv;
-    }
-  }
+  if (indices)
+    for (int j = 0; j < n; ++j) indices[base + j] = cs[j];
+  slow_row_values(self, deg, nb, cs, n, data + base);
   }
 }
 
@@ -499,34 +541,21 @@ void p1::launch_fill_fallback(p1_plan *plan, int *indices, double *data, cudaStr
 }
 
 void p1::launch_fill_cold(p1_ctx *ctx, const Own &own, int n_own, const Rows &rows, int slim_op,
-                          const double2 *coords, const int *indptr, const int *slow_rows,
-                          const int *n_slow_dev, int *indices, double *data, int *status,
-                          cudaStream_t s) {
+                          const double2 *coords, const int *indptr, int *indices, double *data,
+                          int *status, cudaStream_t s) {
   if (n_own <= 0) return;
-  const unsigned sg = (unsigned)(ctx->sm_count * 2);
   prof_begin(ctx, "fill_rows", s);
   if (slim_op == P1_OP_STIFFNESS)
     fill_gather_kernel<<<grid_for(n_own, FR), FR, 0, s>>>(n_own, own, rows.acc, rows.slim,
                                                          StiffnessValues{coords}, indptr, indices,
-                                                         data, status);
+                                                         data, status, 1);
   else if (slim_op == P1_OP_MASS)
     fill_gather_kernel<<<grid_for(n_own, FR), FR, 0, s>>>(n_own, own, rows.acc, rows.slim,
                                                          MassValues{coords}, indptr, indices, data,
-                                                         status);
+                                                         status, 1);
   else
     fill_rows_kernel<<<grid_for(n_own, FR), FR, 0, s>>>(n_own, own, 0, rows.acc, rows.rec, indptr,
-                                                       indices, data, status);
-  prof_end(ctx, s);
-  prof_begin(ctx, "fill_slow", s);
-  if (slim_op == P1_OP_STIFFNESS)
-    fill_slow_kernel<<<sg, SLOW_THREADS, 0, s>>>(slow_rows, 0, own, rows, StiffnessValues{coords},
-                                                 indptr, indices, data, nullptr, n_slow_dev, status);
-  else if (slim_op == P1_OP_MASS)
-    fill_slow_kernel<<<sg, SLOW_THREADS, 0, s>>>(slow_rows, 0, own, rows, MassValues{coords},
-                                                 indptr, indices, data, nullptr, n_slow_dev, status);
-  else
-    fill_slow_kernel<<<sg, SLOW_THREADS, 0, s>>>(slow_rows, 0, own, rows, NoValues{}, indptr,
-                                                 indices, data, nullptr, n_slow_dev, status);
+                                                       indices, data, status, 1);
   prof_end(ctx, s);
 }
 

@@ -128,5 +128,7 @@ void prof_end(p1_ctx *ctx, cudaStream_t s);
 // when write_total is true (out then has n+1 entries).
 int exclusive_scan_i32(p1_ctx *ctx, const int *in, int *out, int64_t n,
                        bool write_total, cudaStream_t s);
+// in-place exclusive scan of n block sums by one block; sums[n] = total (-1: beyond int32)
+void scan_sums(int *sums, int n, cudaStream_t s);
 
 }  // namespace p1

@@ -327,12 +327,12 @@ void overflow_collect(p1_plan *plan, int *cursor, int *next_free, cudaStream_t s
 // the device in plan->tctr[0]) and the slow rows
 void launch_fill_fallback(p1_plan *plan, int *indices, double *data, cudaStream_t s);
 struct Rows;
-// assemble.cu: the fill kernels of p1_assemble_cold (status words and the length of the
-// slow-row list are read on the device; slim_op != 0: 8-byte slots, values recomputed)
+// assemble.cu: the fill kernel of p1_assemble_cold (the status words are read on the
+// device, open fans are filled by the row's own thread; slim_op != 0: 8-byte slots,
+// values recomputed)
 void launch_fill_cold(p1_ctx *ctx, const Own &own, int n_own, const Rows &rows, int slim_op,
-                      const double2 *coords, const int *indptr, const int *slow_rows,
-                      const int *n_slow_dev, int *indices, double *data, int *status,
-                      cudaStream_t s);
+                      const double2 *coords, const int *indptr, int *indices, double *data,
+                      int *status, cudaStream_t s);
 // error unless the plan was created with P1_PLAN_KEEP_ELEMENTS
 int require_elements(const p1_plan *plan, const char *who);
 

@@ -101,6 +101,8 @@ scan_down_kernel(const int *__restrict__ in, int *__restrict__ out, int64_t n,
     out[n] = block_sums[gridDim.x];
 }
 
+void scan_sums(int *sums, int n, cudaStream_t s) { scan_sums_kernel<<<1, 1024, 0, s>>>(sums, n); }
+
 int exclusive_scan_i32(p1_ctx *ctx, const int *in, int *out, int64_t n,
                        bool write_total, cudaStream_t s) {
   if (n < 0) return P1_EINVAL;

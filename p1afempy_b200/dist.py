@@ -51,32 +51,42 @@ def nnz_offsets(local_nnz: int, device=None, group=None):
     return int(starts[rank]), int(every.sum()), [int(x) for x in every]
 
 
-def global_row_pointer(indptr, n_rows, world, rank, chunk_log2, group=None):
-    """Interleaved ownership: where the calling rank's rows start in the GLOBAL CSR.
+def global_chunk_offsets(indptr, n_rows, world, rank, chunk_log2, group=None):
+    """Interleaved ownership: where every chunk of the calling rank starts in the
+    GLOBAL CSR -- what places a rank's piece in the global matrix.
 
     indptr: the rank's local row pointer (owned rows + 1, starting at 0, CUDA or
     CPU tensor).  Every rank contributes the nnz of each of its chunks (one
     all-gather of n_rows / 2^chunk_log2 / world integers, the only collective of a
     multi-GPU assembly); an exclusive scan over the chunks in global order gives
-    every chunk its offset.  Returns (global start of every owned row, int64;
-    total nnz as a 0-dim tensor): everything stays on the device, nothing
-    synchronises the host."""
+    every chunk its offset.  Returns (offsets of my chunks, int64; total nnz as a
+    0-dim tensor).  The global position of local row a is
+    ``offsets[a >> chunk_log2] + indptr[a] - indptr[(a >> chunk_log2) << chunk_log2]``
+    (global_row_pointer materialises it).  A few kilobytes of tensors, everything on
+    the device, nothing synchronises the host."""
     dev = indptr.device
     c = 1 << chunk_log2
     n_chunks = (n_rows + c - 1) >> chunk_log2
     per_rank = (n_chunks + world - 1) // world            # padded: same length on every rank
     n_own = indptr.numel() - 1
-    ip = indptr.to(torch.int64)
     starts = torch.arange(0, per_rank * c, c, dtype=torch.int64, device=dev).clamp_(max=n_own)
     ends = (starts + c).clamp_(max=n_own)
-    mine = ip[ends] - ip[starts]                           # nnz of my chunks (0: padding)
+    mine = (indptr[ends] - indptr[starts]).to(torch.int64)   # nnz of my chunks (0: padding)
     every = torch.empty(world * per_rank, dtype=torch.int64, device=dev)
     dist.all_gather_into_tensor(every, mine, group=group)
     in_order = every.reshape(world, per_rank).t().reshape(-1)   # chunk q * world + r
     offs = torch.cumsum(in_order, 0) - in_order
-    my_offs = offs.reshape(per_rank, world)[:, rank]
-    q = torch.arange(n_own, dtype=torch.int64, device=dev) >> chunk_log2
-    return my_offs[q] + ip[:-1] - ip[q << chunk_log2], in_order.sum()
+    return offs.reshape(per_rank, world)[:, rank].contiguous(), in_order.sum()
+
+
+def global_row_pointer(indptr, n_rows, world, rank, chunk_log2, group=None):
+    """-> (global start of every owned row, int64; total nnz): global_chunk_offsets
+    spread over the rows."""
+    offs, total = global_chunk_offsets(indptr, n_rows, world, rank, chunk_log2, group=group)
+    n_own = indptr.numel() - 1
+    ip = indptr.to(torch.int64)
+    q = torch.arange(n_own, dtype=torch.int64, device=indptr.device) >> chunk_log2
+    return offs[q] + ip[:-1] - ip[q << chunk_log2], total
 
 
 def _place(g_indptr, g_indices, g_data, rows, indptr, indices, data):
@@ -194,6 +204,10 @@ class DistributedMesh:
     def load_vector_midpoint(self, f_centroid):
         """Entries of the legacy load vector (solvers.py:414-426) at the owned rows."""
         return self.local.load_vector_midpoint(f_centroid)
+
+    def global_chunk_offsets(self, indptr):
+        return global_chunk_offsets(indptr, self.n_nodes, self.world, self.rank,
+                                    self.chunk_log2, group=self.group)
 
     def global_row_pointer(self, indptr):
         return global_row_pointer(indptr, self.n_nodes, self.world, self.rank, self.chunk_log2,

@@ -809,15 +809,19 @@ def test_cold_assembly_falls_back_to_the_plan_route(api):
     flip = (d1[:, 0] * d2[:, 1] - d1[:, 1] * d2[:, 0]) < 0
     e[flip] = e[flip][:, [0, 2, 1]]
     assert np.bincount(e.reshape(-1)).max() > 8
-    c, e5, _ = H.perturbed_square(4)
+    c, e5, b5 = H.perturbed_square(4)
     c2 = np.vstack([c, c + [2., 0.]])
     e2 = np.vstack([e5, e5 + c.shape[0]])
-    centre = int(np.argmin(np.abs(c - 0.5).sum(axis=1)))
-    e2[e2 == centre + c.shape[0]] = centre           # bow tie
-    for cc, ee, bit in ((pts, e, _lib.STATUS_SLOWPATH), (c2, e2, _lib.STATUS_RETRY)):
+    inner = np.setdiff1d(np.flatnonzero(np.bincount(e5.reshape(-1)) == 4), np.vstack(b5))
+    centre = int(inner[len(inner) // 2])
+    e2[e2 == centre + c.shape[0]] = centre           # bow tie: two closed fans of 4 (a valid row)
+    c0, e0, _ = meshgen.criss_square()
+    e0 = np.vstack([e0, e0])     # every element twice: the centre's fan "closes" with repeats
+    for cc, ee, bit in ((pts, e, _lib.STATUS_SLOWPATH), (c0, e0, _lib.STATUS_RETRY),
+                        (c2, e2, 0)):
         with DeviceMesh(cc, ee) as mesh:
             cold = mesh.assemble_cold(_lib.OP_STIFFNESS)
-            assert int(cold.status[0].item()) & bit
+            assert int(cold.status[0].item()) == bit
             ip, ix, data = [t.cpu().numpy() for t in cold.wait()]
         ref = orc.stiffness_coo(cc, ee).tocsr()
         assert np.array_equal(ip, ref.indptr) and np.array_equal(ix, ref.indices)
