@@ -627,6 +627,15 @@ class DeviceMesh:
         return eta
 
     # ------------------------------------------------------------ host side
+    def widen_indices(self, t):
+        """int32 index tensor -> int64 (p1_widen_indices): what scipy's index dtype
+        rule asks for when max(9 M, N) > 2^31 - 1."""
+        t = t.contiguous()
+        out = self._empty(t.shape, torch.int64)
+        _lib.check(self._lib.p1_widen_indices(self.ctx, _ptr(t), t.numel(), _ptr(out),
+                                              _stream(self.device)))
+        return out
+
     def to_scipy(self, indptr, indices, data, inferred_shape):
         """CSR triple (CUDA) -> scipy.sparse.csr_matrix equal to
         ``reference(...).tocsr()``: shape max_index+1 when the reference lets
@@ -639,15 +648,7 @@ class DeviceMesh:
         idx_dtype = scipy_index_dtype(self.n_elements, n, n)
         ip = indptr[:n + 1]
         if idx_dtype == np.int64:
-            ip64 = self._empty(ip.shape, torch.int64)
-            ix64 = self._empty(indices.shape, torch.int64)
-            _lib.check(self._lib.p1_widen_indices(self.ctx, _ptr(ip.contiguous()),
-                                                  ip.numel(), _ptr(ip64),
-                                                  _stream(self.device)))
-            _lib.check(self._lib.p1_widen_indices(self.ctx, _ptr(indices),
-                                                  indices.numel(), _ptr(ix64),
-                                                  _stream(self.device)))
-            ip, indices = ip64, ix64
+            ip, indices = self.widen_indices(ip), self.widen_indices(indices)
         h_ip, h_ix, h_data = to_host(ip), to_host(indices), to_host(data)
         if n == 0:
             return csr_matrix((0, 0), dtype=np.float64)

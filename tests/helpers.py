@@ -45,6 +45,18 @@ def f_nl(x): return 1.7 * x ** 2 + 0.3 * x ** 3
 def u_nodal(c): return np.sin(np.pi * c[:, 0]) * np.sin(np.pi * c[:, 1])
 
 
+def values_close_by_row(data, ref, rtol=1e-12):
+    """The value part of the parity check: |v - v_ref| <= rtol * max|row of ref|."""
+    counts = np.diff(ref.indptr)
+    rowmax = np.zeros(ref.shape[0])
+    nz = counts > 0
+    rowmax[nz] = np.maximum.reduceat(np.abs(ref.data), ref.indptr[:-1][nz])
+    scale = np.repeat(rowmax, counts)
+    err = np.abs(data - ref.data)
+    bad = err > rtol * scale
+    assert not bad.any(), (int(bad.sum()), float((err / np.maximum(scale, 1e-300)).max()))
+
+
 def csr_values_close(a, ref, rtol=1e-12):
     """SURVEY.md section 8(d) parity check: identical index arrays (dtype and
     shape included), values within rtol * max|row of ref|."""

@@ -149,3 +149,54 @@ def test_device_refine_nvb_matches_host():
             assert np.array_equal(et.cpu().numpy(), e)
             for x, y in zip(bt, b):
                 assert np.array_equal(x.cpu().numpy(), y)
+
+
+@pytest.mark.parametrize('world,chunk', [(2, 5), (4, 3)])
+def test_every_operator_on_interleaved_shares(world, chunk):
+    """Mass, generalised stiffness, weighted mass (plan route: P1_OP_LOCAL; cold
+    route: inside the scatter) and both load vectors on the rows of every rank
+    (emulated one after the other) == the one-GPU result restricted to those rows,
+    bit for bit."""
+    from p1afempy_b200 import _lib, cubature
+    from p1afempy_b200.device import DeviceMesh
+    c, e, _ = H.graded_square()
+    w, p = cubature.resolve_rule(cubature.CubatureRuleEnum.DAYTAYLOR)
+    ct, et = torch.from_numpy(c).cuda(), torch.from_numpy(e.astype(np.int32)).cuda()
+    u = torch.from_numpy(H.u_nodal(c)).cuda()
+    with DeviceMesh(ct, et) as mesh:
+        xq = mesh.quadrature_points(p)
+        qs = [torch.from_numpy(np.stack([f(xq[q].cpu().numpy()) for q in range(len(w))])).cuda()
+              for f in (H.a11, H.a12, H.a21, H.a22)]
+        fq = torch.from_numpy(np.stack([H.f_load(xq[q].cpu().numpy())
+                                        for q in range(len(w))])).cuda()
+        fc = torch.from_numpy(H.f_load(mesh.centroids().cpu().numpy())).cuda()
+        phiq = (1. + mesh.nodal_at_quadrature(u, p) ** 2).contiguous()
+        whole = {'mass': mesh.mass_csr(), 'general': mesh.general_stiffness_csr(*qs, w),
+                 'weighted': mesh.weighted_mass_csr(phiq, w, p)}
+        whole = {k: [t.cpu().numpy() for t in v] for k, v in whole.items()}
+        b_full = mesh.load_vector(fq, w, p).cpu().numpy()
+        b0_full = mesh.load_vector_midpoint(fc).cpu().numpy()
+    ref_g = orc.general_stiffness_coo(c, e, H.a11, H.a12, H.a21, H.a22, w, p).tocsr()
+    H.values_close_by_row(whole['general'][2], ref_g, 1e-12)
+    for rank in range(world):
+        with DeviceMesh(ct, et, interleave=(world, rank, chunk)) as mesh:
+            rows = mesh.global_rows().cpu().numpy()
+            got = {'mass': mesh.mass_csr(), 'general': mesh.general_stiffness_csr(*qs, w),
+                   'weighted': mesh.weighted_mass_csr(phiq, w, p)}
+            w_args = _lib.QuadArgs(None, None, None, None, phiq.data_ptr(), w.ctypes.data,
+                                   p.ctypes.data, len(w))
+            g_args = _lib.QuadArgs(qs[0].data_ptr(), qs[1].data_ptr(), qs[2].data_ptr(),
+                                   qs[3].data_ptr(), None, w.ctypes.data, None, len(w))
+            cold = {'mass': mesh.assemble_cold(_lib.OP_MASS).wait(),
+                    'general': mesh.assemble_cold(_lib.OP_GENERAL, quad=g_args).wait(),
+                    'weighted': mesh.assemble_cold(_lib.OP_WEIGHTED, quad=w_args).wait()}
+            for name, (ip, ix, data) in list(got.items()) + list(cold.items()):
+                fip, fix, fdata = whole[name]
+                lens = np.diff(fip)[rows]
+                src = (np.repeat(fip[rows] - np.concatenate([[0], np.cumsum(lens)[:-1]]), lens)
+                       + np.arange(int(lens.sum())))
+                assert np.array_equal(np.diff(ip.cpu().numpy()), lens), name
+                assert np.array_equal(ix.cpu().numpy(), fix[src]), name
+                assert np.array_equal(data.cpu().numpy(), fdata[src]), name
+            assert np.array_equal(mesh.load_vector(fq, w, p).cpu().numpy(), b_full[rows])
+            assert np.array_equal(mesh.load_vector_midpoint(fc).cpu().numpy(), b0_full[rows])

@@ -447,7 +447,7 @@ def test_unstructured_delaunay_mesh(api):
     e[flip] = e[flip][:, [0, 2, 1]]
     valence = np.bincount(e.reshape(-1))
     assert valence.max() > 8
-    H.csr_values_close(api[0].get_stiffness_matrix(pts, e), orc.stiffness_coo(pts, e).tocsr(), 1e-11)
+    H.csr_values_close(api[0].get_stiffness_matrix(pts, e), orc.stiffness_coo(pts, e).tocsr(), RTOL)
     H.csr_values_close(api[0].get_mass_matrix(pts, e), orc.mass_coo(pts, e).tocsr(), RTOL)
     w, p = cubature.resolve_rule(cubature.CubatureRuleEnum.DAYTAYLOR)
     u = H.u_nodal(pts)
@@ -496,16 +496,16 @@ def test_device_resident_api_and_plan_reuse():
         assert ip.is_cuda and ix.dtype == torch.int32 and a.dtype == torch.float64
         assert np.array_equal(ip.cpu().numpy(), ref_a.indptr)
         assert np.array_equal(ix.cpu().numpy(), ref_a.indices)
-        assert np.abs(a.cpu().numpy() - ref_a.data).max() <= 1e-11 * np.abs(ref_a.data).max()
+        H.values_close_by_row(a.cpu().numpy(), ref_a, RTOL)
         plan_before = mesh._plan.value
         none_ip, none_ix, m = mesh.mass_csr(pattern=False)       # values only
         assert none_ip is None and none_ix is None and mesh._plan.value == plan_before
-        assert np.abs(m.cpu().numpy() - ref_m.data).max() <= 1e-12 * np.abs(ref_m.data).max()
+        H.values_close_by_row(m.cpu().numpy(), ref_m, RTOL)
         xq = mesh.quadrature_points(p)
         qs = [torch.from_numpy(np.stack([f(xq[q].cpu().numpy()) for q in range(len(w))])).cuda()
               for f in (H.a11, H.a12, H.a21, H.a22)]
         _, _, g = mesh.general_stiffness_csr(*qs, w, pattern=False)
-        assert np.abs(g.cpu().numpy() - ref_g.data).max() <= 1e-11 * np.abs(ref_g.data).max()
+        H.values_close_by_row(g.cpu().numpy(), ref_g, RTOL)
     with DeviceMesh(ct, et) as cold:     # quadrature sums inside the scatter
         gip, gix, g2 = cold.general_stiffness_csr(*qs, w, fused=True)
         assert np.array_equal(gix.cpu().numpy(), ref_g.indices)
@@ -832,6 +832,35 @@ def test_cold_assembly_falls_back_to_the_plan_route(api):
     with pytest.raises(IndexError):
         mesh.assemble_cold(_lib.OP_STIFFNESS).wait()
     mesh.close()
+
+
+def test_to_scipy_int64_branch(api, monkeypatch):
+    """scipy switches the CSR index dtype to int64 when max(9 M, N) > 2^31 - 1
+    (scipy/sparse/_coo.py:419; the 256M-triangle mesh of the sweep).  The same code
+    path on a small mesh: the rule is forced, the device widens its int32 arrays
+    (p1_widen_indices) and the matrix still equals the reference's."""
+    import torch
+    from p1afempy_b200 import device
+    assert device.scipy_index_dtype(268435456, 134234113, 134234113) == np.int64
+    assert device.scipy_index_dtype(67108864, 33562625, 33562625) == np.int32
+    monkeypatch.setattr(device, 'scipy_index_dtype', lambda *a: np.int64)
+    widened = []
+    real = device.DeviceMesh.widen_indices
+    monkeypatch.setattr(device.DeviceMesh, 'widen_indices',
+                        lambda self, t: widened.append(real(self, t)) or widened[-1])
+    c, e, _ = H.perturbed_square(4)
+    for fn, ref in ((api[0].get_stiffness_matrix, orc.stiffness_coo(c, e).tocsr()),
+                    (api[0].get_mass_matrix, orc.mass_coo(c, e).tocsr())):
+        del widened[:]
+        a = fn(c, e)
+        # (scipy's constructor narrows int64 arrays whose values fit int32 again; at
+        # 256M triangles they do not: tests/test_gpu_fullsize.py)
+        assert len(widened) == 2 and all(t.dtype == torch.int64 for t in widened)
+        assert np.array_equal(widened[0].cpu().numpy(), ref.indptr)
+        assert np.array_equal(widened[1].cpu().numpy(), ref.indices)
+        assert a.has_sorted_indices and a.shape == ref.shape
+        assert np.array_equal(a.indptr, ref.indptr) and np.array_equal(a.indices, ref.indices)
+        H.values_close_by_row(a.data, ref, RTOL)
 
 
 def test_integration_md_stub_is_real(api):
