@@ -339,6 +339,69 @@ int p1_boundary_edges(p1_ctx *ctx, const double *coords,
                       const int32_t *edges, int64_t n_edges, double *length,
                       double *midpoint, void *stream);
 
+/* ------------------------------------------------------------------------
+ * The callers either side of the assembly path.
+ * ---------------------------------------------------------------------- */
+
+/* mesh.py:495-528 get_element_to_neighbours: neighbours[3 T + i] = the element that
+ * shares edge i (vertex i -> vertex i+1) of element T, -1 on the boundary.  Needs a
+ * plan that remembers its elements (P1_PLAN_KEEP_ELEMENTS or P1_PLAN_TOPOLOGY |
+ * P1_PLAN_SLOT_INDEX) over all rows.  SYNCHRONISES when the twins are built. */
+int p1_element_neighbours(const p1_plan *plan, int64_t *neighbours, void *stream);
+
+/* refinement.py:508-718 refineNVB in two stages around the caller's allocation of the
+ * refined mesh (p1_geometric_data provides element2edges / edge2nodes / boundary2edges).
+ * refinement.py:556-567: sort_for_longest_egde rotates the elements IN PLACE. */
+int p1_nvb_sort_longest_edge(p1_ctx *ctx, const double *coords, int32_t *elements,
+                             int64_t n_elements, void *stream);
+/* Stage 1 (refinement.py:574-592 and the counts of 625-637): edges of the marked
+ * elements, closure over the reference edges, numbering of the new nodes in edge
+ * order.  Scratch (device, int32): edge_flag (E), edge_new (E+1), child_first (M+1),
+ * bnd_before (K+1).  counts_host: [0] new nodes, [1] refined elements, [2+j] split
+ * edges of boundary j.  SYNCHRONISES. */
+int p1_nvb_plan(p1_ctx *ctx, int64_t n_elements, int64_t n_edges,
+                const int64_t *element2edges, const int64_t *marked, int64_t n_marked,
+                const int64_t *boundary2edges, const int64_t *boundary_offsets_host,
+                int n_boundaries, int32_t *edge_flag, int32_t *edge_new,
+                int32_t *child_first, int32_t *bnd_before, int64_t *counts_host,
+                void *stream);
+/* Stage 2 (refinement.py:8-31, 594-716): midpoints (and embedded values) of the new
+ * nodes behind the old ones, the refined boundaries (unsplit edges, then first halves,
+ * then second halves), the children of every element in the reference's order.
+ * new_coords / new_embed already hold the old nodes' values in their first n_nodes
+ * entries; new_boundaries_host: host array of device pointers. */
+int p1_nvb_apply(p1_ctx *ctx, const double *coords, int64_t n_nodes,
+                 const int32_t *elements, int64_t n_elements, int64_t n_edges,
+                 const int64_t *element2edges, const int64_t *edge2nodes,
+                 const int32_t *boundary_nodes, const int64_t *boundary2edges,
+                 const int64_t *boundary_offsets_host, int n_boundaries,
+                 const int32_t *edge_flag, const int32_t *edge_new,
+                 const int32_t *child_first, const int32_t *bnd_before,
+                 const int64_t *counts_host, const double *embed, int sorted,
+                 double *new_coords, double *new_embed, int32_t *new_elements,
+                 int32_t *const *new_boundaries_host, void *stream);
+
+/* solvers.py:601-618 apply_neumann: out = b + bincount over the Neumann edges of
+ * |E| g(midpoint) / 2 (first endpoints, then second endpoints).  SYNCHRONISES. */
+int p1_apply_neumann(p1_ctx *ctx, const double *coords, int64_t n_nodes,
+                     const int32_t *edges, int64_t n_edges, const double *g_mid,
+                     const double *b, double *out, void *stream);
+/* y = y0 + alpha A x on a device CSR (int32 indices): the Dirichlet lift b - A x_D
+ * (solvers.py:679-681) and A x of the energy (solvers.py:695).  y0 may be NULL. */
+int p1_csr_spmv(p1_ctx *ctx, int64_t n_rows, const int32_t *indptr, const int32_t *indices,
+                const double *data, const double *x, double alpha, const double *y0,
+                double *y, void *stream);
+/* a . b, fixed summation tree.  SYNCHRONISES. */
+int p1_dot(p1_ctx *ctx, int64_t n, const double *a, const double *b, double *result_host,
+           void *stream);
+/* solvers.py:688-693 without leaving the device: Jacobi-preconditioned conjugate
+ * gradient on the free nodes (fixed[i] != 0: x[i] keeps its Dirichlet value; rows and
+ * columns of fixed nodes are lifted to the right-hand side).  SYNCHRONISES. */
+int p1_pcg(p1_ctx *ctx, int64_t n, const int32_t *indptr, const int32_t *indices,
+           const double *data, const double *b, const unsigned char *fixed, double *x,
+           double tol, int max_iter, int *iterations_host, double *relative_residual_host,
+           void *stream);
+
 #ifdef __cplusplus
 }
 #endif

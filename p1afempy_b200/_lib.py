@@ -80,6 +80,17 @@ PROTOTYPES = {
     'p1_plan_info': [_vp, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64),
                      C.POINTER(_i64)],
     'p1_assemble_csr': [_vp, _int, _vp, _vp, _vp, _vp, _vp, _vp],
+    'p1_element_neighbours': [_vp, _vp, _vp],
+    'p1_nvb_sort_longest_edge': [_vp, _vp, _vp, _i64, _vp],
+    'p1_nvb_plan': [_vp, _i64, _i64, _vp, _vp, _i64, _vp, _vp, _int, _vp, _vp, _vp, _vp, _vp,
+                    _vp],
+    'p1_nvb_apply': [_vp, _vp, _i64, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _int, _vp, _vp,
+                     _vp, _vp, _vp, _vp, _int, _vp, _vp, _vp, _vp, _vp],
+    'p1_apply_neumann': [_vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp],
+    'p1_csr_spmv': [_vp, _i64, _vp, _vp, _vp, _vp, C.c_double, _vp, _vp, _vp],
+    'p1_dot': [_vp, _i64, _vp, _vp, C.POINTER(C.c_double), _vp],
+    'p1_pcg': [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, C.c_double, _int,
+               C.POINTER(_int), C.POINTER(C.c_double), _vp],
     'p1_assemble_cold': [_vp, _vp, _i64, _i64, _int, _int, _int, _int, _vp, _vp,
                          C.POINTER(QuadArgs), _i64, _vp, _vp, _vp, _vp, _vp],
     'p1_mass_triplets': [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp],

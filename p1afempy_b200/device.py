@@ -613,6 +613,14 @@ class DeviceMesh:
         pieces = [b2e[offsets[j]:offsets[j + 1]] for j in range(len(parts))]
         return e2e, e2n[:n_edges.value], pieces
 
+    def element_neighbours(self):
+        """(M, 3) int64: the element across every edge, -1 on the boundary
+        (mesh.py:495-528)."""
+        out = self._empty((self.n_elements, 3), torch.int64)
+        _lib.check(self._lib.p1_element_neighbours(self._element_plan(True), _ptr(out),
+                                                   _stream(self.device)))
+        return out
+
     def eta_r(self, x, dirichlet, neumann, neumann_term, f_centroid):
         x = to_device_f64(x, self.device, (self.n_nodes,))
         fc = to_device_f64(f_centroid, self.device, (self.n_elements,))

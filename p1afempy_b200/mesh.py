@@ -4,7 +4,8 @@ from __future__ import annotations
 
 from .device import DeviceMesh, to_host
 
-__all__ = ['get_area', 'get_directional_vectors', 'provide_geometric_data']
+__all__ = ['get_area', 'get_directional_vectors', 'provide_geometric_data',
+           'get_element_to_neighbours']
 
 
 def get_area(coordinates, elements):
@@ -29,3 +30,11 @@ def provide_geometric_data(elements, boundaries):
     with DeviceMesh(None, elements) as mesh:
         e2e, e2n, b2e = mesh.geometric_data(list(boundaries))
         return to_host(e2e), to_host(e2n), [to_host(b) for b in b2e]
+
+
+def get_element_to_neighbours(elements):
+    """element2neighbours[k, i] = the element sharing edge i (vertex i -> vertex i+1)
+    of element k, -1 on the boundary (mesh.py:495-528; SURVEY.md section 8(f), rank
+    4).  From the half-edge twins of the assembly path's node fans; int64."""
+    with DeviceMesh(None, elements) as mesh:
+        return to_host(mesh.element_neighbours())

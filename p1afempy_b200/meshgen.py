@@ -198,32 +198,10 @@ def refine_uniform_device(coords, elements, boundaries):
 
     coords (N,2) float64, elements (M,3) int32, boundaries: list of (K,2) int32
     CUDA tensors.  Same output as ``refine_nvb(c, e, arange(M), b)`` (hence as
-    the reference's ``refineNVB``), bit for bit: the edge numbering comes from
-    ``p1_geometric_data`` (the device implementation of
-    mesh.provide_geometric_data), the rest is index arithmetic
-    (refinement.py:593-716, case bisec(3) for every element)."""
+    the reference's ``refineNVB``), bit for bit."""
     import torch
-    from .device import DeviceMesh
-    n = coords.shape[0]
-    with DeviceMesh(None, elements, n_nodes=n, check=False) as mesh:
-        e2e, e2n, b2e = mesh.geometric_data(boundaries)
-    mid = (coords[e2n[:, 0]] + coords[e2n[:, 1]]) / 2.
-    new_coords = torch.cat([coords, mid])
-    del mid, e2n
-    nn = (e2e + n).to(torch.int32)
-    del e2e
-    v0, v1, v2 = elements[:, 0], elements[:, 1], elements[:, 2]
-    m0, m1, m2 = nn[:, 0], nn[:, 1], nn[:, 2]
-    children = torch.stack([
-        torch.stack([m0, v2, m2], 1), torch.stack([v0, m0, m2], 1),
-        torch.stack([m0, v1, m1], 1), torch.stack([v2, m0, m1], 1)], 1)
-    new_elements = children.reshape(-1, 3).contiguous()
-    new_boundaries = []
-    for b, be in zip(boundaries, b2e):
-        mids = (be + n).to(torch.int32)
-        new_boundaries.append(torch.cat([torch.stack([b[:, 0], mids], 1),
-                                         torch.stack([mids, b[:, 1]], 1)]).contiguous())
-    return new_coords, new_elements, new_boundaries
+    marked = torch.arange(elements.shape[0], dtype=torch.int64, device=elements.device)
+    return refine_nvb_device(coords, elements, marked, boundaries)
 
 
 def unit_square_device(k: int, device=None, host_levels: int = 6):
@@ -244,65 +222,8 @@ def refine_nvb_device(coords, elements, marked, boundaries):
     """Newest vertex bisection of the MARKED elements on the GPU; same output as
     ``refine_nvb`` / the reference's ``refineNVB`` (refinement.py:508-718), bit
     for bit.  coords (N,2) float64, elements (M,3) int32, marked int64 indices,
-    boundaries: list of (K,2) int32 -- all CUDA tensors.
-
-    The edge numbering is ``p1_geometric_data`` (CUDA); closure, numbering of the
-    new nodes and child generation are tensor index arithmetic.  This is mesh
-    infrastructure for device-resident adaptive loops and large benchmark
-    meshes, not part of the assembly path."""
-    import torch
-    from .device import DeviceMesh
-    n, m = coords.shape[0], elements.shape[0]
-    dev = coords.device
-    with DeviceMesh(None, elements, n_nodes=n, check=False) as mesh:
-        e2e, e2n, b2e = mesh.geometric_data(boundaries)
-    split = torch.zeros(e2n.shape[0], dtype=torch.bool, device=dev)
-    split[e2e[marked].reshape(-1)] = True
-    while True:  # closure: a split edge forces the reference edge of its elements
-        flags = split[e2e]
-        need = ~flags[:, 0] & (flags[:, 1] | flags[:, 2])
-        if not bool(need.any()):
-            break
-        split[e2e[need, 0]] = True
-    chosen = torch.nonzero(split).reshape(-1)
-    new_id = torch.zeros(e2n.shape[0], dtype=torch.int64, device=dev)
-    new_id[chosen] = n + torch.arange(chosen.numel(), dtype=torch.int64, device=dev)
-    mid = (coords[e2n[chosen, 0]] + coords[e2n[chosen, 1]]) / 2.
-    new_coords = torch.cat([coords, mid])
-    new_boundaries = []
-    for b, be in zip(boundaries, b2e):
-        if b.numel():
-            nn_b = new_id[be]
-            hit = torch.nonzero(nn_b).reshape(-1)
-            if hit.numel():
-                mids = nn_b[hit].to(torch.int32)
-                b = torch.cat([b[nn_b == 0], torch.stack([b[hit, 0], mids], 1),
-                               torch.stack([mids, b[hit, 1]], 1)]).contiguous()
-        new_boundaries.append(b)
-    nn = new_id[e2e]
-    s0, s1, s2 = nn[:, 0] != 0, nn[:, 1] != 0, nn[:, 2] != 0
-    kinds = {'b1': s0 & ~s1 & ~s2, 'b12': s0 & s1 & ~s2, 'b13': s0 & ~s1 & s2,
-             'b123': s0 & s1 & s2}
-    n_child = torch.ones(m, dtype=torch.int64, device=dev)
-    n_child[kinds['b1']] = 2
-    n_child[kinds['b12']] = 3
-    n_child[kinds['b13']] = 3
-    n_child[kinds['b123']] = 4
-    first = torch.cumsum(n_child, 0) - n_child
-    out = torch.zeros((int(n_child.sum()), 3), dtype=torch.int32, device=dev)
-    keep = ~s0
-    out[first[keep]] = elements[keep]
-    nn = nn.to(torch.int32)
-    v0, v1, v2 = elements[:, 0], elements[:, 1], elements[:, 2]
-    m0, m1, m2 = nn[:, 0], nn[:, 1], nn[:, 2]
-
-    def put(sel, children):
-        base = first[sel]
-        for j, (a, b_, c) in enumerate(children):
-            out[base + j] = torch.stack([a[sel], b_[sel], c[sel]], 1)
-
-    put(kinds['b1'], [(v2, v0, m0), (v1, v2, m0)])
-    put(kinds['b12'], [(v2, v0, m0), (m0, v1, m1), (v2, m0, m1)])
-    put(kinds['b13'], [(m0, v2, m2), (v0, m0, m2), (v1, v2, m0)])
-    put(kinds['b123'], [(m0, v2, m2), (v0, m0, m2), (m0, v1, m1), (v2, m0, m1)])
+    boundaries: list of (K,2) int32 -- all CUDA tensors.  (CUDA kernels:
+    p1afempy_b200.refinement.refine_nvb_device.)"""
+    from .refinement import refine_nvb_device as run
+    new_coords, out, new_boundaries, _ = run(coords, elements, marked, boundaries)
     return new_coords, out, new_boundaries

@@ -180,46 +180,113 @@ def get_load_vector_of_composition_nonlinear_with_fem(f, u, coordinates, element
 
 
 # ---------------------------------------------------------------------------
-# The reference's driver on top of the accelerated path (SURVEY.md section 8(f),
-# "next" rank 2: the consumer side).  Host orchestration exactly as in
-# /root/reference/p1afempy/solvers.py:601-697; assembly and load vector run on
-# the GPU, the sparse direct solve stays scipy's, as in the reference.
+# The reference's driver ("next" rank 2: the consumer side of
+# the path, /root/reference/p1afempy/solvers.py:601-697).  Assembly, load vector,
+# Neumann load, Dirichlet lift and energy run on the device on the device-resident
+# CSR; ``solver='direct'`` (default) then hands the free-node system to scipy's
+# direct solver like the reference does, ``solver='pcg'`` solves it on the GPU
+# (Jacobi-preconditioned CG, p1_pcg), so that the matrix never crosses PCIe.
 # ---------------------------------------------------------------------------
+
+def _neumann_on_device(mesh, neumann_t, g, b_t):
+    """b + Neumann contributions on the device (p1_boundary_edges, p1_apply_neumann)."""
+    import ctypes as C                                   # noqa: F401
+    from . import _lib
+    from .device import _ptr, _stream
+    _, mid = mesh.boundary_edges(neumann_t)
+    gm = _callback_at(g, mid)
+    if not isinstance(gm, torch.Tensor):
+        gm = torch.from_numpy(np.ascontiguousarray(gm, dtype=np.float64)).to(b_t.device)
+    out = torch.empty_like(b_t)
+    _lib.check(mesh._lib.p1_apply_neumann(
+        mesh.ctx, _ptr(mesh.coords), mesh.n_nodes, _ptr(neumann_t), int(neumann_t.shape[0]),
+        _ptr(gm.contiguous()), _ptr(b_t), _ptr(out), _stream(mesh.device)))
+    return out
+
 
 def apply_neumann(neumann_bc, coordinates, g, b):
     """b + Neumann contributions (solvers.py:601-618): every boundary edge adds
-    |E| g(midpoint) / 2 to both of its nodes (sequential bincount order)."""
-    neumann_bc = np.asarray(neumann_bc)
-    cn1 = coordinates[neumann_bc[:, 0], :]
-    cn2 = coordinates[neumann_bc[:, 1], :]
-    gm = _values_on_host(g, (cn1 + cn2) / 2, neumann_bc.shape[0])
-    share = np.sqrt(np.sum(np.square(cn2 - cn1), axis=1)) * gm / 2.
-    return b + np.bincount(
-        np.concatenate([neumann_bc[:, 0], neumann_bc[:, 1]]).astype(np.int64),
-        weights=np.concatenate([share, share]), minlength=b.size)
+    |E| g(midpoint) / 2 to both of its nodes, summed like the reference's bincount
+    (first endpoints, then second endpoints)."""
+    from .device import to_device_f64, to_device_indices
+    neumann_bc = np.asarray(neumann_bc).reshape(-1, 2)
+    b = np.asarray(b, dtype=np.float64)
+    with DeviceMesh(coordinates, np.zeros((0, 3), dtype=np.int64), check=False) as mesh:
+        if mesh.n_nodes < b.size:
+            raise ValueError('apply_neumann: b has more entries than there are coordinates')
+        n_t = to_device_indices(neumann_bc, mesh.device, mesh.ctx).reshape(-1, 2)
+        b_t = to_device_f64(np.concatenate([b, np.zeros(mesh.n_nodes - b.size)]), mesh.device)
+        return to_host(_neumann_on_device(mesh, n_t, g, b_t))[:b.size]
 
 
 def solve_laplace(coordinates, elements, dirichlet, neumann, f, g, uD,
-                  cubature_rule=None):
+                  cubature_rule=None, solver='direct', tol=1e-12, max_iter=None,
+                  return_info=False):
     """-Laplace u = f with mixed boundary conditions (solvers.py:621-697).
-    Returns (x, energy)."""
-    from scipy.sparse import csc_matrix
-    from scipy.sparse.linalg import spsolve
+    Returns (x, energy) [, info with solver='pcg' and return_info].
+
+    solver='direct': scipy's sparse direct solver on the free nodes, as the reference.
+    solver='pcg'   : conjugate gradient on the device; the matrix stays on the GPU
+                     (tol: relative residual, max_iter: default 10 N)."""
+    import ctypes as C
+    from . import _lib
+    from .device import _ptr, _stream, to_device_f64, to_device_indices
+    if solver not in ('direct', 'pcg'):
+        raise ValueError("solver must be 'direct' or 'pcg'")
     coordinates = np.asarray(coordinates, dtype=np.float64)
     n = coordinates.shape[0]
-    x = np.zeros(n)
-    a = get_stiffness_matrix(coordinates=coordinates, elements=elements)
-    if a.shape[0] < n:                      # trailing unused nodes (inferred shape)
-        raise ValueError('solve_laplace: every node must belong to an element')
-    fixed = np.unique(np.asarray(dirichlet))
-    x[fixed] = _values_on_host(uD, coordinates[fixed, :], fixed.shape[0])
-    b = get_right_hand_side(coordinates=coordinates, elements=elements, f=f,
-                            cubature_rule=cubature_rule) - a.dot(x)
-    neumann = np.asarray(neumann)
-    if neumann.size > 0:
-        b = apply_neumann(neumann_bc=neumann, coordinates=coordinates, g=g, b=b)
+    weights = points = None
+    if cubature_rule is not None:
+        weights, points = resolve_rule(cubature_rule)
+    with DeviceMesh(coordinates, elements) as mesh:
+        _need_inferable(mesh)
+        dev, stream = torch.device('cuda', mesh.device), _stream(mesh.device)
+        ip, ix, data = mesh.stiffness_csr()
+        if mesh.max_index + 1 < n:             # trailing unused nodes (inferred shape)
+            raise ValueError('solve_laplace: every node must belong to an element')
+        # prescribed values at the Dirichlet nodes
+        fixed = np.unique(np.asarray(dirichlet))
+        fixed_t = torch.from_numpy(fixed.astype(np.int64)).to(dev)
+        ud = _callback_at(uD, mesh.coords[fixed_t])
+        if not isinstance(ud, torch.Tensor):
+            ud = torch.from_numpy(np.ascontiguousarray(ud, dtype=np.float64)).to(dev)
+        x = torch.zeros(n, dtype=torch.float64, device=dev)
+        x[fixed_t] = ud
+        # right-hand side: load vector - A x_D (+ Neumann)
+        if points is None:
+            b = mesh.load_vector_midpoint(_callback_at(f, mesh.centroids()))
+        else:
+            (fq,) = _callback_at_points((f,), mesh.quadrature_points(points))
+            b = mesh.load_vector(fq, weights, points)
+        if solver == 'direct':      # (p1_pcg lifts x_D itself: its first residual is b - A x)
+            _lib.check(mesh._lib.p1_csr_spmv(mesh.ctx, n, _ptr(ip), _ptr(ix), _ptr(data),
+                                             _ptr(x), -1.0, _ptr(b), _ptr(b), stream))
+        neumann = np.asarray(neumann)
+        if neumann.size > 0:
+            n_t = to_device_indices(neumann.reshape(-1, 2), mesh.device, mesh.ctx).reshape(-1, 2)
+            b = _neumann_on_device(mesh, n_t, g, b)
+        if solver == 'pcg':
+            mask = torch.zeros(n, dtype=torch.uint8, device=dev)
+            mask[fixed_t] = 1
+            its, res = C.c_int(), C.c_double()
+            _lib.check(mesh._lib.p1_pcg(mesh.ctx, n, _ptr(ip), _ptr(ix), _ptr(data), _ptr(b),
+                                        _ptr(mask), _ptr(x), float(tol),
+                                        int(max_iter if max_iter is not None else 10 * n),
+                                        C.byref(its), C.byref(res), stream))
+            ax = torch.empty_like(x)
+            _lib.check(mesh._lib.p1_csr_spmv(mesh.ctx, n, _ptr(ip), _ptr(ix), _ptr(data),
+                                             _ptr(x), 1.0, None, _ptr(ax), stream))
+            energy = C.c_double()
+            _lib.check(mesh._lib.p1_dot(mesh.ctx, n, _ptr(x), _ptr(ax), C.byref(energy), stream))
+            out = (to_host(x), energy.value)
+            return out + ({'iterations': its.value, 'relative_residual': res.value},) \
+                if return_info else out
+        # the reference's direct solve on the host (the only step that needs A there)
+        from scipy.sparse import csc_matrix
+        from scipy.sparse.linalg import spsolve
+        a = csc_matrix(mesh.to_scipy(ip, ix, data, inferred_shape=True))
+        xh, bh = to_host(x), to_host(b)
     free = np.setdiff1d(np.arange(0, n), fixed, assume_unique=True)
-    a = csc_matrix(a)
-    x[free] = spsolve(a[free, :][:, free], b[free], use_umfpack=True)
-    energy = x.dot(a.dot(x))
-    return x, energy
+    xh[free] = spsolve(a[free, :][:, free], bh[free], use_umfpack=True)
+    energy = xh.dot(a.dot(xh))
+    return xh, energy

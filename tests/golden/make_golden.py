@@ -196,6 +196,62 @@ def sanity_case():
     print('sanity', [float(out['energy%d' % k]) for k in range(4)])
 
 
+def afem_case():
+    """The callers either side of the path: refineNVB with
+    to_embed / sort_for_longest_egde (refinement.py:508-718; test_refinement.py:11-114
+    and its fixtures tests/data/refined_nvb/*), get_element_to_neighbours
+    (mesh.py:495-528; test_mesh.py:504-530 with the MATLAB fixture)."""
+    out = {}
+    # the reference's own L-shape case
+    d = DATA / 'l_shape_mesh'
+    c, e = io.read_mesh(path_to_coordinates=d / 'l_shape_coordinates.dat',
+                        path_to_elements=d / 'l_shape_elements.dat')
+    bcs = [io.read_boundary_condition(d / ('l_shape_bc_%d.dat' % j)) for j in range(3)]
+    marked = np.array([0, 1, 3, 5])
+    rc, re_, rb, _ = ref.refinement.refineNVB(coordinates=c, elements=e, marked_elements=marked,
+                                             boundary_conditions=bcs)
+    r = DATA / 'refined_nvb'
+    out.update(l_c=c, l_e=e, l_b0=bcs[0], l_b1=bcs[1], l_b2=bcs[2], l_marked=marked,
+               l_rc=rc, l_re=re_, l_rb0=rb[0], l_rb1=rb[1], l_rb2=rb[2],
+               l_rc_file=np.loadtxt(r / 'l_shape_coordinates_refined.dat'),
+               l_re_file=np.loadtxt(r / 'l_shape_elements_refined.dat').astype(np.int64) - 1)
+    # several adaptive steps with an embedded nodal vector, both element layouts
+    rng = np.random.default_rng(3)
+    for tag, sort in (('plain', False), ('sorted', True)):
+        c, e, b = H.perturbed_square(3)
+        e = e.copy()
+        emb = H.u_nodal(c)
+        for step in range(4):
+            marked = np.flatnonzero(rng.random(e.shape[0]) < 0.3)
+            out['%s_in_c%d' % (tag, step)] = c
+            out['%s_in_e%d' % (tag, step)] = e.copy()
+            out['%s_in_emb%d' % (tag, step)] = emb
+            out['%s_marked%d' % (tag, step)] = marked
+            for j, x in enumerate(b):
+                out['%s_in_b%d_%d' % (tag, step, j)] = x
+            c, e, b, emb = ref.refinement.refineNVB(
+                coordinates=c, elements=e, marked_elements=marked, boundary_conditions=b,
+                to_embed=emb, sort_for_longest_egde=sort)
+            out['%s_sorted_e%d' % (tag, step)] = out['%s_in_e%d' % (tag, step)] if not sort else None
+            out['%s_c%d' % (tag, step)] = c
+            out['%s_e%d' % (tag, step)] = e.copy()   # (the next step sorts e in place)
+            out['%s_emb%d' % (tag, step)] = emb
+            for j, x in enumerate(b):
+                out['%s_b%d_%d' % (tag, step, j)] = x
+            out['%s_nb' % tag] = np.array(len(b))
+    out = {k: v for k, v in out.items() if v is not None}
+    # neighbours: MATLAB fixture and a graded mesh
+    g = DATA / 'get_neighbours'
+    em = np.loadtxt(g / 'elements_matlab.dat').astype(np.int64) - 1
+    out.update(nb_elements_matlab=em,
+               nb_matlab=np.loadtxt(g / 'element2neighbours_matlab.dat').astype(np.int64) - 1,
+               nb_reference_matlab=ref.mesh.get_element_to_neighbours(em))
+    cg, eg, _ = H.graded_square()
+    out.update(nb_elements_graded=eg, nb_reference_graded=ref.mesh.get_element_to_neighbours(eg))
+    np.savez_compressed(os.path.join(HERE, 'afem.npz'), **out)
+    print('afem', len(out))
+
+
 if __name__ == '__main__':
     full_case('perturbed_s4', *H.perturbed_square(4))
     full_case('graded', *H.graded_square())
@@ -206,3 +262,4 @@ if __name__ == '__main__':
     ahw_case()
     edge_numbering_case()
     sanity_case()
+    afem_case()

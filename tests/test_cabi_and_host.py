@@ -141,3 +141,24 @@ def test_cubature_stand_ins_are_named_and_announced():
             assert abs((w * p[:, 0] ** a * p[:, 1] ** b).sum() - exact) < 1e-15
     w1, p1 = cub.resolve_rule(cub.CubatureRuleEnum.MIDPOINT)
     assert np.array_equal(w1, [0.5]) and np.array_equal(p1, [[1. / 3., 1. / 3.]])
+
+
+def test_io_helpers(tmp_path):
+    """The reference's text readers (io_helpers.py:5-132: uint32 indices, optional
+    1-based shift, a single boundary edge keeps two dimensions) and the binary
+    save_mesh / load_mesh round trip."""
+    from p1afempy_b200 import io_helpers as io
+    c = np.array([[0., 0.], [1., 0.], [0., 1.], [1., 1.]])
+    e = np.array([[1, 2, 3], [2, 4, 3]])
+    np.savetxt(tmp_path / 'c.dat', c)
+    np.savetxt(tmp_path / 'e.dat', e, fmt='%d')
+    np.savetxt(tmp_path / 'b.dat', np.array([[1, 2]]), fmt='%d')
+    cc, ee = io.read_mesh(path_to_coordinates=tmp_path / 'c.dat',
+                          path_to_elements=tmp_path / 'e.dat', shift_indices=True)
+    assert np.array_equal(cc, c) and ee.dtype == np.uint32 and np.array_equal(ee, e - 1)
+    b = io.read_boundary_condition(tmp_path / 'b.dat', shift_indices=True)
+    assert b.shape == (1, 2) and b.dtype == np.uint32 and np.array_equal(b, [[0, 1]])
+    io.save_mesh(tmp_path / 'mesh', c, e - 1, [b, np.zeros((0, 2), dtype=int)])
+    c2, e2, b2 = io.load_mesh(tmp_path / 'mesh.npz')
+    assert np.array_equal(c2, c) and np.array_equal(e2, e - 1) and e2.dtype == np.int32
+    assert len(b2) == 2 and np.array_equal(b2[0], b) and b2[1].shape == (0, 2)
