@@ -99,7 +99,7 @@ def reference_call(op, c, e, b):
     thread -- numpy/scipy do not thread this path."""
     from oracle import p1_oracle as orc
     from p1afempy_b200 import cubature
-    w, p = cubature.resolve_rule(cubature.CubatureRuleEnum.DAYTAYLOR)
+    w, p = cubature.resolve_rule(cubature.CubatureRuleEnum.CONICAL_GAUSS_4X4)
     if op == 'stiffness':
         return orc.stiffness_coo(c, e).tocsr()
     if op == 'mass':
@@ -299,10 +299,13 @@ class Workload:
         self.gen_s = time.perf_counter() - t0
         self.c, self.e, self.bnd = c, e, bnd
         self.m, self.nn = int(e.shape[0]), int(c.shape[0])
-        self.w, self.p = cubature.resolve_rule(cubature.CubatureRuleEnum.DAYTAYLOR)
+        self.w, self.p = cubature.resolve_rule(cubature.CubatureRuleEnum.CONICAL_GAUSS_4X4)
         self.n_qp = int(self.w.shape[0])
-        inter = (world, rank, 12) if world > 1 else None
+        # N > 1: matrices and load vectors are dealt out by rows (chunks of 4096), the
+        # estimator by contiguous element blocks
+        inter = (world, rank, 12) if world > 1 and op != 'eta' else None
         self.mesh = DeviceMesh(c, e, device=local_rank, interleave=inter)
+        self.block = (self.m * rank // world, self.m * (rank + 1) // world)
         self.statuses = []
         x, y = c[:, 0], c[:, 1]
         pi = float(np.pi)
@@ -353,9 +356,13 @@ class Workload:
                 return cold, offs, total
             return cold
         if op == 'load':
-            return mesh.load_vector(self.fq, self.w, self.p)
+            out = mesh.load_vector(self.fq, self.w, self.p)
+            mesh.close()        # cold: the next call builds its plan again (N > 1: plan route)
+            return out
+        if self.world > 1:
+            return mesh.eta_r_block(self.u, self.dirichlet, self.none, None, self.fc, *self.block)
         out = mesh.eta_r(self.u, self.dirichlet, self.none, None, self.fc)
-        mesh.close()            # cold: the next call builds its plan again
+        mesh.close()
         return out
 
     def check(self, nnz_expected):
@@ -385,8 +392,6 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     op, level = args.op, args.level
-    if world > 1 and op in ('load', 'eta'):
-        raise SystemExit('--op %s is measured on one GPU (DESIGN.md section 6)' % op)
     m, nn, nnz = mesh_counts(level)
     wl = Workload(op, level, world, rank, local_rank)
     assert wl.m == m and wl.nn == nn
@@ -496,9 +501,11 @@ def run_b200(args):
                                % (op, level, m, nn, nnz,
                                   ', %d-point rule, coefficient values array-fed' % wl.n_qp
                                   if op in ('general', 'weighted', 'load') else ''),
-                   'parallelism': ('rows dealt to %d GPUs in chunks of 4096, inputs replicated; one '
-                                   'all-gather of per-chunk nnz (global row pointer) per step'
-                                   % world) if world > 1 else '1 GPU',
+                   'parallelism': (('contiguous element blocks on %d GPUs, inputs replicated, no '
+                                    'collective' % world) if op == 'eta' else
+                                   ('rows dealt to %d GPUs in chunks of 4096, inputs replicated; one '
+                                    'all-gather of per-chunk nnz (global row pointer) per step'
+                                    % world)) if world > 1 else '1 GPU',
                    'l2': 'inputs (%.0f MB) and outputs exceed the 126 MB L2 and every step '
                          'allocates fresh outputs; no flush needed' % ((12 * m + 16 * nn) / 1e6),
                    'mesh_generation_s': wl.gen_s},
@@ -522,7 +529,7 @@ def run_e2e(args, wl, world, rank, local_rank, m):
     from p1afempy_b200 import cubature, indicators, solvers
     from p1afempy_b200.device import to_host
     op = args.op
-    rule = cubature.CubatureRuleEnum.DAYTAYLOR
+    rule = cubature.CubatureRuleEnum.CONICAL_GAUSS_4X4
     n_e2e = max(1, min(args.steps, args.e2e_steps))
     c, e = wl.c, wl.e
 

@@ -47,17 +47,15 @@ def main():
     ap.add_argument('--cpu-level', type=int, default=9)
     args = ap.parse_args()
     import torch
-    from bench import generate_mesh
-    from p1afempy_b200 import cubature, meshgen
+    from p1afempy_b200 import _lib, cubature, meshgen, options
     from p1afempy_b200.device import DeviceMesh
     from oracle import p1_oracle as orc
     import helpers as H
 
-    keep = {args.cpu_level: None}
-    c, e = generate_mesh(args.level, keep)
-    cc, ce = keep[args.cpu_level]
+    c, e, _ = meshgen.unit_square(args.level)
+    cc, ce, _ = meshgen.unit_square(args.cpu_level)
     m, mc = e.shape[0], ce.shape[0]
-    w, p = cubature.resolve_rule(cubature.CubatureRuleEnum.DAYTAYLOR)
+    w, p = cubature.resolve_rule(cubature.CubatureRuleEnum.CONICAL_GAUSS_4X4)
     nq = w.shape[0]
     mesh = DeviceMesh(c, e)
     dev = mesh.coords.device
@@ -83,9 +81,22 @@ def main():
     fc = torch.sin(2. * np.pi * cent[:, 0]) * torch.cos(3. * np.pi * cent[:, 1]) + 1.
     del xq, x, y
 
-    record('stiffness->CSR', gpu_time(lambda: mesh.stiffness_csr()),
+    record('stiffness->CSR (cold, no host sync: p1_assemble_cold)',
+           gpu_time(lambda: mesh.assemble_cold(_lib.OP_STIFFNESS)),
            cpu_time(lambda: orc.stiffness_coo(cc, ce).tocsr()), 64.0)
-    record('mass->CSR', gpu_time(lambda: mesh.mass_csr()),
+    record('stiffness->CSR (cold, plan route)', gpu_time(lambda: mesh.stiffness_csr()), None, 64.0)
+    options.plan_flags = _lib.PLAN_TILED
+    record('stiffness->CSR (cold, tiled plan: P1_PLAN_TILED)',
+           gpu_time(lambda: mesh.stiffness_csr()), None, 64.0)
+    options.plan_flags = 0
+    reused = DeviceMesh(c, e, reuse=True)
+    reused.stiffness_csr()
+    record('stiffness->CSR values (plan reused: numeric refill only)',
+           gpu_time(lambda: reused.stiffness_csr(pattern=False)), None,
+           8.0 * 3.5 + 12.0 + 8.0)
+    reused.close()
+    del reused
+    record('mass->CSR (cold, no host sync)', gpu_time(lambda: mesh.assemble_cold(_lib.OP_MASS)),
            cpu_time(lambda: orc.mass_coo(cc, ce).tocsr()), 64.0)
     record('general stiffness->CSR (coefficients array-fed)',
            gpu_time(lambda: mesh.general_stiffness_csr(q11, q12, q21, q22, w)),

@@ -333,6 +333,25 @@ int p1_eta_r(const p1_plan *plan, const double *coords, const double *x,
              const int32_t *neumann, int64_t n_neumann,
              const double *neumann_term, const double *f_centroid,
              double *eta, void *stream);
+/* Multi-GPU eta_R: the indicators of an element block [m0, m1) only need the sub-mesh
+ * of the elements that touch a node of the block.  p1_block_submesh flags the block's
+ * nodes (node_flag: n_nodes bytes) and numbers the elements of the sub-mesh (pos:
+ * n_elements + 1 ints; counts_host: [0] their number, [1] where the block starts among
+ * them -- its elements stay consecutive); p1_block_submesh_fill writes them (and their
+ * global indices); p1_eta_r_partial is p1_eta_r on such a sub-mesh: boundary edges not
+ * listed because they are the cut through the mesh are no error.  The block's
+ * indicators computed this way are the global ones bit for bit. */
+int p1_block_submesh(p1_ctx *ctx, const int32_t *elements, int64_t n_elements,
+                     int64_t n_nodes, int64_t m0, int64_t m1, unsigned char *node_flag,
+                     int32_t *pos, int64_t *counts_host, void *stream);
+int p1_block_submesh_fill(p1_ctx *ctx, const int32_t *elements, int64_t n_elements,
+                          const int32_t *pos, int32_t *sub_elements, int32_t *sub_ids,
+                          void *stream);
+int p1_eta_r_partial(const p1_plan *plan, const double *coords, const double *x,
+                     const int32_t *dirichlet, int64_t n_dirichlet,
+                     const int32_t *neumann, int64_t n_neumann,
+                     const double *neumann_term, const double *f_centroid,
+                     double *eta, void *stream);
 /* |E_j| and midpoints of boundary edges (indicators.py:70-76): length (K),
  * midpoint (K x 2). */
 int p1_boundary_edges(p1_ctx *ctx, const double *coords,

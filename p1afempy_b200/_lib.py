@@ -81,6 +81,9 @@ PROTOTYPES = {
                      C.POINTER(_i64)],
     'p1_assemble_csr': [_vp, _int, _vp, _vp, _vp, _vp, _vp, _vp],
     'p1_element_neighbours': [_vp, _vp, _vp],
+    'p1_block_submesh': [_vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp],
+    'p1_block_submesh_fill': [_vp, _vp, _i64, _vp, _vp, _vp, _vp],
+    'p1_eta_r_partial': [_vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp],
     'p1_nvb_sort_longest_edge': [_vp, _vp, _vp, _i64, _vp],
     'p1_nvb_plan': [_vp, _i64, _i64, _vp, _vp, _i64, _vp, _vp, _int, _vp, _vp, _vp, _vp, _vp,
                     _vp],

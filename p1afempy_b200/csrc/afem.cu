@@ -577,3 +577,107 @@ extern "C" int p1_pcg(p1_ctx *ctx, int64_t n, const int32_t *indptr, const int32
   if (relative_residual_host) *relative_residual_host = rr0 > 0. ? sqrt(rr / rr0) : 0.;
   return P1_OK;
 }
+
+// ------------------------------------------------- element blocks (multi-GPU eta_R)
+// The estimator of an element needs its three neighbours, hence the complete fans of
+// its three nodes.  A rank that owns the element block [m0, m1) therefore works on the
+// sub-mesh of all elements that touch a node of the block (the block and a ring of
+// neighbours): the indicators of the block's elements computed there are the global
+// ones bit for bit.
+namespace p1 {
+__global__ void __launch_bounds__(AT)
+block_nodes_kernel(const int *__restrict__ elements, int64_t m0, int64_t m1, int N,
+                   unsigned char *__restrict__ node_flag, int *__restrict__ bad) {
+  for (int64_t i = 3 * m0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < 3 * m1;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int v = elements[i];
+    if ((unsigned)v >= (unsigned)N) { *bad = 1; continue; }
+    node_flag[v] = 1;
+  }
+}
+__global__ void __launch_bounds__(AT)
+block_keep_kernel(const int *__restrict__ elements, int64_t M, int N,
+                  const unsigned char *__restrict__ node_flag, int *__restrict__ keep,
+                  int *__restrict__ bad) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < M; t += stride) {
+    const int a = __ldg(elements + 3 * t), b = __ldg(elements + 3 * t + 1),
+              c = __ldg(elements + 3 * t + 2);
+    if ((unsigned)a >= (unsigned)N || (unsigned)b >= (unsigned)N || (unsigned)c >= (unsigned)N) {
+      *bad = 1;
+      keep[t] = 0;
+      continue;
+    }
+    keep[t] = (node_flag[a] | node_flag[b] | node_flag[c]) != 0;
+  }
+}
+__global__ void __launch_bounds__(AT)
+block_gather_kernel(const int *__restrict__ elements, int64_t M, const int *__restrict__ pos,
+                    int *__restrict__ sub_elements, int *__restrict__ sub_ids) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < M; t += stride) {
+    const int p = pos[t];
+    if (pos[t + 1] == p) continue;
+    sub_elements[3 * (int64_t)p] = elements[3 * t];
+    sub_elements[3 * (int64_t)p + 1] = elements[3 * t + 1];
+    sub_elements[3 * (int64_t)p + 2] = elements[3 * t + 2];
+    if (sub_ids) sub_ids[p] = (int)t;
+  }
+}
+}  // namespace p1
+
+// Stage 1: node_flag[v] = 1 for the nodes of the block (N bytes, caller's), pos (M + 1
+// ints, caller's) = exclusive scan of "element touches a flagged node".
+// counts_host: [0] elements of the sub-mesh, [1] position of element m0 in it (the
+// block's elements follow one another there).  SYNCHRONISES.
+extern "C" int p1_block_submesh(p1_ctx *ctx, const int32_t *elements, int64_t n_elements,
+                                int64_t n_nodes, int64_t m0, int64_t m1,
+                                unsigned char *node_flag, int32_t *pos, int64_t *counts_host,
+                                void *stream) {
+  P1_REQUIRE(ctx && counts_host && n_elements >= 0 && n_nodes >= 0 && m0 >= 0 && m0 <= m1 &&
+                 m1 <= n_elements, "bad argument");
+  P1_REQUIRE(n_elements == 0 || (elements && node_flag && pos), "null array");
+  DeviceGuard guard(ctx);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t M = n_elements;
+  counts_host[0] = counts_host[1] = 0;
+  if (M == 0) return P1_OK;
+  cudaMemsetAsync(ctx->d_flags, 0, 8 * sizeof(int), s);
+  cudaMemsetAsync(node_flag, 0, (size_t)n_nodes, s);
+  if (m1 > m0)
+    block_nodes_kernel<<<agrid(ctx, 3 * (m1 - m0)), AT, 0, s>>>(elements, m0, m1, (int)n_nodes,
+                                                                node_flag, ctx->d_flags);
+  int *keep = nullptr;
+  P1_TRY(pool_alloc(ctx, &keep, (size_t)M + 1, s));
+  block_keep_kernel<<<agrid(ctx, M), AT, 0, s>>>(elements, M, (int)n_nodes, node_flag, keep,
+                                                 ctx->d_flags);
+  int rc = exclusive_scan_i32(ctx, keep, pos, M, true, s);
+  pool_free(ctx, keep, s);
+  if (rc) return rc;
+  int h[2] = {0, 0};
+  cudaMemcpyAsync(&h[0], pos + M, sizeof(int), cudaMemcpyDeviceToHost, s);
+  cudaMemcpyAsync(&h[1], pos + m0, sizeof(int), cudaMemcpyDeviceToHost, s);
+  cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, sizeof(int), cudaMemcpyDeviceToHost, s);
+  P1_CUDA(cudaStreamSynchronize(s));
+  if (ctx->h_flags[0]) {
+    set_error("p1_block_submesh: element index out of range [0, %lld)", (long long)n_nodes);
+    return P1_EINDEX;
+  }
+  counts_host[0] = h[0];
+  counts_host[1] = h[1];
+  return P1_OK;
+}
+
+// Stage 2: the sub-mesh's elements (counts[0] x 3) and, optionally, their global indices.
+extern "C" int p1_block_submesh_fill(p1_ctx *ctx, const int32_t *elements, int64_t n_elements,
+                                     const int32_t *pos, int32_t *sub_elements,
+                                     int32_t *sub_ids, void *stream) {
+  P1_REQUIRE(ctx && n_elements >= 0 && (n_elements == 0 || (elements && pos && sub_elements)),
+             "bad argument");
+  DeviceGuard guard(ctx);
+  if (n_elements > 0)
+    block_gather_kernel<<<agrid(ctx, n_elements), AT, 0, (cudaStream_t)stream>>>(
+        elements, n_elements, pos, sub_elements, sub_ids);
+  P1_CUDA(cudaGetLastError());
+  return P1_OK;
+}

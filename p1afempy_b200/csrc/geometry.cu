@@ -635,11 +635,38 @@ extern "C" int p1_geometric_data(const p1_plan *cplan, const int32_t *boundary_n
   return P1_OK;
 }
 
+static int eta_r_impl(const p1_plan *cplan, const double *coords, const double *x,
+                      const int32_t *dirichlet, int64_t n_dirichlet,
+                      const int32_t *neumann, int64_t n_neumann,
+                      const double *neumann_term, const double *f_centroid,
+                      double *eta, void *stream, bool partial);
+
 extern "C" int p1_eta_r(const p1_plan *cplan, const double *coords, const double *x,
                         const int32_t *dirichlet, int64_t n_dirichlet,
                         const int32_t *neumann, int64_t n_neumann,
                         const double *neumann_term, const double *f_centroid,
                         double *eta, void *stream) {
+  return eta_r_impl(cplan, coords, x, dirichlet, n_dirichlet, neumann, n_neumann, neumann_term,
+                    f_centroid, eta, stream, false);
+}
+
+// The estimator on a SUB-mesh (an element block and its ring, p1_block_submesh): open
+// half-edges that no boundary lists are the cut through the mesh, not an error; the
+// indicators of the elements next to the cut are meaningless and the caller drops them.
+extern "C" int p1_eta_r_partial(const p1_plan *cplan, const double *coords, const double *x,
+                                const int32_t *dirichlet, int64_t n_dirichlet,
+                                const int32_t *neumann, int64_t n_neumann,
+                                const double *neumann_term, const double *f_centroid,
+                                double *eta, void *stream) {
+  return eta_r_impl(cplan, coords, x, dirichlet, n_dirichlet, neumann, n_neumann, neumann_term,
+                    f_centroid, eta, stream, true);
+}
+
+static int eta_r_impl(const p1_plan *cplan, const double *coords, const double *x,
+                      const int32_t *dirichlet, int64_t n_dirichlet,
+                      const int32_t *neumann, int64_t n_neumann,
+                      const double *neumann_term, const double *f_centroid,
+                      double *eta, void *stream, bool partial) {
   P1_REQUIRE(cplan, "null plan");
   p1_plan *p = const_cast<p1_plan *>(cplan);
   p1_ctx *ctx = p->ctx;
@@ -651,7 +678,7 @@ extern "C" int p1_eta_r(const p1_plan *cplan, const double *coords, const double
   DeviceGuard guard(ctx);
   cudaStream_t s = (cudaStream_t)stream;
   P1_TRY(ensure_twins(p, s));
-  if (p->n_open != n_dirichlet + n_neumann) {
+  if (!partial && p->n_open != n_dirichlet + n_neumann) {
     set_error("p1_eta_r: shape mismatch: the mesh has %lld boundary edges but "
               "dirichlet+neumann list %lld", (long long)p->n_open,
               (long long)(n_dirichlet + n_neumann));

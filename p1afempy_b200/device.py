@@ -621,18 +621,57 @@ class DeviceMesh:
                                                    _stream(self.device)))
         return out
 
-    def eta_r(self, x, dirichlet, neumann, neumann_term, f_centroid):
+    def eta_r(self, x, dirichlet, neumann, neumann_term, f_centroid, partial=False):
+        """partial: this mesh is a cut-out of a larger one (eta_r_block): open edges
+        that no boundary lists are the cut, not an error."""
         x = to_device_f64(x, self.device, (self.n_nodes,))
         fc = to_device_f64(f_centroid, self.device, (self.n_elements,))
         nt = (to_device_f64(neumann_term, self.device, (neumann.shape[0],))
               if neumann.shape[0] else None)
         eta = self._empty(self.n_elements)
-        _lib.check(self._lib.p1_eta_r(
+        fn = self._lib.p1_eta_r_partial if partial else self._lib.p1_eta_r
+        _lib.check(fn(
             self._element_plan(True), _ptr(self.coords), _ptr(x),
             _ptr(dirichlet) if dirichlet.shape[0] else None, int(dirichlet.shape[0]),
             _ptr(neumann) if neumann.shape[0] else None, int(neumann.shape[0]),
             _ptr(nt), _ptr(fc), _ptr(eta), _stream(self.device)))
         return eta
+
+    def eta_r_block(self, x, dirichlet, neumann, neumann_term, f_centroid, m0, m1):
+        """eta_R of the elements [m0, m1) only -- one rank's share of a multi-GPU
+        estimator (indicators.py:7-86): computed on the sub-mesh of the elements that
+        touch a node of the block (p1_block_submesh), where the block's indicators are
+        the global ones bit for bit.  dirichlet / neumann / neumann_term: the GLOBAL
+        boundary lists; f_centroid: (M,) values for all elements."""
+        m, n = self.n_elements, self.n_nodes
+        m0, m1 = int(m0), int(m1)
+        flag = self._empty(n, torch.uint8)
+        pos = self._empty(m + 1, torch.int32)
+        counts = np.zeros(2, dtype=np.int64)
+        _lib.check(self._lib.p1_block_submesh(
+            self.ctx, _ptr(self.elements), m, n, m0, m1, _ptr(flag), _ptr(pos),
+            counts.ctypes.data_as(C.c_void_p), _stream(self.device)))
+        n_sub, start = int(counts[0]), int(counts[1])
+        sub = self._empty((n_sub, 3), torch.int32)
+        ids = self._empty(n_sub, torch.int32)
+        _lib.check(self._lib.p1_block_submesh_fill(
+            self.ctx, _ptr(self.elements), m, _ptr(pos), _ptr(sub), _ptr(ids),
+            _stream(self.device)))
+        del pos
+
+        def inside(edges):      # boundary edges of the sub-mesh that matter: both nodes flagged
+            if edges.shape[0] == 0:
+                return torch.zeros(0, dtype=torch.bool, device=flag.device)
+            return (flag[edges[:, 0].long()] & flag[edges[:, 1].long()]).bool()
+        kd, kn = inside(dirichlet), inside(neumann)
+        d_sub, n_sub_edges = dirichlet[kd].contiguous(), neumann[kn].contiguous()
+        term = None
+        if neumann.shape[0]:
+            term = to_device_f64(neumann_term, self.device, (neumann.shape[0],))[kn].contiguous()
+        fc = to_device_f64(f_centroid, self.device, (m,))[ids.long()].contiguous()
+        with DeviceMesh(self.coords, sub, device=self.device, check=False) as part:
+            eta = part.eta_r(x, d_sub, n_sub_edges, term, fc, partial=True)
+        return eta[start:start + (m1 - m0)]
 
     # ------------------------------------------------------------ host side
     def widen_indices(self, t):

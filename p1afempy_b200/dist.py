@@ -205,6 +205,20 @@ class DistributedMesh:
         """Entries of the legacy load vector (solvers.py:414-426) at the owned rows."""
         return self.local.load_vector_midpoint(f_centroid)
 
+    def element_block(self):
+        """The calling rank's contiguous block of elements [m0, m1) (the estimator is
+        per element: it is dealt out by elements, not by rows)."""
+        m = self.local.n_elements
+        return m * self.rank // self.world, m * (self.rank + 1) // self.world
+
+    def eta_r(self, x, dirichlet, neumann, neumann_term, f_centroid):
+        """compute_eta_r (indicators.py:7-86) of the rank's element block: (m1 - m0,)
+        indicators, equal to the one-GPU result bit for bit.  Arguments as
+        DeviceMesh.eta_r (global boundary lists, f at all centroids).  No collective:
+        concatenating the ranks' pieces in rank order gives the whole vector."""
+        m0, m1 = self.element_block()
+        return self.local.eta_r_block(x, dirichlet, neumann, neumann_term, f_centroid, m0, m1)
+
     def global_chunk_offsets(self, indptr):
         return global_chunk_offsets(indptr, self.n_nodes, self.world, self.rank,
                                     self.chunk_log2, group=self.group)

@@ -200,3 +200,29 @@ def test_every_operator_on_interleaved_shares(world, chunk):
                 assert np.array_equal(data.cpu().numpy(), fdata[src]), name
             assert np.array_equal(mesh.load_vector(fq, w, p).cpu().numpy(), b_full[rows])
             assert np.array_equal(mesh.load_vector_midpoint(fc).cpu().numpy(), b0_full[rows])
+
+
+@pytest.mark.parametrize('world', [2, 5])
+def test_eta_r_by_element_blocks(world):
+    """Multi-GPU estimator: every rank (emulated) computes eta_R of its element block
+    on the sub-mesh of the elements touching the block's nodes; the pieces in rank
+    order are the one-GPU vector bit for bit -- with Dirichlet and Neumann parts."""
+    from p1afempy_b200.device import DeviceMesh, to_device_indices
+    for c, e, b in (H.graded_square(), H.perturbed_square(5)):
+        allb = np.vstack(b)
+        cut = (3 * allb.shape[0]) // 5
+        x = H.u_nodal(c) + 0.1 * c[:, 0]
+        ref = orc.eta_r(x, c, e, allb[:cut], allb[cut:], H.f_load, H.g_neu)
+        with DeviceMesh(c, e) as mesh:
+            d = to_device_indices(allb[:cut], mesh.device, mesh.ctx)
+            n = to_device_indices(allb[cut:], mesh.device, mesh.ctx)
+            length, mid = mesh.boundary_edges(n)
+            term = length * torch.from_numpy(H.g_neu(mid.cpu().numpy())).cuda()
+            fc = torch.from_numpy(H.f_load(mesh.centroids().cpu().numpy())).cuda()
+            xt = torch.from_numpy(x).cuda()
+            whole = mesh.eta_r(xt, d, n, term, fc).cpu().numpy()
+            assert np.array_equal(whole, ref)
+            m = e.shape[0]
+            pieces = [mesh.eta_r_block(xt, d, n, term, fc, m * r // world, m * (r + 1) // world)
+                      for r in range(world)]
+            assert np.array_equal(torch.cat(pieces).cpu().numpy(), ref)

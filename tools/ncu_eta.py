@@ -18,7 +18,7 @@ from p1afempy_b200.device import DeviceMesh
 level = int(sys.argv[1]) if len(sys.argv) > 1 else 12
 c, e = generate_mesh(level)
 mesh = DeviceMesh(c, e)
-w, p = cubature.resolve_rule(cubature.CubatureRuleEnum.DAYTAYLOR)
+w, p = cubature.resolve_rule(cubature.CubatureRuleEnum.CONICAL_GAUSS_4X4)
 xq = mesh.quadrature_points(p)
 fq = torch.sin(xq[..., 0]) + xq[..., 1]
 del xq

@@ -9,7 +9,7 @@ level = int(sys.argv[1])
 c, e = generate_mesh(level)
 ctx, dev = context(0); lib = _lib.load()
 mesh = DeviceMesh(c, e)
-w, p = cubature.resolve_rule(cubature.CubatureRuleEnum.DAYTAYLOR)
+w, p = cubature.resolve_rule(cubature.CubatureRuleEnum.CONICAL_GAUSS_4X4)
 xq = mesh.quadrature_points(p); fq = torch.sin(xq[..., 0]) + xq[..., 1]; del xq
 u = torch.sin(mesh.coords[:, 0]); fc = torch.ones(mesh.n_elements, dtype=torch.float64, device='cuda')
 b = torch.from_numpy(np.vstack(meshgen_boundary(level)).astype(np.int32)).cuda()
