@@ -46,11 +46,14 @@ struct p1_prof {
 };
 
 struct p1_arena {
-  struct Block { void *ptr; size_t bytes; bool used; cudaStream_t last; };
+  struct Block { void *ptr; size_t bytes; bool used; cudaStream_t last; unsigned long long tick; };
   std::vector<Block> blocks;
   std::mutex lock;
-  // unused blocks beyond this many bytes go back to the driver (largest first): torch's
-  // allocator cannot reclaim what sits here (p1_ctx_set_cache_limit)
+  unsigned long long clock = 0;
+  // unused blocks beyond this many bytes go back to the driver, least recently used
+  // first (not largest first: that evicts the record block the next call of a loop asks
+  // for again -- 34 GB at 256M triangles, re-allocated every step); torch's allocator
+  // cannot reclaim what sits here (p1_ctx_set_cache_limit)
   size_t limit = (size_t)48 << 30;
 };
 
@@ -74,6 +77,7 @@ int arena_alloc(p1_ctx *ctx, void **ptr, size_t bytes, cudaStream_t s) {
       if (b.last != s) cudaStreamSynchronize(b.last);
       b.used = true;
       b.last = s;
+      b.tick = ++ar->clock;
       *ptr = b.ptr;
       return P1_OK;
     }
@@ -97,7 +101,7 @@ int arena_alloc(p1_ctx *ctx, void **ptr, size_t bytes, cudaStream_t s) {
     return P1_ECUDA;
   }
   std::lock_guard<std::mutex> g(ar->lock);
-  ar->blocks.push_back({p, bytes, true, s});
+  ar->blocks.push_back({p, bytes, true, s, ++ar->clock});
   *ptr = p;
   return P1_OK;
 }
@@ -106,14 +110,14 @@ void arena_free(p1_ctx *ctx, void *ptr, cudaStream_t s) {
   p1_arena *ar = ctx->arena;
   std::lock_guard<std::mutex> g(ar->lock);
   for (auto &b : ar->blocks)
-    if (b.ptr == ptr) { b.used = false; b.last = s; break; }
+    if (b.ptr == ptr) { b.used = false; b.last = s; b.tick = ++ar->clock; break; }
   size_t idle = 0;
   for (auto &b : ar->blocks)
     if (!b.used) idle += b.bytes;
   while (idle > ar->limit) {
-    int big = -1;
+    int big = -1;  // (the least recently used idle block)
     for (int i = 0; i < (int)ar->blocks.size(); ++i)
-      if (!ar->blocks[i].used && (big < 0 || ar->blocks[i].bytes > ar->blocks[big].bytes)) big = i;
+      if (!ar->blocks[i].used && (big < 0 || ar->blocks[i].tick < ar->blocks[big].tick)) big = i;
     if (big < 0) break;
     cudaStreamSynchronize(ar->blocks[big].last);  // queued work may still use it
     cudaFree(ar->blocks[big].ptr);
