@@ -352,6 +352,15 @@ int p1_eta_r_partial(const p1_plan *plan, const double *coords, const double *x,
                      const int32_t *neumann, int64_t n_neumann,
                      const double *neumann_term, const double *f_centroid,
                      double *eta, void *stream);
+/* Multi-GPU matrices, interleaved ownership: the stored entries of each of the calling
+ * rank's chunks (out: per_rank int64, chunks beyond the rank's last one count 0) and,
+ * from the all-gathered values of every rank (every[r * per_rank + q]), the offset of
+ * each of its chunks in the GLOBAL CSR plus the global nnz -- one launch each around
+ * the one collective of a multi-GPU assembly. */
+int p1_chunk_nnz(p1_ctx *ctx, const int32_t *indptr, int64_t n_own, int chunk_log2,
+                 int64_t per_rank, int64_t *out, void *stream);
+int p1_chunk_offsets(p1_ctx *ctx, const int64_t *every, int world, int64_t per_rank, int rank,
+                     int64_t *mine, int64_t *total, void *stream);
 /* |E_j| and midpoints of boundary edges (indicators.py:70-76): length (K),
  * midpoint (K x 2). */
 int p1_boundary_edges(p1_ctx *ctx, const double *coords,

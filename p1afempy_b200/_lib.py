@@ -81,6 +81,8 @@ PROTOTYPES = {
                      C.POINTER(_i64)],
     'p1_assemble_csr': [_vp, _int, _vp, _vp, _vp, _vp, _vp, _vp],
     'p1_element_neighbours': [_vp, _vp, _vp],
+    'p1_chunk_nnz': [_vp, _vp, _i64, _int, _i64, _vp, _vp],
+    'p1_chunk_offsets': [_vp, _vp, _int, _i64, _int, _vp, _vp, _vp],
     'p1_block_submesh': [_vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp],
     'p1_block_submesh_fill': [_vp, _vp, _i64, _vp, _vp, _vp, _vp],
     'p1_eta_r_partial': [_vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp],

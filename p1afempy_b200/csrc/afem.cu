@@ -681,3 +681,76 @@ extern "C" int p1_block_submesh_fill(p1_ctx *ctx, const int32_t *elements, int64
   P1_CUDA(cudaGetLastError());
   return P1_OK;
 }
+
+// ------------------------------------------------ multi-GPU: global row pointer
+// Interleaved ownership (chunks of 2^c rows dealt round-robin): a rank's piece is
+// placed in the global CSR by the offset of each of its chunks.  chunk_nnz: the stored
+// entries of each of my chunks (one launch); after the all-gather of all ranks' values
+// chunk_offsets scans them in global chunk order (chunk q * world + r sits at
+// every[r * per_rank + q]) and keeps mine (one block).
+namespace p1 {
+__global__ void __launch_bounds__(AT)
+chunk_nnz_kernel(const int *__restrict__ indptr, int n_own, int cshift, int per_rank,
+                 long long *__restrict__ out) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= per_rank) return;
+  const long long lo = min((long long)q << cshift, (long long)n_own);
+  const long long hi = min(((long long)q + 1) << cshift, (long long)n_own);
+  out[q] = (long long)indptr[hi] - indptr[lo];
+}
+__global__ void __launch_bounds__(1024)
+chunk_offsets_kernel(const long long *__restrict__ every, int world, int per_rank, int rank,
+                     long long *__restrict__ mine, long long *__restrict__ total) {
+  __shared__ long long warp_sums[32];
+  __shared__ long long carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  const int n = world * per_rank;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int base = 0; base < n; base += 1024) {
+    const int g = base + threadIdx.x;           // global chunk index
+    const int r = g % world, q = g / world;
+    const long long v = g < n ? every[(long long)r * per_rank + q] : 0;
+    long long inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const long long t = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += t;
+    }
+    if (lane == 31) warp_sums[warp] = inc;
+    __syncthreads();
+    long long before = 0;
+    for (int w = 0; w < warp; ++w) before += warp_sums[w];
+    const long long carry = carry_s;
+    if (g < n && r == rank) mine[q] = carry + before + inc - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = carry + before + inc;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = carry_s;
+}
+}  // namespace p1
+
+extern "C" int p1_chunk_nnz(p1_ctx *ctx, const int32_t *indptr, int64_t n_own, int chunk_log2,
+                            int64_t per_rank, int64_t *out, void *stream) {
+  P1_REQUIRE(ctx && indptr && out && n_own >= 0 && per_rank >= 0 && chunk_log2 >= 0 &&
+                 chunk_log2 < 31, "bad argument");
+  DeviceGuard guard(ctx);
+  if (per_rank > 0)
+    chunk_nnz_kernel<<<grid_for(per_rank, AT), AT, 0, (cudaStream_t)stream>>>(
+        indptr, (int)n_own, chunk_log2, (int)per_rank, (long long *)out);
+  P1_CUDA(cudaGetLastError());
+  return P1_OK;
+}
+
+extern "C" int p1_chunk_offsets(p1_ctx *ctx, const int64_t *every, int world, int64_t per_rank,
+                                int rank, int64_t *mine, int64_t *total, void *stream) {
+  P1_REQUIRE(ctx && every && mine && total && world >= 1 && rank >= 0 && rank < world &&
+                 per_rank >= 0, "bad argument");
+  DeviceGuard guard(ctx);
+  chunk_offsets_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(
+      (const long long *)every, world, (int)per_rank, rank, (long long *)mine,
+      (long long *)total);
+  P1_CUDA(cudaGetLastError());
+  return P1_OK;
+}

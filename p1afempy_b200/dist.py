@@ -69,10 +69,23 @@ def global_chunk_offsets(indptr, n_rows, world, rank, chunk_log2, group=None):
     n_chunks = (n_rows + c - 1) >> chunk_log2
     per_rank = (n_chunks + world - 1) // world            # padded: same length on every rank
     n_own = indptr.numel() - 1
+    every = torch.empty(world * per_rank, dtype=torch.int64, device=dev)
+    if dev.type == 'cuda':       # two launches around the collective (csrc/afem.cu)
+        from . import _lib
+        from .device import _ptr, _stream, context
+        ctx, _ = context(dev.index)
+        lib = _lib.load()
+        mine = torch.empty(per_rank, dtype=torch.int64, device=dev)
+        _lib.check(lib.p1_chunk_nnz(ctx, _ptr(indptr), n_own, chunk_log2, per_rank, _ptr(mine),
+                                    _stream(dev.index)))
+        dist.all_gather_into_tensor(every, mine, group=group)
+        offs = torch.empty(per_rank + 1, dtype=torch.int64, device=dev)
+        _lib.check(lib.p1_chunk_offsets(ctx, _ptr(every), world, per_rank, rank, _ptr(offs),
+                                        _ptr(offs[per_rank:]), _stream(dev.index)))
+        return offs[:per_rank], offs[per_rank]
     starts = torch.arange(0, per_rank * c, c, dtype=torch.int64, device=dev).clamp_(max=n_own)
     ends = (starts + c).clamp_(max=n_own)
     mine = (indptr[ends] - indptr[starts]).to(torch.int64)   # nnz of my chunks (0: padding)
-    every = torch.empty(world * per_rank, dtype=torch.int64, device=dev)
     dist.all_gather_into_tensor(every, mine, group=group)
     in_order = every.reshape(world, per_rank).t().reshape(-1)   # chunk q * world + r
     offs = torch.cumsum(in_order, 0) - in_order

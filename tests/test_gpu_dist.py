@@ -99,8 +99,30 @@ def _nccl_worker(rank, world, port, result_path):
     try:
         c, e, b = meshgen.unit_square(6)
         c = meshgen.perturb_interior(c, b, 0.002)
-        dm = pdist.DistributedMesh(c, e, device=rank)
-        out = dm.gather(*dm.stiffness_csr(), root=0)
+        dm = pdist.DistributedMesh(c, e, device=rank, chunk_log2=6)
+        ip, ix, data = dm.stiffness_csr()
+        # where my chunks start in the global CSR (two kernels around one all-gather)
+        full = orc.stiffness_coo(c, e).tocsr()
+        offs, total = dm.global_chunk_offsets(ip)
+        mine = np.arange(rank, (c.shape[0] + 63) // 64, world)
+        assert int(total) == full.nnz
+        assert np.array_equal(offs.cpu().numpy()[:mine.size], full.indptr[mine * 64])
+        gptr, _ = dm.global_row_pointer(ip)
+        assert np.array_equal(gptr.cpu().numpy(), full.indptr[dm.global_rows().cpu().numpy()])
+        # the estimator by element blocks
+        allb = np.vstack(b)
+        from p1afempy_b200.device import to_device_indices
+        d = to_device_indices(allb, rank, dm.local.ctx)
+        none = torch.zeros((0, 2), dtype=torch.int32, device='cuda')
+        x = H.u_nodal(c)
+        fc = torch.from_numpy(H.f_load((c[e[:, 0]] + c[e[:, 1]] + c[e[:, 2]]) / 3.)).cuda()
+        eta = dm.eta_r(torch.from_numpy(x).cuda(), d, none, None, fc).cpu().numpy()
+        m0, m1 = dm.element_block()
+        ref_eta = orc.eta_r(x, c, e, allb, np.zeros((0, 2), dtype=int),
+                            lambda r: H.f_load((c[e[:, 0]] + c[e[:, 1]] + c[e[:, 2]]) / 3.),
+                            H.g_neu)
+        assert np.array_equal(eta, ref_eta[m0:m1])
+        out = dm.gather(ip, ix, data, root=0)
         if rank == 0:
             ref = orc.stiffness_coo(c, e).tocsr()
             gi, gx, gd = (t.cpu().numpy() for t in out)
@@ -111,6 +133,15 @@ def _nccl_worker(rank, world, port, result_path):
         dm.close()
     finally:
         dist.destroy_process_group()
+
+
+def test_one_rank_nccl(tmp_path):
+    """The NCCL code path with a world of one (any box): DistributedMesh, the global
+    row pointer kernels, the estimator by element blocks, the gather."""
+    import torch.multiprocessing as mp
+    result = tmp_path / 'r.txt'
+    mp.spawn(_nccl_worker, args=(1, _free_port(), str(result)), nprocs=1, join=True)
+    assert result.read_text() == 'ok'
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs')
