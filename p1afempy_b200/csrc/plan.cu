@@ -167,52 +167,29 @@ __device__ __forceinline__ void scatter_element(int64_t t, const int (&e)[3], in
   }
 }
 
-// Two consecutive triangles at once: NVB siblings share two of their three
-// vertices, so the 6 vertex references are grouped in registers -- one atomic
-// per DISTINCT node (typically 4 instead of 6).  The kernel is bound by LSU
-// operations per lane; the 15 comparisons are free.
-template <class V, int TOPO>
-__device__ __forceinline__ void scatter_pair(int64_t t, const int (&id)[6], int N,
-                                             const Own &own,
-                                             unsigned long long *__restrict__ acc,
-                                             Rec *__restrict__ rec,
-                                             int *__restrict__ rec_elem, const V &values,
-                                             int &mx, bool &bad, int *flags, int (&where)[6],
-                                             const SpillDesc *spill = nullptr) {
-  // where[i]: slot index of reference i (TOPO 1: the caller stores them, 48 bytes
-  // per thread at once -- 4-byte stores per record cost 1.2 ms at 64M)
-#pragma unroll
-  for (int i = 0; i < 6; ++i) where[i] = -1;
-  bool valid[2], touched[2], mine[6];
+// Phase 1 of a triangle pair: one atomic per DISTINCT owned node; returns the slot of
+// each of the 6 references, 5 bits each (30: full row and beyond).  (The kernel keeps
+// no pipe busy: LSU wavefronts 55 %, issue 32 %, DRAM 60 % --
+// profiles/r02_default_path_64M_ncu_full.csv.)
+__device__ __forceinline__ unsigned pair_claim(const int (&id)[6], int N, const Own &own,
+                                               unsigned long long *__restrict__ acc, int &mx,
+                                               bool &bad) {
+  bool valid[2], mine[6];
   int row[6];
 #pragma unroll
   for (int j = 0; j < 2; ++j) {
     valid[j] = (unsigned)id[3 * j] < (unsigned)N && (unsigned)id[3 * j + 1] < (unsigned)N &&
                (unsigned)id[3 * j + 2] < (unsigned)N;
     bad = bad || !valid[j];
-    touched[j] = false;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
       const int i = 3 * j + k;
       row[i] = 0;
       mine[i] = valid[j] && own.owns(id[i], row[i]);
-      touched[j] = touched[j] || mine[i];
       if (valid[j]) mx = max(mx, id[i]);
     }
   }
-  if (!(touched[0] || touched[1])) return;
-  // (coordinates are NOT shared between the two triangles: lanes of one gather
-  // instruction that hit the same sector already cost one LSU wavefront, and the
-  // selects cost more than they save -- measured 2.20 ms with, 2.14 ms without)
-  double2 z[6];
-  if constexpr (V::needs_xy) {
-#pragma unroll
-    for (int i = 0; i < 6; ++i) {
-      z[i] = make_double2(0., 0.);
-      if (touched[i / 3]) z[i] = __ldg(values.coords + id[i]);
-    }
-  }
-  unsigned slot[6], base[6];
+  unsigned base[6], packed = 0;
 #pragma unroll
   for (int i = 0; i < 6; ++i) {
     base[i] = 0;
@@ -236,8 +213,52 @@ __device__ __forceinline__ void scatter_pair(int64_t t, const int (&id)[6], int 
         }
       base[i] = (unsigned)atomicAdd(acc + row[i], ((unsigned long long)h << 32) + cnt);
     }
-    slot[i] = mine[i] ? base[i] + rank : 0xffu;
+    packed |= min(base[i] + rank, 30u) << (5 * i);
   }
+  return packed;
+}
+
+// Phase 2: the values of the two triangles and one slot store per owned reference.
+template <class V, int TOPO>
+__device__ __forceinline__ void pair_deliver(int64_t t, const int (&id)[6], unsigned packed, int N,
+                                             const Own &own, Rec *__restrict__ rec,
+                                             int *__restrict__ rec_elem, const V &values,
+                                             int *flags, int (&where)[6],
+                                             const SpillDesc *spill = nullptr) {
+  // where[i]: slot index of reference i (TOPO 1: the caller stores them, 48 bytes
+  // per thread at once -- 4-byte stores per record cost 1.2 ms at 64M)
+#pragma unroll
+  for (int i = 0; i < 6; ++i) where[i] = -1;
+  bool valid[2], touched[2], mine[6];
+  int row[6];
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    valid[j] = (unsigned)id[3 * j] < (unsigned)N && (unsigned)id[3 * j + 1] < (unsigned)N &&
+               (unsigned)id[3 * j + 2] < (unsigned)N;
+    touched[j] = false;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int i = 3 * j + k;
+      row[i] = 0;
+      mine[i] = valid[j] && own.owns(id[i], row[i]);
+      touched[j] = touched[j] || mine[i];
+    }
+  }
+  if (!(touched[0] || touched[1])) return;
+  // (coordinates are NOT shared between the two triangles: lanes of one gather
+  // instruction that hit the same sector already cost one LSU wavefront, and the
+  // selects cost more than they save -- measured 2.20 ms with, 2.14 ms without)
+  double2 z[6];
+  if constexpr (V::needs_xy) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      z[i] = make_double2(0., 0.);
+      if (touched[i / 3]) z[i] = __ldg(values.coords + id[i]);
+    }
+  }
+  unsigned slot[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) slot[i] = mine[i] ? (packed >> (5 * i)) & 31u : 0xffu;
   bool over = false;  // some owned reference found its row full
 #pragma unroll
   for (int j = 0; j < 2; ++j) {
@@ -324,6 +345,22 @@ __device__ __forceinline__ void scatter_pair(int64_t t, const int (&id)[6], int 
   }
 }
 
+// Two consecutive triangles at once: NVB siblings share two of their three
+// vertices, so the 6 vertex references are grouped in registers -- one atomic
+// per DISTINCT node (typically 4 instead of 6).  The kernel is bound by LSU
+// operations per lane; the 15 comparisons are free.
+template <class V, int TOPO>
+__device__ __forceinline__ void scatter_pair(int64_t t, const int (&id)[6], int N,
+                                             const Own &own,
+                                             unsigned long long *__restrict__ acc,
+                                             Rec *__restrict__ rec,
+                                             int *__restrict__ rec_elem, const V &values,
+                                             int &mx, bool &bad, int *flags, int (&where)[6],
+                                             const SpillDesc *spill = nullptr) {
+  const unsigned packed = pair_claim(id, N, own, acc, mx, bad);
+  pair_deliver<V, TOPO>(t, id, packed, N, own, rec, rec_elem, values, flags, where, spill);
+}
+
 // `vec` != 0: elements is 16-byte aligned; a thread then reads 4 triangles =
 // 12 indices as three 128-bit loads (the scalar form reads 12 B at stride 12 B
 // and spends 0.45 ms just scanning 64M triangles).
@@ -347,12 +384,18 @@ scatter_kernel(const int *__restrict__ elements, int64_t M, int N, Own own, int 
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t quads = vec ? M / 4 : 0;
   const int4 *e4 = reinterpret_cast<const int4 *>(elements);
+  // (prefetching the next quad's indices -- the kernel waits on memory: long-scoreboard
+  // stalls 13 per issue at 24 warps per SM -- costs 36 registers, i.e. a resident block:
+  // 2.13 -> 2.60 ms at 64M)
   for (int64_t g = tid; g < quads; g += stride) {
     const int4 p = __ldg(e4 + 3 * g), q = __ldg(e4 + 3 * g + 1), r = __ldg(e4 + 3 * g + 2);
     if constexpr (!OVERFLOW && PAIRS) {
       const int ab[6] = {p.x, p.y, p.z, p.w, q.x, q.y}, cd[6] = {q.z, q.w, r.x, r.y, r.z, r.w};
       int w0[6], w1[6];
       const SpillDesc *sp = reinterpret_cast<const SpillDesc *>(cursor);
+      // (claiming both pairs before delivering the first -- eight atomics in flight per
+      // thread instead of four -- was measured at 64M: stiffness scatter 2.13 -> 2.51 ms,
+      // mass 2.19 -> 2.16: the atomics' latency is not what the kernel waits for)
       scatter_pair<V, TOPO>(4 * g, ab, N, own, acc, rec, rec_elem, values, mx, bad, flags, w0, sp);
       scatter_pair<V, TOPO>(4 * g + 2, cd, N, own, acc, rec, rec_elem, values, mx, bad, flags, w1,
                             sp);
