@@ -211,7 +211,12 @@ int p1_assemble_csr(const p1_plan *plan, int op, const double *coords,
  * the capacity; P1_STATUS_RETRY: as P1_ERETRY) or reports the error (INDEX).
  * world / rank / chunk_log2 as for p1_plan_create_interleaved (1, 0, 0: all rows).
  * qa: P1_OP_GENERAL / P1_OP_WEIGHTED only, else NULL.  Scratch memory returns to the
- * context's arena in stream order. */
+ * context's arena in stream order.
+ * Meshes of at most 4M triangles (P1_OP_STIFFNESS / MASS / LOCAL, profiler off): the
+ * second call with exactly the same arguments (pointers, sizes, stream) records the
+ * launch sequence as a CUDA graph and later calls replay it with ONE launch; the
+ * arrays' CONTENT may change freely between calls.  The context keeps the 8 most
+ * recently used graphs with their scratch until p1_ctx_trim / p1_ctx_destroy. */
 #define P1_STATUS_INDEX 1
 #define P1_STATUS_RETRY 16
 #define P1_STATUS_SLOWPATH 64

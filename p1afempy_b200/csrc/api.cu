@@ -126,6 +126,8 @@ void arena_free(p1_ctx *ctx, void *ptr, cudaStream_t s) {
   }
 }
 
+bool prof_enabled(const p1_ctx *ctx) { return ctx && ctx->prof && ctx->prof->on; }
+
 void prof_begin(p1_ctx *ctx, const char *name, cudaStream_t s) {
   if (!ctx || !ctx->prof || !ctx->prof->on) return;
   p1_prof::Span sp{name, ctx->prof->get(), ctx->prof->get()};
@@ -177,6 +179,7 @@ extern "C" int p1_profile_report(p1_ctx *ctx, char *buf, int64_t cap) {
 extern "C" int p1_ctx_trim(p1_ctx *ctx) {
   P1_REQUIRE(ctx, "null ctx");
   DeviceGuard guard(ctx);
+  cold_cache_clear(ctx);
   std::lock_guard<std::mutex> g(ctx->arena->lock);
   cudaDeviceSynchronize();
   auto &bl = ctx->arena->blocks;
@@ -219,6 +222,8 @@ extern "C" int p1_ctx_create(int device, p1_ctx **out) {
   ctx->d_flags = nullptr;
   ctx->h_flags = nullptr;
   ctx->prof = nullptr;
+  ctx->cold = nullptr;
+  ctx->rowptr_resident = 0;
   ctx->arena = new p1_arena();
   if (cudaMalloc((void **)&ctx->d_flags, 8 * sizeof(int)) != cudaSuccess ||
       cudaMallocHost((void **)&ctx->h_flags, 8 * sizeof(int)) != cudaSuccess) {
@@ -237,6 +242,7 @@ extern "C" int p1_ctx_destroy(p1_ctx *ctx) {
   if (ctx->d_flags) cudaFree(ctx->d_flags);
   if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
   if (ctx->prof) { ctx->prof->drain(); delete ctx->prof; }
+  cold_cache_clear(ctx);
   if (ctx->arena) {
     cudaDeviceSynchronize();
     for (auto &b : ctx->arena->blocks) cudaFree(b.ptr);

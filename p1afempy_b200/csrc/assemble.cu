@@ -382,8 +382,79 @@ __device__ __forceinline__ void slow_row_values(int self, int deg, const Rec *nb
 // from inside the fast kernels, by the thread that owns the row: no row list, no
 // extra launch.  Same routine, same bits as fill_slow_kernel.  (noinline: the hot
 // path keeps its registers)
+// The irregular row a mesh has many of -- ONE open, repeat-free fan around a node of the
+// mesh boundary: deg + 2 columns (the fan's first `prev` has no `next` to merge with),
+// found by the all-pairs comparison of row_from_records, in registers.  False: not such a
+// row.  Same sums as slow_row_values: an entry is next-value + prev-value of (at most) two
+// records, the diagonal adds the (k,k) entries in ascending column of `next`.
+// nb: global or local memory.
+__device__ __forceinline__ bool open_fan_row(int self, int deg, const Rec *nb, int *cs,
+                                             double *vs) {
+  int nx[GROUP], pv[GROUP], slot[GROUP];
+  double vd[GROUP], vn[GROUP], vp[GROUP], mvp[GROUP];
+#pragma unroll
+  for (int i = 0; i < GROUP; ++i) {
+    nx[i] = 0x7fffffff - i;
+    pv[i] = -2 - i;
+    vd[i] = vn[i] = vp[i] = 0.;
+    if (i < deg) {
+      const Rec r = nb[i];
+      nx[i] = r.nx; pv[i] = rec_prev(r);
+      vd[i] = r.vd; vn[i] = r.vn; vp[i] = r.vp;
+    }
+  }
+  bool ok = true;
+  int slot_self = 0, unmated = 0, n_first = 0, first_col = 0;
+  double first_val = 0.;
+#pragma unroll
+  for (int i = 0; i < GROUP; ++i) {
+    int below = 0;
+    bool mated = false, sourced = false;
+    mvp[i] = 0.;
+#pragma unroll
+    for (int j = 0; j < GROUP; ++j) {
+      below += nx[j] < nx[i];
+      if (pv[j] == nx[i]) { mvp[i] = vp[j]; mated = true; }
+      sourced = sourced || nx[j] == pv[i];
+      if (j > i) ok = ok && nx[j] != nx[i] && pv[j] != pv[i];
+    }
+    const bool live = i < deg;
+    ok = ok && (!live || (nx[i] != self && pv[i] != self));
+    unmated += live && !mated;
+    if (live && !sourced) { ++n_first; first_col = pv[i]; first_val = vp[i]; }
+    slot[i] = below + (self < nx[i]);
+    slot_self += live && nx[i] < self;
+  }
+  if (!ok || unmated != 1 || n_first != 1) return false;
+  int slot_first = self < first_col;
+#pragma unroll
+  for (int i = 0; i < GROUP; ++i) {
+    slot_first += nx[i] < first_col;  // (unused slots hold columns above any node)
+    slot[i] += first_col < nx[i];
+  }
+  slot_self += first_col < self;
+  vs[slot_first] = 0.;
+#pragma unroll
+  for (int i = 0; i < GROUP; ++i)
+    if (i < deg) vs[slot[i]] = vd[i];
+  double diag = 0.;
+  for (int q = 0; q < deg + 2; ++q)
+    if (q != slot_self) diag += vs[q];
+#pragma unroll
+  for (int i = 0; i < GROUP; ++i)
+    if (i < deg) {
+      if (cs) cs[slot[i]] = nx[i];
+      vs[slot[i]] = vn[i] + mvp[i];
+    }
+  if (cs) { cs[slot_first] = first_col; cs[slot_self] = self; }
+  vs[slot_first] = 0. + first_val;
+  vs[slot_self] = diag;
+  return true;
+}
+
 __device__ __noinline__ void slow_row_inline(int self, int deg, const Rec *nb, int *cs_out,
                                              double *vs_out) {
+  if (open_fan_row(self, deg, nb, cs_out, vs_out)) return;
   int cs[2 * GROUP + 1];
   const int n = slow_row_columns(self, deg, nb, cs);
   if (cs_out)

@@ -52,6 +52,7 @@ enum : int {
 
 struct p1_prof;
 struct p1_arena;
+struct p1_cold_cache;
 struct p1_ctx {
   int device;
   int sm_count;
@@ -59,6 +60,8 @@ struct p1_ctx {
   int *h_flags;        // pinned mirror
   p1_prof *prof;       // per-kernel CUDA-event timing, off unless enabled
   p1_arena *arena;     // cached scratch blocks
+  p1_cold_cache *cold; // CUDA graphs of small cold assemblies (plan.cu), or null
+  int rowptr_resident; // tiles of the fused row-pointer kernel resident at once (0: not asked yet)
   // The status words, their mirror and the profiler are one per context: every entry
   // point holds this lock from start to return (DeviceGuard), so calls on one context
   // from several host threads serialise instead of clearing each other's flags.
@@ -115,6 +118,9 @@ inline unsigned grid_for(int64_t n, int block, int per_thread = 1) {
 
 // Per-kernel timing with CUDA events on the launching stream (bench.py reads
 // it through p1_profile_report).  No-ops unless p1_profile_enable(ctx, 1).
+bool prof_enabled(const p1_ctx *ctx);
+// releases the cached CUDA graphs of p1_assemble_cold and their scratch (plan.cu)
+void cold_cache_clear(p1_ctx *ctx);
 void prof_begin(p1_ctx *ctx, const char *name, cudaStream_t s);
 void prof_end(p1_ctx *ctx, cudaStream_t s);
 #define P1_TIMED(ctx, name, s, ...)                                           \

@@ -19,6 +19,8 @@
 // the spill lists for rows with more than 8 records, split / row lengths, the
 // plan-free load vectors (p1_load_vector*_direct), row partitioning for
 // multi-GPU, plan_build and the p1_plan_* entry points.
+#include <cooperative_groups.h>
+
 #include "plan.cuh"
 #include <stdlib.h>
 #include <vector>
@@ -1538,25 +1540,38 @@ namespace p1 {
 // records: the plan route (FLAG_SLOWPATH).  Both passes recompute the lengths from the
 // nodes' counters (8 bytes per row) instead of storing them.
 
-// length of row a (see above); big: more than 8 records
-__device__ __forceinline__ int cold_row_length(const Rows &rows, const Own &own, int a,
-                                               unsigned long long v, bool &big) {
+// length of row a (see above) from its counter alone, or -1: an open fan, which
+// open_row_length counts from the row's records.  big: more than 8 records
+__device__ __forceinline__ int cold_row_length(unsigned long long v, bool &big) {
   const int deg = (int)(unsigned)v;
   if (deg > GROUP) { big = true; return 0; }
   if (deg == 0) return 0;
   if ((unsigned)(v >> 32) == 0u) return 1 + deg;  // closed fan (verified when the row is filled)
-  // open fan: distinct values of {self} U {next_i} U {prev_i}
+  return -1;
+}
+
+// open fan (1 <= deg <= 8): distinct values of {self} U {next_i} U {prev_i}.  All records
+// are requested before the first is looked at: a thread meets these rows one after the
+// other, and on a small mesh (one row in 128 on the boundary at 1M triangles) the slowest
+// warp's chain of record misses was a third of the kernel (20 us before, 13 us after).
+__device__ __noinline__ int open_row_length(const Rows &rows, const Own &own, int a, int deg) {
   const int self = own.global(a);
+  int ex[GROUP], ey[GROUP];
+#pragma unroll
+  for (int p = 0; p < GROUP; ++p) {
+    const int2 e = p < deg ? rows.edge(a, deg, p) : make_int2(self, self);
+    ex[p] = e.x;
+    ey[p] = e.y & NODE_MASK;
+  }
   int n = 1;
-  for (int p = 0; p < deg; ++p) {
-    const int2 ep = rows.edge(a, deg, p);
-    const int x = ep.x, y = ep.y & NODE_MASK;
+#pragma unroll
+  for (int p = 0; p < GROUP; ++p) {
+    const int x = ex[p], y = ey[p];
     bool fx = x != self, fy = y != self && y != x;
-    for (int q = 0; q < deg; ++q) {
-      const int2 eq = rows.edge(a, deg, q);
-      const int qx = eq.x, qy = eq.y & NODE_MASK;
-      fx = fx && !(q < p && qx == x);
-      fy = fy && qx != y && !(q < p && qy == y);
+#pragma unroll
+    for (int q = 0; q < GROUP; ++q) {
+      fx = fx && !(q < p && ex[q] == x);
+      fy = fy && ex[q] != y && !(q < p && ey[q] == y);
     }
     n += fx + fy;
   }
@@ -1569,12 +1584,32 @@ __device__ __forceinline__ int cold_row_length(const Rows &rows, const Own &own,
 // for the four kernels replaced.  Reduce / scan of sums / final pass it is.)
 constexpr int RP_THREADS = 256, RP_ITEMS = 8, RP_TILE = RP_THREADS * RP_ITEMS;
 
-template <bool FINAL>
+// What a cold assembly starts from, in one launch (three memset nodes cost a small mesh's
+// graph 10 us): zeroed counters / tile sums / spill list, and the caller's status words
+// (all zero but [1], the largest index met: -1).
+__global__ void __launch_bounds__(256)
+cold_init_kernel(ulonglong2 *__restrict__ acc2, size_t pairs, int *__restrict__ status) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < pairs; i += stride)
+    acc2[i] = make_ulonglong2(0ull, 0ull);
+  if (blockIdx.x == 0 && threadIdx.x < 8) status[threadIdx.x] = threadIdx.x == 1 ? -1 : 0;
+}
+
+// MODE 0: the tiles' sums; MODE 1: the row pointer, from the scanned sums.  MODE 2: both in
+// ONE cooperative launch, for a grid that is resident at once (a mesh of up to ~4M
+// triangles) -- the lengths stay in registers across the grid barrier and every tile adds
+// up the sums of the tiles before it: at 1M triangles 30 us of 107 were the three launches'
+// latencies.
+constexpr int RP_REDUCE = 0, RP_FINAL = 1, RP_FUSED = 2;
+
+template <int MODE>
 __global__ void __launch_bounds__(RP_THREADS)
 rowptr_kernel(int n_own, Own own, Rows rows, int *__restrict__ indptr,
-              int *__restrict__ tile_sums /* n_tiles + 1; scanned when FINAL */,
+              int *__restrict__ tile_sums /* n_tiles + 1; scanned when MODE 1 */,
               int *__restrict__ status, int64_t cap) {
+  constexpr bool FINAL = MODE != RP_REDUCE;
   __shared__ int warp_sums[RP_THREADS / 32];
+  __shared__ int base_s[RP_THREADS / 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int first = blockIdx.x * RP_TILE + threadIdx.x * RP_ITEMS;
   bool big = false;
@@ -1584,14 +1619,23 @@ rowptr_kernel(int n_own, Own own, Rows rows, int *__restrict__ indptr,
 #pragma unroll
     for (int i = 0; i < RP_ITEMS; i += 2) {
       const ulonglong2 v = src[i >> 1];
-      len[i] = cold_row_length(rows, own, first + i, v.x, big);
-      len[i + 1] = cold_row_length(rows, own, first + i + 1, v.y, big);
+      len[i] = cold_row_length(v.x, big);
+      len[i + 1] = cold_row_length(v.y, big);
     }
   } else {
 #pragma unroll
     for (int i = 0; i < RP_ITEMS; ++i)
-      len[i] = first + i < n_own ? cold_row_length(rows, own, first + i, rows.acc[first + i], big)
-                                 : 0;
+      len[i] = first + i < n_own ? cold_row_length(rows.acc[first + i], big) : 0;
+  }
+  unsigned open = 0;
+#pragma unroll
+  for (int i = 0; i < RP_ITEMS; ++i) open |= len[i] < 0 ? 1u << i : 0u;
+  while (open) {  // (as many rounds as the warp's unluckiest thread has open rows)
+    const int j = __ffs(open) - 1;
+    open &= open - 1;
+    const int n = open_row_length(rows, own, first + j, rows.deg(first + j));
+#pragma unroll
+    for (int i = 0; i < RP_ITEMS; ++i) len[i] = i == j ? n : len[i];
   }
 #pragma unroll
   for (int i = 0; i < RP_ITEMS; ++i) sum += len[i];
@@ -1609,12 +1653,28 @@ rowptr_kernel(int n_own, Own own, Rows rows, int *__restrict__ indptr,
     before += w < warp ? warp_sums[w] : 0;
     total += warp_sums[w];
   }
-  if (!FINAL) {
+  if (MODE != RP_FINAL) {
     if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
     if (big) atomicOr(status, FLAG_SLOWPATH);
-    return;
+    if (!FINAL) return;
   }
-  int run = tile_sums[blockIdx.x] + before + inc - sum;
+  int base;
+  if (MODE == RP_FUSED) {
+    __threadfence();
+    cooperative_groups::this_grid().sync();
+    int part = 0;
+    for (int t = threadIdx.x; t < (int)blockIdx.x; t += RP_THREADS) part += __ldcg(tile_sums + t);
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+    if (lane == 0) base_s[warp] = part;
+    __syncthreads();
+    base = 0;
+#pragma unroll
+    for (int w = 0; w < RP_THREADS / 32; ++w) base += base_s[w];
+  } else {
+    base = tile_sums[blockIdx.x];
+  }
+  int run = base + before + inc - sum;
   if (first + RP_ITEMS <= n_own && ((uintptr_t)indptr & 15) == 0) {
     int out[RP_ITEMS];
 #pragma unroll
@@ -1631,13 +1691,58 @@ rowptr_kernel(int n_own, Own own, Rows rows, int *__restrict__ indptr,
     }
   }
   if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
-    const int nnz = tile_sums[gridDim.x];  // (-1: beyond int32, scan_sums_kernel)
+    // (-1: beyond int32, scan_sums_kernel; a resident grid's rows cannot get there)
+    const int nnz = MODE == RP_FUSED ? base + total : tile_sums[gridDim.x];
     indptr[n_own] = nnz;
     status[6] = nnz;
     if (nnz < 0 || (int64_t)nnz > cap) atomicOr(status, FLAG_SLOWPATH);
   }
 }
 }  // namespace p1
+
+// Small meshes are launch-bound (1M triangles: 8 launches for 65 us of kernels), and an
+// adaptive or time-stepping loop assembles into the same buffers again and again: the
+// launch sequence of a cold assembly of at most COLD_GRAPH_MAX triangles is captured once
+// per set of arguments (on a private stream: the caller's may be the legacy default
+// stream) and replayed as ONE CUDA graph launch afterwards.  A cached graph keeps its
+// scratch blocks; the least recently used of COLD_GRAPH_SLOTS entries makes room.
+constexpr int64_t COLD_GRAPH_MAX = 1 << 22;
+constexpr int COLD_GRAPH_SLOTS = 8;
+struct ColdKey {
+  const void *elements, *coords, *local, *indptr, *indices, *data, *status;
+  int64_t M, N, capacity;
+  int chunk_log2, world, rank, op;
+  cudaStream_t stream;
+  bool operator==(const ColdKey &o) const { return memcmp(this, &o, sizeof(ColdKey)) == 0; }
+};
+struct ColdGraph {
+  ColdKey key;
+  cudaGraphExec_t exec;
+  void *acc, *slots;
+  unsigned long long tick;
+};
+struct p1_cold_cache {
+  std::vector<ColdGraph> entries;
+  // arguments met once: a graph is only built for a call that repeats, so a caller who
+  // brings fresh buffers every time (an adaptive loop) never pays for a capture
+  ColdKey seen[16];
+  int n_seen = 0, next_seen = 0;
+  cudaStream_t capture = nullptr;
+  unsigned long long clock = 0;
+};
+
+void p1::cold_cache_clear(p1_ctx *ctx) {
+  if (!ctx || !ctx->cold) return;
+  cudaDeviceSynchronize();
+  for (auto &g : ctx->cold->entries) {
+    cudaGraphExecDestroy(g.exec);
+    pool_free(ctx, g.acc, g.key.stream);
+    pool_free(ctx, g.slots, g.key.stream);
+  }
+  if (ctx->cold->capture) cudaStreamDestroy(ctx->cold->capture);
+  delete ctx->cold;
+  ctx->cold = nullptr;
+}
 
 extern "C" int p1_assemble_cold(p1_ctx *ctx, const int32_t *elements, int64_t n_elements,
                                 int64_t n_nodes, int chunk_log2, int world, int rank, int op,
@@ -1677,7 +1782,7 @@ extern "C" int p1_assemble_cold(p1_ctx *ctx, const int32_t *elements, int64_t n_
 
   // one zeroed block: the nodes' counters, the scan's tile sums, the (empty) spill list
   const int n_tiles = (n_own + RP_TILE - 1) / RP_TILE;
-  const size_t words = (size_t)n_own + 1 + (size_t)(n_tiles + 4) / 2 + 8;
+  const size_t words = ((size_t)n_own + 1 + (size_t)(n_tiles + 4) / 2 + 8 + 1) & ~(size_t)1;
   unsigned long long *acc = nullptr;
   Rec *rec = nullptr;
   int2 *slots = nullptr;
@@ -1686,7 +1791,133 @@ extern "C" int p1_assemble_cold(p1_ctx *ctx, const int32_t *elements, int64_t n_
     for (void *b : {(void *)acc, (void *)rec, (void *)slots, (void *)d_weights, (void *)d_points})
       pool_free(ctx, b, s);
   };
+  // the whole launch sequence, on stream q
+  auto enqueue = [&](cudaStream_t q) {
+    int *tile_sums = reinterpret_cast<int *>(acc + n_own + 1);
+    // (capacity 0: a record that finds its row full is dropped; the row is then reported)
+    SpillDesc *d_spill =
+        reinterpret_cast<SpillDesc *>(acc + n_own + 1 + (size_t)(n_tiles + 4) / 2);
+    cold_init_kernel<<<min(grid_for((int64_t)(words / 2), 256), (unsigned)(ctx->sm_count * 8)), 256,
+                       0, q>>>(reinterpret_cast<ulonglong2 *>(acc), words / 2, status);
+    if (quad) {
+      cudaMemcpyAsync(d_weights, qa->weights_host, qa->n_qp * sizeof(double),
+                      cudaMemcpyHostToDevice, q);
+      if (qa->points_host)
+        cudaMemcpyAsync(d_points, qa->points_host, 2 * qa->n_qp * sizeof(double),
+                        cudaMemcpyHostToDevice, q);
+    }
+    const unsigned eg = min(grid_for(M, THREADS), (unsigned)(ctx->sm_count * 32));
+    prof_begin(ctx, "scatter", q);
+    if (slim)
+      launch_scatter_slots<3>(ctx, eg, q, elements, M, N, own, acc, slots, NoValues{}, true,
+                              nullptr, nullptr, status);
+    else
+      launch_scatter<false>(ctx, eg, q, op, elements, M, N, own, acc, rec, nullptr,
+                            reinterpret_cast<int *>(d_spill), coords, local, qa, d_weights,
+                            d_points, status);
+    prof_end(ctx, q);
+    const Rows rows{acc, rec, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, slots};
+    if (n_own > 0) {
+      if (ctx->rowptr_resident == 0) {  // tiles that are resident at once, or -1
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rowptr_kernel<RP_FUSED>,
+                                                          RP_THREADS, 0) != cudaSuccess)
+          cudaGetLastError();
+        ctx->rowptr_resident = per_sm > 0 ? per_sm * ctx->sm_count : -1;
+      }
+      P1_TIMED(ctx, "rowptr", q, {
+        if (n_tiles <= ctx->rowptr_resident) {
+          int n_arg = n_own;
+          Own own_arg = own;
+          Rows rows_arg = rows;
+          int64_t cap_arg = capacity;
+          void *args[] = {&n_arg, &own_arg, &rows_arg, &indptr, &tile_sums, &status, &cap_arg};
+          cudaLaunchCooperativeKernel((const void *)rowptr_kernel<RP_FUSED>, dim3(n_tiles),
+                                      dim3(RP_THREADS), args, 0, q);
+        } else {
+          rowptr_kernel<RP_REDUCE><<<n_tiles, RP_THREADS, 0, q>>>(n_own, own, rows, indptr,
+                                                                 tile_sums, status, capacity);
+          scan_sums(tile_sums, n_tiles, q);
+          rowptr_kernel<RP_FINAL><<<n_tiles, RP_THREADS, 0, q>>>(n_own, own, rows, indptr,
+                                                                tile_sums, status, capacity);
+        }
+      });
+      launch_fill_cold(ctx, own, n_own, rows, slim ? op : 0, (const double2 *)coords, indptr,
+                       indices, data, status, q);
+    } else {
+      cudaMemsetAsync(indptr, 0, sizeof(int), q);
+    }
+  };
   int rc = P1_OK;
+
+  // ---- small mesh, same arguments as before: one graph launch
+  const bool graphable = !quad && M > 0 && M <= COLD_GRAPH_MAX && n_own > 0 && !prof_enabled(ctx);
+  if (graphable) {
+    if (!ctx->cold) ctx->cold = new p1_cold_cache();
+    p1_cold_cache *cc = ctx->cold;
+    ColdKey key;
+    memset(&key, 0, sizeof(key));
+    key.elements = elements; key.coords = coords; key.local = local; key.indptr = indptr;
+    key.indices = indices; key.data = data; key.status = status;
+    key.M = M; key.N = n_nodes; key.capacity = capacity;
+    key.chunk_log2 = chunk_log2; key.world = world; key.rank = rank; key.op = op;
+    key.stream = s;
+    for (auto &g : cc->entries)
+      if (g.key == key) {
+        g.tick = ++cc->clock;
+        P1_CUDA(cudaGraphLaunch(g.exec, s));
+        return P1_OK;
+      }
+    bool repeated = false;
+    for (int i = 0; i < cc->n_seen; ++i) repeated |= cc->seen[i] == key;
+    if (!repeated) {
+      cc->seen[cc->next_seen] = key;
+      cc->next_seen = (cc->next_seen + 1) % 16;
+      cc->n_seen = cc->n_seen < 16 ? cc->n_seen + 1 : 16;
+    }
+    // the second call with these arguments: capture (nothing executes while capturing)
+    if (repeated && !cc->capture &&
+        cudaStreamCreateWithFlags(&cc->capture, cudaStreamNonBlocking) != cudaSuccess) {
+      cc->capture = nullptr;
+      cudaGetLastError();
+    }
+    if (repeated && cc->capture &&
+        (rc = pool_alloc(ctx, &acc, words, s)) == P1_OK &&
+        (rc = slim ? pool_alloc(ctx, &slots, (size_t)n_own * GROUP, s)
+                   : pool_alloc(ctx, &rec, (size_t)n_own * GROUP, s)) == P1_OK) {
+      cudaGraph_t graph = nullptr;
+      cudaGraphExec_t exec = nullptr;
+      bool ok = cudaStreamBeginCapture(cc->capture, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+      if (ok) {
+        enqueue(cc->capture);
+        ok = cudaStreamEndCapture(cc->capture, &graph) == cudaSuccess && graph != nullptr;
+      }
+      if (ok) ok = cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
+      if (graph) cudaGraphDestroy(graph);
+      if (ok) {
+        if ((int)cc->entries.size() >= COLD_GRAPH_SLOTS) {  // the least recently used leaves
+          int old = 0;
+          for (int i = 1; i < (int)cc->entries.size(); ++i)
+            if (cc->entries[i].tick < cc->entries[old].tick) old = i;
+          ColdGraph &g = cc->entries[old];
+          cudaStreamSynchronize(g.key.stream);
+          cudaGraphExecDestroy(g.exec);
+          pool_free(ctx, g.acc, g.key.stream);
+          pool_free(ctx, g.slots, g.key.stream);
+          cc->entries.erase(cc->entries.begin() + old);
+        }
+        cc->entries.push_back(ColdGraph{key, exec, acc, slim ? (void *)slots : (void *)rec,
+                                        ++cc->clock});
+        P1_CUDA(cudaGraphLaunch(exec, s));
+        return P1_OK;
+      }
+      cudaGetLastError();  // capture refused: the plain launch sequence below
+    }
+    release();
+    acc = nullptr; rec = nullptr; slots = nullptr;
+    if (rc) return rc;
+  }
+
   if ((rc = pool_alloc(ctx, &acc, words, s)) ||
       (slim ? (rc = pool_alloc(ctx, &slots, (size_t)n_own * GROUP, s))
             : (rc = pool_alloc(ctx, &rec, (size_t)n_own * GROUP, s))) ||
@@ -1695,43 +1926,7 @@ extern "C" int p1_assemble_cold(p1_ctx *ctx, const int32_t *elements, int64_t n_
     release();
     return rc;
   }
-  int *tile_sums = reinterpret_cast<int *>(acc + n_own + 1);
-  // (capacity 0: a record that finds its row full is dropped; the row is then reported)
-  SpillDesc *d_spill = reinterpret_cast<SpillDesc *>(acc + n_own + 1 + (size_t)(n_tiles + 4) / 2);
-  cudaMemsetAsync(status, 0, 8 * sizeof(int), s);
-  cudaMemsetAsync(status + 1, 0xff, sizeof(int), s);
-  cudaMemsetAsync(acc, 0, words * sizeof(unsigned long long), s);
-  if (quad) {
-    cudaMemcpyAsync(d_weights, qa->weights_host, qa->n_qp * sizeof(double),
-                    cudaMemcpyHostToDevice, s);
-    if (qa->points_host)
-      cudaMemcpyAsync(d_points, qa->points_host, 2 * qa->n_qp * sizeof(double),
-                      cudaMemcpyHostToDevice, s);
-  }
-  const unsigned eg = min(grid_for(M, THREADS), (unsigned)(ctx->sm_count * 32));
-  prof_begin(ctx, "scatter", s);
-  if (slim)
-    launch_scatter_slots<3>(ctx, eg, s, elements, M, N, own, acc, slots, NoValues{}, true, nullptr,
-                            nullptr, status);
-  else
-    launch_scatter<false>(ctx, eg, s, op, elements, M, N, own, acc, rec, nullptr,
-                          reinterpret_cast<int *>(d_spill), coords, local, qa, d_weights,
-                          d_points, status);
-  prof_end(ctx, s);
-  const Rows rows{acc, rec, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, slots};
-  if (n_own > 0) {
-    P1_TIMED(ctx, "rowptr", s, {
-      rowptr_kernel<false><<<n_tiles, RP_THREADS, 0, s>>>(n_own, own, rows, indptr, tile_sums,
-                                                         status, capacity);
-      scan_sums(tile_sums, n_tiles, s);
-      rowptr_kernel<true><<<n_tiles, RP_THREADS, 0, s>>>(n_own, own, rows, indptr, tile_sums,
-                                                        status, capacity);
-    });
-    launch_fill_cold(ctx, own, n_own, rows, slim ? op : 0, (const double2 *)coords, indptr,
-                     indices, data, status, s);
-  } else {
-    cudaMemsetAsync(indptr, 0, sizeof(int), s);
-  }
+  enqueue(s);
   if (cudaGetLastError() != cudaSuccess) {
     set_error("p1_assemble_cold: %s", cudaGetErrorString(cudaGetLastError()));
     rc = P1_ECUDA;

@@ -458,11 +458,13 @@ class DeviceMesh:
             1, self.n_nodes // max(1, self.rows[1] - self.rows[0]))
         return 2 * self.n_rows + int(1.3 * 3 * self.n_elements / world) + 4096
 
-    def assemble_cold(self, op, local=None, pattern=True, quad=None, keepalive=None):
+    def assemble_cold(self, op, local=None, pattern=True, quad=None, keepalive=None, out=None):
         """Cold assembly without a host synchronisation (p1_assemble_cold): returns a
         ColdAssembly at once; nothing is cached on the mesh.  op: OP_STIFFNESS /
         OP_MASS / OP_LOCAL (local: (M, 9) CUDA tensor) / OP_GENERAL / OP_WEIGHTED
-        (quad: _lib.QuadArgs)."""
+        (quad: _lib.QuadArgs).  out: a ColdAssembly of an earlier call on a mesh of
+        the same size, whose arrays are overwritten (a time-stepping loop; on meshes of
+        at most 4M triangles the library then replays the call as one CUDA graph)."""
         if self.interleave is not None:
             world, rank, chunk_log2 = self.interleave
         elif self.rows == (0, self.n_nodes):
@@ -472,10 +474,16 @@ class DeviceMesh:
         if self.interleave is not None:
             self.n_rows = int(interleaved_count(self.n_nodes, world, rank, chunk_log2))
         cap = self.cold_capacity()
-        indptr = self._empty(self.n_rows + 1, torch.int32)
-        indices = self._empty(cap, torch.int32) if pattern else None
-        data = self._empty(cap)
-        status = self._empty(8, torch.int32)
+        if out is not None:
+            indptr, indices, data, status = out.indptr, out.indices, out.data, out.status
+            if (indptr.numel() != self.n_rows + 1 or data.numel() != cap
+                    or (indices is None) != (not pattern) or data.device.index != self.device):
+                raise ValueError('assemble_cold: out= belongs to a mesh of another size')
+        else:
+            indptr = self._empty(self.n_rows + 1, torch.int32)
+            indices = self._empty(cap, torch.int32) if pattern else None
+            data = self._empty(cap)
+            status = self._empty(8, torch.int32)
         _lib.check(self._lib.p1_assemble_cold(
             self.ctx, _ptr(self.elements), self.n_elements, self.n_nodes, chunk_log2, world,
             rank, op, _ptr(self.coords), _ptr(local), C.byref(quad) if quad is not None else None,

@@ -794,6 +794,73 @@ def test_cold_assembly_without_host_sync(mesh_case):
                 assert np.array_equal(x, y)
 
 
+def test_cold_assembly_replayed_as_a_graph(api):
+    """A cold assembly of a small mesh into the same arrays is captured on its second
+    call and replayed as one CUDA graph afterwards (plan.cu, COLD_GRAPH_MAX): every
+    call must give the plan route's CSR, also after the mesh's CONTENT changed in place,
+    after more argument sets than the cache holds, on a side stream, and after a trim."""
+    import torch
+    from p1afempy_b200 import _lib
+    from p1afempy_b200.device import DeviceMesh, context
+    c, e, _ = H.perturbed_square(5)
+    ct, et = torch.from_numpy(c).cuda(), torch.from_numpy(e.astype(np.int32)).cuda()
+    lib = _lib.load()
+
+    def expect(op):
+        with DeviceMesh(ct.clone(), et.clone()) as m:
+            return [t.cpu().numpy() for t in m.assemble(op)]
+
+    def same(cold, ref):
+        assert int(cold.status[0].item()) == 0
+        for x, y in zip(ref, cold.wait()):
+            assert np.array_equal(x, y.cpu().numpy())
+
+    with DeviceMesh(ct, et) as mesh:
+        for op in (_lib.OP_STIFFNESS, _lib.OP_MASS):
+            ref = expect(op)
+            cold = None
+            for _ in range(4):                  # plain, capture, replay, replay
+                cold = mesh.assemble_cold(op, out=cold)
+                same(cold, ref)
+                cold._done = None
+                cold.data.fill_(-1.)            # a replay has to write everything again
+                cold.indptr.zero_()
+        # the coordinates move, same arrays: the graph reads the new content
+        ct.mul_(1.5)
+        ref = expect(_lib.OP_MASS)
+        cold = mesh.assemble_cold(_lib.OP_MASS, out=cold)
+        same(cold, ref)
+        # more argument sets than graph slots; the first set comes back afterwards
+        ref = expect(_lib.OP_STIFFNESS)
+        sets = [None] * 11
+        for _ in range(3):
+            for i in range(len(sets)):
+                sets[i] = mesh.assemble_cold(_lib.OP_STIFFNESS, out=sets[i])
+                same(sets[i], ref)
+                sets[i]._done = None
+        # another stream
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            cold = None
+            for _ in range(3):
+                cold = mesh.assemble_cold(_lib.OP_STIFFNESS, out=cold)
+                same(cold, ref)
+                cold._done = None
+        side.synchronize()
+        # a trim drops the graphs and their scratch; the next call starts over
+        assert lib.p1_ctx_trim(context()[0]) == 0
+        for _ in range(3):
+            sets[0] = mesh.assemble_cold(_lib.OP_STIFFNESS, out=sets[0])
+            same(sets[0], ref)
+            sets[0]._done = None
+        with pytest.raises(ValueError):
+            with DeviceMesh(*[torch.from_numpy(a).cuda() for a in
+                              (H.perturbed_square(3)[0],
+                               H.perturbed_square(3)[1].astype(np.int32))]) as other:
+                other.assemble_cold(_lib.OP_STIFFNESS, out=sets[0])
+
+
 def test_cold_assembly_falls_back_to_the_plan_route(api):
     """Status words instead of return codes: a node with more than 8 elements
     (P1_STATUS_SLOWPATH), a non-manifold vertex (P1_STATUS_RETRY) and an index out
