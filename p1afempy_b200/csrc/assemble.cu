@@ -390,39 +390,37 @@ __device__ __forceinline__ void slow_row_values(int self, int deg, const Rec *nb
 // nb: global or local memory.
 __device__ __forceinline__ bool open_fan_row(int self, int deg, const Rec *nb, int *cs,
                                              double *vs) {
-  int nx[GROUP], pv[GROUP], slot[GROUP];
-  double vd[GROUP], vn[GROUP], vp[GROUP], mvp[GROUP];
+  // Only the indices live in registers, the values are fetched again where they are
+  // used: a callee that needs 90 registers made fill_rows_kernel spill one of its own
+  // in the prologue of EVERY thread (+0.03 ms at 64M triangles).
+  int nx[GROUP], pv[GROUP], meta[GROUP];  // meta: slot | mate << 4 (mate 8: none)
 #pragma unroll
   for (int i = 0; i < GROUP; ++i) {
     nx[i] = 0x7fffffff - i;
     pv[i] = -2 - i;
-    vd[i] = vn[i] = vp[i] = 0.;
     if (i < deg) {
-      const Rec r = nb[i];
-      nx[i] = r.nx; pv[i] = rec_prev(r);
-      vd[i] = r.vd; vn[i] = r.vn; vp[i] = r.vp;
+      nx[i] = nb[i].nx;
+      pv[i] = nb[i].pvk & NODE_MASK;
     }
   }
   bool ok = true;
-  int slot_self = 0, unmated = 0, n_first = 0, first_col = 0;
-  double first_val = 0.;
+  int slot_self = 0, unmated = 0, n_first = 0, first_col = 0, first_rec = 0;
 #pragma unroll
   for (int i = 0; i < GROUP; ++i) {
-    int below = 0;
-    bool mated = false, sourced = false;
-    mvp[i] = 0.;
+    int below = 0, mate = GROUP;
+    bool sourced = false;
 #pragma unroll
     for (int j = 0; j < GROUP; ++j) {
       below += nx[j] < nx[i];
-      if (pv[j] == nx[i]) { mvp[i] = vp[j]; mated = true; }
+      mate = pv[j] == nx[i] ? j : mate;
       sourced = sourced || nx[j] == pv[i];
       if (j > i) ok = ok && nx[j] != nx[i] && pv[j] != pv[i];
     }
     const bool live = i < deg;
     ok = ok && (!live || (nx[i] != self && pv[i] != self));
-    unmated += live && !mated;
-    if (live && !sourced) { ++n_first; first_col = pv[i]; first_val = vp[i]; }
-    slot[i] = below + (self < nx[i]);
+    unmated += live && mate == GROUP;
+    if (live && !sourced) { ++n_first; first_col = pv[i]; first_rec = i; }
+    meta[i] = (below + (self < nx[i])) | (mate << 4);
     slot_self += live && nx[i] < self;
   }
   if (!ok || unmated != 1 || n_first != 1) return false;
@@ -430,31 +428,34 @@ __device__ __forceinline__ bool open_fan_row(int self, int deg, const Rec *nb, i
 #pragma unroll
   for (int i = 0; i < GROUP; ++i) {
     slot_first += nx[i] < first_col;  // (unused slots hold columns above any node)
-    slot[i] += first_col < nx[i];
+    meta[i] += first_col < nx[i];
   }
   slot_self += first_col < self;
   vs[slot_first] = 0.;
 #pragma unroll
   for (int i = 0; i < GROUP; ++i)
-    if (i < deg) vs[slot[i]] = vd[i];
+    if (i < deg) vs[meta[i] & 15] = nb[i].vd;
   double diag = 0.;
   for (int q = 0; q < deg + 2; ++q)
     if (q != slot_self) diag += vs[q];
 #pragma unroll
   for (int i = 0; i < GROUP; ++i)
     if (i < deg) {
-      if (cs) cs[slot[i]] = nx[i];
-      vs[slot[i]] = vn[i] + mvp[i];
+      const int mate = meta[i] >> 4;
+      if (cs) cs[meta[i] & 15] = nx[i];
+      vs[meta[i] & 15] = nb[i].vn + (mate < GROUP ? nb[mate].vp : 0.);
     }
   if (cs) { cs[slot_first] = first_col; cs[slot_self] = self; }
-  vs[slot_first] = 0. + first_val;
+  vs[slot_first] = 0. + nb[first_rec].vp;
   vs[slot_self] = diag;
   return true;
 }
 
 __device__ __noinline__ void slow_row_inline(int self, int deg, const Rec *nb, int *cs_out,
                                              double *vs_out) {
+#ifndef P1_AB_OLD_OPEN
   if (open_fan_row(self, deg, nb, cs_out, vs_out)) return;
+#endif
   int cs[2 * GROUP + 1];
   const int n = slow_row_columns(self, deg, nb, cs);
   if (cs_out)

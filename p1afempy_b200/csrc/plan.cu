@@ -1554,12 +1554,21 @@ __device__ __forceinline__ int cold_row_length(unsigned long long v, bool &big) 
 // are requested before the first is looked at: a thread meets these rows one after the
 // other, and on a small mesh (one row in 128 on the boundary at 1M triangles) the slowest
 // warp's chain of record misses was a third of the kernel (20 us before, 13 us after).
-__device__ __noinline__ int open_row_length(const Rows &rows, const Own &own, int a, int deg) {
-  const int self = own.global(a);
+// (by value: a reference to the kernel's Rows would make every thread copy it to its stack)
+__device__ __noinline__ int open_row_length(const Rec *rec, const int2 *slim, int a, int self,
+                                            int deg) {
   int ex[GROUP], ey[GROUP];
 #pragma unroll
   for (int p = 0; p < GROUP; ++p) {
-    const int2 e = p < deg ? rows.edge(a, deg, p) : make_int2(self, self);
+    int2 e = make_int2(self, self);
+    if (p < deg) {
+      if (slim) {
+        e = slim[(int64_t)a * GROUP + p];
+      } else {
+        const Rec *r = rec + (int64_t)a * GROUP + p;
+        e = make_int2(r->nx, r->pvk);
+      }
+    }
     ex[p] = e.x;
     ey[p] = e.y & NODE_MASK;
   }
@@ -1633,7 +1642,8 @@ rowptr_kernel(int n_own, Own own, Rows rows, int *__restrict__ indptr,
   while (open) {  // (as many rounds as the warp's unluckiest thread has open rows)
     const int j = __ffs(open) - 1;
     open &= open - 1;
-    const int n = open_row_length(rows, own, first + j, rows.deg(first + j));
+    const int n = open_row_length(rows.rec, rows.slim, first + j, own.global(first + j),
+                                  rows.deg(first + j));
 #pragma unroll
     for (int i = 0; i < RP_ITEMS; ++i) len[i] = i == j ? n : len[i];
   }
@@ -1797,8 +1807,14 @@ extern "C" int p1_assemble_cold(p1_ctx *ctx, const int32_t *elements, int64_t n_
     // (capacity 0: a record that finds its row full is dropped; the row is then reported)
     SpillDesc *d_spill =
         reinterpret_cast<SpillDesc *>(acc + n_own + 1 + (size_t)(n_tiles + 4) / 2);
+#ifdef P1_AB_MEMSET
+    cudaMemsetAsync(status, 0, 8 * sizeof(int), q);
+    cudaMemsetAsync(status + 1, 0xff, sizeof(int), q);
+    cudaMemsetAsync(acc, 0, words * sizeof(unsigned long long), q);
+#else
     cold_init_kernel<<<min(grid_for((int64_t)(words / 2), 256), (unsigned)(ctx->sm_count * 8)), 256,
                        0, q>>>(reinterpret_cast<ulonglong2 *>(acc), words / 2, status);
+#endif
     if (quad) {
       cudaMemcpyAsync(d_weights, qa->weights_host, qa->n_qp * sizeof(double),
                       cudaMemcpyHostToDevice, q);
@@ -1825,8 +1841,9 @@ extern "C" int p1_assemble_cold(p1_ctx *ctx, const int32_t *elements, int64_t n_
           cudaGetLastError();
         ctx->rowptr_resident = per_sm > 0 ? per_sm * ctx->sm_count : -1;
       }
-      P1_TIMED(ctx, "rowptr", q, {
-        if (n_tiles <= ctx->rowptr_resident) {
+      const bool fused = n_tiles <= ctx->rowptr_resident;
+      P1_TIMED(ctx, fused ? "rowptr_fused" : "rowptr", q, {
+        if (fused) {
           int n_arg = n_own;
           Own own_arg = own;
           Rows rows_arg = rows;
