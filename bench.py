@@ -303,9 +303,15 @@ class Workload:
         self.n_qp = int(self.w.shape[0])
         # N > 1: matrices and load vectors are dealt out by rows (chunks of 4096), the
         # estimator by contiguous element blocks
-        inter = (world, rank, 12) if world > 1 and op != 'eta' else None
-        self.mesh = DeviceMesh(c, e, device=local_rank, interleave=inter)
+        inter = (world, rank, 12) if world > 1 and op not in ('eta', 'load') else None
         self.block = (self.m * rank // world, self.m * (rank + 1) // world)
+        if world > 1 and op == 'load':
+            # the load vector is dealt out by ELEMENTS: the rank's block over all N nodes,
+            # the ranks' partial vectors added by one all-reduce (dist.load_vector_reduced)
+            self.mesh = DeviceMesh(c, e[self.block[0]:self.block[1]], device=local_rank,
+                                   n_nodes=self.nn, check=False)
+        else:
+            self.mesh = DeviceMesh(c, e, device=local_rank, interleave=inter)
         self.statuses = []
         self.out = None        # the output arrays, overwritten by every step
         x, y = c[:, 0], c[:, 1]
@@ -359,7 +365,10 @@ class Workload:
             return cold
         if op == 'load':
             out = mesh.load_vector(self.fq, self.w, self.p)
-            mesh.close()        # cold: the next call builds its plan again (N > 1: plan route)
+            mesh.close()        # cold: nothing is kept for the next call
+            if self.world > 1:
+                import torch.distributed as dist
+                dist.all_reduce(out)
             return out
         if self.world > 1:
             return mesh.eta_r_block(self.u, self.dirichlet, self.none, None, self.fc, *self.block)
@@ -408,6 +417,8 @@ def run_b200(args):
     wl.check(nnz)
     if world > 1 and op in ('stiffness', 'mass', 'general', 'weighted'):
         assert int(out[2].item()) == nnz, (int(out[2].item()), nnz)
+    if op == 'load':    # the entries of the load vector add up to the integral of f (= 1)
+        assert out.shape[0] == nn and abs(float(out.sum().item()) - 1.) < 1e-6, float(out.sum())
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -513,6 +524,9 @@ def run_b200(args):
                                   if op in ('general', 'weighted', 'load') else ''),
                    'parallelism': (('contiguous element blocks on %d GPUs, inputs replicated, no '
                                     'collective' % world) if op == 'eta' else
+                                   ('contiguous element blocks on %d GPUs (f(x_q) of the block only), '
+                                    'one all-reduce of the partial vectors per step: the whole '
+                                    'vector on every rank' % world) if op == 'load' else
                                    ('rows dealt to %d GPUs in chunks of 4096, inputs replicated; one '
                                     'all-gather of per-chunk nnz (global row pointer) per step'
                                     % world)) if world > 1 else '1 GPU',

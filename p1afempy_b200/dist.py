@@ -218,6 +218,53 @@ class DistributedMesh:
         """Entries of the legacy load vector (solvers.py:414-426) at the owned rows."""
         return self.local.load_vector_midpoint(f_centroid)
 
+    # The two methods above repeat the element loop on every rank (each rank needs the
+    # local loads of every element that touches its rows: nearly all of them), which is
+    # bit-identical to one GPU but does not scale.  The *_reduced forms deal out the
+    # ELEMENTS instead -- SURVEY.md section 8(e): "for vectors ncclReduceScatter" --: the
+    # rank assembles the vector of its contiguous element block over all N nodes and one
+    # NCCL all-reduce adds the ranks' partial vectors.  The sums are associated by block,
+    # so the result agrees with the reference to rounding (<= 1e-12 of the sum of the
+    # absolute contributions; the contract for vectors), not bit for bit, and depends on
+    # the number of ranks in the last bits.
+    def _block_mesh(self):
+        from .device import DeviceMesh
+        if getattr(self, '_block', None) is None:
+            m0, m1 = self.element_block()
+            self._block = DeviceMesh(self.local.coords, self.local.elements[m0:m1],
+                                     device=self.local.device, n_nodes=self.n_nodes, check=False)
+        return self._block
+
+    def _block_values(self, values, lead):
+        """values for all M elements, or for the rank's block only -> the block's"""
+        m0, m1 = self.element_block()
+        m = self.local.n_elements
+        if values.shape[-1] == m and m != m1 - m0:
+            values = values[..., m0:m1]
+        if values.shape[-1] != m1 - m0:
+            raise ValueError('expected values for %d (all) or %d (the block\'s) elements, got %s'
+                             % (m, m1 - m0, tuple(values.shape)))
+        return values.contiguous()
+
+    def load_vector_reduced(self, fq, weights, points):
+        """The cubature load vector (solvers.py:540-598), complete on every rank.
+        fq: (n_qp, M) values of f at the quadrature points of all elements, or
+        (n_qp, m1 - m0) for the rank's element_block() only."""
+        from .device import to_device_f64
+        fq = self._block_values(to_device_f64(fq, self.local.device), 0)
+        b = self._block_mesh().load_vector(fq, weights, points)
+        dist.all_reduce(b, group=self.group)
+        return b
+
+    def load_vector_midpoint_reduced(self, f_centroid):
+        """The legacy load vector (solvers.py:414-426), complete on every rank.
+        f_centroid: (M,) or the block's (m1 - m0,) values."""
+        from .device import to_device_f64
+        fc = self._block_values(to_device_f64(f_centroid, self.local.device), 0)
+        b = self._block_mesh().load_vector_midpoint(fc)
+        dist.all_reduce(b, group=self.group)
+        return b
+
     def element_block(self):
         """The calling rank's contiguous block of elements [m0, m1) (the estimator is
         per element: it is dealt out by elements, not by rows)."""
@@ -248,4 +295,7 @@ class DistributedMesh:
                           root=root, group=self.group)
 
     def close(self):
+        if getattr(self, '_block', None) is not None:
+            self._block.close()
+            self._block = None
         self.local.close()

@@ -122,6 +122,22 @@ def _nccl_worker(rank, world, port, result_path):
                             lambda r: H.f_load((c[e[:, 0]] + c[e[:, 1]] + c[e[:, 2]]) / 3.),
                             H.g_neu)
         assert np.array_equal(eta, ref_eta[m0:m1])
+        # load vectors by element blocks + one all-reduce: complete on every rank
+        from p1afempy_b200 import cubature
+        w, p = cubature.resolve_rule(cubature.CubatureRuleEnum.CONICAL_GAUSS_4X4)
+        xq = dm.local.quadrature_points(p).cpu().numpy()
+        fq = np.stack([H.f_load(xq[q]) for q in range(w.shape[0])])
+        ref_b = orc.load_vector_cubature(c, e, H.f_load, w, p)
+        scale = 1e-12 * np.abs(ref_b).max()
+        got_b = dm.load_vector_reduced(torch.from_numpy(fq).cuda(), w, p).cpu().numpy()
+        assert got_b.shape == ref_b.shape and np.abs(got_b - ref_b).max() <= scale
+        got_b = dm.load_vector_reduced(torch.from_numpy(fq[:, m0:m1].copy()).cuda(), w, p)
+        assert np.abs(got_b.cpu().numpy() - ref_b).max() <= scale
+        ref_b0 = orc.load_vector_midpoint(c, e, H.f_load)
+        got_b0 = dm.load_vector_midpoint_reduced(fc).cpu().numpy()
+        # (fc above is f at (c0 + c1 + c2) / 3, the oracle evaluates f at the reference's
+        # c0 + (d21 + d31) / 3: equal to rounding only, also with one rank)
+        assert np.abs(got_b0 - ref_b0).max() <= 1e-12 * np.abs(ref_b0).max()
         out = dm.gather(ip, ix, data, root=0)
         if rank == 0:
             ref = orc.stiffness_coo(c, e).tocsr()
@@ -231,6 +247,33 @@ def test_every_operator_on_interleaved_shares(world, chunk):
                 assert np.array_equal(data.cpu().numpy(), fdata[src]), name
             assert np.array_equal(mesh.load_vector(fq, w, p).cpu().numpy(), b_full[rows])
             assert np.array_equal(mesh.load_vector_midpoint(fc).cpu().numpy(), b0_full[rows])
+
+
+@pytest.mark.parametrize('world', [3, 8])
+def test_load_vector_by_element_blocks(world):
+    """What DistributedMesh.load_vector_reduced adds up: the vectors of contiguous
+    element blocks over all N nodes.  Their sum in rank order agrees with the
+    reference to rounding (sums associated by block), each block's vector is the
+    reference's for that block bit for bit."""
+    from p1afempy_b200 import cubature
+    from p1afempy_b200.device import DeviceMesh
+    c, e, _ = H.perturbed_square(5)
+    w, p = cubature.resolve_rule(cubature.CubatureRuleEnum.CONICAL_GAUSS_4X4)
+    ct, et = torch.from_numpy(c).cuda(), torch.from_numpy(e.astype(np.int32)).cuda()
+    with DeviceMesh(ct, et) as mesh:
+        xq = mesh.quadrature_points(p).cpu().numpy()
+    fq = np.stack([H.f_load(xq[q]) for q in range(w.shape[0])])
+    ref = orc.load_vector_cubature(c, e, H.f_load, w, p)
+    m, n = e.shape[0], c.shape[0]
+    total = np.zeros(n)
+    for r in range(world):
+        m0, m1 = m * r // world, m * (r + 1) // world
+        with DeviceMesh(ct, et[m0:m1], n_nodes=n, check=False) as part:
+            b = part.load_vector(torch.from_numpy(fq[:, m0:m1].copy()).cuda(), w, p).cpu().numpy()
+        assert b.shape == (n,)
+        assert np.array_equal(b, orc.load_vector_cubature(c, e[m0:m1], H.f_load, w, p))
+        total += b
+    assert np.abs(total - ref).max() <= 1e-12 * np.abs(ref).max()
 
 
 @pytest.mark.parametrize('world', [2, 5])
