@@ -35,6 +35,9 @@ __device__ void slow_row_inline(int self, int deg, const Rec *nb, int *cs_out, d
 // One row from its <= 8 records: cs / vs point at the row's place (the block's
 // staged image or the output itself; cs may be null).  False when the fan is not
 // closed and repeat-free.
+// HALF: the 16-byte slots {next, prev|k, v} of p1_assemble_cold's mass matrix (local row
+// (2v, v, v)) instead of records.
+template <bool HALF = false>
 __device__ __forceinline__ bool row_from_records(int self, int deg, const Rec *row, int *cs,
                                                  double *vs) {
   int nx[GROUP], pv[GROUP], slot[GROUP];
@@ -46,12 +49,23 @@ __device__ __forceinline__ bool row_from_records(int self, int deg, const Rec *r
     pv[i] = -2 - i;
     vd[i] = vn[i] = vp[i] = 0.;
     if (i < deg) {
-      const Rec r = load_rec(row + i);
-      nx[i] = r.nx; pv[i] = rec_prev(r);
-      vd[i] = r.vd; vn[i] = r.vn; vp[i] = r.vp;
+      if constexpr (HALF) {
+        const int4 h = __ldg(reinterpret_cast<const int4 *>(row) + i);
+        nx[i] = h.x; pv[i] = h.y & NODE_MASK;
+        vn[i] = vp[i] = __hiloint2double(h.w, h.z);
+        vd[i] = 2. * vn[i];
+      } else {
+        const Rec r = load_rec(row + i);
+        nx[i] = r.nx; pv[i] = rec_prev(r);
+        vd[i] = r.vd; vn[i] = r.vn; vp[i] = r.vp;
+      }
     }
   }
-  // all pairs, in registers
+  // all pairs, in registers.  (Measured and dropped: the mate as an INDEX with the (k,k+2)
+  // entries fetched from a per-thread column in shared memory, and "no repeats" tested on
+  // the ranks instead of pair by pair -- 140 of 1030 instructions less, 16 shared-memory
+  // operations more per row: 1.99 -> 2.09 ms at 64M.  The kernel is bound by its LSU
+  // wavefronts (61 % of peak) and HBM (58 %), not by issue slots (46 %).)
   bool ok = true;
 #pragma unroll
   for (int i = 0; i < GROUP; ++i) {
@@ -90,7 +104,11 @@ __device__ __forceinline__ bool row_from_records(int self, int deg, const Rec *r
   return true;
 }
 
-__global__ void __launch_bounds__(FR, P1_FILL_MIN_BLOCKS)
+#ifndef P1_FILL_MIN_BLOCKS_HALF
+#define P1_FILL_MIN_BLOCKS_HALF P1_FILL_MIN_BLOCKS
+#endif
+template <bool HALF = false>
+__global__ void __launch_bounds__(FR, HALF ? P1_FILL_MIN_BLOCKS_HALF : P1_FILL_MIN_BLOCKS)
 fill_rows_kernel(int n_own, Own own, int exact,
                  const unsigned long long *__restrict__ acc, const Rec *__restrict__ rec,
                  const int *__restrict__ indptr, int *__restrict__ indices,
@@ -113,7 +131,10 @@ fill_rows_kernel(int n_own, Own own, int exact,
     hash = (unsigned)(v >> 32);
     ob = __ldg(indptr + row0 + tid);
   }
-  const Rec *row = rec + (int64_t)(row0 + tid) * GROUP;  // the row's 8 slots
+  // the row's 8 slots (HALF: 16 bytes each)
+  const Rec *row = HALF ? reinterpret_cast<const Rec *>(reinterpret_cast<const int4 *>(rec) +
+                                                        (int64_t)(row0 + tid) * GROUP)
+                        : rec + (int64_t)(row0 + tid) * GROUP;
   const bool process = deg >= 1 && deg <= GROUP && (exact || hash == 0u);
   if (process) {
     // staged: the row is built in the block's image; otherwise (irregular rows
@@ -122,12 +143,24 @@ fill_rows_kernel(int n_own, Own own, int exact,
     double *vs = out_staged ? vals_s + (ob - obeg) : data + ob;
     // exact plan: a row that fails is in slow_rows.  Hash plan: the shortcut
     // "closed fan => 1 + #records columns" does not hold for this row.
-    if (!row_from_records(own.global(row0 + tid), deg, row, cs, vs) && !exact)
+    if (!row_from_records<HALF>(own.global(row0 + tid), deg, row, cs, vs) && !exact)
       atomicOr(flags, FLAG_RETRY);
   } else if (inline_slow && deg >= 1 && deg <= GROUP) {  // an open fan (p1_assemble_cold)
-    slow_row_inline(own.global(row0 + tid), deg, row,
-                    out_staged ? cols_s + (ob - obeg) : (indices ? indices + ob : nullptr),
-                    out_staged ? vals_s + (ob - obeg) : data + ob);
+    int *cs = out_staged ? cols_s + (ob - obeg) : (indices ? indices + ob : nullptr);
+    double *vs = out_staged ? vals_s + (ob - obeg) : data + ob;
+    if constexpr (HALF) {
+      Rec made[GROUP];
+      for (int i = 0; i < deg; ++i) {
+        const int4 h = reinterpret_cast<const int4 *>(row)[i];
+        made[i].nx = h.x;
+        made[i].pvk = h.y;
+        made[i].vn = made[i].vp = __hiloint2double(h.w, h.z);
+        made[i].vd = 2. * made[i].vn;
+      }
+      slow_row_inline(own.global(row0 + tid), deg, made, cs, vs);
+    } else {
+      slow_row_inline(own.global(row0 + tid), deg, row, cs, vs);
+    }
   }
   __syncthreads();
   if (out_staged) {
@@ -625,9 +658,13 @@ void p1::launch_fill_cold(p1_ctx *ctx, const Own &own, int n_own, const Rows &ro
     fill_gather_kernel<<<grid_for(n_own, FR), FR, 0, s>>>(n_own, own, rows.acc, rows.slim,
                                                          MassValues{coords}, indptr, indices, data,
                                                          status, 1);
+  else if (rows.half)
+    fill_rows_kernel<true><<<grid_for(n_own, FR), FR, 0, s>>>(
+        n_own, own, 0, rows.acc, reinterpret_cast<const Rec *>(rows.half), indptr, indices, data,
+        status, 1);
   else
-    fill_rows_kernel<<<grid_for(n_own, FR), FR, 0, s>>>(n_own, own, 0, rows.acc, rows.rec, indptr,
-                                                       indices, data, status, 1);
+    fill_rows_kernel<false><<<grid_for(n_own, FR), FR, 0, s>>>(n_own, own, 0, rows.acc, rows.rec,
+                                                              indptr, indices, data, status, 1);
   prof_end(ctx, s);
 }
 
@@ -735,7 +772,7 @@ extern "C" int p1_assemble_csr(const p1_plan *cplan, int op, const double *coord
   P1_CUDA(cudaMemsetAsync(ctx->d_flags, 0, sizeof(int), s));
   if (n_own > 0)
     P1_TIMED(ctx, "fill_rows", s,
-             (fill_rows_kernel<<<grid_for(n_own, FR), FR, 0, s>>>(
+             (fill_rows_kernel<false><<<grid_for(n_own, FR), FR, 0, s>>>(
                  n_own, own, plan->exact ? 1 : 0, plan->acc, plan->rec, plan->indptr, indices,
                  data, ctx->d_flags)));
   if (plan->n_slow > 0)

@@ -59,6 +59,8 @@ constexpr int SC_THREADS = P1_SCATTER_THREADS;  // scatter block size
 //      2: vector payload -- one 16-byte slot {element code, 0, v[0] as two words}:
 //         what a load vector needs of an incidence, no topology at all
 //      3: slim plan -- one 8-byte slot {next, prev|k}; the fill recomputes the values
+//      4: one 16-byte slot {next, prev|k, v[1] as two words} for an operator whose
+//         local row is (2 v, v, v): the mass matrix (area/6 = 2 (area/12) exactly)
 template <int TOPO>
 __device__ __forceinline__ void store_slot(Rec *rec, int *rec_elem, int64_t pos, int nx,
                                            int pvk, const double (&v)[3], int code) {
@@ -72,6 +74,9 @@ __device__ __forceinline__ void store_slot(Rec *rec, int *rec_elem, int64_t pos,
         make_int4(code, 0, __double2loint(v[0]), __double2hiint(v[0]));
   } else if constexpr (TOPO == 3) {
     reinterpret_cast<int2 *>(rec)[pos] = make_int2(nx, pvk);
+  } else if constexpr (TOPO == 4) {
+    reinterpret_cast<int4 *>(rec)[pos] =
+        make_int4(nx, pvk, __double2loint(v[1]), __double2hiint(v[1]));
   } else {
     Rec r;
     r.nx = nx; r.pvk = pvk;
@@ -440,7 +445,7 @@ static void launch_one(bool pairs, unsigned grid, cudaStream_t s, const int *ele
         elements, M, N, own, vec, acc, rec, rec_elem, cursor, values, fl);
 }
 
-// 16-byte slots instead of records (MODE 1: topology, 2: vector payload)
+// slots instead of records (MODE 1: topology, 2: vector payload, 3: slim, 4: (2v, v, v) rows)
 template <int MODE, class V>
 static void launch_scatter_slots(p1_ctx *ctx, unsigned grid, cudaStream_t s, const int *elements,
                                  int64_t M, int N, Own own, unsigned long long *acc, void *slots_,
@@ -1555,8 +1560,8 @@ __device__ __forceinline__ int cold_row_length(unsigned long long v, bool &big) 
 // other, and on a small mesh (one row in 128 on the boundary at 1M triangles) the slowest
 // warp's chain of record misses was a third of the kernel (20 us before, 13 us after).
 // (by value: a reference to the kernel's Rows would make every thread copy it to its stack)
-__device__ __noinline__ int open_row_length(const Rec *rec, const int2 *slim, int a, int self,
-                                            int deg) {
+__device__ __noinline__ int open_row_length(const Rec *rec, const int2 *slim, const int4 *half,
+                                            int a, int self, int deg) {
   int ex[GROUP], ey[GROUP];
 #pragma unroll
   for (int p = 0; p < GROUP; ++p) {
@@ -1564,6 +1569,9 @@ __device__ __noinline__ int open_row_length(const Rec *rec, const int2 *slim, in
     if (p < deg) {
       if (slim) {
         e = slim[(int64_t)a * GROUP + p];
+      } else if (half) {
+        const int4 h = half[(int64_t)a * GROUP + p];
+        e = make_int2(h.x, h.y);
       } else {
         const Rec *r = rec + (int64_t)a * GROUP + p;
         e = make_int2(r->nx, r->pvk);
@@ -1642,8 +1650,8 @@ rowptr_kernel(int n_own, Own own, Rows rows, int *__restrict__ indptr,
   while (open) {  // (as many rounds as the warp's unluckiest thread has open rows)
     const int j = __ffs(open) - 1;
     open &= open - 1;
-    const int n = open_row_length(rows.rec, rows.slim, first + j, own.global(first + j),
-                                  rows.deg(first + j));
+    const int n = open_row_length(rows.rec, rows.slim, rows.half, first + j,
+                                  own.global(first + j), rows.deg(first + j));
 #pragma unroll
     for (int i = 0; i < RP_ITEMS; ++i) len[i] = i == j ? n : len[i];
   }
@@ -1789,6 +1797,9 @@ extern "C" int p1_assemble_cold(p1_ctx *ctx, const int32_t *elements, int64_t n_
   const int N = (int)n_nodes;
   const int64_t M = n_elements;
   const bool slim = world > 1 && (op == P1_OP_STIFFNESS || op == P1_OP_MASS);
+  // one GPU, mass matrix: the local row of an incidence is (2v, v, v), so a record is 16
+  // bytes {next, prev|k, v}: half the record bytes through HBM in both directions
+  const bool half = !slim && op == P1_OP_MASS;
 
   // one zeroed block: the nodes' counters, the scan's tile sums, the (empty) spill list
   const int n_tiles = (n_own + RP_TILE - 1) / RP_TILE;
@@ -1796,10 +1807,17 @@ extern "C" int p1_assemble_cold(p1_ctx *ctx, const int32_t *elements, int64_t n_
   unsigned long long *acc = nullptr;
   Rec *rec = nullptr;
   int2 *slots = nullptr;
+  int4 *halves = nullptr;
   double *d_weights = nullptr, *d_points = nullptr;
   auto release = [&]() {
-    for (void *b : {(void *)acc, (void *)rec, (void *)slots, (void *)d_weights, (void *)d_points})
+    for (void *b : {(void *)acc, (void *)rec, (void *)slots, (void *)halves, (void *)d_weights,
+                    (void *)d_points})
       pool_free(ctx, b, s);
+  };
+  auto alloc_rows = [&]() {  // the rows' 8 slots, in the layout of this call
+    return slim   ? pool_alloc(ctx, &slots, (size_t)n_own * GROUP, s)
+           : half ? pool_alloc(ctx, &halves, (size_t)n_own * GROUP, s)
+                  : pool_alloc(ctx, &rec, (size_t)n_own * GROUP, s);
   };
   // the whole launch sequence, on stream q
   auto enqueue = [&](cudaStream_t q) {
@@ -1827,12 +1845,15 @@ extern "C" int p1_assemble_cold(p1_ctx *ctx, const int32_t *elements, int64_t n_
     if (slim)
       launch_scatter_slots<3>(ctx, eg, q, elements, M, N, own, acc, slots, NoValues{}, true,
                               nullptr, nullptr, status);
+    else if (half)
+      launch_scatter_slots<4>(ctx, eg, q, elements, M, N, own, acc, halves,
+                              MassValues{(const double2 *)coords}, true, nullptr, nullptr, status);
     else
       launch_scatter<false>(ctx, eg, q, op, elements, M, N, own, acc, rec, nullptr,
                             reinterpret_cast<int *>(d_spill), coords, local, qa, d_weights,
                             d_points, status);
     prof_end(ctx, q);
-    const Rows rows{acc, rec, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, slots};
+    const Rows rows{acc, rec, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, slots, halves};
     if (n_own > 0) {
       if (ctx->rowptr_resident == 0) {  // tiles that are resident at once, or -1
         int per_sm = 0;
@@ -1900,8 +1921,7 @@ extern "C" int p1_assemble_cold(p1_ctx *ctx, const int32_t *elements, int64_t n_
     }
     if (repeated && cc->capture &&
         (rc = pool_alloc(ctx, &acc, words, s)) == P1_OK &&
-        (rc = slim ? pool_alloc(ctx, &slots, (size_t)n_own * GROUP, s)
-                   : pool_alloc(ctx, &rec, (size_t)n_own * GROUP, s)) == P1_OK) {
+        (rc = alloc_rows()) == P1_OK) {
       cudaGraph_t graph = nullptr;
       cudaGraphExec_t exec = nullptr;
       bool ok = cudaStreamBeginCapture(cc->capture, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
@@ -1923,21 +1943,20 @@ extern "C" int p1_assemble_cold(p1_ctx *ctx, const int32_t *elements, int64_t n_
           pool_free(ctx, g.slots, g.key.stream);
           cc->entries.erase(cc->entries.begin() + old);
         }
-        cc->entries.push_back(ColdGraph{key, exec, acc, slim ? (void *)slots : (void *)rec,
-                                        ++cc->clock});
+        cc->entries.push_back(ColdGraph{
+            key, exec, acc, slim ? (void *)slots : (half ? (void *)halves : (void *)rec),
+            ++cc->clock});
         P1_CUDA(cudaGraphLaunch(exec, s));
         return P1_OK;
       }
       cudaGetLastError();  // capture refused: the plain launch sequence below
     }
     release();
-    acc = nullptr; rec = nullptr; slots = nullptr;
+    acc = nullptr; rec = nullptr; slots = nullptr; halves = nullptr;
     if (rc) return rc;
   }
 
-  if ((rc = pool_alloc(ctx, &acc, words, s)) ||
-      (slim ? (rc = pool_alloc(ctx, &slots, (size_t)n_own * GROUP, s))
-            : (rc = pool_alloc(ctx, &rec, (size_t)n_own * GROUP, s))) ||
+  if ((rc = pool_alloc(ctx, &acc, words, s)) || (rc = alloc_rows()) ||
       (quad && ((rc = pool_alloc(ctx, &d_weights, (size_t)qa->n_qp, s)) ||
                 (rc = pool_alloc(ctx, &d_points, (size_t)2 * qa->n_qp, s))))) {
     release();

@@ -157,10 +157,15 @@ struct Rows {
   const int4 *tspill;  // ... and the few records beyond 8 per row (.w = row)
   int n_tspill;
   const int2 *slim;  // slim plans: {next, prev | k << 29}, values recomputed by the fill
+  const int4 *half;  // p1_assemble_cold, mass matrix: {next, prev | k << 29, v}, local row (2v, v, v)
   __device__ __forceinline__ int deg(int a) const { return (int)(unsigned)acc[a]; }
   // (next, prev | k << 29) of record i of row a, whatever the storage
   __device__ __forceinline__ int2 edge(int a, int deg, int i) const {
     if (slim) return slim[(int64_t)a * 8 + i];
+    if (half) {
+      const int4 h = half[(int64_t)a * 8 + i];
+      return make_int2(h.x, h.y);
+    }
     const Rec *r = ptr(a, deg) + i;
     return make_int2(r->nx, r->pvk);
   }
