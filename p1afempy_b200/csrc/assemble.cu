@@ -37,9 +37,10 @@ __device__ void slow_row_inline(int self, int deg, const Rec *nb, int *cs_out, d
 // closed and repeat-free.
 // HALF: the 16-byte slots {next, prev|k, v} of p1_assemble_cold's mass matrix (local row
 // (2v, v, v)) instead of records.
+// stride: distance between the row's slots, in slots (1, or Own::lay)
 template <bool HALF = false>
 __device__ __forceinline__ bool row_from_records(int self, int deg, const Rec *row, int *cs,
-                                                 double *vs) {
+                                                 double *vs, int64_t stride = 1) {
   int nx[GROUP], pv[GROUP], slot[GROUP];
   double vd[GROUP], vn[GROUP], vp[GROUP], mvp[GROUP];
   int slot_self = 0;
@@ -50,12 +51,12 @@ __device__ __forceinline__ bool row_from_records(int self, int deg, const Rec *r
     vd[i] = vn[i] = vp[i] = 0.;
     if (i < deg) {
       if constexpr (HALF) {
-        const int4 h = __ldg(reinterpret_cast<const int4 *>(row) + i);
+        const int4 h = __ldg(reinterpret_cast<const int4 *>(row) + i * stride);
         nx[i] = h.x; pv[i] = h.y & NODE_MASK;
         vn[i] = vp[i] = __hiloint2double(h.w, h.z);
         vd[i] = 2. * vn[i];
       } else {
-        const Rec r = load_rec(row + i);
+        const Rec r = load_rec(row + i * stride);
         nx[i] = r.nx; pv[i] = rec_prev(r);
         vd[i] = r.vd; vn[i] = r.vn; vp[i] = r.vp;
       }
@@ -131,10 +132,11 @@ fill_rows_kernel(int n_own, Own own, int exact,
     hash = (unsigned)(v >> 32);
     ob = __ldg(indptr + row0 + tid);
   }
-  // the row's 8 slots (HALF: 16 bytes each)
-  const Rec *row = HALF ? reinterpret_cast<const Rec *>(reinterpret_cast<const int4 *>(rec) +
-                                                        (int64_t)(row0 + tid) * GROUP)
-                        : rec + (int64_t)(row0 + tid) * GROUP;
+  // the row's 8 slots (HALF: 16 bytes each), `stride` slots apart
+  const int64_t stride = own.lay ? own.lay : 1;
+  const int64_t first = own.pos(row0 + tid, 0);
+  const Rec *row = HALF ? reinterpret_cast<const Rec *>(reinterpret_cast<const int4 *>(rec) + first)
+                        : rec + first;
   const bool process = deg >= 1 && deg <= GROUP && (exact || hash == 0u);
   if (process) {
     // staged: the row is built in the block's image; otherwise (irregular rows
@@ -143,19 +145,23 @@ fill_rows_kernel(int n_own, Own own, int exact,
     double *vs = out_staged ? vals_s + (ob - obeg) : data + ob;
     // exact plan: a row that fails is in slow_rows.  Hash plan: the shortcut
     // "closed fan => 1 + #records columns" does not hold for this row.
-    if (!row_from_records<HALF>(own.global(row0 + tid), deg, row, cs, vs) && !exact)
+    if (!row_from_records<HALF>(own.global(row0 + tid), deg, row, cs, vs, stride) && !exact)
       atomicOr(flags, FLAG_RETRY);
   } else if (inline_slow && deg >= 1 && deg <= GROUP) {  // an open fan (p1_assemble_cold)
     int *cs = out_staged ? cols_s + (ob - obeg) : (indices ? indices + ob : nullptr);
     double *vs = out_staged ? vals_s + (ob - obeg) : data + ob;
-    if constexpr (HALF) {
+    if (HALF || stride != 1) {  // the row's records side by side, in local memory
       Rec made[GROUP];
       for (int i = 0; i < deg; ++i) {
-        const int4 h = reinterpret_cast<const int4 *>(row)[i];
-        made[i].nx = h.x;
-        made[i].pvk = h.y;
-        made[i].vn = made[i].vp = __hiloint2double(h.w, h.z);
-        made[i].vd = 2. * made[i].vn;
+        if constexpr (HALF) {
+          const int4 h = reinterpret_cast<const int4 *>(row)[i * stride];
+          made[i].nx = h.x;
+          made[i].pvk = h.y;
+          made[i].vn = made[i].vp = __hiloint2double(h.w, h.z);
+          made[i].vd = 2. * made[i].vn;
+        } else {
+          made[i] = row[i * stride];
+        }
       }
       slow_row_inline(own.global(row0 + tid), deg, made, cs, vs);
     } else {

@@ -133,7 +133,7 @@ __device__ __forceinline__ void scatter_element(int64_t t, const int (&e)[3], in
           over |= 1u << k;
           continue;
         }
-        pos = (int64_t)a * GROUP + slot;
+        pos = own.pos(a, slot);
       }
       store_slot<TOPO>(rec, rec_elem, pos, nx, pv | (k << NODE_BITS), v[k],
                        (int)((t << 2) | k));
@@ -280,7 +280,7 @@ __device__ __forceinline__ void pair_deliver(int64_t t, const int (&id)[6], unsi
         if (mine[i]) over = true;
         continue;
       }
-      const int64_t pos = (int64_t)row[i] * GROUP + slot[i];
+      const int64_t pos = own.pos(row[i], slot[i]);
       where[i] = (int)pos;
       store_slot<TOPO>(rec, TOPO == 1 ? nullptr : rec_elem, pos, e[k == 2 ? 0 : k + 1],
                        e[k == 0 ? 2 : k - 1] | (k << NODE_BITS), v[k],
@@ -1561,20 +1561,20 @@ __device__ __forceinline__ int cold_row_length(unsigned long long v, bool &big) 
 // warp's chain of record misses was a third of the kernel (20 us before, 13 us after).
 // (by value: a reference to the kernel's Rows would make every thread copy it to its stack)
 __device__ __noinline__ int open_row_length(const Rec *rec, const int2 *slim, const int4 *half,
-                                            int a, int self, int deg) {
+                                            int lay, int a, int self, int deg) {
   int ex[GROUP], ey[GROUP];
 #pragma unroll
   for (int p = 0; p < GROUP; ++p) {
     int2 e = make_int2(self, self);
     if (p < deg) {
+      const int64_t at = lay ? (int64_t)p * lay + a : (int64_t)a * GROUP + p;
       if (slim) {
-        e = slim[(int64_t)a * GROUP + p];
+        e = slim[at];
       } else if (half) {
-        const int4 h = half[(int64_t)a * GROUP + p];
+        const int4 h = half[at];
         e = make_int2(h.x, h.y);
       } else {
-        const Rec *r = rec + (int64_t)a * GROUP + p;
-        e = make_int2(r->nx, r->pvk);
+        e = make_int2(rec[at].nx, rec[at].pvk);
       }
     }
     ex[p] = e.x;
@@ -1650,7 +1650,7 @@ rowptr_kernel(int n_own, Own own, Rows rows, int *__restrict__ indptr,
   while (open) {  // (as many rounds as the warp's unluckiest thread has open rows)
     const int j = __ffs(open) - 1;
     open &= open - 1;
-    const int n = open_row_length(rows.rec, rows.slim, rows.half, first + j,
+    const int n = open_row_length(rows.rec, rows.slim, rows.half, own.lay, first + j,
                                   own.global(first + j), rows.deg(first + j));
 #pragma unroll
     for (int i = 0; i < RP_ITEMS; ++i) len[i] = i == j ? n : len[i];
@@ -1792,11 +1792,12 @@ extern "C" int p1_assemble_cold(p1_ctx *ctx, const int32_t *elements, int64_t n_
   int wshift = -1;
   for (int b = 0; b < 31; ++b)
     if ((1 << b) == world) wshift = b;
-  const Own own{0, (int)n_nodes, chunk_log2, world, rank, wshift};
+  Own own{0, (int)n_nodes, chunk_log2, world, rank, wshift, 0};
   const int n_own = (int)own.count();
   const int N = (int)n_nodes;
   const int64_t M = n_elements;
   const bool slim = world > 1 && (op == P1_OP_STIFFNESS || op == P1_OP_MASS);
+  if (!slim) own.lay = n_own;  // records slot-major (plan.cuh: Own::lay)
   // one GPU, mass matrix: the local row of an incidence is (2v, v, v), so a record is 16
   // bytes {next, prev|k, v}: half the record bytes through HBM in both directions
   const bool half = !slim && op == P1_OP_MASS;

@@ -30,6 +30,15 @@ struct SpillDesc {
 struct Own {
   int rb, re, cshift, world, rank;
   int wshift;  // log2(world) when world is a power of two, else -1
+  // p1_assemble_cold stores the rows' 8 slots SLOT-major, slot i of row a at [i * lay + a]
+  // (lay = number of owned rows): the fill's loads of slot i for 32 consecutive rows are
+  // then contiguous (8 L1 wavefronts per 256-bit load instruction instead of 32).
+  // 0: row-major, [a * 8 + i] (plans).
+  int lay;
+  __host__ __device__ __forceinline__ int64_t pos(int a, unsigned slot) const {
+    const int rs = lay ? 1 : 8, ss = lay ? lay : 1;
+    return (int64_t)a * rs + (int64_t)slot * ss;
+  }
   __host__ __device__ __forceinline__ bool owns(int e, int &a) const {
     const unsigned x = (unsigned)(e - rb);
     if (x >= (unsigned)(re - rb)) return false;
