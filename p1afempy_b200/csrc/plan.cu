@@ -23,6 +23,7 @@
 
 #include "plan.cuh"
 #include <stdlib.h>
+#include <type_traits>
 #include <vector>
 
 namespace p1 {
@@ -380,11 +381,11 @@ __device__ __forceinline__ void scatter_pair(int64_t t, const int (&id)[6], int 
 // what ptxas picks without a min-blocks hint --, 99 registers 2.74 ms, 64 with
 // spills 2.35 ms, 48 with spills 2.82 ms)
 template <class V, bool OVERFLOW, bool PAIRS, int TOPO>
-__global__ void __launch_bounds__(SC_THREADS)
-scatter_kernel(const int *__restrict__ elements, int64_t M, int N, Own own, int vec,
-               unsigned long long *__restrict__ acc, Rec *__restrict__ rec,
-               int *__restrict__ rec_elem, int *__restrict__ cursor, V values,
-               int *__restrict__ flags) {
+__device__ __forceinline__ void
+scatter_body(const int *__restrict__ elements, int64_t M, int N, const Own &own, int vec,
+             unsigned long long *__restrict__ acc, Rec *__restrict__ rec,
+             int *__restrict__ rec_elem, int *__restrict__ cursor, const V &values,
+             int *__restrict__ flags) {
   int mx = -1;
   bool bad = false;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -433,10 +434,39 @@ scatter_kernel(const int *__restrict__ elements, int64_t M, int N, Own own, int 
   }
 }
 
+template <class V, bool OVERFLOW, bool PAIRS, int TOPO>
+__global__ void __launch_bounds__(SC_THREADS)
+scatter_kernel(const int *__restrict__ elements, int64_t M, int N, Own own, int vec,
+               unsigned long long *__restrict__ acc, Rec *__restrict__ rec,
+               int *__restrict__ rec_elem, int *__restrict__ cursor, V values,
+               int *__restrict__ flags) {
+  scatter_body<V, OVERFLOW, PAIRS, TOPO>(elements, M, N, own, vec, acc, rec, rec_elem, cursor,
+                                         values, flags);
+}
+
+// The same kernel with room for two blocks per SM stated: GeneralValues keeps 16 coefficient
+// loads in flight and wants the registers for it -- without the hint ptxas settles on 103
+// registers and the scatter takes 9.1 ms at 64M, with it on 120+ and 8.0 ms.  (A hint on
+// the other value sources changes THEIR allocation, e.g. stiffness 80 -> 118 registers.)
+template <class V, bool OVERFLOW, bool PAIRS, int TOPO>
+__global__ void __launch_bounds__(SC_THREADS, 2)
+scatter_kernel_wide(const int *__restrict__ elements, int64_t M, int N, Own own, int vec,
+                    unsigned long long *__restrict__ acc, Rec *__restrict__ rec,
+                    int *__restrict__ rec_elem, int *__restrict__ cursor, V values,
+                    int *__restrict__ flags) {
+  scatter_body<V, OVERFLOW, PAIRS, TOPO>(elements, M, N, own, vec, acc, rec, rec_elem, cursor,
+                                         values, flags);
+}
+
 template <class V, bool OVERFLOW>
 static void launch_one(bool pairs, unsigned grid, cudaStream_t s, const int *elements, int64_t M,
                        int N, Own own, int vec, unsigned long long *acc, Rec *rec,
                        int *rec_elem, int *cursor, V values, int *fl) {
+  if constexpr (std::is_same<V, GeneralValues>::value && !OVERFLOW) {
+    scatter_kernel_wide<V, OVERFLOW, false, 0><<<grid, SC_THREADS, 0, s>>>(
+        elements, M, N, own, vec, acc, rec, rec_elem, cursor, values, fl);
+    return;
+  }
   if (pairs && !OVERFLOW)
     scatter_kernel<V, OVERFLOW, true, 0><<<grid, SC_THREADS, 0, s>>>(
         elements, M, N, own, vec, acc, rec, rec_elem, cursor, values, fl);
