@@ -91,7 +91,13 @@ def main():
     options.plan_flags = 0
     reused = DeviceMesh(c, e, reuse=True)
     reused.stiffness_csr()
-    record('stiffness->CSR values (plan reused: numeric refill only)',
+    record('stiffness->CSR values (DeviceMesh(reuse=True), pattern=False: new values on an '
+           'unchanged mesh; cold path without the index arrays)',
+           gpu_time(lambda: reused.stiffness_csr(pattern=False)), None,
+           8.0 * 3.5 + 12.0 + 8.0)
+    reused._cold_refill = False
+    record('stiffness->CSR values (the same through p1_assemble_csr on the kept plan: records '
+           'refreshed in place, then filled)',
            gpu_time(lambda: reused.stiffness_csr(pattern=False)), None,
            8.0 * 3.5 + 12.0 + 8.0)
     reused.close()

@@ -518,6 +518,32 @@ def test_device_resident_api_and_plan_reuse():
         assert np.array_equal(b.cpu().numpy(), orc.load_vector_midpoint(pts, e, H.f_load))
 
 
+def test_new_values_on_a_kept_plan_take_the_cold_path(mesh_case):
+    """DeviceMesh(reuse=True): a second operator on the unchanged mesh is assembled by
+    the cold path (faster than refreshing the plan's records in place) and gives the
+    bits of the plan route; the plan stays for the vector / edge consumers."""
+    import torch
+    from p1afempy_b200 import _lib
+    from p1afempy_b200.device import DeviceMesh
+    c, e, _ = mesh_case
+    ct, et = torch.from_numpy(c).cuda(), torch.from_numpy(e.astype(np.int32)).cuda()
+    with DeviceMesh(ct, et) as plain:
+        ref_ip, ref_ix, ref_m = [t.cpu().numpy() for t in plain.mass_csr()]
+    with DeviceMesh(ct, et, reuse=True) as mesh:
+        mesh.stiffness_csr()
+        plan_before = mesh._plan.value
+        regular = int(mesh.assemble_cold(_lib.OP_MASS).status.cpu()[0]) == 0
+        ip, ix, m = mesh.mass_csr()
+        assert mesh._plan.value == plan_before and mesh._cold_refill == regular
+        assert np.array_equal(ip.cpu().numpy(), ref_ip) and np.array_equal(ix.cpu().numpy(), ref_ix)
+        assert np.array_equal(m.cpu().numpy(), ref_m)
+        none_ip, none_ix, m2 = mesh.mass_csr(pattern=False)
+        assert none_ip is None and none_ix is None and np.array_equal(m2.cpu().numpy(), ref_m)
+        mesh._cold_refill = False                # the in-place refresh of the kept plan
+        _, _, m3 = mesh.mass_csr(pattern=False)
+        assert np.array_equal(m3.cpu().numpy(), ref_m)
+
+
 def test_topology_plan_matches_element_keeping_plan():
     """P1_PLAN_TOPOLOGY (16-byte slots, no values, no row pointer) serves load
     vectors, edge numbering and eta_R with the same bits as the element-keeping
