@@ -396,7 +396,7 @@ scatter_body(const int *__restrict__ elements, int64_t M, int N, const Own &own,
   // stalls 13 per issue at 24 warps per SM -- costs 36 registers, i.e. a resident block:
   // 2.13 -> 2.60 ms at 64M)
   for (int64_t g = tid; g < quads; g += stride) {
-    const int4 p = __ldg(e4 + 3 * g), q = __ldg(e4 + 3 * g + 1), r = __ldg(e4 + 3 * g + 2);
+    const int4 p = __ldcs(e4 + 3 * g), q = __ldcs(e4 + 3 * g + 1), r = __ldcs(e4 + 3 * g + 2);  // streamed
     if constexpr (!OVERFLOW && PAIRS) {
       const int ab[6] = {p.x, p.y, p.z, p.w, q.x, q.y}, cd[6] = {q.z, q.w, r.x, r.y, r.z, r.w};
       int w0[6], w1[6];
@@ -804,7 +804,7 @@ __device__ __forceinline__ void load_scatter_body(const int *__restrict__ elemen
   const int64_t quads = M / 4;
   const int4 *e4 = reinterpret_cast<const int4 *>(elements);
   for (int64_t g = tid; g < quads; g += stride) {
-    const int4 p = __ldg(e4 + 3 * g), q = __ldg(e4 + 3 * g + 1), r = __ldg(e4 + 3 * g + 2);
+    const int4 p = __ldcs(e4 + 3 * g), q = __ldcs(e4 + 3 * g + 1), r = __ldcs(e4 + 3 * g + 2);  // streamed
     const int id[12] = {p.x, p.y, p.z, p.w, q.x, q.y, q.z, q.w, r.x, r.y, r.z, r.w};
     double area[4];
 #pragma unroll
