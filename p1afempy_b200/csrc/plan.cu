@@ -379,7 +379,8 @@ __device__ __forceinline__ void scatter_pair(int64_t t, const int (&id)[6], int 
 // 1.01 ms), so multi-GPU plans use the plain form.
 // (register allocation of the PAIRS form, measured at 64M: 80 registers 2.20 ms --
 // what ptxas picks without a min-blocks hint --, 99 registers 2.74 ms, 64 with
-// spills 2.35 ms, 48 with spills 2.82 ms)
+// spills 2.35 ms, 48 with spills 2.82 ms; 72 registers with blocks of 128 threads, 7 per
+// SM: 2.32 ms; blocks of 128 threads at 80 registers: 2.34 ms)
 template <class V, bool OVERFLOW, bool PAIRS, int TOPO>
 __device__ __forceinline__ void
 scatter_body(const int *__restrict__ elements, int64_t M, int N, const Own &own, int vec,
