@@ -357,6 +357,11 @@ __device__ __forceinline__ void pair_deliver(int64_t t, const int (&id)[6], unsi
 // vertices, so the 6 vertex references are grouped in registers -- one atomic
 // per DISTINCT node (typically 4 instead of 6).  The kernel is bound by LSU
 // operations per lane; the 15 comparisons are free.
+// (Requesting the six coordinates BEFORE the atomics, so that the two latencies overlap --
+// same 80 registers -- was measured at 64M: stiffness scatter 2.19 -> 2.30 ms.  Like the
+// two experiments noted in scatter_body, more requests in flight per warp make it slower:
+// the kernel sits at the rate at which the memory system takes divergent requests, ~8 per
+// triangle, not at their latency.)
 template <class V, int TOPO>
 __device__ __forceinline__ void scatter_pair(int64_t t, const int (&id)[6], int N,
                                              const Own &own,
