@@ -887,6 +887,44 @@ def test_cold_assembly_replayed_as_a_graph(api):
                 other.assemble_cold(_lib.OP_STIFFNESS, out=sets[0])
 
 
+def test_cold_assembly_from_two_threads(api):
+    """Two host threads share the context (one per device), each on its own stream and
+    its own output arrays: the entry points serialise on the context's lock, the cached
+    graphs are keyed by stream and arrays, and every result is the plan route's."""
+    import threading
+    import torch
+    from p1afempy_b200 import _lib
+    from p1afempy_b200.device import DeviceMesh
+    c, e, _ = H.perturbed_square(5)
+    ct, et = torch.from_numpy(c).cuda(), torch.from_numpy(e.astype(np.int32)).cuda()
+    with DeviceMesh(ct, et) as m:
+        refs = {op: [t.cpu().numpy() for t in m.assemble(op)]
+                for op in (_lib.OP_STIFFNESS, _lib.OP_MASS)}
+    torch.cuda.synchronize()
+    errors = []
+
+    def work(op):
+        try:
+            stream = torch.cuda.Stream()
+            with torch.cuda.stream(stream), DeviceMesh(ct, et) as mesh:
+                cold = None
+                for _ in range(40):
+                    cold = mesh.assemble_cold(op, out=cold)
+                    got = [t.cpu().numpy() for t in cold.wait()]
+                    cold._done = None
+                    for x, y in zip(refs[op], got):
+                        if not np.array_equal(x, y):
+                            raise AssertionError('mismatch in thread of op %d' % op)
+        except Exception as ex:       # noqa: BLE001  (reported in the main thread)
+            errors.append(ex)
+    threads = [threading.Thread(target=work, args=(op,)) for op in refs]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+
+
 def test_cold_assembly_falls_back_to_the_plan_route(api):
     """Status words instead of return codes: a node with more than 8 elements
     (P1_STATUS_SLOWPATH), a non-manifold vertex (P1_STATUS_RETRY) and an index out
