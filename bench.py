@@ -143,11 +143,12 @@ def reference_level(op, level, runs, budget_s):
         avail = psutil.virtual_memory().available
     except Exception:
         avail = 32 << 30
-    for l in range(level, 5, -1):
+    lowest = min(level, 6)
+    for l in range(level, lowest - 1, -1):
         m = mesh_counts(l)[0]
         if m * REF_S_PER_TRI[op] * runs <= budget_s and m * REF_PEAK_B_PER_TRI[op] <= 0.6 * avail:
             return l
-    return 6
+    return lowest
 
 
 class ClockSampler(threading.Thread):
