@@ -963,6 +963,19 @@ def test_cold_assembly_falls_back_to_the_plan_route(api):
     with pytest.raises(IndexError):
         mesh.assemble_cold(_lib.OP_STIFFNESS).wait()
     mesh.close()
+    # nnz above the capacity 2 N + 3 M: two triangles that share ONE vertex (5 nodes, 6
+    # edges, all on the boundary: nnz = 17 > 16) -- reported, nothing written, plan route
+    ct = np.array([[0., 0.], [1., 0.], [0., 1.], [-1., 0.], [0., -1.]])
+    et = np.array([[0, 1, 2], [0, 3, 4]])
+    with DeviceMesh(ct, et) as mesh:
+        assert mesh.cold_capacity() == 16
+        cold = mesh.assemble_cold(_lib.OP_STIFFNESS)
+        assert int(cold.status[0].item()) == _lib.STATUS_SLOWPATH
+        assert int(cold.status[6].item()) == 17
+        ip, ix, data = [t.cpu().numpy() for t in cold.wait()]
+    ref = orc.stiffness_coo(ct, et).tocsr()
+    assert ref.nnz == 17 and np.array_equal(ip, ref.indptr) and np.array_equal(ix, ref.indices)
+    assert np.abs(data - ref.data).max() <= RTOL * np.abs(ref.data).max()
 
 
 def test_to_scipy_int64_branch(api, monkeypatch):
